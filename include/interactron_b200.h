@@ -1,0 +1,169 @@
+/*
+ * interactron_b200 — C ABI of the B200 (sm_100a) kernels behind the Interactron
+ * test-time-adaptation hot path.
+ *
+ * The reference (allenai/interactron) has no FFI layer: every arithmetic step of
+ * the path is an ATen call made from Python.  Each entry point below therefore
+ * cites the reference *call site* (file:line under /root/reference) whose
+ * arithmetic it replaces.  Conventions:
+ *   - plain `extern "C"`, raw device pointers + explicit sizes/strides (in ELEMENTS
+ *     unless stated), the CUDA stream as an opaque `void*` (cudaStream_t);
+ *   - no allocation, no ownership transfer, no host sync inside any call;
+ *   - return 0 on success, negative on error; the message is in itn_last_error();
+ *   - re-entrant per stream; every launch is CUDA-graph capturable.
+ * Everything is fp32 in memory; GEMMs compute in TF32 on tcgen05 tensor cores.
+ */
+#ifndef INTERACTRON_B200_H
+#define INTERACTRON_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ITN_OK 0
+#define ITN_ERR_ARG -1
+#define ITN_ERR_CUDA -2
+#define ITN_ERR_UNSUPPORTED -3
+
+/* Last error message of the calling thread ("" if none). */
+const char* itn_last_error(void);
+/* Library/ABI version and build arch string, e.g. "interactron_b200 0.1 sm_100a". */
+const char* itn_version(void);
+/* Number of kernels launched by this library since load (all threads). */
+long long itn_launch_count(void);
+
+/* ------------------------------------------------------------------ GEMM --- */
+/* One matrix operand of a (batched) GEMM.  `major` says which logical dim is
+ * contiguous in memory: 0 = the contraction dim K (row-major [rows,K], e.g. an
+ * nn.Linear weight [N,K] or an activation [M,K]); 1 = the M (for A) / N (for B)
+ * dim (i.e. the matrix is stored [K,rows]).  `ld` is the stride between
+ * consecutive indices of the NON-contiguous dim.  sb0/sb1 are the strides of the
+ * outer/inner batch index (0 broadcasts the operand over that batch dim). */
+typedef struct {
+  const float* ptr;
+  int major;
+  long long ld;
+  long long sb0, sb1;
+} itn_operand_t;
+
+enum { ITN_ACT_NONE = 0, ITN_ACT_RELU = 1, ITN_ACT_GELU = 2 };
+enum { ITN_EPI_NONE = 0, ITN_EPI_RELU_MASK = 1, ITN_EPI_GELU_GRAD = 2 };
+
+/* C[b0,b1] = epilogue( alpha * A[b0,b1] (MxK) * B[b0,b1]^T (NxK)^T ), batch = nb0*nb1.
+ * Epilogue order per element:  v = alpha*acc; v += bias[n]; if (C2) C2 = v;
+ * v = act(v); epi (RELU_MASK: v = aux>0 ? v : 0; GELU_GRAD: v *= gelu'(aux));
+ * v += residual; if (accumulate) v += C; C = v.
+ * Replaces: every nn.Linear / F.linear, the 1x1 input_proj conv, bmm/baddbmm of
+ * nn.MultiheadAttention and the `q @ k.T`, `att @ v` of CausalSelfAttention on
+ * the path, forward and backward (models/detr_models/transformer.py:148-161,
+ * 211-232; models/detr_models/detr.py:68-72,299-311; models/gpt.py:43-56,68-78,
+ * 197-198; models/transformer.py:49-63; models/new_transformer.py:36-56), and
+ * the matching autograd mm/bmm backward nodes of models/interactron.py:51-52. */
+typedef struct {
+  int M, N, K;
+  int nb0, nb1;
+  itn_operand_t A, B;
+  float* C;              long long ldc,   c_sb0,    c_sb1;
+  const float* bias;     long long        bias_sb0, bias_sb1;
+  const float* residual; long long ldr,   r_sb0,    r_sb1;
+  const float* aux;      long long ldaux, aux_sb0,  aux_sb1;
+  float* C2;             long long ldc2,  c2_sb0,   c2_sb1;
+  float alpha;
+  int act;
+  int epi;
+  int accumulate;
+} itn_gemm_desc_t;
+
+/* tcgen05/TMA path.  Requires 16-byte aligned operand bases and ld/sb* multiples
+ * of 4 elements; returns ITN_ERR_UNSUPPORTED otherwise (use itn_gemm_simt). */
+int itn_gemm_tf32(const itn_gemm_desc_t* d, void* stream);
+/* 1 if the descriptor satisfies the TMA constraints of itn_gemm_tf32. */
+int itn_gemm_tf32_supported(const itn_gemm_desc_t* d);
+/* CUDA-core fp32 GEMM with the same descriptor and epilogue, any alignment.
+ * Used for the few unaligned / degenerate shapes (N=1 data-grad) on the path. */
+int itn_gemm_simt(const itn_gemm_desc_t* d, void* stream);
+
+/* ------------------------------------------------------------- row-wise --- */
+/* y = LayerNorm(x) * gamma + beta over the last dim `cols` (eps as given;
+ * the reference uses nn.LayerNorm default 1e-5: detr_models/transformer.py:139-140,
+ * 198-200; models/gpt.py:64-65,97).  Rows are split in `groups` equal groups;
+ * group g uses gamma/beta + g*gb_stride (per-episode fast weights).  mean/rstd
+ * ([rows], may be NULL) are saved for the backward. */
+int itn_layernorm_fwd(const float* x, const float* gamma, const float* beta,
+                      float* y, float* mean, float* rstd,
+                      long long rows, int cols, int groups, long long gb_stride,
+                      float eps, void* stream);
+/* dx = d LayerNorm; dgamma/dbeta ([groups, cols], may be NULL) are OVERWRITTEN
+ * with the per-group sums.  Replaces native_layer_norm_backward under
+ * models/interactron.py:51-52. */
+int itn_layernorm_bwd(const float* dy, const float* x, const float* mean,
+                      const float* rstd, const float* gamma,
+                      float* dx, float* dgamma, float* dbeta,
+                      long long rows, int cols, int groups, long long gb_stride,
+                      void* stream);
+
+/* In-place row softmax of scale*s + mask over `cols` (row stride ld).
+ * key_mask (may be NULL) is uint8 [mask_batches, cols], 1 = padded key (-inf);
+ * row r uses mask row (r / rows_per_mask).  Replaces F.softmax in
+ * nn.MultiheadAttention (transformer.py:154,219-226) and models/gpt.py:48-50. */
+int itn_softmax_fwd(float* s, long long rows, int cols, long long ld, float scale,
+                    const unsigned char* key_mask, long long rows_per_mask,
+                    void* stream);
+/* ds = scale * p * (dp - sum(p*dp)) written in place over dp. */
+int itn_softmax_bwd(const float* p, float* dp, long long rows, int cols,
+                    long long ld, float scale, void* stream);
+
+/* out[g, c] = sum_r x[g, r, c]  (bias gradients): x is [groups, rows, cols]
+ * with row stride ld; out [groups, cols] OVERWRITTEN. */
+int itn_colsum(const float* x, float* out, int groups, long long rows, int cols,
+               long long ld, void* stream);
+
+/* --------------------------------------------------------- element-wise --- */
+/* out = a + b (b broadcast with period b_elems: b[i % b_elems]). */
+int itn_add(const float* a, const float* b, float* out, long long n,
+            long long b_elems, void* stream);
+/* Strided 2-D copy: dst[r*ldd + c] = src[r*lds + c]. */
+int itn_copy2d(const float* src, long long lds, float* dst, long long ldd,
+               long long rows, int cols, void* stream);
+/* y = sigmoid(x)   (detr.py:72 `.sigmoid()`). */
+int itn_sigmoid_fwd(const float* x, float* y, long long n, void* stream);
+/* dx = dy * y * (1-y). */
+int itn_sigmoid_bwd(const float* dy, const float* y, float* dx, long long n,
+                    void* stream);
+/* Learned loss: per group g of n values, loss[g] = ||x_g||_2 and
+ * dx_g = x_g / ||x_g||  (torch.norm + its backward seed, models/interactron.py:50). */
+int itn_l2norm_fwd_bwd(const float* x, float* loss, float* dx, int groups, int n,
+                       void* stream);
+
+/* Fused fast-weight step (utils/meta_utils.py:135-142 sgd_step):
+ *   theta_out = theta - clip(lr * g, -clip, +clip)
+ * theta may be broadcast over `groups` episodes (theta_stride 0); g and
+ * theta_out are [groups, n].  clip_mask (may be NULL, uint8 [groups,n]) receives
+ * 1 where the step was inside the clip band (d step/d g = lr), else 0. */
+int itn_sgd_clip_update(const float* theta, long long theta_stride, const float* g,
+                        float* theta_out, unsigned char* clip_mask, int groups,
+                        long long n, float lr, float clip, void* stream);
+
+/* DETR sine position embedding (detr_models/position_encoding.py:28-48,
+ * normalize=True, scale 2*pi, temperature 10000, num_pos_feats=feats per axis).
+ * mask uint8 [frames,h,w] (1 = padded) -> pos [frames, h*w, 2*feats] token-major. */
+int itn_pos_embed_sine(const unsigned char* mask, float* pos, int frames, int h,
+                       int w, int feats, void* stream);
+
+/* ------------------------------------------------------ matcher/criterion --- */
+/* HungarianMatcher cost matrix (detr_models/matcher.py:53-71, util/box_ops.py:8-58):
+ * for frame f, query q, target t (targets of all frames concatenated, frame f owns
+ * [tgt_off[f], tgt_off[f+1])):  C = w_bbox*L1(box_q, box_t) - w_class*softmax(logits_q)[label_t]
+ *   - w_giou*GIoU(xyxy(box_q), xyxy(box_t)).  Only the block-diagonal the
+ * reference uses is produced: cost is [sum_f Q*T_f] packed frame after frame,
+ * row-major [Q, T_f] per frame.  logits [frames,Q,classes], boxes [frames,Q,4]
+ * cxcywh, tgt_boxes [T,4] cxcywh, tgt_labels int64 [T], tgt_off int32 [frames+1]. */
+int itn_matcher_cost(const float* logits, const float* boxes, const float* tgt_boxes,
+                     const long long* tgt_labels, const int* tgt_off, float* cost,
+                     int frames, int queries, int classes, float w_class,
+                     float w_bbox, float w_giou, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* INTERACTRON_B200_H */

@@ -1,0 +1,51 @@
+// Shared host-side helpers: error reporting, launch accounting.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/interactron_b200.h"
+
+namespace itn {
+
+int set_error(int code, const char* fmt, ...);
+extern std::atomic<long long> g_launches;
+
+inline int check_launch(const char* what) {
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return set_error(ITN_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+  }
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return ITN_OK;
+}
+
+#define ITN_REQUIRE(cond, ...)                              \
+  do {                                                      \
+    if (!(cond)) return itn::set_error(ITN_ERR_ARG, __VA_ARGS__); \
+  } while (0)
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__device__ __forceinline__ float gelu_erf(float x) {
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+  const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+
+}  // namespace itn

@@ -1,0 +1,238 @@
+// Element-wise HBM-bound kernels: fused fast-weight SGD step, add, strided copy,
+// sigmoid fwd/bwd, learned-loss L2 norm, DETR sine position embedding.
+// 128-bit accesses, grid-stride loops sized in multiples of the SM count.
+#include "itn_common.cuh"
+
+namespace itn {
+
+constexpr int kSMs = 148;
+
+static inline unsigned grid_for(long long work_items, int threads, int max_ctas_per_sm = 8) {
+  long long blocks = (work_items + threads - 1) / threads;
+  const long long cap = (long long)kSMs * max_ctas_per_sm;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (unsigned)blocks;
+}
+
+// theta_out = theta - clip(lr*g).  n4 = n/4 vector part, scalar tail handled by block 0.
+__global__ void __launch_bounds__(256)
+sgd_clip_update_kernel(const float* __restrict__ theta, long long theta_stride,
+                       const float* __restrict__ g, float* __restrict__ out,
+                       unsigned char* __restrict__ mask, long long n, float lr, float clip) {
+  const int grp = blockIdx.y;
+  const float* th = theta + grp * theta_stride;
+  const float* gg = g + (long long)grp * n;
+  float* oo = out + (long long)grp * n;
+  unsigned char* mm = mask ? mask + (long long)grp * n : nullptr;
+  const long long n4 = n >> 2;
+  const float4* th4 = reinterpret_cast<const float4*>(th);
+  const float4* g4 = reinterpret_cast<const float4*>(gg);
+  float4* o4 = reinterpret_cast<float4*>(oo);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 t = th4[i];
+    const float4 gv = __ldcs(g4 + i);
+    float4 st, o;
+    st.x = lr * gv.x; st.y = lr * gv.y; st.z = lr * gv.z; st.w = lr * gv.w;
+    o.x = t.x - fminf(fmaxf(st.x, -clip), clip);
+    o.y = t.y - fminf(fmaxf(st.y, -clip), clip);
+    o.z = t.z - fminf(fmaxf(st.z, -clip), clip);
+    o.w = t.w - fminf(fmaxf(st.w, -clip), clip);
+    o4[i] = o;
+    if (mm) {
+      uchar4 m;
+      m.x = fabsf(st.x) <= clip; m.y = fabsf(st.y) <= clip;
+      m.z = fabsf(st.z) <= clip; m.w = fabsf(st.w) <= clip;
+      reinterpret_cast<uchar4*>(mm)[i] = m;
+    }
+  }
+  if (blockIdx.x == 0) {
+    for (long long i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) {
+      const float st = lr * gg[i];
+      oo[i] = th[i] - fminf(fmaxf(st, -clip), clip);
+      if (mm) mm[i] = fabsf(st) <= clip;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
+           long long n, long long b_elems) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long n4 = n >> 2;
+  if ((b_elems & 3) == 0) {
+    const float4* a4 = reinterpret_cast<const float4*>(a);
+    const float4* b4 = reinterpret_cast<const float4*>(b);
+    float4* o4 = reinterpret_cast<float4*>(out);
+    const long long bq = b_elems >> 2;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+      const float4 x = a4[i], y = b4[i % bq];
+      o4[i] = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
+    }
+    if (blockIdx.x == 0)
+      for (long long i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x)
+        out[i] = a[i] + b[i % b_elems];
+  } else {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+      out[i] = a[i] + b[i % b_elems];
+  }
+}
+
+__global__ void __launch_bounds__(256)
+copy2d_kernel(const float* __restrict__ src, long long lds, float* __restrict__ dst, long long ldd,
+              long long rows, int cols) {
+  const long long total = rows * cols;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long r = i / cols;
+    const int c = (int)(i - r * cols);
+    dst[r * ldd + c] = src[r * lds + c];
+  }
+}
+
+__global__ void __launch_bounds__(256)
+sigmoid_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    y[i] = 1.0f / (1.0f + expf(-x[i]));
+}
+
+__global__ void __launch_bounds__(256)
+sigmoid_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y,
+                   float* __restrict__ dx, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float s = y[i];
+    dx[i] = dy[i] * s * (1.0f - s);
+  }
+}
+
+// One block per group: loss = sqrt(sum x^2); dx = x / loss.
+__global__ void __launch_bounds__(256)
+l2norm_fwd_bwd_kernel(const float* __restrict__ x, float* __restrict__ loss,
+                      float* __restrict__ dx, int n) {
+  __shared__ float sm[8];
+  const float* xg = x + (long long)blockIdx.x * n;
+  float a = 0.f;
+  for (int i = threadIdx.x; i < n; i += 256) a += xg[i] * xg[i];
+  a = warp_sum(a);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = a;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) t += sm[i];
+  const float nrm = sqrtf(t);
+  if (threadIdx.x == 0 && loss) loss[blockIdx.x] = nrm;
+  if (dx) {
+    const float inv = 1.0f / nrm;
+    float* dg = dx + (long long)blockIdx.x * n;
+    for (int i = threadIdx.x; i < n; i += 256) dg[i] = xg[i] * inv;
+  }
+}
+
+// One block per frame.  y_embed/x_embed = cumulative counts of unpadded cells,
+// normalised by the last row/column (+1e-6) times 2*pi; channel c of an axis is
+// sin (c even) / cos (c odd) of embed / 10000^(2*(c/2)/feats); y channels first.
+__global__ void __launch_bounds__(256)
+pos_embed_sine_kernel(const unsigned char* __restrict__ mask, float* __restrict__ pos, int h, int w,
+                      int feats) {
+  extern __shared__ float sh[];
+  float* ye = sh;            // [h*w]
+  float* xe = sh + h * w;    // [h*w]
+  const unsigned char* m = mask + (long long)blockIdx.x * h * w;
+  for (int j = threadIdx.x; j < w; j += blockDim.x) {
+    float c = 0.f;
+    for (int i = 0; i < h; ++i) {
+      c += m[i * w + j] ? 0.f : 1.f;
+      ye[i * w + j] = c;
+    }
+  }
+  for (int i = threadIdx.x; i < h; i += blockDim.x) {
+    float c = 0.f;
+    for (int j = 0; j < w; ++j) {
+      c += m[i * w + j] ? 0.f : 1.f;
+      xe[i * w + j] = c;
+    }
+  }
+  __syncthreads();
+  const float two_pi = 6.283185307179586f;
+  const int D = 2 * feats;
+  float* out = pos + (long long)blockIdx.x * h * w * D;
+  for (int idx = threadIdx.x; idx < h * w * D; idx += blockDim.x) {
+    const int t = idx / D, c = idx - t * D;
+    const int i = t / w, j = t - i * w;
+    const bool is_y = c < feats;
+    const int cc = is_y ? c : c - feats;
+    const float e = is_y ? ye[t] / (ye[(h - 1) * w + j] + 1e-6f) * two_pi
+                         : xe[t] / (xe[i * w + (w - 1)] + 1e-6f) * two_pi;
+    const float dim_t = powf(10000.0f, (float)(2 * (cc / 2)) / (float)feats);
+    const float v = e / dim_t;
+    out[idx] = (cc & 1) ? cosf(v) : sinf(v);
+  }
+}
+
+}  // namespace itn
+
+using namespace itn;
+
+extern "C" int itn_sgd_clip_update(const float* theta, long long theta_stride, const float* g,
+                                   float* theta_out, unsigned char* clip_mask, int groups,
+                                   long long n, float lr, float clip, void* stream) {
+  ITN_REQUIRE(theta && g && theta_out && groups > 0 && n > 0, "sgd_clip_update: bad arguments");
+  ITN_REQUIRE(((uintptr_t)theta & 15) == 0 && ((uintptr_t)g & 15) == 0 &&
+                  ((uintptr_t)theta_out & 15) == 0,
+              "sgd_clip_update: pointers must be 16-byte aligned");
+  ITN_REQUIRE(groups == 1 || ((n & 3) == 0 && (theta_stride & 3) == 0),
+              "sgd_clip_update: n and theta_stride must be multiples of 4 when groups > 1");
+  ITN_REQUIRE(!clip_mask || ((uintptr_t)clip_mask & 3) == 0, "sgd_clip_update: mask must be 4-byte aligned");
+  dim3 grid(grid_for(n >> 2, 256, 8), groups);
+  sgd_clip_update_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      theta, theta_stride, g, theta_out, clip_mask, n, lr, clip);
+  return check_launch("sgd_clip_update_kernel");
+}
+
+extern "C" int itn_add(const float* a, const float* b, float* out, long long n, long long b_elems,
+                       void* stream) {
+  ITN_REQUIRE(a && b && out && n > 0 && b_elems > 0, "add: bad arguments");
+  ITN_REQUIRE((((uintptr_t)a | (uintptr_t)b | (uintptr_t)out) & 15) == 0, "add: pointers must be 16-byte aligned");
+  add_kernel<<<grid_for(n >> 2, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, b, out, n, b_elems);
+  return check_launch("add_kernel");
+}
+
+extern "C" int itn_copy2d(const float* src, long long lds, float* dst, long long ldd, long long rows,
+                          int cols, void* stream) {
+  ITN_REQUIRE(src && dst && rows > 0 && cols > 0, "copy2d: bad arguments");
+  copy2d_kernel<<<grid_for(rows * cols, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, lds, dst, ldd, rows, cols);
+  return check_launch("copy2d_kernel");
+}
+
+extern "C" int itn_sigmoid_fwd(const float* x, float* y, long long n, void* stream) {
+  ITN_REQUIRE(x && y && n > 0, "sigmoid_fwd: bad arguments");
+  sigmoid_fwd_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, n);
+  return check_launch("sigmoid_fwd_kernel");
+}
+
+extern "C" int itn_sigmoid_bwd(const float* dy, const float* y, float* dx, long long n,
+                               void* stream) {
+  ITN_REQUIRE(dy && y && dx && n > 0, "sigmoid_bwd: bad arguments");
+  sigmoid_bwd_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(dy, y, dx, n);
+  return check_launch("sigmoid_bwd_kernel");
+}
+
+extern "C" int itn_l2norm_fwd_bwd(const float* x, float* loss, float* dx, int groups, int n,
+                                  void* stream) {
+  ITN_REQUIRE(x && groups > 0 && n > 0, "l2norm_fwd_bwd: bad arguments");
+  l2norm_fwd_bwd_kernel<<<groups, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, loss, dx, n);
+  return check_launch("l2norm_fwd_bwd_kernel");
+}
+
+extern "C" int itn_pos_embed_sine(const unsigned char* mask, float* pos, int frames, int h, int w,
+                                  int feats, void* stream) {
+  ITN_REQUIRE(mask && pos && frames > 0 && h > 0 && w > 0 && feats > 0, "pos_embed_sine: bad arguments");
+  const size_t smem = 2ull * h * w * sizeof(float);
+  ITN_REQUIRE(smem <= 48 * 1024, "pos_embed_sine: feature map %dx%d too large", h, w);
+  pos_embed_sine_kernel<<<frames, 256, smem, static_cast<cudaStream_t>(stream)>>>(mask, pos, h, w, feats);
+  return check_launch("pos_embed_sine_kernel");
+}

@@ -1,0 +1,443 @@
+// Batched TF32 GEMM on tcgen05 tensor cores (sm_100a), operands staged by TMA,
+// accumulator in TMEM, fused epilogue.  See include/interactron_b200.h
+// (itn_gemm_tf32) for the contract and the reference call sites it replaces.
+//
+// CTA = 192 threads: warp 0 TMA producer, warp 1 TMEM owner + MMA issuer (one
+// elected lane issues tcgen05.mma.kind::tf32 128xBNx8), warps 2-5 epilogue
+// (TMEM -> registers -> per-warp smem transpose -> coalesced global stores).
+// One CTA produces one 128 x BN tile of one batch entry; the K loop runs over a
+// STAGES-deep ring of {A tile, B tile} filled with SWIZZLE_128B TMA boxes whose
+// inner extent is 32 floats (= one 128-byte swizzle row).  Both operand majors
+// are supported through the UMMA descriptors, so forward (x W^T), data-grad
+// (dy W) and weight-grad (dy^T x) all run without materialising transposes.
+// Out-of-bounds rows/cols/K are zero-filled by TMA and masked in the epilogue,
+// so ragged sizes (N=1236, K=1496, M=250, ...) need no padding in HBM.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <mutex>
+
+#include "itn_common.cuh"
+#include "itn_ptx.cuh"
+
+namespace itn {
+
+constexpr int kBM = 128;
+constexpr int kBK = 32;                    // floats per k-block = 128 B swizzle row
+constexpr int kAtomBytes = 32 * kBK * 4;   // one 32(mn) x 32(k) MN-major box = 4096 B
+constexpr int kThreads = 192;
+
+struct GemmKParams {
+  int M, N, K;
+  int nb1;
+  int a_m0, a_m1, b_m0, b_m1;  // 0 when the operand is broadcast over that batch dim
+  float* C;              long long ldc,   c_sb0,    c_sb1;
+  const float* bias;     long long        bias_sb0, bias_sb1;
+  const float* residual; long long ldr,   r_sb0,    r_sb1;
+  const float* aux;      long long ldaux, aux_sb0,  aux_sb1;
+  float* C2;             long long ldc2,  c2_sb0,   c2_sb1;
+  float alpha;
+  int act, epi, accumulate;
+};
+
+// Per-batch-entry epilogue pointers.
+struct EpiPtrs {
+  float* C;
+  const float* bias;
+  const float* residual;
+  const float* aux;
+  float* C2;
+};
+
+__device__ __forceinline__ EpiPtrs make_epi_ptrs(const GemmKParams& p, int b0, int b1) {
+  EpiPtrs e;
+  e.C = p.C + b0 * p.c_sb0 + b1 * p.c_sb1;
+  e.bias = p.bias ? p.bias + b0 * p.bias_sb0 + b1 * p.bias_sb1 : nullptr;
+  e.residual = p.residual ? p.residual + b0 * p.r_sb0 + b1 * p.r_sb1 : nullptr;
+  e.aux = p.aux ? p.aux + b0 * p.aux_sb0 + b1 * p.aux_sb1 : nullptr;
+  e.C2 = p.C2 ? p.C2 + b0 * p.c2_sb0 + b1 * p.c2_sb1 : nullptr;
+  return e;
+}
+
+__device__ __forceinline__ void epilogue_store(const GemmKParams& p, const EpiPtrs& e, int row,
+                                               int col, float acc, float bias_v) {
+  float v = p.alpha * acc + bias_v;
+  if (e.C2) e.C2[(long long)row * p.ldc2 + col] = v;
+  if (p.act == ITN_ACT_RELU) v = fmaxf(v, 0.0f);
+  else if (p.act == ITN_ACT_GELU) v = gelu_erf(v);
+  if (p.epi == ITN_EPI_RELU_MASK) {
+    v = e.aux[(long long)row * p.ldaux + col] > 0.0f ? v : 0.0f;
+  } else if (p.epi == ITN_EPI_GELU_GRAD) {
+    v *= gelu_erf_grad(e.aux[(long long)row * p.ldaux + col]);
+  }
+  if (e.residual) v += e.residual[(long long)row * p.ldr + col];
+  float* c = e.C + (long long)row * p.ldc + col;
+  if (p.accumulate) v += *c;
+  *c = v;
+}
+
+template <int BN>
+struct TileCfg {
+  static constexpr int kStages = (BN == 128) ? 3 : 4;
+  static constexpr int kABytes = kBM * kBK * 4;
+  static constexpr int kBBytes = BN * kBK * 4;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTmemCols = BN < 32 ? 32 : BN;
+  // stages + barriers (full, empty, tmem_full) + tmem ptr + 1024 alignment slack
+  static constexpr int kSmemBytes = kStages * kStageBytes + (2 * kStages + 1) * 8 + 16 + 1024;
+  static_assert(kStages * kStageBytes >= 4 * 32 * 33 * 4, "epilogue staging must fit in the ring");
+};
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kThreads)
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const GemmKParams p) {
+  using Cfg = TileCfg<BN>;
+  constexpr int STAGES = Cfg::kStages;
+
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B atoms need 1024-byte aligned tiles.
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN;
+  const int m0 = blockIdx.y * kBM;
+  const int b0 = blockIdx.z / p.nb1;
+  const int b1 = blockIdx.z % p.nb1;
+  const int num_kb = (p.K + kBK - 1) / kBK;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_ptr_smem);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ------------------------------------------------------- TMA producer
+    if (lane == 0) {
+      const int a_c0 = b0 * p.a_m0, a_c1 = b1 * p.a_m1;
+      const int b_c0 = b0 * p.b_m0, b_c1 = b1 * p.b_m1;
+      int s = 0;
+      uint32_t ph = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_expect_tx(&full_bar[s], Cfg::kStageBytes);
+        uint8_t* sa = smem + s * Cfg::kStageBytes;
+        uint8_t* sb = sa + Cfg::kABytes;
+        const int k0 = kb * kBK;
+        if (!A_MN) {
+          tma_load_4d(sa, &tmA, &full_bar[s], k0, m0, a_c1, a_c0);
+        } else {
+#pragma unroll
+          for (int j = 0; j < kBM / 32; ++j)
+            tma_load_4d(sa + j * kAtomBytes, &tmA, &full_bar[s], m0 + 32 * j, k0, a_c1, a_c0);
+        }
+        if (!B_MN) {
+          tma_load_4d(sb, &tmB, &full_bar[s], k0, n0, b_c1, b_c0);
+        } else {
+#pragma unroll
+          for (int j = 0; j < BN / 32; ++j)
+            tma_load_4d(sb + j * kAtomBytes, &tmB, &full_bar[s], n0 + 32 * j, k0, b_c1, b_c0);
+        }
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // --------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_tf32(kBM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * Cfg::kStageBytes);
+        const uint32_t sb = sa + Cfg::kABytes;
+#pragma unroll
+        for (int k = 0; k < kBK / 8; ++k) {
+          // K-major: 8 floats = 32 B further along the swizzled 128 B row.
+          // MN-major: 8 k-rows = one 1024 B swizzle atom further.
+          const uint64_t ad = A_MN ? umma_smem_desc(sa + k * 1024, kAtomBytes, 1024)
+                                   : umma_smem_desc(sa + k * 32, 16, 1024);
+          const uint64_t bd = B_MN ? umma_smem_desc(sb + k * 1024, kAtomBytes, 1024)
+                                   : umma_smem_desc(sb + k * 32, 16, 1024);
+          umma_tf32(tmem_base, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);  // frees the smem slot once the MMAs have read it
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+      umma_commit(tmem_full_bar);  // accumulator complete
+    }
+  } else {
+    // ----------------------------------------------------------- epilogue
+    const int ew = warp - 2;    // staging buffer index
+    const int lg = warp & 3;    // TMEM lane group this warp may read: lanes [32*lg, 32*lg+32)
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    // All MMAs have retired, so the operand ring is free: reuse it for the transpose.
+    float* st = reinterpret_cast<float*>(smem) + ew * (32 * 33);
+    const EpiPtrs e = make_epi_ptrs(p, b0, b1);
+    const int row_base = m0 + lg * 32;
+    if (row_base < p.M) {
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = n0 + c * 32;
+        if (col0 >= p.N) break;
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) st[lane * 33 + j] = __uint_as_float(v[j]);
+        __syncwarp();
+        const int col = col0 + lane;
+        const bool col_ok = col < p.N;
+        const float bias_v = (e.bias && col_ok) ? e.bias[col] : 0.0f;
+        const int rmax = min(32, p.M - row_base);
+        if (col_ok) {
+          for (int r = 0; r < rmax; ++r)
+            epilogue_store(p, e, row_base + r, col, st[r * 33 + lane], bias_v);
+        }
+        __syncwarp();
+      }
+    }
+    tc_fence_before();
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------- SIMT path
+// CUDA-core fp32 GEMM with identical semantics, arbitrary alignment.
+__global__ void __launch_bounds__(256)
+gemm_simt_kernel(const float* A, long long sam, long long sak, long long a_sb0, long long a_sb1,
+                 const float* B, long long sbn, long long sbk, long long b_sb0, long long b_sb1,
+                 const GemmKParams p) {
+  __shared__ float sA[16][33];
+  __shared__ float sB[16][33];
+  const int b0 = blockIdx.z / p.nb1, b1 = blockIdx.z % p.nb1;
+  A += b0 * a_sb0 + b1 * a_sb1;
+  B += b0 * b_sb0 + b1 * b_sb1;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  for (int k0 = 0; k0 < p.K; k0 += 16) {
+    for (int i = threadIdx.x; i < 32 * 16; i += 256) {
+      const int kk = i & 15, r = i >> 4;
+      const int k = k0 + kk;
+      const int m = m0 + r, n = n0 + r;
+      sA[kk][r] = (m < p.M && k < p.K) ? A[m * sam + k * sak] : 0.f;
+      sB[kk][r] = (n < p.N && k < p.K) ? B[n * sbn + k * sbk] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      const float a0 = sA[kk][ty], a1 = sA[kk][ty + 16];
+      const float c0 = sB[kk][tx], c1 = sB[kk][tx + 16];
+      acc[0][0] = fmaf(a0, c0, acc[0][0]);
+      acc[0][1] = fmaf(a0, c1, acc[0][1]);
+      acc[1][0] = fmaf(a1, c0, acc[1][0]);
+      acc[1][1] = fmaf(a1, c1, acc[1][1]);
+    }
+    __syncthreads();
+  }
+  const EpiPtrs e = make_epi_ptrs(p, b0, b1);
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int row = m0 + ty + 16 * i, col = n0 + tx + 16 * j;
+      if (row < p.M && col < p.N)
+        epilogue_store(p, e, row, col, acc[i][j], e.bias ? e.bias[col] : 0.f);
+    }
+}
+
+// ------------------------------------------------------------------- host
+using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                              const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                              const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeFn get_encode_fn() {
+  static EncodeFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) ==
+            cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeFn>(f);
+  });
+  return fn;
+}
+
+static bool operand_tma_ok(const itn_operand_t& o, int nb0, int nb1) {
+  if (reinterpret_cast<uintptr_t>(o.ptr) & 15) return false;
+  if (o.ld <= 0 || (o.ld & 3)) return false;
+  if (nb1 > 1 && o.sb1 != 0 && ((o.sb1 & 3) || o.sb1 < 0)) return false;
+  if (nb0 > 1 && o.sb0 != 0 && ((o.sb0 & 3) || o.sb0 < 0)) return false;
+  return true;
+}
+
+// rows = M (A) or N (B).  box_rows = tile extent along `rows` for the K-major case.
+static int make_operand_map(CUtensorMap* tm, const itn_operand_t& o, int rows, int K, int nb0,
+                            int nb1, int box_rows, int* mul0, int* mul1) {
+  EncodeFn enc = get_encode_fn();
+  if (!enc) return set_error(ITN_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  const bool bc0 = (nb0 <= 1) || o.sb0 == 0;
+  const bool bc1 = (nb1 <= 1) || o.sb1 == 0;
+  *mul0 = bc0 ? 0 : 1;
+  *mul1 = bc1 ? 0 : 1;
+  const cuuint64_t inner = o.major == 0 ? K : rows;
+  const cuuint64_t outer = o.major == 0 ? rows : K;
+  cuuint64_t gdim[4] = {inner, outer, bc1 ? 1ull : (cuuint64_t)nb1, bc0 ? 1ull : (cuuint64_t)nb0};
+  const cuuint64_t dense = (cuuint64_t)o.ld * outer * 4;
+  cuuint64_t gstr[3] = {(cuuint64_t)o.ld * 4, bc1 ? dense : (cuuint64_t)o.sb1 * 4,
+                        bc0 ? dense : (cuuint64_t)o.sb0 * 4};
+  cuuint32_t box[4] = {32, o.major == 0 ? (cuuint32_t)box_rows : 32u, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(o.ptr), gdim, gstr,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(ITN_ERR_CUDA,
+                     "cuTensorMapEncodeTiled failed (%d): dims %llu %llu %llu %llu strides %llu "
+                     "%llu %llu box %u %u",
+                     (int)r, gdim[0], gdim[1], gdim[2], gdim[3], gstr[0], gstr[1], gstr[2], box[0],
+                     box[1]);
+  return ITN_OK;
+}
+
+static void fill_kparams(GemmKParams& p, const itn_gemm_desc_t* d) {
+  p.M = d->M; p.N = d->N; p.K = d->K;
+  p.nb1 = d->nb1 < 1 ? 1 : d->nb1;
+  p.a_m0 = p.a_m1 = p.b_m0 = p.b_m1 = 0;
+  p.C = d->C; p.ldc = d->ldc; p.c_sb0 = d->c_sb0; p.c_sb1 = d->c_sb1;
+  p.bias = d->bias; p.bias_sb0 = d->bias_sb0; p.bias_sb1 = d->bias_sb1;
+  p.residual = d->residual; p.ldr = d->ldr; p.r_sb0 = d->r_sb0; p.r_sb1 = d->r_sb1;
+  p.aux = d->aux; p.ldaux = d->ldaux; p.aux_sb0 = d->aux_sb0; p.aux_sb1 = d->aux_sb1;
+  p.C2 = d->C2; p.ldc2 = d->ldc2; p.c2_sb0 = d->c2_sb0; p.c2_sb1 = d->c2_sb1;
+  p.alpha = d->alpha; p.act = d->act; p.epi = d->epi; p.accumulate = d->accumulate;
+}
+
+static int validate(const itn_gemm_desc_t* d) {
+  ITN_REQUIRE(d != nullptr, "gemm: null descriptor");
+  ITN_REQUIRE(d->M > 0 && d->N > 0 && d->K > 0, "gemm: M,N,K must be positive (%d,%d,%d)", d->M,
+              d->N, d->K);
+  ITN_REQUIRE(d->A.ptr && d->B.ptr && d->C, "gemm: null A/B/C");
+  ITN_REQUIRE(d->nb0 >= 1 && d->nb1 >= 1, "gemm: batch counts must be >= 1");
+  ITN_REQUIRE((long long)d->nb0 * d->nb1 <= 65535, "gemm: batch %d x %d exceeds gridDim.z", d->nb0,
+              d->nb1);
+  ITN_REQUIRE(d->epi == ITN_EPI_NONE || d->aux != nullptr, "gemm: epi mode %d needs aux", d->epi);
+  ITN_REQUIRE(d->A.major == 0 || d->A.major == 1, "gemm: bad A.major");
+  ITN_REQUIRE(d->B.major == 0 || d->B.major == 1, "gemm: bad B.major");
+  return ITN_OK;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch_tile(const itn_gemm_desc_t* d, cudaStream_t stream) {
+  using Cfg = TileCfg<BN>;
+  GemmKParams p;
+  fill_kparams(p, d);
+  CUtensorMap tmA, tmB;
+  int rc = make_operand_map(&tmA, d->A, d->M, d->K, d->nb0, d->nb1, kBM, &p.a_m0, &p.a_m1);
+  if (rc) return rc;
+  rc = make_operand_map(&tmB, d->B, d->N, d->K, d->nb0, d->nb1, BN, &p.b_m0, &p.b_m1);
+  if (rc) return rc;
+  auto kern = gemm_tf32_kernel<BN, A_MN, B_MN>;
+  static bool attr_set = false;  // per instantiation
+  if (!attr_set) {
+    cudaError_t e =
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess)
+      return set_error(ITN_ERR_CUDA, "gemm: cudaFuncSetAttribute(%d B): %s", Cfg::kSmemBytes,
+                       cudaGetErrorString(e));
+    attr_set = true;
+  }
+  dim3 grid((d->N + BN - 1) / BN, (d->M + kBM - 1) / kBM, d->nb0 * d->nb1);
+  kern<<<grid, kThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
+  return check_launch("gemm_tf32_kernel");
+}
+
+template <int BN>
+static int launch_major(const itn_gemm_desc_t* d, cudaStream_t s) {
+  if (d->A.major == 0) {
+    return d->B.major == 0 ? launch_tile<BN, false, false>(d, s) : launch_tile<BN, false, true>(d, s);
+  }
+  return d->B.major == 0 ? launch_tile<BN, true, false>(d, s) : launch_tile<BN, true, true>(d, s);
+}
+
+static int pick_bn(const itn_gemm_desc_t* d) {
+  if (d->N <= 32) return 32;
+  if (d->N <= 64) return 64;
+  const long long tiles_m = (d->M + kBM - 1) / kBM;
+  const long long batch = (long long)d->nb0 * d->nb1;
+  const int cand[3] = {256, 128, 64};
+  for (int i = 0; i < 3; ++i) {
+    const int bn = cand[i];
+    if (bn > 64 && d->N < bn && d->N <= bn / 2) continue;
+    const long long ctas = tiles_m * ((d->N + bn - 1) / bn) * batch;
+    if (ctas >= 120) return bn;
+  }
+  return 64;
+}
+
+}  // namespace itn
+
+extern "C" int itn_gemm_tf32_supported(const itn_gemm_desc_t* d) {
+  if (!d || d->M <= 0 || d->N <= 0 || d->K <= 0) return 0;
+  return itn::operand_tma_ok(d->A, d->nb0, d->nb1) && itn::operand_tma_ok(d->B, d->nb0, d->nb1);
+}
+
+extern "C" int itn_gemm_tf32(const itn_gemm_desc_t* d, void* stream) {
+  int rc = itn::validate(d);
+  if (rc) return rc;
+  if (!itn_gemm_tf32_supported(d))
+    return itn::set_error(ITN_ERR_UNSUPPORTED,
+                          "gemm_tf32: operands must be 16-byte aligned with ld/batch strides "
+                          "multiples of 4 elements");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int bn = itn::pick_bn(d);
+  if (const char* f = getenv("ITN_GEMM_BN")) {
+    const int v = atoi(f);
+    if (v == 32 || v == 64 || v == 128 || v == 256) bn = v;
+  }
+  switch (bn) {
+    case 32: return itn::launch_major<32>(d, s);
+    case 64: return itn::launch_major<64>(d, s);
+    case 128: return itn::launch_major<128>(d, s);
+    default: return itn::launch_major<256>(d, s);
+  }
+}
+
+extern "C" int itn_gemm_simt(const itn_gemm_desc_t* d, void* stream) {
+  int rc = itn::validate(d);
+  if (rc) return rc;
+  itn::GemmKParams p;
+  itn::fill_kparams(p, d);
+  const long long sam = d->A.major == 0 ? d->A.ld : 1, sak = d->A.major == 0 ? 1 : d->A.ld;
+  const long long sbn = d->B.major == 0 ? d->B.ld : 1, sbk = d->B.major == 0 ? 1 : d->B.ld;
+  dim3 grid((d->N + 31) / 32, (d->M + 31) / 32, d->nb0 * d->nb1);
+  itn::gemm_simt_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      d->A.ptr, sam, sak, d->A.sb0, d->A.sb1, d->B.ptr, sbn, sbk, d->B.sb0, d->B.sb1, p);
+  return itn::check_launch("gemm_simt_kernel");
+}

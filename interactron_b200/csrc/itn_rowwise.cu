@@ -1,0 +1,274 @@
+// Row-wise HBM-bound kernels: LayerNorm fwd/bwd, softmax fwd/bwd, column sums.
+// One warp per row, warp-shuffle reductions, coalesced (float4 where the row
+// stride allows) accesses.  Contracts in include/interactron_b200.h.
+#include "itn_common.cuh"
+
+namespace itn {
+
+// ------------------------------------------------------------- LayerNorm fwd
+// cols = VPL * 128: lane owns float4 chunks lane, lane+32, ...
+template <int VPL>
+__global__ void __launch_bounds__(256)
+layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, float* __restrict__ y,
+                     float* __restrict__ mean_out, float* __restrict__ rstd_out, long long rows,
+                     long long rows_per_group, long long gb_stride, float eps) {
+  constexpr int cols = VPL * 128;
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * cols);
+  float4 v[VPL];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    v[i] = xr[lane + 32 * i];
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  const float mean = warp_sum(s) * (1.0f / cols);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / cols) + eps);
+  const long long g = row / rows_per_group;
+  const float4* gr = reinterpret_cast<const float4*>(gamma + g * gb_stride);
+  const float4* br = reinterpret_cast<const float4*>(beta + g * gb_stride);
+  float4* yr = reinterpret_cast<float4*>(y + row * cols);
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const float4 ga = gr[lane + 32 * i], be = br[lane + 32 * i];
+    float4 o;
+    o.x = (v[i].x - mean) * rstd * ga.x + be.x;
+    o.y = (v[i].y - mean) * rstd * ga.y + be.y;
+    o.z = (v[i].z - mean) * rstd * ga.z + be.z;
+    o.w = (v[i].w - mean) * rstd * ga.w + be.w;
+    yr[lane + 32 * i] = o;
+  }
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mean;
+    if (rstd_out) rstd_out[row] = rstd;
+  }
+}
+
+// ------------------------------------------------------------- LayerNorm bwd
+template <int VPL>
+__global__ void __launch_bounds__(256)
+layernorm_bwd_dx_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                        const float* __restrict__ mean, const float* __restrict__ rstd,
+                        const float* __restrict__ gamma, float* __restrict__ dx, long long rows,
+                        long long rows_per_group, long long gb_stride) {
+  constexpr int cols = VPL * 128;
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float mu = mean[row], rs = rstd[row];
+  const long long g = row / rows_per_group;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * cols);
+  const float4* dr = reinterpret_cast<const float4*>(dy + row * cols);
+  const float4* gr = reinterpret_cast<const float4*>(gamma + g * gb_stride);
+  float4 xh[VPL], dg[VPL];
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const float4 xv = xr[lane + 32 * i], dv = dr[lane + 32 * i], ga = gr[lane + 32 * i];
+    xh[i].x = (xv.x - mu) * rs; xh[i].y = (xv.y - mu) * rs;
+    xh[i].z = (xv.z - mu) * rs; xh[i].w = (xv.w - mu) * rs;
+    dg[i].x = dv.x * ga.x; dg[i].y = dv.y * ga.y; dg[i].z = dv.z * ga.z; dg[i].w = dv.w * ga.w;
+    s1 += (dg[i].x + dg[i].y) + (dg[i].z + dg[i].w);
+    s2 += (dg[i].x * xh[i].x + dg[i].y * xh[i].y) + (dg[i].z * xh[i].z + dg[i].w * xh[i].w);
+  }
+  const float m1 = warp_sum(s1) * (1.0f / cols);
+  const float m2 = warp_sum(s2) * (1.0f / cols);
+  float4* or_ = reinterpret_cast<float4*>(dx + row * cols);
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    float4 o;
+    o.x = rs * (dg[i].x - m1 - xh[i].x * m2);
+    o.y = rs * (dg[i].y - m1 - xh[i].y * m2);
+    o.z = rs * (dg[i].z - m1 - xh[i].z * m2);
+    o.w = rs * (dg[i].w - m1 - xh[i].w * m2);
+    or_[lane + 32 * i] = o;
+  }
+}
+
+// dgamma[g,c] = sum_r dy*xhat, dbeta[g,c] = sum_r dy over the rows of group g.
+// Block = 32 columns x 32 row-lanes; fixed summation order (deterministic).
+__global__ void __launch_bounds__(1024)
+layernorm_bwd_gb_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                        const float* __restrict__ mean, const float* __restrict__ rstd,
+                        float* __restrict__ dgamma, float* __restrict__ dbeta,
+                        long long rows_per_group, int cols) {
+  __shared__ float sg[32][33];
+  __shared__ float sb[32][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int g = blockIdx.y;
+  const long long r0 = (long long)g * rows_per_group;
+  float ag = 0.f, ab = 0.f;
+  if (c < cols) {
+    for (long long r = threadIdx.y; r < rows_per_group; r += 32) {
+      const long long row = r0 + r;
+      const float d = dy[row * cols + c];
+      ag += d * (x[row * cols + c] - mean[row]) * rstd[row];
+      ab += d;
+    }
+  }
+  sg[threadIdx.y][threadIdx.x] = ag;
+  sb[threadIdx.y][threadIdx.x] = ab;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < cols) {
+    float tg = 0.f, tb = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      tg += sg[i][threadIdx.x];
+      tb += sb[i][threadIdx.x];
+    }
+    if (dgamma) dgamma[(long long)g * cols + c] = tg;
+    if (dbeta) dbeta[(long long)g * cols + c] = tb;
+  }
+}
+
+// ------------------------------------------------------------------ softmax
+// One warp per row, online max/sum pass then a normalising pass (the row is
+// re-read from L1/L2, never from HBM: rows are <= 8 KB).
+__global__ void __launch_bounds__(256)
+softmax_fwd_kernel(float* __restrict__ s, long long rows, int cols, long long ld, float scale,
+                   const unsigned char* __restrict__ key_mask, long long rows_per_mask) {
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  float* r = s + row * ld;
+  const unsigned char* mk = key_mask ? key_mask + (row / rows_per_mask) * cols : nullptr;
+  float m = -INFINITY, l = 0.f;
+  for (int c = lane; c < cols; c += 32) {
+    float v = r[c] * scale;
+    if (mk && mk[c]) v = -INFINITY;
+    if (v > m) {
+      l = l * __expf(m - v) + 1.0f;
+      m = v;
+    } else if (v != -INFINITY) {
+      l += __expf(v - m);
+    }
+  }
+  const float gm = warp_max(m);
+  l = (m == -INFINITY) ? 0.f : l * __expf(m - gm);
+  const float inv = 1.0f / warp_sum(l);
+  for (int c = lane; c < cols; c += 32) {
+    float v = r[c] * scale;
+    if (mk && mk[c]) v = -INFINITY;
+    r[c] = __expf(v - gm) * inv;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+softmax_bwd_kernel(const float* __restrict__ p, float* __restrict__ dp, long long rows, int cols,
+                   long long ld, float scale) {
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float* pr = p + row * ld;
+  float* dr = dp + row * ld;
+  float acc = 0.f;
+  for (int c = lane; c < cols; c += 32) acc += pr[c] * dr[c];
+  const float dot = warp_sum(acc);
+  for (int c = lane; c < cols; c += 32) dr[c] = scale * pr[c] * (dr[c] - dot);
+}
+
+// ------------------------------------------------------------------- colsum
+__global__ void __launch_bounds__(1024)
+colsum_kernel(const float* __restrict__ x, float* __restrict__ out, long long rows, int cols,
+              long long ld) {
+  __shared__ float sm[32][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int g = blockIdx.y;
+  const float* xg = x + (long long)g * rows * ld;
+  float a = 0.f;
+  if (c < cols)
+    for (long long r = threadIdx.y; r < rows; r += 32) a += xg[r * ld + c];
+  sm[threadIdx.y][threadIdx.x] = a;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) t += sm[i][threadIdx.x];
+    out[(long long)g * cols + c] = t;
+  }
+}
+
+}  // namespace itn
+
+using namespace itn;
+
+extern "C" int itn_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y,
+                                 float* mean, float* rstd, long long rows, int cols, int groups,
+                                 long long gb_stride, float eps, void* stream) {
+  ITN_REQUIRE(x && gamma && beta && y, "layernorm_fwd: null pointer");
+  ITN_REQUIRE(rows > 0 && groups > 0 && rows % groups == 0,
+              "layernorm_fwd: rows (%lld) must be a positive multiple of groups (%d)", rows, groups);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  const long long rpg = rows / groups;
+  switch (cols) {
+    case 128: layernorm_fwd_kernel<1><<<grid, 256, 0, s>>>(x, gamma, beta, y, mean, rstd, rows, rpg, gb_stride, eps); break;
+    case 256: layernorm_fwd_kernel<2><<<grid, 256, 0, s>>>(x, gamma, beta, y, mean, rstd, rows, rpg, gb_stride, eps); break;
+    case 512: layernorm_fwd_kernel<4><<<grid, 256, 0, s>>>(x, gamma, beta, y, mean, rstd, rows, rpg, gb_stride, eps); break;
+    case 1024: layernorm_fwd_kernel<8><<<grid, 256, 0, s>>>(x, gamma, beta, y, mean, rstd, rows, rpg, gb_stride, eps); break;
+    default: return set_error(ITN_ERR_UNSUPPORTED, "layernorm_fwd: cols must be 128/256/512/1024, got %d", cols);
+  }
+  return check_launch("layernorm_fwd_kernel");
+}
+
+extern "C" int itn_layernorm_bwd(const float* dy, const float* x, const float* mean,
+                                 const float* rstd, const float* gamma, float* dx, float* dgamma,
+                                 float* dbeta, long long rows, int cols, int groups,
+                                 long long gb_stride, void* stream) {
+  ITN_REQUIRE(dy && x && mean && rstd && gamma && dx, "layernorm_bwd: null pointer");
+  ITN_REQUIRE(rows > 0 && groups > 0 && rows % groups == 0,
+              "layernorm_bwd: rows (%lld) must be a positive multiple of groups (%d)", rows, groups);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  const long long rpg = rows / groups;
+  switch (cols) {
+    case 128: layernorm_bwd_dx_kernel<1><<<grid, 256, 0, s>>>(dy, x, mean, rstd, gamma, dx, rows, rpg, gb_stride); break;
+    case 256: layernorm_bwd_dx_kernel<2><<<grid, 256, 0, s>>>(dy, x, mean, rstd, gamma, dx, rows, rpg, gb_stride); break;
+    case 512: layernorm_bwd_dx_kernel<4><<<grid, 256, 0, s>>>(dy, x, mean, rstd, gamma, dx, rows, rpg, gb_stride); break;
+    case 1024: layernorm_bwd_dx_kernel<8><<<grid, 256, 0, s>>>(dy, x, mean, rstd, gamma, dx, rows, rpg, gb_stride); break;
+    default: return set_error(ITN_ERR_UNSUPPORTED, "layernorm_bwd: cols must be 128/256/512/1024, got %d", cols);
+  }
+  int rc = check_launch("layernorm_bwd_dx_kernel");
+  if (rc) return rc;
+  if (dgamma || dbeta) {
+    dim3 g2((cols + 31) / 32, groups);
+    layernorm_bwd_gb_kernel<<<g2, dim3(32, 32), 0, s>>>(dy, x, mean, rstd, dgamma, dbeta, rpg, cols);
+    rc = check_launch("layernorm_bwd_gb_kernel");
+  }
+  return rc;
+}
+
+extern "C" int itn_softmax_fwd(float* sc, long long rows, int cols, long long ld, float scale,
+                               const unsigned char* key_mask, long long rows_per_mask,
+                               void* stream) {
+  ITN_REQUIRE(sc && rows > 0 && cols > 0 && ld >= cols, "softmax_fwd: bad arguments");
+  ITN_REQUIRE(!key_mask || rows_per_mask > 0, "softmax_fwd: rows_per_mask must be > 0 with a mask");
+  softmax_fwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      sc, rows, cols, ld, scale, key_mask, rows_per_mask);
+  return check_launch("softmax_fwd_kernel");
+}
+
+extern "C" int itn_softmax_bwd(const float* p, float* dp, long long rows, int cols, long long ld,
+                               float scale, void* stream) {
+  ITN_REQUIRE(p && dp && rows > 0 && cols > 0 && ld >= cols, "softmax_bwd: bad arguments");
+  softmax_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      p, dp, rows, cols, ld, scale);
+  return check_launch("softmax_bwd_kernel");
+}
+
+extern "C" int itn_colsum(const float* x, float* out, int groups, long long rows, int cols,
+                          long long ld, void* stream) {
+  ITN_REQUIRE(x && out && groups > 0 && rows > 0 && cols > 0 && ld >= cols, "colsum: bad arguments");
+  dim3 grid((cols + 31) / 32, groups);
+  colsum_kernel<<<grid, dim3(32, 32), 0, static_cast<cudaStream_t>(stream)>>>(x, out, rows, cols, ld);
+  return check_launch("colsum_kernel");
+}

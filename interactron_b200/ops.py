@@ -1,0 +1,280 @@
+"""Tensor-level wrappers over the C ABI (`CudaOps`).
+
+Every method takes/returns torch CUDA tensors (fp32) and launches exactly the
+hand-written sm_100a kernels of libinteractron_b200.so on torch's current
+stream; torch is used only for device memory and views.  The orchestration
+modules (`detr_t`, `fusion_a`, `fusion_b`, `episode`) are written against this
+small interface; `oracle/sim_ops.py` implements the same interface with plain
+torch CPU ops and exists only so the tests can check the hand-derived backward
+passes against the reference's autograd without a GPU.
+"""
+import ctypes as C
+import os
+
+import torch
+
+from . import _lib
+
+ACT = {None: 0, "none": 0, "relu": 1, "gelu": 2}
+EPI = {None: 0, "none": 0, "relu_mask": 1, "gelu_grad": 2}
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _as4d(t):
+    while t.dim() < 4:
+        t = t.unsqueeze(0)
+    if t.dim() != 4:
+        raise ValueError(f"at most two batch dims supported, got shape {tuple(t.shape)}")
+    return t
+
+
+class CudaOps:
+    """The product backend.  Requires a CUDA device and the built shared library."""
+
+    name = "cuda"
+
+    def __init__(self, device="cuda:0"):
+        if not torch.cuda.is_available():
+            raise _lib.ItnError("interactron_b200 needs a CUDA device (sm_100a); there is no CPU path")
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        self.force_simt = os.environ.get("ITN_FORCE_SIMT", "0") == "1"
+        self.n_tf32 = 0
+        self.n_simt = 0
+
+    # ------------------------------------------------------------ plumbing
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def empty(self, *shape):
+        return torch.empty(*shape, dtype=torch.float32, device=self.device)
+
+    def zeros(self, *shape):
+        return torch.zeros(*shape, dtype=torch.float32, device=self.device)
+
+    def launch_count(self):
+        return int(self.lib.itn_launch_count())
+
+    # ---------------------------------------------------------------- GEMM
+    @staticmethod
+    def _operand(t4, nb0, nb1, is_a):
+        """t4: [b0,b1,M,K] for A, [b0,b1,K,N] for B (any strides).  -> (Operand, keepalive)."""
+        if is_a:
+            rows, k = t4.shape[2], t4.shape[3]
+            s_rows, s_k = t4.stride(2), t4.stride(3)
+        else:
+            k, rows = t4.shape[2], t4.shape[3]
+            s_k, s_rows = t4.stride(2), t4.stride(3)
+        k_contig = k == 1 or s_k == 1
+        r_contig = rows == 1 or s_rows == 1
+        pad4 = lambda v: max(4, (v + 3) // 4 * 4)
+        ld_k = s_rows if rows > 1 else pad4(k)      # ld if K is the contiguous dim
+        ld_r = s_k if k > 1 else pad4(rows)         # ld if rows is the contiguous dim
+        if k_contig and ld_k % 4 == 0:
+            major, ld = 0, ld_k
+        elif r_contig and ld_r % 4 == 0:
+            major, ld = 1, ld_r
+        elif k_contig:
+            major, ld = 0, ld_k                     # unaligned: the SIMT kernel takes it
+        elif r_contig:
+            major, ld = 1, ld_r
+        else:
+            t4 = t4.contiguous()
+            return CudaOps._operand(t4, nb0, nb1, is_a)
+        op = _lib.Operand()
+        op.ptr = t4.data_ptr()
+        op.major = major
+        op.ld = ld
+        op.sb0 = t4.stride(0) if t4.shape[0] > 1 else 0
+        op.sb1 = t4.stride(1) if t4.shape[1] > 1 else 0
+        return op, t4
+
+    def matmul(self, a, b, *, bias=None, act=None, residual=None, out=None, out_pre=None,
+               alpha=1.0, accumulate=False, epi=None, aux=None):
+        """out = epilogue(alpha * a @ b), a [..,M,K], b [..,K,N]; see itn_gemm_desc_t."""
+        rank = max(a.dim(), b.dim(), 2)
+        a4, b4 = _as4d(a), _as4d(b)
+        M, K = a4.shape[2], a4.shape[3]
+        K2, N = b4.shape[2], b4.shape[3]
+        if K != K2:
+            raise ValueError(f"matmul inner dims differ: {tuple(a.shape)} @ {tuple(b.shape)}")
+        nb0 = max(a4.shape[0], b4.shape[0])
+        nb1 = max(a4.shape[1], b4.shape[1])
+        for t in (a4, b4):
+            if t.shape[0] not in (1, nb0) or t.shape[1] not in (1, nb1):
+                raise ValueError(f"batch dims not broadcastable: {tuple(a.shape)} @ {tuple(b.shape)}")
+        if out is None:
+            out = self.empty(nb0, nb1, M, N)
+            ret = out.reshape(out.shape[4 - rank:])
+        else:
+            ret = out
+        d = _lib.GemmDesc()
+        d.M, d.N, d.K, d.nb0, d.nb1 = M, N, K, nb0, nb1
+        d.A, keep_a = self._operand(a4, nb0, nb1, True)
+        d.B, keep_b = self._operand(b4, nb0, nb1, False)
+
+        def mat(t, what):
+            t4 = _as4d(t)
+            if tuple(t4.shape[2:]) != (M, N) or (N > 1 and t4.stride(3) != 1):
+                raise ValueError(f"{what} must be [..,{M},{N}] with unit inner stride, got "
+                                 f"{tuple(t.shape)} strides {t.stride()}")
+            sb0 = t4.stride(0) if t4.shape[0] > 1 else 0
+            sb1 = t4.stride(1) if t4.shape[1] > 1 else 0
+            return t4.data_ptr(), t4.stride(2), sb0, sb1
+
+        d.C, d.ldc, d.c_sb0, d.c_sb1 = mat(out, "out")
+        o4 = _as4d(out)
+        if o4.shape[0] != nb0 or o4.shape[1] != nb1:
+            raise ValueError("out batch dims must match the broadcast batch")
+        if bias is not None:
+            b3 = bias
+            while b3.dim() < 3:
+                b3 = b3.unsqueeze(0)
+            if b3.shape[-1] != N or (N > 1 and b3.stride(-1) != 1):
+                raise ValueError("bias must be [..,N] contiguous in N")
+            d.bias = b3.data_ptr()
+            d.bias_sb0 = b3.stride(0) if b3.shape[0] > 1 else 0
+            d.bias_sb1 = b3.stride(1) if b3.shape[1] > 1 else 0
+        if residual is not None:
+            d.residual, d.ldr, d.r_sb0, d.r_sb1 = mat(residual, "residual")
+        if aux is not None:
+            d.aux, d.ldaux, d.aux_sb0, d.aux_sb1 = mat(aux, "aux")
+        if out_pre is not None:
+            d.C2, d.ldc2, d.c2_sb0, d.c2_sb1 = mat(out_pre, "out_pre")
+        d.alpha = float(alpha)
+        d.act = ACT[act]
+        d.epi = EPI[epi]
+        d.accumulate = 1 if accumulate else 0
+        if not self.force_simt and self.lib.itn_gemm_tf32_supported(C.byref(d)):
+            _lib.check(self.lib.itn_gemm_tf32(C.byref(d), self._stream()))
+            self.n_tf32 += 1
+        else:
+            _lib.check(self.lib.itn_gemm_simt(C.byref(d), self._stream()))
+            self.n_simt += 1
+        del keep_a, keep_b
+        return ret
+
+    # ------------------------------------------------------------ row-wise
+    def layernorm_fwd(self, x, gamma, beta, eps=1e-5):
+        """x [rows, D] contiguous; gamma/beta [G, D] (G divides rows).  -> y, mean, rstd."""
+        rows, cols = x.shape
+        g2, b2 = gamma.reshape(-1, cols), beta.reshape(-1, cols)
+        groups = g2.shape[0]
+        assert x.is_contiguous() and g2.is_contiguous() and b2.is_contiguous()
+        y = self.empty(rows, cols)
+        mean, rstd = self.empty(rows), self.empty(rows)
+        _lib.check(self.lib.itn_layernorm_fwd(_ptr(x), _ptr(g2), _ptr(b2), _ptr(y), _ptr(mean), _ptr(rstd),
+                                              rows, cols, groups, cols, eps, self._stream()))
+        return y, mean, rstd
+
+    def layernorm_bwd(self, dy, x, mean, rstd, gamma, need_wgrad=True):
+        """-> dx [rows,D], dgamma [G,D], dbeta [G,D] (None if not need_wgrad)."""
+        rows, cols = x.shape
+        g2 = gamma.reshape(-1, cols)
+        groups = g2.shape[0]
+        assert dy.is_contiguous() and x.is_contiguous()
+        dx = self.empty(rows, cols)
+        dg = self.empty(groups, cols) if need_wgrad else None
+        db = self.empty(groups, cols) if need_wgrad else None
+        _lib.check(self.lib.itn_layernorm_bwd(_ptr(dy), _ptr(x), _ptr(mean), _ptr(rstd), _ptr(g2), _ptr(dx),
+                                              _ptr(dg), _ptr(db), rows, cols, groups, cols, self._stream()))
+        return dx, dg, db
+
+    def softmax_(self, s, cols, scale, key_mask=None, rows_per_mask=1):
+        """In-place softmax over the first `cols` entries of the last dim of contiguous `s`."""
+        assert s.is_contiguous()
+        ld = s.shape[-1]
+        rows = s.numel() // ld
+        if key_mask is not None:
+            assert key_mask.dtype == torch.uint8 and key_mask.is_contiguous() and key_mask.shape[-1] == cols
+        _lib.check(self.lib.itn_softmax_fwd(_ptr(s), rows, cols, ld, float(scale), _ptr(key_mask),
+                                            rows_per_mask, self._stream()))
+        return s
+
+    def softmax_bwd_(self, p, dp, cols, scale):
+        """dp <- scale * p * (dp - rowsum(p*dp)) in place."""
+        assert p.is_contiguous() and dp.is_contiguous() and p.shape == dp.shape
+        ld = p.shape[-1]
+        rows = p.numel() // ld
+        _lib.check(self.lib.itn_softmax_bwd(_ptr(p), _ptr(dp), rows, cols, ld, float(scale), self._stream()))
+        return dp
+
+    def colsum(self, x):
+        """x [G, rows, cols] (row stride arbitrary, inner contiguous) -> [G, cols]."""
+        if x.dim() == 2:
+            x = x.unsqueeze(0)
+        G, rows, cols = x.shape
+        assert x.stride(2) == 1 or cols == 1
+        assert G == 1 or x.stride(0) == rows * x.stride(1)
+        out = self.empty(G, cols)
+        _lib.check(self.lib.itn_colsum(_ptr(x), _ptr(out), G, rows, cols, x.stride(1), self._stream()))
+        return out
+
+    # -------------------------------------------------------- element-wise
+    def add(self, a, b):
+        """a + b, with b broadcast over the leading dims of a (b = a's trailing block)."""
+        assert a.is_contiguous() and b.is_contiguous() and a.numel() % b.numel() == 0
+        out = self.empty(a.shape)
+        _lib.check(self.lib.itn_add(_ptr(a), _ptr(b), _ptr(out), a.numel(), b.numel(), self._stream()))
+        return out
+
+    def copy2d_(self, dst, src):
+        """dst[r, c] = src[r, c] for 2-D views with unit inner stride."""
+        assert dst.shape == src.shape and dst.dim() == 2
+        assert (dst.stride(1) == 1 and src.stride(1) == 1) or dst.shape[1] == 1
+        _lib.check(self.lib.itn_copy2d(_ptr(src), src.stride(0), _ptr(dst), dst.stride(0), dst.shape[0],
+                                       dst.shape[1], self._stream()))
+        return dst
+
+    def sigmoid(self, x):
+        assert x.is_contiguous()
+        y = self.empty(x.shape)
+        _lib.check(self.lib.itn_sigmoid_fwd(_ptr(x), _ptr(y), x.numel(), self._stream()))
+        return y
+
+    def sigmoid_bwd(self, dy, y):
+        assert dy.is_contiguous() and y.is_contiguous()
+        dx = self.empty(y.shape)
+        _lib.check(self.lib.itn_sigmoid_bwd(_ptr(dy), _ptr(y), _ptr(dx), y.numel(), self._stream()))
+        return dx
+
+    def l2norm_fwd_bwd(self, x):
+        """x [G, n] -> (||x_g|| [G], x_g/||x_g|| [G, n])."""
+        assert x.is_contiguous() and x.dim() == 2
+        G, n = x.shape
+        loss, dx = self.empty(G), self.empty(G, n)
+        _lib.check(self.lib.itn_l2norm_fwd_bwd(_ptr(x), _ptr(loss), _ptr(dx), G, n, self._stream()))
+        return loss, dx
+
+    def sgd_clip_update(self, theta, g, lr, clip=0.01, want_mask=False):
+        """theta [n] (shared) or [G,n]; g [G,n] -> theta' [G,n] (, uint8 mask)."""
+        assert g.is_contiguous() and g.dim() == 2 and theta.is_contiguous()
+        G, n = g.shape
+        stride = 0 if theta.dim() == 1 or theta.shape[0] == 1 else n
+        out = self.empty(G, n)
+        mask = torch.empty(G, n, dtype=torch.uint8, device=self.device) if want_mask else None
+        _lib.check(self.lib.itn_sgd_clip_update(_ptr(theta), stride, _ptr(g), _ptr(out), _ptr(mask), G, n,
+                                                float(lr), float(clip), self._stream()))
+        return (out, mask) if want_mask else out
+
+    def pos_embed_sine(self, mask, feats=128):
+        """mask [F,h,w] bool/uint8 (1 = padded) -> [F, h*w, 2*feats]."""
+        m = mask.to(torch.uint8).contiguous()
+        F_, h, w = m.shape
+        pos = self.empty(F_, h * w, 2 * feats)
+        _lib.check(self.lib.itn_pos_embed_sine(_ptr(m), _ptr(pos), F_, h, w, feats, self._stream()))
+        return pos
+
+    def matcher_cost(self, logits, boxes, tgt_boxes, tgt_labels, tgt_off, w_class, w_bbox, w_giou):
+        """Block-diagonal HungarianMatcher cost, packed per frame ([Q, T_f] row-major)."""
+        F_, Q, Cn = logits.shape
+        assert logits.is_contiguous() and boxes.is_contiguous() and tgt_boxes.is_contiguous()
+        total = int(tgt_boxes.shape[0])
+        cost = self.empty(max(Q * total, 1))
+        _lib.check(self.lib.itn_matcher_cost(_ptr(logits), _ptr(boxes), _ptr(tgt_boxes), _ptr(tgt_labels),
+                                             _ptr(tgt_off), _ptr(cost), F_, Q, Cn, float(w_class),
+                                             float(w_bbox), float(w_giou), self._stream()))
+        return cost

@@ -1,0 +1,265 @@
+"""Per-kernel parity of the CUDA ops (through the C ABI) against plain torch fp32/fp64.
+
+Tolerances: TF32 GEMMs 2e-3 relative L2 against an fp64 product (TF32 keeps 10 mantissa
+bits); everything else is fp32 arithmetic and must agree to 1e-5 relative.
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+TF32_TOL = 2e-3
+FP32_TOL = 1e-5
+
+
+def rel(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from interactron_b200.ops import CudaOps
+    return CudaOps()
+
+
+def _mk(shape, transposed, gen):
+    if transposed:
+        t = torch.randn(*shape[:-2], shape[-1], shape[-2], generator=gen, device="cuda")
+        return t.transpose(-1, -2)
+    return torch.randn(*shape, generator=gen, device="cuda")
+
+
+@pytest.mark.parametrize("a_mn", [False, True])
+@pytest.mark.parametrize("b_mn", [False, True])
+@pytest.mark.parametrize("shape", [(128, 128, 32), (1805, 256, 256), (250, 1236, 256), (256, 2048, 1805),
+                                   (1236, 256, 250), (364, 32, 361), (512, 1496, 252), (2060, 512, 2048)])
+def test_gemm_tf32_majors(ops, a_mn, b_mn, shape):
+    M, N, K = shape
+    gen = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
+    a = _mk((M, K), a_mn, gen)
+    b = _mk((K, N), not b_mn, gen)
+    n0 = ops.n_tf32
+    out = ops.matmul(a, b)
+    # TMA needs the non-contiguous stride of each operand to be a multiple of 4 floats
+    aligned = ((M if a_mn else K) % 4 == 0) and ((N if b_mn else K) % 4 == 0)
+    assert (ops.n_tf32 == n0 + 1) == aligned, "tcgen05 path must serve every TMA-aligned shape"
+    assert rel(out, a.double() @ b.double()) < TF32_TOL
+
+
+@pytest.mark.parametrize("bn", ["32", "64", "128", "256"])
+def test_gemm_tf32_tile_widths(ops, bn, monkeypatch):
+    monkeypatch.setenv("ITN_GEMM_BN", bn)
+    gen = torch.Generator(device="cuda").manual_seed(int(bn))
+    a = torch.randn(3, 300, 200, generator=gen, device="cuda")
+    w = torch.randn(3, 520, 200, generator=gen, device="cuda")
+    out = ops.matmul(a, w.transpose(-1, -2))
+    assert rel(out, a.double() @ w.double().transpose(-1, -2)) < TF32_TOL
+
+
+def test_gemm_unaligned_goes_simt(ops):
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    a = torch.randn(250, 1, generator=gen, device="cuda")
+    w = torch.randn(1, 512, generator=gen, device="cuda")
+    out = ops.matmul(a, w)
+    assert rel(out, a.double() @ w.double()) < FP32_TOL
+
+
+def test_gemm_heads_views(ops):
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    F_, L, H, hd = 5, 361, 8, 32
+    q, k, v = (torch.randn(F_, L, H * hd, generator=gen, device="cuda") for _ in range(3))
+    qh, kh, vh = (t.view(F_, L, H, hd).permute(0, 2, 1, 3) for t in (q, k, v))
+    ldp = (L + 3) // 4 * 4
+    s = torch.zeros(F_, H, L, ldp, device="cuda")[..., :L]
+    ops.matmul(qh, kh.transpose(-1, -2), out=s)
+    assert rel(s, qh.double() @ kh.double().transpose(-1, -2)) < TF32_TOL
+    o = torch.empty(F_, L, H * hd, device="cuda")
+    oh = o.view(F_, L, H, hd).permute(0, 2, 1, 3)
+    ops.matmul(s, vh, out=oh)
+    assert rel(oh, s.double() @ vh.double()) < TF32_TOL
+    dv = ops.matmul(s.transpose(-1, -2), oh)
+    assert rel(dv, s.double().transpose(-1, -2) @ oh.double()) < TF32_TOL
+
+
+@pytest.mark.parametrize("simt", [False, True])
+def test_gemm_epilogues(ops, simt):
+    ops.force_simt = simt
+    try:
+        gen = torch.Generator(device="cuda").manual_seed(3)
+        M, N, K = 300, 260, 96
+        a = torch.randn(M, K, generator=gen, device="cuda")
+        w = torch.randn(N, K, generator=gen, device="cuda")
+        bias = torch.randn(N, generator=gen, device="cuda")
+        res = torch.randn(M, N, generator=gen, device="cuda")
+        aux = torch.randn(M, N, generator=gen, device="cuda")
+        base = a.double() @ w.double().t()
+        tol = FP32_TOL if simt else TF32_TOL
+        assert rel(ops.matmul(a, w.t(), bias=bias), base + bias.double()) < tol
+        o = ops.matmul(a, w.t(), bias=bias, act="relu", residual=res)
+        assert rel(o, torch.relu(base + bias.double()) + res.double()) < tol
+        pre = torch.empty(M, N, device="cuda")
+        o = ops.matmul(a, w.t(), bias=bias, act="gelu", out_pre=pre)
+        assert rel(o, torch.nn.functional.gelu(base + bias.double())) < tol
+        assert rel(pre, base + bias.double()) < tol
+        o = ops.matmul(a, w.t(), epi="relu_mask", aux=aux)
+        assert rel(o, base * (aux > 0).double()) < tol
+        x = aux.double().requires_grad_(True)
+        torch.nn.functional.gelu(x).sum().backward()
+        o = ops.matmul(a, w.t(), epi="gelu_grad", aux=aux)
+        assert rel(o, base * x.grad) < tol
+        c = res.clone()
+        ops.matmul(a, w.t(), out=c, accumulate=True, alpha=0.5)
+        assert rel(c, 0.5 * base + res.double()) < tol
+    finally:
+        ops.force_simt = False
+
+
+@pytest.mark.parametrize("cols", [256, 512])
+@pytest.mark.parametrize("groups", [1, 3])
+def test_layernorm_fwd_bwd(ops, cols, groups):
+    gen = torch.Generator(device="cuda").manual_seed(cols + groups)
+    rows = 3 * 250
+    x = torch.randn(rows, cols, generator=gen, device="cuda") * 2 + 0.5
+    gamma = torch.randn(groups, cols, generator=gen, device="cuda")
+    beta = torch.randn(groups, cols, generator=gen, device="cuda")
+    dy = torch.randn(rows, cols, generator=gen, device="cuda")
+    y, mean, rstd = ops.layernorm_fwd(x, gamma, beta)
+    dx, dg, db = ops.layernorm_bwd(dy, x, mean, rstd, gamma)
+    xr = x.double().view(groups, -1, cols).requires_grad_(True)
+    gr = gamma.double().requires_grad_(True)
+    br = beta.double().requires_grad_(True)
+    yr = torch.nn.functional.layer_norm(xr, (cols,)) * gr[:, None] + br[:, None]
+    yr.backward(dy.double().view(groups, -1, cols))
+    assert rel(y, yr.reshape(rows, cols)) < FP32_TOL
+    assert rel(dx, xr.grad.reshape(rows, cols)) < FP32_TOL
+    assert rel(dg, gr.grad) < FP32_TOL
+    assert rel(db, br.grad) < FP32_TOL
+
+
+@pytest.mark.parametrize("cols", [50, 255, 361, 1805, 2060])
+def test_softmax_fwd_bwd(ops, cols):
+    gen = torch.Generator(device="cuda").manual_seed(cols)
+    ld = (cols + 3) // 4 * 4
+    rows = 97
+    s = torch.randn(rows, ld, generator=gen, device="cuda") * 3
+    dp = torch.randn(rows, ld, generator=gen, device="cuda")
+    scale = 0.176
+    sr = (s[:, :cols].double() * scale).requires_grad_(True)
+    pr = torch.softmax(sr, -1)
+    pr.backward(dp[:, :cols].double())
+    p = ops.softmax_(s.clone(), cols, scale)
+    assert rel(p[:, :cols], pr) < FP32_TOL
+    ds = ops.softmax_bwd_(p, dp.clone(), cols, scale)
+    assert rel(ds[:, :cols], sr.grad * scale) < 5 * FP32_TOL
+
+
+def test_softmax_key_mask(ops):
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    B, H, L, Lk = 2, 4, 50, 361
+    ld = 364
+    s = torch.randn(B, H, L, ld, generator=gen, device="cuda")
+    mask = (torch.rand(B, Lk, generator=gen, device="cuda") < 0.3)
+    ref = torch.softmax(s[..., :Lk].double().masked_fill(mask[:, None, None, :], float("-inf")), -1)
+    p = ops.softmax_(s.clone(), Lk, 1.0, key_mask=mask.to(torch.uint8).contiguous(), rows_per_mask=H * L)
+    assert rel(p[..., :Lk], ref) < FP32_TOL
+
+
+def test_colsum_add_copy_sigmoid_norm(ops):
+    gen = torch.Generator(device="cuda").manual_seed(2)
+    x = torch.randn(3, 1805, 256, generator=gen, device="cuda")
+    assert rel(ops.colsum(x), x.double().sum(1)) < FP32_TOL
+    pos = torch.randn(1805, 256, generator=gen, device="cuda")
+    assert rel(ops.add(x, pos), x + pos) < 1e-7
+    dst = torch.zeros(250, 1496, device="cuda")
+    src = torch.randn(250, 256, generator=gen, device="cuda")
+    ops.copy2d_(dst[:, 4:260], src)
+    assert torch.equal(dst[:, 4:260], src) and dst[:, :4].abs().sum() == 0
+    z = torch.randn(250, 4, generator=gen, device="cuda")
+    y = ops.sigmoid(z)
+    assert rel(y, torch.sigmoid(z.double())) < FP32_TOL
+    dy = torch.randn(250, 4, generator=gen, device="cuda")
+    assert rel(ops.sigmoid_bwd(dy, y), dy.double() * y.double() * (1 - y.double())) < FP32_TOL
+    v = torch.randn(4, 250, generator=gen, device="cuda")
+    loss, dv = ops.l2norm_fwd_bwd(v)
+    assert rel(loss, v.double().norm(dim=1)) < FP32_TOL
+    assert rel(dv, v.double() / v.double().norm(dim=1, keepdim=True)) < FP32_TOL
+
+
+@pytest.mark.parametrize("groups", [1, 4])
+def test_sgd_clip_update_bit_exact(ops, groups):
+    """The fused step must equal p - clip(lr*g) of utils/meta_utils.py:135-142 bit for bit."""
+    gen = torch.Generator(device="cuda").manual_seed(9)
+    n = 14_798_296 if groups == 1 else 1_000_004
+    theta = torch.randn(n, generator=gen, device="cuda")
+    g = torch.randn(groups, n, generator=gen, device="cuda") * 20
+    out, mask = ops.sgd_clip_update(theta, g, 1e-3, 0.01, want_mask=True)
+    ref = theta[None] - torch.clip(1e-3 * g, min=-0.01, max=0.01)
+    assert torch.equal(out, ref)
+    assert torch.equal(mask.bool(), (1e-3 * g).abs() <= 0.01)
+
+
+def test_pos_embed_sine_matches_formula(ops):
+    gen = torch.Generator(device="cuda").manual_seed(4)
+    F_, h, w = 3, 19, 19
+    mask = torch.zeros(F_, h, w, dtype=torch.bool, device="cuda")
+    mask[1, :, 15:] = True
+    mask[2, 17:, :] = True
+    pos = ops.pos_embed_sine(mask)
+    not_mask = ~mask
+    y_embed = not_mask.cumsum(1, dtype=torch.float32)
+    x_embed = not_mask.cumsum(2, dtype=torch.float32)
+    eps, scale = 1e-6, 2 * 3.141592653589793
+    y_embed = y_embed / (y_embed[:, -1:, :] + eps) * scale
+    x_embed = x_embed / (x_embed[:, :, -1:] + eps) * scale
+    dim_t = torch.arange(128, dtype=torch.float32, device="cuda")
+    dim_t = 10000 ** (2 * (dim_t // 2) / 128)
+    px = x_embed[:, :, :, None] / dim_t
+    py = y_embed[:, :, :, None] / dim_t
+    px = torch.stack((px[:, :, :, 0::2].sin(), px[:, :, :, 1::2].cos()), dim=4).flatten(3)
+    py = torch.stack((py[:, :, :, 0::2].sin(), py[:, :, :, 1::2].cos()), dim=4).flatten(3)
+    ref = torch.cat((py, px), dim=3).reshape(F_, h * w, 256)
+    assert (pos - ref).abs().max().item() < 2e-5
+    del gen
+
+
+def test_matcher_cost_block_diagonal(ops):
+    gen = torch.Generator(device="cuda").manual_seed(6)
+    F_, Q, Cn = 5, 50, 1236
+    logits = torch.randn(F_, Q, Cn, generator=gen, device="cuda")
+    boxes = torch.rand(F_, Q, 4, generator=gen, device="cuda") * 0.5 + 0.1
+    sizes = [3, 8, 5, 4, 6]
+    T = sum(sizes)
+    tb = torch.cat([torch.rand(T, 2, generator=gen, device="cuda") * 0.6 + 0.2,
+                    torch.rand(T, 2, generator=gen, device="cuda") * 0.3 + 0.05], 1).contiguous()
+    tl = torch.randint(1, 1235, (T,), generator=gen, device="cuda")
+    off = torch.tensor([0] + list(torch.tensor(sizes).cumsum(0)), dtype=torch.int32, device="cuda")
+    cost = ops.matcher_cost(logits, boxes, tb, tl, off, 1.0, 5.0, 2.0)
+
+    def xyxy(b):
+        cx, cy, w, h = b.unbind(-1)
+        return torch.stack([cx - 0.5 * w, cy - 0.5 * h, cx + 0.5 * w, cy + 0.5 * h], -1)
+
+    def giou(a, b):
+        area1 = (a[:, 2] - a[:, 0]) * (a[:, 3] - a[:, 1])
+        area2 = (b[:, 2] - b[:, 0]) * (b[:, 3] - b[:, 1])
+        lt = torch.max(a[:, None, :2], b[:, :2])
+        rb = torch.min(a[:, None, 2:], b[:, 2:])
+        wh = (rb - lt).clamp(min=0)
+        inter = wh[..., 0] * wh[..., 1]
+        union = area1[:, None] + area2 - inter
+        iou = inter / union
+        lt = torch.min(a[:, None, :2], b[:, :2])
+        rb = torch.max(a[:, None, 2:], b[:, 2:])
+        wh = (rb - lt).clamp(min=0)
+        area = wh[..., 0] * wh[..., 1]
+        return iou - (area - union) / area
+
+    prob = logits.flatten(0, 1).softmax(-1)
+    ob = boxes.flatten(0, 1)
+    Cfull = 5.0 * torch.cdist(ob, tb, p=1) - prob[:, tl] - 2.0 * giou(xyxy(ob), xyxy(tb))
+    Cfull = Cfull.view(F_, Q, T)
+    o = 0
+    for f, n in enumerate(sizes):
+        blk = cost[Q * o: Q * (o + n)].view(Q, n)
+        assert (blk - Cfull[f, :, o:o + n]).abs().max().item() < 1e-5
+        o += n
