@@ -52,7 +52,13 @@ enum { ITN_EPI_NONE = 0, ITN_EPI_RELU_MASK = 1, ITN_EPI_GELU_GRAD = 2 };
 /* C[b0,b1] = epilogue( alpha * A[b0,b1] (MxK) * B[b0,b1]^T (NxK)^T ), batch = nb0*nb1.
  * Epilogue order per element:  v = alpha*acc; v += bias[n]; if (C2) C2 = v;
  * v = act(v); epi (RELU_MASK: v = aux>0 ? v : 0; GELU_GRAD: v *= gelu'(aux));
- * v += residual; if (accumulate) v += C; C = v.
+ * v += residual; if (accumulate) v += C; if (round_out) v = rn_tf32(v); C = v.
+ * tcgen05 kind::tf32 TRUNCATES its fp32 operands to 10 mantissa bits, which biases
+ * every product by about -4e-4 per operand.  The path therefore keeps every tensor
+ * that feeds a GEMM already rounded-to-nearest to TF32 ("TF32-clean"): producers
+ * round on store (round_out here, y_r/dx_r in LayerNorm, the softmax kernels,
+ * itn_round_tf32 for weights), so the tensor core sees exactly the stored value
+ * and the remaining error is unbiased.
  * Replaces: every nn.Linear / F.linear, the 1x1 input_proj conv, bmm/baddbmm of
  * nn.MultiheadAttention and the `q @ k.T`, `att @ v` of CausalSelfAttention on
  * the path, forward and backward (models/detr_models/transformer.py:148-161,
@@ -72,6 +78,7 @@ typedef struct {
   int act;
   int epi;
   int accumulate;
+  int round_out;
 } itn_gemm_desc_t;
 
 /* tcgen05/TMA path.  Requires 16-byte aligned operand bases and ld/sb* multiples
@@ -88,30 +95,32 @@ int itn_gemm_simt(const itn_gemm_desc_t* d, void* stream);
  * the reference uses nn.LayerNorm default 1e-5: detr_models/transformer.py:139-140,
  * 198-200; models/gpt.py:64-65,97).  Rows are split in `groups` equal groups;
  * group g uses gamma/beta + g*gb_stride (per-episode fast weights).  mean/rstd
- * ([rows], may be NULL) are saved for the backward. */
+ * ([rows], may be NULL) are saved for the backward.  y_r (may be NULL) receives a
+ * TF32-rounded copy of y for GEMM consumers; y itself stays full fp32. */
 int itn_layernorm_fwd(const float* x, const float* gamma, const float* beta,
-                      float* y, float* mean, float* rstd,
+                      float* y, float* y_r, float* mean, float* rstd,
                       long long rows, int cols, int groups, long long gb_stride,
                       float eps, void* stream);
 /* dx = d LayerNorm; dgamma/dbeta ([groups, cols], may be NULL) are OVERWRITTEN
- * with the per-group sums.  Replaces native_layer_norm_backward under
- * models/interactron.py:51-52. */
+ * with the per-group sums; dx_r (may be NULL) is a TF32-rounded copy of dx.
+ * Replaces native_layer_norm_backward under models/interactron.py:51-52. */
 int itn_layernorm_bwd(const float* dy, const float* x, const float* mean,
                       const float* rstd, const float* gamma,
-                      float* dx, float* dgamma, float* dbeta,
+                      float* dx, float* dx_r, float* dgamma, float* dbeta,
                       long long rows, int cols, int groups, long long gb_stride,
                       void* stream);
 
 /* In-place row softmax of scale*s + mask over `cols` (row stride ld).
  * key_mask (may be NULL) is uint8 [mask_batches, cols], 1 = padded key (-inf);
- * row r uses mask row (r / rows_per_mask).  Replaces F.softmax in
+ * row r uses mask row (r / rows_per_mask).  round_out: store TF32-rounded
+ * probabilities (they only feed GEMMs).  Replaces F.softmax in
  * nn.MultiheadAttention (transformer.py:154,219-226) and models/gpt.py:48-50. */
 int itn_softmax_fwd(float* s, long long rows, int cols, long long ld, float scale,
                     const unsigned char* key_mask, long long rows_per_mask,
-                    void* stream);
+                    int round_out, void* stream);
 /* ds = scale * p * (dp - sum(p*dp)) written in place over dp. */
 int itn_softmax_bwd(const float* p, float* dp, long long rows, int cols,
-                    long long ld, float scale, void* stream);
+                    long long ld, float scale, int round_out, void* stream);
 
 /* out[g, c] = sum_r x[g, r, c]  (bias gradients): x is [groups, rows, cols]
  * with row stride ld; out [groups, cols] OVERWRITTEN. */
@@ -119,12 +128,14 @@ int itn_colsum(const float* x, float* out, int groups, long long rows, int cols,
                long long ld, void* stream);
 
 /* --------------------------------------------------------- element-wise --- */
-/* out = a + b (b broadcast with period b_elems: b[i % b_elems]). */
+/* out = a + b (b broadcast with period b_elems: b[i % b_elems]); optional TF32 rounding. */
 int itn_add(const float* a, const float* b, float* out, long long n,
-            long long b_elems, void* stream);
-/* Strided 2-D copy: dst[r*ldd + c] = src[r*lds + c]. */
+            long long b_elems, int round_out, void* stream);
+/* Strided 2-D copy: dst[r*ldd + c] = src[r*lds + c]; optional TF32 rounding. */
 int itn_copy2d(const float* src, long long lds, float* dst, long long ldd,
-               long long rows, int cols, void* stream);
+               long long rows, int cols, int round_out, void* stream);
+/* dst = rn_tf32(src) (dst may equal src): makes weights / inputs TF32-clean. */
+int itn_round_tf32(const float* src, float* dst, long long n, void* stream);
 /* y = sigmoid(x)   (detr.py:72 `.sigmoid()`). */
 int itn_sigmoid_fwd(const float* x, float* y, long long n, void* stream);
 /* dx = dy * y * (1-y). */
@@ -138,10 +149,11 @@ int itn_l2norm_fwd_bwd(const float* x, float* loss, float* dx, int groups, int n
 /* Fused fast-weight step (utils/meta_utils.py:135-142 sgd_step):
  *   theta_out = theta - clip(lr * g, -clip, +clip)
  * theta may be broadcast over `groups` episodes (theta_stride 0); g and
- * theta_out are [groups, n].  clip_mask (may be NULL, uint8 [groups,n]) receives
+ * theta_out are [groups, n].  theta_out_r (may be NULL) receives the TF32-rounded
+ * copy used as GEMM weights.  clip_mask (may be NULL, uint8 [groups,n]) receives
  * 1 where the step was inside the clip band (d step/d g = lr), else 0. */
 int itn_sgd_clip_update(const float* theta, long long theta_stride, const float* g,
-                        float* theta_out, unsigned char* clip_mask, int groups,
+                        float* theta_out, float* theta_out_r, unsigned char* clip_mask, int groups,
                         long long n, float lr, float clip, void* stream);
 
 /* DETR sine position embedding (detr_models/position_encoding.py:28-48,

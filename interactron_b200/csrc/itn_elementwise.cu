@@ -19,11 +19,13 @@ static inline unsigned grid_for(long long work_items, int threads, int max_ctas_
 __global__ void __launch_bounds__(256)
 sgd_clip_update_kernel(const float* __restrict__ theta, long long theta_stride,
                        const float* __restrict__ g, float* __restrict__ out,
-                       unsigned char* __restrict__ mask, long long n, float lr, float clip) {
+                       float* __restrict__ out_r, unsigned char* __restrict__ mask, long long n,
+                       float lr, float clip) {
   const int grp = blockIdx.y;
   const float* th = theta + grp * theta_stride;
   const float* gg = g + (long long)grp * n;
   float* oo = out + (long long)grp * n;
+  float* orr = out_r ? out_r + (long long)grp * n : nullptr;
   unsigned char* mm = mask ? mask + (long long)grp * n : nullptr;
   const long long n4 = n >> 2;
   const float4* th4 = reinterpret_cast<const float4*>(th);
@@ -40,6 +42,9 @@ sgd_clip_update_kernel(const float* __restrict__ theta, long long theta_stride,
     o.z = t.z - fminf(fmaxf(st.z, -clip), clip);
     o.w = t.w - fminf(fmaxf(st.w, -clip), clip);
     o4[i] = o;
+    if (orr)
+      reinterpret_cast<float4*>(orr)[i] =
+          make_float4(rn_tf32(o.x), rn_tf32(o.y), rn_tf32(o.z), rn_tf32(o.w));
     if (mm) {
       uchar4 m;
       m.x = fabsf(st.x) <= clip; m.y = fabsf(st.y) <= clip;
@@ -50,7 +55,9 @@ sgd_clip_update_kernel(const float* __restrict__ theta, long long theta_stride,
   if (blockIdx.x == 0) {
     for (long long i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) {
       const float st = lr * gg[i];
-      oo[i] = th[i] - fminf(fmaxf(st, -clip), clip);
+      const float o = th[i] - fminf(fmaxf(st, -clip), clip);
+      oo[i] = o;
+      if (orr) orr[i] = rn_tf32(o);
       if (mm) mm[i] = fabsf(st) <= clip;
     }
   }
@@ -58,7 +65,7 @@ sgd_clip_update_kernel(const float* __restrict__ theta, long long theta_stride,
 
 __global__ void __launch_bounds__(256)
 add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
-           long long n, long long b_elems) {
+           long long n, long long b_elems, int round_out) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long n4 = n >> 2;
   if ((b_elems & 3) == 0) {
@@ -68,27 +75,47 @@ add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __re
     const long long bq = b_elems >> 2;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
       const float4 x = a4[i], y = b4[i % bq];
-      o4[i] = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
+      float4 o = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
+      if (round_out) o = make_float4(rn_tf32(o.x), rn_tf32(o.y), rn_tf32(o.z), rn_tf32(o.w));
+      o4[i] = o;
     }
     if (blockIdx.x == 0)
-      for (long long i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x)
-        out[i] = a[i] + b[i % b_elems];
+      for (long long i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) {
+        const float o = a[i] + b[i % b_elems];
+        out[i] = round_out ? rn_tf32(o) : o;
+      }
   } else {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-      out[i] = a[i] + b[i % b_elems];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+      const float o = a[i] + b[i % b_elems];
+      out[i] = round_out ? rn_tf32(o) : o;
+    }
   }
 }
 
 __global__ void __launch_bounds__(256)
 copy2d_kernel(const float* __restrict__ src, long long lds, float* __restrict__ dst, long long ldd,
-              long long rows, int cols) {
+              long long rows, int cols, int round_out) {
   const long long total = rows * cols;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
     const long long r = i / cols;
     const int c = (int)(i - r * cols);
-    dst[r * ldd + c] = src[r * lds + c];
+    const float v = src[r * lds + c];
+    dst[r * ldd + c] = round_out ? rn_tf32(v) : v;
   }
+}
+
+__global__ void __launch_bounds__(256)
+round_tf32_kernel(const float* __restrict__ src, float* __restrict__ dst, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long n4 = n >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = reinterpret_cast<const float4*>(src)[i];
+    reinterpret_cast<float4*>(dst)[i] =
+        make_float4(rn_tf32(v.x), rn_tf32(v.y), rn_tf32(v.z), rn_tf32(v.w));
+  }
+  if (blockIdx.x == 0)
+    for (long long i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) dst[i] = rn_tf32(src[i]);
 }
 
 __global__ void __launch_bounds__(256)
@@ -177,7 +204,8 @@ pos_embed_sine_kernel(const unsigned char* __restrict__ mask, float* __restrict_
 using namespace itn;
 
 extern "C" int itn_sgd_clip_update(const float* theta, long long theta_stride, const float* g,
-                                   float* theta_out, unsigned char* clip_mask, int groups,
+                                   float* theta_out, float* theta_out_r, unsigned char* clip_mask,
+                                   int groups,
                                    long long n, float lr, float clip, void* stream) {
   ITN_REQUIRE(theta && g && theta_out && groups > 0 && n > 0, "sgd_clip_update: bad arguments");
   ITN_REQUIRE(((uintptr_t)theta & 15) == 0 && ((uintptr_t)g & 15) == 0 &&
@@ -186,26 +214,34 @@ extern "C" int itn_sgd_clip_update(const float* theta, long long theta_stride, c
   ITN_REQUIRE(groups == 1 || ((n & 3) == 0 && (theta_stride & 3) == 0),
               "sgd_clip_update: n and theta_stride must be multiples of 4 when groups > 1");
   ITN_REQUIRE(!clip_mask || ((uintptr_t)clip_mask & 3) == 0, "sgd_clip_update: mask must be 4-byte aligned");
+  ITN_REQUIRE(!theta_out_r || ((uintptr_t)theta_out_r & 15) == 0, "sgd_clip_update: theta_out_r must be 16-byte aligned");
   dim3 grid(grid_for(n >> 2, 256, 8), groups);
   sgd_clip_update_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      theta, theta_stride, g, theta_out, clip_mask, n, lr, clip);
+      theta, theta_stride, g, theta_out, theta_out_r, clip_mask, n, lr, clip);
   return check_launch("sgd_clip_update_kernel");
 }
 
 extern "C" int itn_add(const float* a, const float* b, float* out, long long n, long long b_elems,
-                       void* stream) {
+                       int round_out, void* stream) {
   ITN_REQUIRE(a && b && out && n > 0 && b_elems > 0, "add: bad arguments");
   ITN_REQUIRE((((uintptr_t)a | (uintptr_t)b | (uintptr_t)out) & 15) == 0, "add: pointers must be 16-byte aligned");
-  add_kernel<<<grid_for(n >> 2, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, b, out, n, b_elems);
+  add_kernel<<<grid_for(n >> 2, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, b, out, n, b_elems, round_out);
   return check_launch("add_kernel");
 }
 
 extern "C" int itn_copy2d(const float* src, long long lds, float* dst, long long ldd, long long rows,
-                          int cols, void* stream) {
+                          int cols, int round_out, void* stream) {
   ITN_REQUIRE(src && dst && rows > 0 && cols > 0, "copy2d: bad arguments");
   copy2d_kernel<<<grid_for(rows * cols, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      src, lds, dst, ldd, rows, cols);
+      src, lds, dst, ldd, rows, cols, round_out);
   return check_launch("copy2d_kernel");
+}
+
+extern "C" int itn_round_tf32(const float* src, float* dst, long long n, void* stream) {
+  ITN_REQUIRE(src && dst && n > 0, "round_tf32: bad arguments");
+  ITN_REQUIRE((((uintptr_t)src | (uintptr_t)dst) & 15) == 0, "round_tf32: pointers must be 16-byte aligned");
+  round_tf32_kernel<<<grid_for(n >> 2, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, dst, n);
+  return check_launch("round_tf32_kernel");
 }
 
 extern "C" int itn_sigmoid_fwd(const float* x, float* y, long long n, void* stream) {

@@ -6,7 +6,7 @@
 // elected lane issues tcgen05.mma.kind::tf32 128xBNx8), warps 2-5 epilogue
 // (TMEM -> registers -> per-warp smem transpose -> coalesced global stores).
 // One CTA produces one 128 x BN tile of one batch entry; the K loop runs over a
-// STAGES-deep ring of {A tile, B tile} filled with SWIZZLE_128B TMA boxes whose
+// STAGES-deep ring of {A tile, B tile} filled with 128-byte-swizzled TMA boxes whose
 // inner extent is 32 floats (= one 128-byte swizzle row).  Both operand majors
 // are supported through the UMMA descriptors, so forward (x W^T), data-grad
 // (dy W) and weight-grad (dy^T x) all run without materialising transposes.
@@ -37,7 +37,7 @@ struct GemmKParams {
   const float* aux;      long long ldaux, aux_sb0,  aux_sb1;
   float* C2;             long long ldc2,  c2_sb0,   c2_sb1;
   float alpha;
-  int act, epi, accumulate;
+  int act, epi, accumulate, round_out;
 };
 
 // Per-batch-entry epilogue pointers.
@@ -73,7 +73,7 @@ __device__ __forceinline__ void epilogue_store(const GemmKParams& p, const EpiPt
   if (e.residual) v += e.residual[(long long)row * p.ldr + col];
   float* c = e.C + (long long)row * p.ldc + col;
   if (p.accumulate) v += *c;
-  *c = v;
+  *c = p.round_out ? rn_tf32(v) : v;
 }
 
 template <int BN>
@@ -171,12 +171,15 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const uint32_t sb = sa + Cfg::kABytes;
 #pragma unroll
         for (int k = 0; k < kBK / 8; ++k) {
-          // K-major: 8 floats = 32 B further along the swizzled 128 B row.
-          // MN-major: 8 k-rows = one 1024 B swizzle atom further.
-          const uint64_t ad = A_MN ? umma_smem_desc(sa + k * 1024, kAtomBytes, 1024)
-                                   : umma_smem_desc(sa + k * 32, 16, 1024);
-          const uint64_t bd = B_MN ? umma_smem_desc(sb + k * 1024, kAtomBytes, 1024)
-                                   : umma_smem_desc(sb + k * 32, 16, 1024);
+          // K-major (SWIZZLE_128B): rows of 32 floats, 8-row groups 1024 B apart (SBO); the
+          //   k-th MMA starts 8 floats = 32 B further along the swizzled row.
+          // MN-major (SWIZZLE_128B_BASE32B): k-rows of 32 mn-floats, 4-row swizzle atoms 512 B
+          //   apart (SBO), 32-wide mn blocks one TMA box = 4096 B apart (LBO); the k-th MMA
+          //   starts 8 k-rows = 1024 B further.
+          const uint64_t ad = A_MN ? umma_smem_desc(sa + k * 1024, kAtomBytes, 512, kLayoutSW128Base32)
+                                   : umma_smem_desc(sa + k * 32, 16, 1024, kLayoutSW128);
+          const uint64_t bd = B_MN ? umma_smem_desc(sb + k * 1024, kAtomBytes, 512, kLayoutSW128Base32)
+                                   : umma_smem_desc(sb + k * 32, 16, 1024, kLayoutSW128);
           umma_tf32(tmem_base, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
         }
         umma_commit(&empty_bar[s]);  // frees the smem slot once the MMAs have read it
@@ -316,7 +319,8 @@ static int make_operand_map(CUtensorMap* tm, const itn_operand_t& o, int rows, i
   cuuint32_t box[4] = {32, o.major == 0 ? (cuuint32_t)box_rows : 32u, 1, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(o.ptr), gdim, gstr,
-                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   o.major == 0 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return set_error(ITN_ERR_CUDA,
@@ -337,6 +341,7 @@ static void fill_kparams(GemmKParams& p, const itn_gemm_desc_t* d) {
   p.aux = d->aux; p.ldaux = d->ldaux; p.aux_sb0 = d->aux_sb0; p.aux_sb1 = d->aux_sb1;
   p.C2 = d->C2; p.ldc2 = d->ldc2; p.c2_sb0 = d->c2_sb0; p.c2_sb1 = d->c2_sb1;
   p.alpha = d->alpha; p.act = d->act; p.epi = d->epi; p.accumulate = d->accumulate;
+  p.round_out = d->round_out;
 }
 
 static int validate(const itn_gemm_desc_t* d) {

@@ -110,18 +110,22 @@ __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// Shared-memory matrix descriptor (sm_100 "version 1"), SWIZZLE_128B.
+// Shared-memory matrix descriptor (sm_100 "version 1").
 //   bits [0,14)  start address >> 4        bits [16,30) leading byte offset >> 4
 //   bits [32,46) stride byte offset >> 4   bits [46,48) version = 1
-//   bits [61,64) layout type: 2 = SWIZZLE_128B
+//   bits [61,64) layout type: 2 = SWIZZLE_128B (16-byte chunks, K-major operands),
+//                             1 = SWIZZLE_128B_BASE32B (32-byte chunks: the only layout the
+//                                 tensor core accepts for MN-major 32-bit (tf32) operands)
+constexpr uint32_t kLayoutSW128 = 2;
+constexpr uint32_t kLayoutSW128Base32 = 1;
 __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t lbo_bytes,
-                                                   uint32_t sbo_bytes) {
+                                                   uint32_t sbo_bytes, uint32_t layout_type) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((saddr >> 4) & 0x3FFF);
   d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(2) << 61;
+  d |= static_cast<uint64_t>(layout_type) << 61;
   return d;
 }
 

@@ -11,7 +11,7 @@ template <int VPL>
 __global__ void __launch_bounds__(256)
 layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                      const float* __restrict__ beta, float* __restrict__ y,
-                     float* __restrict__ mean_out, float* __restrict__ rstd_out, long long rows,
+                     float* __restrict__ y_r, float* __restrict__ mean_out, float* __restrict__ rstd_out, long long rows,
                      long long rows_per_group, long long gb_stride, float eps) {
   constexpr int cols = VPL * 128;
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -37,6 +37,7 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
   const float4* gr = reinterpret_cast<const float4*>(gamma + g * gb_stride);
   const float4* br = reinterpret_cast<const float4*>(beta + g * gb_stride);
   float4* yr = reinterpret_cast<float4*>(y + row * cols);
+  float4* yrr = y_r ? reinterpret_cast<float4*>(y_r + row * cols) : nullptr;
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
     const float4 ga = gr[lane + 32 * i], be = br[lane + 32 * i];
@@ -46,6 +47,7 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
     o.z = (v[i].z - mean) * rstd * ga.z + be.z;
     o.w = (v[i].w - mean) * rstd * ga.w + be.w;
     yr[lane + 32 * i] = o;
+    if (yrr) yrr[lane + 32 * i] = make_float4(rn_tf32(o.x), rn_tf32(o.y), rn_tf32(o.z), rn_tf32(o.w));
   }
   if (lane == 0) {
     if (mean_out) mean_out[row] = mean;
@@ -58,8 +60,9 @@ template <int VPL>
 __global__ void __launch_bounds__(256)
 layernorm_bwd_dx_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                         const float* __restrict__ mean, const float* __restrict__ rstd,
-                        const float* __restrict__ gamma, float* __restrict__ dx, long long rows,
-                        long long rows_per_group, long long gb_stride) {
+                        const float* __restrict__ gamma, float* __restrict__ dx,
+                        float* __restrict__ dx_r, long long rows, long long rows_per_group,
+                        long long gb_stride) {
   constexpr int cols = VPL * 128;
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -83,6 +86,7 @@ layernorm_bwd_dx_kernel(const float* __restrict__ dy, const float* __restrict__ 
   const float m1 = warp_sum(s1) * (1.0f / cols);
   const float m2 = warp_sum(s2) * (1.0f / cols);
   float4* or_ = reinterpret_cast<float4*>(dx + row * cols);
+  float4* orr = dx_r ? reinterpret_cast<float4*>(dx_r + row * cols) : nullptr;
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
     float4 o;
@@ -91,6 +95,7 @@ layernorm_bwd_dx_kernel(const float* __restrict__ dy, const float* __restrict__ 
     o.z = rs * (dg[i].z - m1 - xh[i].z * m2);
     o.w = rs * (dg[i].w - m1 - xh[i].w * m2);
     or_[lane + 32 * i] = o;
+    if (orr) orr[lane + 32 * i] = make_float4(rn_tf32(o.x), rn_tf32(o.y), rn_tf32(o.z), rn_tf32(o.w));
   }
 }
 
@@ -135,7 +140,8 @@ layernorm_bwd_gb_kernel(const float* __restrict__ dy, const float* __restrict__ 
 // re-read from L1/L2, never from HBM: rows are <= 8 KB).
 __global__ void __launch_bounds__(256)
 softmax_fwd_kernel(float* __restrict__ s, long long rows, int cols, long long ld, float scale,
-                   const unsigned char* __restrict__ key_mask, long long rows_per_mask) {
+                   const unsigned char* __restrict__ key_mask, long long rows_per_mask,
+                   int round_out) {
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -158,13 +164,14 @@ softmax_fwd_kernel(float* __restrict__ s, long long rows, int cols, long long ld
   for (int c = lane; c < cols; c += 32) {
     float v = r[c] * scale;
     if (mk && mk[c]) v = -INFINITY;
-    r[c] = __expf(v - gm) * inv;
+    const float o = __expf(v - gm) * inv;
+    r[c] = round_out ? rn_tf32(o) : o;
   }
 }
 
 __global__ void __launch_bounds__(256)
 softmax_bwd_kernel(const float* __restrict__ p, float* __restrict__ dp, long long rows, int cols,
-                   long long ld, float scale) {
+                   long long ld, float scale, int round_out) {
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -173,7 +180,10 @@ softmax_bwd_kernel(const float* __restrict__ p, float* __restrict__ dp, long lon
   float acc = 0.f;
   for (int c = lane; c < cols; c += 32) acc += pr[c] * dr[c];
   const float dot = warp_sum(acc);
-  for (int c = lane; c < cols; c += 32) dr[c] = scale * pr[c] * (dr[c] - dot);
+  for (int c = lane; c < cols; c += 32) {
+    const float o = scale * pr[c] * (dr[c] - dot);
+    dr[c] = round_out ? rn_tf32(o) : o;
+  }
 }
 
 // ------------------------------------------------------------------- colsum
@@ -202,7 +212,7 @@ colsum_kernel(const float* __restrict__ x, float* __restrict__ out, long long ro
 using namespace itn;
 
 extern "C" int itn_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y,
-                                 float* mean, float* rstd, long long rows, int cols, int groups,
+                                 float* y_r, float* mean, float* rstd, long long rows, int cols, int groups,
                                  long long gb_stride, float eps, void* stream) {
   ITN_REQUIRE(x && gamma && beta && y, "layernorm_fwd: null pointer");
   ITN_REQUIRE(rows > 0 && groups > 0 && rows % groups == 0,
@@ -211,18 +221,18 @@ extern "C" int itn_layernorm_fwd(const float* x, const float* gamma, const float
   const unsigned grid = (unsigned)((rows + 7) / 8);
   const long long rpg = rows / groups;
   switch (cols) {
-    case 128: layernorm_fwd_kernel<1><<<grid, 256, 0, s>>>(x, gamma, beta, y, mean, rstd, rows, rpg, gb_stride, eps); break;
-    case 256: layernorm_fwd_kernel<2><<<grid, 256, 0, s>>>(x, gamma, beta, y, mean, rstd, rows, rpg, gb_stride, eps); break;
-    case 512: layernorm_fwd_kernel<4><<<grid, 256, 0, s>>>(x, gamma, beta, y, mean, rstd, rows, rpg, gb_stride, eps); break;
-    case 1024: layernorm_fwd_kernel<8><<<grid, 256, 0, s>>>(x, gamma, beta, y, mean, rstd, rows, rpg, gb_stride, eps); break;
+    case 128: layernorm_fwd_kernel<1><<<grid, 256, 0, s>>>(x, gamma, beta, y, y_r, mean, rstd, rows, rpg, gb_stride, eps); break;
+    case 256: layernorm_fwd_kernel<2><<<grid, 256, 0, s>>>(x, gamma, beta, y, y_r, mean, rstd, rows, rpg, gb_stride, eps); break;
+    case 512: layernorm_fwd_kernel<4><<<grid, 256, 0, s>>>(x, gamma, beta, y, y_r, mean, rstd, rows, rpg, gb_stride, eps); break;
+    case 1024: layernorm_fwd_kernel<8><<<grid, 256, 0, s>>>(x, gamma, beta, y, y_r, mean, rstd, rows, rpg, gb_stride, eps); break;
     default: return set_error(ITN_ERR_UNSUPPORTED, "layernorm_fwd: cols must be 128/256/512/1024, got %d", cols);
   }
   return check_launch("layernorm_fwd_kernel");
 }
 
 extern "C" int itn_layernorm_bwd(const float* dy, const float* x, const float* mean,
-                                 const float* rstd, const float* gamma, float* dx, float* dgamma,
-                                 float* dbeta, long long rows, int cols, int groups,
+                                 const float* rstd, const float* gamma, float* dx, float* dx_r,
+                                 float* dgamma, float* dbeta, long long rows, int cols, int groups,
                                  long long gb_stride, void* stream) {
   ITN_REQUIRE(dy && x && mean && rstd && gamma && dx, "layernorm_bwd: null pointer");
   ITN_REQUIRE(rows > 0 && groups > 0 && rows % groups == 0,
@@ -231,10 +241,10 @@ extern "C" int itn_layernorm_bwd(const float* dy, const float* x, const float* m
   const unsigned grid = (unsigned)((rows + 7) / 8);
   const long long rpg = rows / groups;
   switch (cols) {
-    case 128: layernorm_bwd_dx_kernel<1><<<grid, 256, 0, s>>>(dy, x, mean, rstd, gamma, dx, rows, rpg, gb_stride); break;
-    case 256: layernorm_bwd_dx_kernel<2><<<grid, 256, 0, s>>>(dy, x, mean, rstd, gamma, dx, rows, rpg, gb_stride); break;
-    case 512: layernorm_bwd_dx_kernel<4><<<grid, 256, 0, s>>>(dy, x, mean, rstd, gamma, dx, rows, rpg, gb_stride); break;
-    case 1024: layernorm_bwd_dx_kernel<8><<<grid, 256, 0, s>>>(dy, x, mean, rstd, gamma, dx, rows, rpg, gb_stride); break;
+    case 128: layernorm_bwd_dx_kernel<1><<<grid, 256, 0, s>>>(dy, x, mean, rstd, gamma, dx, dx_r, rows, rpg, gb_stride); break;
+    case 256: layernorm_bwd_dx_kernel<2><<<grid, 256, 0, s>>>(dy, x, mean, rstd, gamma, dx, dx_r, rows, rpg, gb_stride); break;
+    case 512: layernorm_bwd_dx_kernel<4><<<grid, 256, 0, s>>>(dy, x, mean, rstd, gamma, dx, dx_r, rows, rpg, gb_stride); break;
+    case 1024: layernorm_bwd_dx_kernel<8><<<grid, 256, 0, s>>>(dy, x, mean, rstd, gamma, dx, dx_r, rows, rpg, gb_stride); break;
     default: return set_error(ITN_ERR_UNSUPPORTED, "layernorm_bwd: cols must be 128/256/512/1024, got %d", cols);
   }
   int rc = check_launch("layernorm_bwd_dx_kernel");
@@ -249,19 +259,19 @@ extern "C" int itn_layernorm_bwd(const float* dy, const float* x, const float* m
 
 extern "C" int itn_softmax_fwd(float* sc, long long rows, int cols, long long ld, float scale,
                                const unsigned char* key_mask, long long rows_per_mask,
-                               void* stream) {
+                               int round_out, void* stream) {
   ITN_REQUIRE(sc && rows > 0 && cols > 0 && ld >= cols, "softmax_fwd: bad arguments");
   ITN_REQUIRE(!key_mask || rows_per_mask > 0, "softmax_fwd: rows_per_mask must be > 0 with a mask");
   softmax_fwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      sc, rows, cols, ld, scale, key_mask, rows_per_mask);
+      sc, rows, cols, ld, scale, key_mask, rows_per_mask, round_out);
   return check_launch("softmax_fwd_kernel");
 }
 
 extern "C" int itn_softmax_bwd(const float* p, float* dp, long long rows, int cols, long long ld,
-                               float scale, void* stream) {
+                               float scale, int round_out, void* stream) {
   ITN_REQUIRE(p && dp && rows > 0 && cols > 0 && ld >= cols, "softmax_bwd: bad arguments");
   softmax_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      p, dp, rows, cols, ld, scale);
+      p, dp, rows, cols, ld, scale, round_out);
   return check_launch("softmax_bwd_kernel");
 }
 
