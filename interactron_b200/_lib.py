@@ -31,6 +31,7 @@ class GemmDesc(C.Structure):
         ("aux", C.c_void_p), ("ldaux", C.c_longlong), ("aux_sb0", C.c_longlong), ("aux_sb1", C.c_longlong),
         ("C2", C.c_void_p), ("ldc2", C.c_longlong), ("c2_sb0", C.c_longlong), ("c2_sb1", C.c_longlong),
         ("alpha", C.c_float), ("act", C.c_int), ("epi", C.c_int), ("accumulate", C.c_int),
+        ("round_out", C.c_int),
     ]
 
 
@@ -43,17 +44,18 @@ SIGNATURES = {
     "itn_gemm_tf32": (_I, [C.POINTER(GemmDesc), _P]),
     "itn_gemm_tf32_supported": (_I, [C.POINTER(GemmDesc)]),
     "itn_gemm_simt": (_I, [C.POINTER(GemmDesc), _P]),
-    "itn_layernorm_fwd": (_I, [_P, _P, _P, _P, _P, _P, _LL, _I, _I, _LL, _F, _P]),
-    "itn_layernorm_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _LL, _I, _I, _LL, _P]),
-    "itn_softmax_fwd": (_I, [_P, _LL, _I, _LL, _F, _P, _LL, _P]),
-    "itn_softmax_bwd": (_I, [_P, _P, _LL, _I, _LL, _F, _P]),
+    "itn_layernorm_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _LL, _I, _I, _LL, _F, _P]),
+    "itn_layernorm_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _LL, _I, _I, _LL, _P]),
+    "itn_softmax_fwd": (_I, [_P, _LL, _I, _LL, _F, _P, _LL, _I, _P]),
+    "itn_softmax_bwd": (_I, [_P, _P, _LL, _I, _LL, _F, _I, _P]),
     "itn_colsum": (_I, [_P, _P, _I, _LL, _I, _LL, _P]),
-    "itn_add": (_I, [_P, _P, _P, _LL, _LL, _P]),
-    "itn_copy2d": (_I, [_P, _LL, _P, _LL, _LL, _I, _P]),
+    "itn_add": (_I, [_P, _P, _P, _LL, _LL, _I, _P]),
+    "itn_copy2d": (_I, [_P, _LL, _P, _LL, _LL, _I, _I, _P]),
+    "itn_round_tf32": (_I, [_P, _P, _LL, _P]),
     "itn_sigmoid_fwd": (_I, [_P, _P, _LL, _P]),
     "itn_sigmoid_bwd": (_I, [_P, _P, _P, _LL, _P]),
     "itn_l2norm_fwd_bwd": (_I, [_P, _P, _P, _I, _I, _P]),
-    "itn_sgd_clip_update": (_I, [_P, _LL, _P, _P, _P, _I, _LL, _F, _F, _P]),
+    "itn_sgd_clip_update": (_I, [_P, _LL, _P, _P, _P, _P, _I, _LL, _F, _F, _P]),
     "itn_pos_embed_sine": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "itn_matcher_cost": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _F, _P]),
 }

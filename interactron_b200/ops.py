@@ -93,8 +93,9 @@ class CudaOps:
         return op, t4
 
     def matmul(self, a, b, *, bias=None, act=None, residual=None, out=None, out_pre=None,
-               alpha=1.0, accumulate=False, epi=None, aux=None):
-        """out = epilogue(alpha * a @ b), a [..,M,K], b [..,K,N]; see itn_gemm_desc_t."""
+               alpha=1.0, accumulate=False, epi=None, aux=None, rnd=False):
+        """out = epilogue(alpha * a @ b), a [..,M,K], b [..,K,N]; see itn_gemm_desc_t.
+        rnd: store `out` rounded to TF32 (set when `out` only feeds further GEMMs)."""
         rank = max(a.dim(), b.dim(), 2)
         a4, b4 = _as4d(a), _as4d(b)
         M, K = a4.shape[2], a4.shape[3]
@@ -148,6 +149,7 @@ class CudaOps:
         d.act = ACT[act]
         d.epi = EPI[epi]
         d.accumulate = 1 if accumulate else 0
+        d.round_out = 1 if rnd else 0
         if not self.force_simt and self.lib.itn_gemm_tf32_supported(C.byref(d)):
             _lib.check(self.lib.itn_gemm_tf32(C.byref(d), self._stream()))
             self.n_tf32 += 1
@@ -159,39 +161,42 @@ class CudaOps:
 
     # ------------------------------------------------------------ row-wise
     def layernorm_fwd(self, x, gamma, beta, eps=1e-5):
-        """x [rows, D] contiguous; gamma/beta [G, D] (G divides rows).  -> y, mean, rstd."""
+        """x [rows, D] contiguous; gamma/beta [G, D] (G divides rows).
+        -> y (fp32), y_r (TF32-rounded copy for GEMM consumers), mean, rstd."""
         rows, cols = x.shape
         g2, b2 = gamma.reshape(-1, cols), beta.reshape(-1, cols)
         groups = g2.shape[0]
         assert x.is_contiguous() and g2.is_contiguous() and b2.is_contiguous()
-        y = self.empty(rows, cols)
+        y, y_r = self.empty(rows, cols), self.empty(rows, cols)
         mean, rstd = self.empty(rows), self.empty(rows)
-        _lib.check(self.lib.itn_layernorm_fwd(_ptr(x), _ptr(g2), _ptr(b2), _ptr(y), _ptr(mean), _ptr(rstd),
-                                              rows, cols, groups, cols, eps, self._stream()))
-        return y, mean, rstd
+        _lib.check(self.lib.itn_layernorm_fwd(_ptr(x), _ptr(g2), _ptr(b2), _ptr(y), _ptr(y_r), _ptr(mean),
+                                              _ptr(rstd), rows, cols, groups, cols, eps, self._stream()))
+        return y, y_r, mean, rstd
 
     def layernorm_bwd(self, dy, x, mean, rstd, gamma, need_wgrad=True):
-        """-> dx [rows,D], dgamma [G,D], dbeta [G,D] (None if not need_wgrad)."""
+        """-> dx, dx_r (TF32-rounded copy) [rows,D], dgamma [G,D], dbeta [G,D] (None if not need_wgrad)."""
         rows, cols = x.shape
         g2 = gamma.reshape(-1, cols)
         groups = g2.shape[0]
         assert dy.is_contiguous() and x.is_contiguous()
-        dx = self.empty(rows, cols)
+        dx, dx_r = self.empty(rows, cols), self.empty(rows, cols)
         dg = self.empty(groups, cols) if need_wgrad else None
         db = self.empty(groups, cols) if need_wgrad else None
         _lib.check(self.lib.itn_layernorm_bwd(_ptr(dy), _ptr(x), _ptr(mean), _ptr(rstd), _ptr(g2), _ptr(dx),
-                                              _ptr(dg), _ptr(db), rows, cols, groups, cols, self._stream()))
-        return dx, dg, db
+                                              _ptr(dx_r), _ptr(dg), _ptr(db), rows, cols, groups, cols,
+                                              self._stream()))
+        return dx, dx_r, dg, db
 
     def softmax_(self, s, cols, scale, key_mask=None, rows_per_mask=1):
-        """In-place softmax over the first `cols` entries of the last dim of contiguous `s`."""
+        """In-place softmax over the first `cols` entries of the last dim of contiguous `s`
+        (stored TF32-rounded: probabilities only feed GEMMs)."""
         assert s.is_contiguous()
         ld = s.shape[-1]
         rows = s.numel() // ld
         if key_mask is not None:
             assert key_mask.dtype == torch.uint8 and key_mask.is_contiguous() and key_mask.shape[-1] == cols
         _lib.check(self.lib.itn_softmax_fwd(_ptr(s), rows, cols, ld, float(scale), _ptr(key_mask),
-                                            rows_per_mask, self._stream()))
+                                            rows_per_mask, 1, self._stream()))
         return s
 
     def softmax_bwd_(self, p, dp, cols, scale):
@@ -199,7 +204,7 @@ class CudaOps:
         assert p.is_contiguous() and dp.is_contiguous() and p.shape == dp.shape
         ld = p.shape[-1]
         rows = p.numel() // ld
-        _lib.check(self.lib.itn_softmax_bwd(_ptr(p), _ptr(dp), rows, cols, ld, float(scale), self._stream()))
+        _lib.check(self.lib.itn_softmax_bwd(_ptr(p), _ptr(dp), rows, cols, ld, float(scale), 1, self._stream()))
         return dp
 
     def colsum(self, x):
@@ -214,20 +219,28 @@ class CudaOps:
         return out
 
     # -------------------------------------------------------- element-wise
-    def add(self, a, b):
+    def add(self, a, b, rnd=False):
         """a + b, with b broadcast over the leading dims of a (b = a's trailing block)."""
         assert a.is_contiguous() and b.is_contiguous() and a.numel() % b.numel() == 0
         out = self.empty(a.shape)
-        _lib.check(self.lib.itn_add(_ptr(a), _ptr(b), _ptr(out), a.numel(), b.numel(), self._stream()))
+        _lib.check(self.lib.itn_add(_ptr(a), _ptr(b), _ptr(out), a.numel(), b.numel(), 1 if rnd else 0,
+                                    self._stream()))
         return out
 
-    def copy2d_(self, dst, src):
+    def copy2d_(self, dst, src, rnd=False):
         """dst[r, c] = src[r, c] for 2-D views with unit inner stride."""
         assert dst.shape == src.shape and dst.dim() == 2
         assert (dst.stride(1) == 1 and src.stride(1) == 1) or dst.shape[1] == 1
         _lib.check(self.lib.itn_copy2d(_ptr(src), src.stride(0), _ptr(dst), dst.stride(0), dst.shape[0],
-                                       dst.shape[1], self._stream()))
+                                       dst.shape[1], 1 if rnd else 0, self._stream()))
         return dst
+
+    def round_tf32(self, x, out=None):
+        """TF32-rounded copy of contiguous x (out may alias x)."""
+        assert x.is_contiguous()
+        out = self.empty(x.shape) if out is None else out
+        _lib.check(self.lib.itn_round_tf32(_ptr(x), _ptr(out), x.numel(), self._stream()))
+        return out
 
     def sigmoid(self, x):
         assert x.is_contiguous()
@@ -250,15 +263,15 @@ class CudaOps:
         return loss, dx
 
     def sgd_clip_update(self, theta, g, lr, clip=0.01, want_mask=False):
-        """theta [n] (shared) or [G,n]; g [G,n] -> theta' [G,n] (, uint8 mask)."""
+        """theta [n] (shared) or [G,n]; g [G,n] -> theta' [G,n], TF32-rounded theta' (, uint8 mask)."""
         assert g.is_contiguous() and g.dim() == 2 and theta.is_contiguous()
         G, n = g.shape
         stride = 0 if theta.dim() == 1 or theta.shape[0] == 1 else n
-        out = self.empty(G, n)
+        out, out_r = self.empty(G, n), self.empty(G, n)
         mask = torch.empty(G, n, dtype=torch.uint8, device=self.device) if want_mask else None
-        _lib.check(self.lib.itn_sgd_clip_update(_ptr(theta), stride, _ptr(g), _ptr(out), _ptr(mask), G, n,
-                                                float(lr), float(clip), self._stream()))
-        return (out, mask) if want_mask else out
+        _lib.check(self.lib.itn_sgd_clip_update(_ptr(theta), stride, _ptr(g), _ptr(out), _ptr(out_r), _ptr(mask),
+                                                G, n, float(lr), float(clip), self._stream()))
+        return (out, out_r, mask) if want_mask else (out, out_r)
 
     def pos_embed_sine(self, mask, feats=128):
         """mask [F,h,w] bool/uint8 (1 = padded) -> [F, h*w, 2*feats]."""
