@@ -101,14 +101,15 @@ int itn_layernorm_fwd(const float* x, const float* gamma, const float* beta,
                       float* y, float* y_r, float* mean, float* rstd,
                       long long rows, int cols, int groups, long long gb_stride,
                       float eps, void* stream);
-/* dx = d LayerNorm; dgamma/dbeta ([groups, cols], may be NULL) are OVERWRITTEN
- * with the per-group sums; dx_r (may be NULL) is a TF32-rounded copy of dx.
+/* dx = d LayerNorm; dgamma/dbeta (may be NULL; group g at + g*dgb_stride, e.g. a slice
+ * of the flat per-episode gradient buffer) are OVERWRITTEN with the per-group sums;
+ * dx_r (may be NULL) is a TF32-rounded copy of dx.
  * Replaces native_layer_norm_backward under models/interactron.py:51-52. */
 int itn_layernorm_bwd(const float* dy, const float* x, const float* mean,
                       const float* rstd, const float* gamma,
                       float* dx, float* dx_r, float* dgamma, float* dbeta,
                       long long rows, int cols, int groups, long long gb_stride,
-                      void* stream);
+                      long long dgb_stride, void* stream);
 
 /* In-place row softmax of scale*s + mask over `cols` (row stride ld).
  * key_mask (may be NULL) is uint8 [mask_batches, cols], 1 = padded key (-inf);
@@ -122,15 +123,20 @@ int itn_softmax_fwd(float* s, long long rows, int cols, long long ld, float scal
 int itn_softmax_bwd(const float* p, float* dp, long long rows, int cols,
                     long long ld, float scale, int round_out, void* stream);
 
-/* out[g, c] = sum_r x[g, r, c]  (bias gradients): x is [groups, rows, cols]
- * with row stride ld; out [groups, cols] OVERWRITTEN. */
+/* out[g*out_stride + c] = sum_r x[g, r, c]  (bias gradients): x is [groups, rows, cols]
+ * with row stride ld and group stride rows*ld; out OVERWRITTEN. */
 int itn_colsum(const float* x, float* out, int groups, long long rows, int cols,
-               long long ld, void* stream);
+               long long ld, long long out_stride, void* stream);
 
 /* --------------------------------------------------------- element-wise --- */
-/* out = a + b (b broadcast with period b_elems: b[i % b_elems]); optional TF32 rounding. */
+/* out[i] = a[i] + b[(i / a_group) * b_group_stride + i % b_elems]: b is a block of b_elems
+ * values broadcast with period b_elems inside each group of a_group consecutive elements of a,
+ * with one b block per group (b_group_stride 0 = one block for everything).  Used for
+ * `x + pos` and `tgt + query_pos` (reference detr_models/transformer.py:144-150,207-219);
+ * optional TF32 rounding of out. */
 int itn_add(const float* a, const float* b, float* out, long long n,
-            long long b_elems, int round_out, void* stream);
+            long long b_elems, long long a_group, long long b_group_stride,
+            int round_out, void* stream);
 /* Strided 2-D copy: dst[r*ldd + c] = src[r*lds + c]; optional TF32 rounding. */
 int itn_copy2d(const float* src, long long lds, float* dst, long long ldd,
                long long rows, int cols, int round_out, void* stream);

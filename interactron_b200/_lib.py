@@ -45,11 +45,11 @@ SIGNATURES = {
     "itn_gemm_tf32_supported": (_I, [C.POINTER(GemmDesc)]),
     "itn_gemm_simt": (_I, [C.POINTER(GemmDesc), _P]),
     "itn_layernorm_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _LL, _I, _I, _LL, _F, _P]),
-    "itn_layernorm_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _LL, _I, _I, _LL, _P]),
+    "itn_layernorm_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _LL, _I, _I, _LL, _LL, _P]),
     "itn_softmax_fwd": (_I, [_P, _LL, _I, _LL, _F, _P, _LL, _I, _P]),
     "itn_softmax_bwd": (_I, [_P, _P, _LL, _I, _LL, _F, _I, _P]),
-    "itn_colsum": (_I, [_P, _P, _I, _LL, _I, _LL, _P]),
-    "itn_add": (_I, [_P, _P, _P, _LL, _LL, _I, _P]),
+    "itn_colsum": (_I, [_P, _P, _I, _LL, _I, _LL, _LL, _P]),
+    "itn_add": (_I, [_P, _P, _P, _LL, _LL, _LL, _LL, _I, _P]),
     "itn_copy2d": (_I, [_P, _LL, _P, _LL, _LL, _I, _I, _P]),
     "itn_round_tf32": (_I, [_P, _P, _LL, _P]),
     "itn_sigmoid_fwd": (_I, [_P, _P, _LL, _P]),

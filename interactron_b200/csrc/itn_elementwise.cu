@@ -65,30 +65,21 @@ sgd_clip_update_kernel(const float* __restrict__ theta, long long theta_stride,
 
 __global__ void __launch_bounds__(256)
 add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
-           long long n, long long b_elems, int round_out) {
+           long long n, long long b_elems, long long a_group, long long b_group_stride,
+           int round_out) {
+  // all of n, b_elems, a_group, b_group_stride are multiples of 4 and pointers 16-byte aligned
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long n4 = n >> 2;
-  if ((b_elems & 3) == 0) {
-    const float4* a4 = reinterpret_cast<const float4*>(a);
-    const float4* b4 = reinterpret_cast<const float4*>(b);
-    float4* o4 = reinterpret_cast<float4*>(out);
-    const long long bq = b_elems >> 2;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-      const float4 x = a4[i], y = b4[i % bq];
-      float4 o = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
-      if (round_out) o = make_float4(rn_tf32(o.x), rn_tf32(o.y), rn_tf32(o.z), rn_tf32(o.w));
-      o4[i] = o;
-    }
-    if (blockIdx.x == 0)
-      for (long long i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) {
-        const float o = a[i] + b[i % b_elems];
-        out[i] = round_out ? rn_tf32(o) : o;
-      }
-  } else {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-      const float o = a[i] + b[i % b_elems];
-      out[i] = round_out ? rn_tf32(o) : o;
-    }
+  const float4* a4 = reinterpret_cast<const float4*>(a);
+  float4* o4 = reinterpret_cast<float4*>(out);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const long long e = i << 2;
+    const long long bi = (e / a_group) * b_group_stride + e % b_elems;
+    const float4 x = a4[i];
+    const float4 y = *reinterpret_cast<const float4*>(b + bi);
+    float4 o = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
+    if (round_out) o = make_float4(rn_tf32(o.x), rn_tf32(o.y), rn_tf32(o.z), rn_tf32(o.w));
+    o4[i] = o;
   }
 }
 
@@ -222,10 +213,15 @@ extern "C" int itn_sgd_clip_update(const float* theta, long long theta_stride, c
 }
 
 extern "C" int itn_add(const float* a, const float* b, float* out, long long n, long long b_elems,
-                       int round_out, void* stream) {
-  ITN_REQUIRE(a && b && out && n > 0 && b_elems > 0, "add: bad arguments");
+                       long long a_group, long long b_group_stride, int round_out, void* stream) {
+  ITN_REQUIRE(a && b && out && n > 0 && b_elems > 0 && a_group > 0 && b_group_stride >= 0,
+              "add: bad arguments");
   ITN_REQUIRE((((uintptr_t)a | (uintptr_t)b | (uintptr_t)out) & 15) == 0, "add: pointers must be 16-byte aligned");
-  add_kernel<<<grid_for(n >> 2, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, b, out, n, b_elems, round_out);
+  ITN_REQUIRE(((n | b_elems | a_group | b_group_stride) & 3) == 0,
+              "add: n, b_elems, a_group, b_group_stride must be multiples of 4");
+  ITN_REQUIRE(a_group % b_elems == 0, "add: a_group must be a multiple of b_elems");
+  add_kernel<<<grid_for(n >> 2, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      a, b, out, n, b_elems, a_group, b_group_stride, round_out);
   return check_launch("add_kernel");
 }
 

@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(1024)
 layernorm_bwd_gb_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                         const float* __restrict__ mean, const float* __restrict__ rstd,
                         float* __restrict__ dgamma, float* __restrict__ dbeta,
-                        long long rows_per_group, int cols) {
+                        long long rows_per_group, int cols, long long dgb_stride) {
   __shared__ float sg[32][33];
   __shared__ float sb[32][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
@@ -130,8 +130,8 @@ layernorm_bwd_gb_kernel(const float* __restrict__ dy, const float* __restrict__ 
       tg += sg[i][threadIdx.x];
       tb += sb[i][threadIdx.x];
     }
-    if (dgamma) dgamma[(long long)g * cols + c] = tg;
-    if (dbeta) dbeta[(long long)g * cols + c] = tb;
+    if (dgamma) dgamma[(long long)g * dgb_stride + c] = tg;
+    if (dbeta) dbeta[(long long)g * dgb_stride + c] = tb;
   }
 }
 
@@ -189,7 +189,7 @@ softmax_bwd_kernel(const float* __restrict__ p, float* __restrict__ dp, long lon
 // ------------------------------------------------------------------- colsum
 __global__ void __launch_bounds__(1024)
 colsum_kernel(const float* __restrict__ x, float* __restrict__ out, long long rows, int cols,
-              long long ld) {
+              long long ld, long long out_stride) {
   __shared__ float sm[32][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   const int g = blockIdx.y;
@@ -203,7 +203,7 @@ colsum_kernel(const float* __restrict__ x, float* __restrict__ out, long long ro
     float t = 0.f;
 #pragma unroll
     for (int i = 0; i < 32; ++i) t += sm[i][threadIdx.x];
-    out[(long long)g * cols + c] = t;
+    out[(long long)g * out_stride + c] = t;
   }
 }
 
@@ -233,7 +233,7 @@ extern "C" int itn_layernorm_fwd(const float* x, const float* gamma, const float
 extern "C" int itn_layernorm_bwd(const float* dy, const float* x, const float* mean,
                                  const float* rstd, const float* gamma, float* dx, float* dx_r,
                                  float* dgamma, float* dbeta, long long rows, int cols, int groups,
-                                 long long gb_stride, void* stream) {
+                                 long long gb_stride, long long dgb_stride, void* stream) {
   ITN_REQUIRE(dy && x && mean && rstd && gamma && dx, "layernorm_bwd: null pointer");
   ITN_REQUIRE(rows > 0 && groups > 0 && rows % groups == 0,
               "layernorm_bwd: rows (%lld) must be a positive multiple of groups (%d)", rows, groups);
@@ -251,7 +251,7 @@ extern "C" int itn_layernorm_bwd(const float* dy, const float* x, const float* m
   if (rc) return rc;
   if (dgamma || dbeta) {
     dim3 g2((cols + 31) / 32, groups);
-    layernorm_bwd_gb_kernel<<<g2, dim3(32, 32), 0, s>>>(dy, x, mean, rstd, dgamma, dbeta, rpg, cols);
+    layernorm_bwd_gb_kernel<<<g2, dim3(32, 32), 0, s>>>(dy, x, mean, rstd, dgamma, dbeta, rpg, cols, dgb_stride);
     rc = check_launch("layernorm_bwd_gb_kernel");
   }
   return rc;
@@ -276,9 +276,9 @@ extern "C" int itn_softmax_bwd(const float* p, float* dp, long long rows, int co
 }
 
 extern "C" int itn_colsum(const float* x, float* out, int groups, long long rows, int cols,
-                          long long ld, void* stream) {
+                          long long ld, long long out_stride, void* stream) {
   ITN_REQUIRE(x && out && groups > 0 && rows > 0 && cols > 0 && ld >= cols, "colsum: bad arguments");
   dim3 grid((cols + 31) / 32, groups);
-  colsum_kernel<<<grid, dim3(32, 32), 0, static_cast<cudaStream_t>(stream)>>>(x, out, rows, cols, ld);
+  colsum_kernel<<<grid, dim3(32, 32), 0, static_cast<cudaStream_t>(stream)>>>(x, out, rows, cols, ld, out_stride);
   return check_launch("colsum_kernel");
 }

@@ -166,26 +166,35 @@ class CudaOps:
         rows, cols = x.shape
         g2, b2 = gamma.reshape(-1, cols), beta.reshape(-1, cols)
         groups = g2.shape[0]
-        assert x.is_contiguous() and g2.is_contiguous() and b2.is_contiguous()
+        assert x.is_contiguous() and g2.stride(1) == 1 and b2.stride(1) == 1
+        assert groups == 1 or g2.stride(0) == b2.stride(0)
         y, y_r = self.empty(rows, cols), self.empty(rows, cols)
         mean, rstd = self.empty(rows), self.empty(rows)
         _lib.check(self.lib.itn_layernorm_fwd(_ptr(x), _ptr(g2), _ptr(b2), _ptr(y), _ptr(y_r), _ptr(mean),
-                                              _ptr(rstd), rows, cols, groups, cols, eps, self._stream()))
+                                              _ptr(rstd), rows, cols, groups, g2.stride(0) if groups > 1 else 0,
+                                              eps, self._stream()))
         return y, y_r, mean, rstd
 
-    def layernorm_bwd(self, dy, x, mean, rstd, gamma, need_wgrad=True):
-        """-> dx, dx_r (TF32-rounded copy) [rows,D], dgamma [G,D], dbeta [G,D] (None if not need_wgrad)."""
+    def layernorm_bwd(self, dy, x, mean, rstd, gamma, dgamma=None, dbeta=None):
+        """-> dx, dx_r (TF32-rounded copy) [rows,D].  dgamma/dbeta: optional [G, D] views
+        (row stride arbitrary, e.g. slices of the flat gradient buffer) that receive the
+        per-group affine gradients."""
         rows, cols = x.shape
         g2 = gamma.reshape(-1, cols)
-        groups = g2.shape[0]
-        assert dy.is_contiguous() and x.is_contiguous()
+        groups = g2.shape[0] if dgamma is None else dgamma.shape[0]
+        assert dy.is_contiguous() and x.is_contiguous() and g2.stride(1) == 1
+        assert g2.shape[0] in (1, groups)
         dx, dx_r = self.empty(rows, cols), self.empty(rows, cols)
-        dg = self.empty(groups, cols) if need_wgrad else None
-        db = self.empty(groups, cols) if need_wgrad else None
+        stride = 0
+        if dgamma is not None:
+            assert dgamma.shape == dbeta.shape == (groups, cols)
+            stride = dgamma.stride(0) if groups > 1 else cols
+            assert groups == 1 or dbeta.stride(0) == stride
+        gb_stride = g2.stride(0) if g2.shape[0] > 1 else 0
         _lib.check(self.lib.itn_layernorm_bwd(_ptr(dy), _ptr(x), _ptr(mean), _ptr(rstd), _ptr(g2), _ptr(dx),
-                                              _ptr(dx_r), _ptr(dg), _ptr(db), rows, cols, groups, cols,
-                                              self._stream()))
-        return dx, dx_r, dg, db
+                                              _ptr(dx_r), _ptr(dgamma), _ptr(dbeta), rows, cols, groups,
+                                              gb_stride, stride, self._stream()))
+        return dx, dx_r
 
     def softmax_(self, s, cols, scale, key_mask=None, rows_per_mask=1):
         """In-place softmax over the first `cols` entries of the last dim of contiguous `s`
@@ -207,23 +216,36 @@ class CudaOps:
         _lib.check(self.lib.itn_softmax_bwd(_ptr(p), _ptr(dp), rows, cols, ld, float(scale), 1, self._stream()))
         return dp
 
-    def colsum(self, x):
-        """x [G, rows, cols] (row stride arbitrary, inner contiguous) -> [G, cols]."""
+    def colsum(self, x, out=None):
+        """x [G, rows, cols] (row stride arbitrary, inner contiguous) -> out [G, cols] (strided ok)."""
         if x.dim() == 2:
             x = x.unsqueeze(0)
         G, rows, cols = x.shape
         assert x.stride(2) == 1 or cols == 1
         assert G == 1 or x.stride(0) == rows * x.stride(1)
-        out = self.empty(G, cols)
-        _lib.check(self.lib.itn_colsum(_ptr(x), _ptr(out), G, rows, cols, x.stride(1), self._stream()))
+        if out is None:
+            out = self.empty(G, cols)
+        assert out.shape == (G, cols) and (cols == 1 or out.stride(1) == 1)
+        _lib.check(self.lib.itn_colsum(_ptr(x), _ptr(out), G, rows, cols, x.stride(1),
+                                       out.stride(0) if G > 1 else cols, self._stream()))
         return out
 
     # -------------------------------------------------------- element-wise
     def add(self, a, b, rnd=False):
-        """a + b, with b broadcast over the leading dims of a (b = a's trailing block)."""
-        assert a.is_contiguous() and b.is_contiguous() and a.numel() % b.numel() == 0
+        """a [G, n, ...] + b, where b is either one block broadcast over everything
+        (a.numel() % b.numel() == 0) or [G, block] with one block per leading group of a."""
+        assert a.is_contiguous()
         out = self.empty(a.shape)
-        _lib.check(self.lib.itn_add(_ptr(a), _ptr(b), _ptr(out), a.numel(), b.numel(), 1 if rnd else 0,
+        n = a.numel()
+        if b.dim() >= 2 and b.shape[0] == a.shape[0] and b.shape[0] > 1 and n != b.numel():
+            G = a.shape[0]
+            assert b[0].is_contiguous()          # blocks may sit G rows apart in a flat buffer
+            b_elems, a_group, b_gs = b.numel() // G, n // G, b.stride(0)
+        else:
+            assert b.is_contiguous()
+            b_elems, a_group, b_gs = b.numel(), n, 0
+        assert n % b_elems == 0
+        _lib.check(self.lib.itn_add(_ptr(a), _ptr(b), _ptr(out), n, b_elems, a_group, b_gs, 1 if rnd else 0,
                                     self._stream()))
         return out
 

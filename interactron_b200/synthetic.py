@@ -10,6 +10,8 @@ import math
 import torch
 
 WEIGHT_SEED = 1234
+ATTN_SHARPEN = 3.0   # q/k/v projection gain: makes the random-init attention maps non-uniform
+BN3_DAMP = 0.5   # damping of the last BN of each bottleneck: keeps random-init trunk features O(1)
 
 
 def _fans(shape):
@@ -41,7 +43,7 @@ def _init_tensor(key, t, gen):
         if "bn" in key or "downsample.1" in key:
             if leaf == "weight":
                 # the last BN of each bottleneck is damped so the random-init trunk keeps O(1) features
-                return (0.25 if ".bn3." in key else 1.0) * (1.0 + u(0.1))
+                return (BN3_DAMP if ".bn3." in key else 1.0) * (1.0 + u(0.1))
             if leaf == "bias":
                 return u(0.05)
         fan_in, fan_out = _fans(shape)
@@ -57,9 +59,11 @@ def _init_tensor(key, t, gen):
         return 1.0 + u(0.1) if leaf == "weight" else u(0.05)
     if t.dim() >= 2:
         if ".model." in "." + key and leaf == "weight":     # GPT linears: N(0, 0.02)
-            return n(0.02)
+            sharp = ATTN_SHARPEN if (".attn.key." in key or ".attn.query." in key) else 1.0
+            return n(0.02 * sharp)
         fan_in, fan_out = _fans(shape)
-        return u(math.sqrt(6.0 / (fan_in + fan_out)))        # xavier-uniform
+        sharp = ATTN_SHARPEN if leaf == "in_proj_weight" else 1.0
+        return u(sharp * math.sqrt(6.0 / (fan_in + fan_out)))   # xavier-uniform
     return u(0.05)                                            # biases
 
 

@@ -1,0 +1,174 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.  Never imported by the product path.
+
+`SimOps` implements the `interactron_b200.ops.CudaOps` interface with plain torch
+ops on the CPU (fp32, or fp64 for tight checks).  It lets the CPU test-suite run the
+hand-derived forward/backward orchestration (detr_t / fusion_a / fusion_b / episode)
+against the reference's autograd without a GPU.  TF32 rounding flags are accepted
+and ignored (the simulation is exact fp32/fp64 arithmetic).
+"""
+import torch
+import torch.nn.functional as F
+
+
+class SimOps:
+    name = "sim"
+
+    def __init__(self, dtype=torch.float32):
+        self.dtype = dtype
+        self.device = torch.device("cpu")
+        self.n_tf32 = 0
+        self.n_simt = 0
+        self.calls = 0
+
+    def empty(self, *shape):
+        return torch.zeros(*shape, dtype=self.dtype)
+
+    def zeros(self, *shape):
+        return torch.zeros(*shape, dtype=self.dtype)
+
+    def launch_count(self):
+        return self.calls
+
+    def matmul(self, a, b, *, bias=None, act=None, residual=None, out=None, out_pre=None,
+               alpha=1.0, accumulate=False, epi=None, aux=None, rnd=False):
+        self.calls += 1
+        v = alpha * torch.matmul(a, b)
+        if bias is not None:
+            v = v + bias.unsqueeze(-2)
+        if out_pre is not None:
+            out_pre.copy_(v.reshape(out_pre.shape) if v.numel() == out_pre.numel() else v)
+        if act == "relu":
+            v = torch.relu(v)
+        elif act == "gelu":
+            v = F.gelu(v)
+        if epi == "relu_mask":
+            v = v * (aux > 0).to(v.dtype)
+        elif epi == "gelu_grad":
+            x = aux
+            cdf = 0.5 * (1 + torch.erf(x * 0.7071067811865476))
+            pdf = torch.exp(-0.5 * x * x) * 0.3989422804014327
+            v = v * (cdf + x * pdf)
+        if residual is not None:
+            v = v + residual
+        if out is None:
+            return v.contiguous()
+        if accumulate:
+            out.add_(v.reshape(out.shape) if v.shape != out.shape else v)
+        else:
+            out.copy_(v.reshape(out.shape) if v.shape != out.shape else v)
+        return out
+
+    def layernorm_fwd(self, x, gamma, beta, eps=1e-5):
+        self.calls += 1
+        rows, cols = x.shape
+        g2, b2 = gamma.reshape(-1, cols), beta.reshape(-1, cols)
+        G = g2.shape[0]
+        mean = x.mean(-1)
+        var = x.var(-1, unbiased=False)
+        rstd = (var + eps).rsqrt()
+        xh = (x - mean[:, None]) * rstd[:, None]
+        y = (xh.view(G, -1, cols) * g2[:, None] + b2[:, None]).reshape(rows, cols)
+        return y, y, mean, rstd
+
+    def layernorm_bwd(self, dy, x, mean, rstd, gamma, dgamma=None, dbeta=None):
+        self.calls += 1
+        rows, cols = x.shape
+        g2 = gamma.reshape(-1, cols)
+        G = g2.shape[0]
+        xh = (x - mean[:, None]) * rstd[:, None]
+        dg_ = (dy.view(G, -1, cols) * g2[:, None]).reshape(rows, cols)
+        m1 = dg_.mean(-1, keepdim=True)
+        m2 = (dg_ * xh).mean(-1, keepdim=True)
+        dx = rstd[:, None] * (dg_ - m1 - xh * m2)
+        if dgamma is not None:
+            Gd = dgamma.shape[0]
+            dgamma.copy_((dy * xh).view(Gd, -1, cols).sum(1))
+            dbeta.copy_(dy.view(Gd, -1, cols).sum(1))
+        return dx, dx
+
+    def softmax_(self, s, cols, scale, key_mask=None, rows_per_mask=1):
+        self.calls += 1
+        ld = s.shape[-1]
+        v = s.reshape(-1, ld)[:, :cols] * scale
+        if key_mask is not None:
+            m = key_mask.reshape(-1, cols).bool().repeat_interleave(rows_per_mask, dim=0)
+            v = v.masked_fill(m, float("-inf"))
+        s.reshape(-1, ld)[:, :cols] = torch.softmax(v, -1)
+        return s
+
+    def softmax_bwd_(self, p, dp, cols, scale):
+        self.calls += 1
+        ld = p.shape[-1]
+        pv = p.reshape(-1, ld)[:, :cols]
+        dv = dp.reshape(-1, ld)[:, :cols]
+        dp.reshape(-1, ld)[:, :cols] = scale * pv * (dv - (pv * dv).sum(-1, keepdim=True))
+        return dp
+
+    def colsum(self, x, out=None):
+        self.calls += 1
+        if x.dim() == 2:
+            x = x.unsqueeze(0)
+        if out is None:
+            return x.sum(1)
+        out.copy_(x.sum(1))
+        return out
+
+    def add(self, a, b, rnd=False):
+        self.calls += 1
+        n = a.numel()
+        if b.dim() >= 2 and b.shape[0] == a.shape[0] and b.shape[0] > 1 and n != b.numel():
+            G = a.shape[0]
+            return (a.reshape(G, -1, b.numel() // G) + b.reshape(G, 1, -1)).reshape(a.shape)
+        return (a.reshape(-1, b.numel()) + b.reshape(1, -1)).reshape(a.shape)
+
+    def copy2d_(self, dst, src, rnd=False):
+        self.calls += 1
+        dst.copy_(src)
+        return dst
+
+    def round_tf32(self, x, out=None):
+        self.calls += 1
+        if out is None:
+            return x.clone()
+        if out.data_ptr() != x.data_ptr():
+            out.copy_(x)
+        return out
+
+    def sigmoid(self, x):
+        self.calls += 1
+        return torch.sigmoid(x)
+
+    def sigmoid_bwd(self, dy, y):
+        self.calls += 1
+        return dy * y * (1 - y)
+
+    def l2norm_fwd_bwd(self, x):
+        self.calls += 1
+        nrm = x.norm(dim=1)
+        return nrm, x / nrm[:, None]
+
+    def sgd_clip_update(self, theta, g, lr, clip=0.01, want_mask=False):
+        self.calls += 1
+        th = theta if theta.dim() == 2 else theta[None]
+        step = lr * g
+        out = th - torch.clip(step, min=-clip, max=clip)
+        if want_mask:
+            return out, out, (step.abs() <= clip).to(torch.uint8)
+        return out, out
+
+    def pos_embed_sine(self, mask, feats=128):
+        self.calls += 1
+        not_mask = ~mask.bool()
+        y_embed = not_mask.cumsum(1, dtype=torch.float32)
+        x_embed = not_mask.cumsum(2, dtype=torch.float32)
+        eps, scale = 1e-6, 2 * 3.141592653589793
+        y_embed = y_embed / (y_embed[:, -1:, :] + eps) * scale
+        x_embed = x_embed / (x_embed[:, :, -1:] + eps) * scale
+        dim_t = torch.arange(feats, dtype=torch.float32)
+        dim_t = 10000 ** (2 * (dim_t // 2) / feats)
+        px = x_embed[:, :, :, None] / dim_t
+        py = y_embed[:, :, :, None] / dim_t
+        px = torch.stack((px[:, :, :, 0::2].sin(), px[:, :, :, 1::2].cos()), dim=4).flatten(3)
+        py = torch.stack((py[:, :, :, 0::2].sin(), py[:, :, :, 1::2].cos()), dim=4).flatten(3)
+        F_, h, w = mask.shape
+        return torch.cat((py, px), dim=3).reshape(F_, h * w, 2 * feats).to(self.dtype)

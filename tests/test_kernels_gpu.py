@@ -155,7 +155,8 @@ def test_layernorm_fwd_bwd(ops, cols, groups):
     beta = torch.randn(groups, cols, generator=gen, device="cuda")
     dy = torch.randn(rows, cols, generator=gen, device="cuda")
     y, y_r, mean, rstd = ops.layernorm_fwd(x, gamma, beta)
-    dx, dx_r, dg, db = ops.layernorm_bwd(dy, x, mean, rstd, gamma)
+    dg, db = torch.empty(groups, cols, device="cuda"), torch.empty(groups, cols, device="cuda")
+    dx, dx_r = ops.layernorm_bwd(dy, x, mean, rstd, gamma, dgamma=dg, dbeta=db)
     assert torch.equal(y_r, tf32_rn(y)) and torch.equal(dx_r, tf32_rn(dx))
     xr = x.double().view(groups, -1, cols).requires_grad_(True)
     gr = gamma.double().requires_grad_(True)
