@@ -1,0 +1,198 @@
+"""Building blocks shared by the DETR transformer and the fusion networks: attention core,
+post-norm decoder layer (forward + hand-derived backward), MLP heads, gradient sink.
+
+Everything is written against the `ops` kernel interface (ops.CudaOps on the B200).  Activations
+are token-major 2-D/3-D tensors; attention heads are strided views of [batch, tokens, heads*hd].
+Tensors that feed a GEMM are stored TF32-rounded by their producer (rnd=True / `_r` twins);
+residual streams and gradient accumulators stay full fp32.
+"""
+
+
+def pad4(n):
+    return (n + 3) // 4 * 4
+
+
+def T(w):
+    return w.transpose(-1, -2)
+
+
+def lin(ops, x, W, b=None, **kw):
+    """x [E,R,K] @ W[Gw,N,K]^T (+ b[Gw,N]) -> [E,R,N]  (nn.Linear with grouped weights)."""
+    return ops.matmul(x, T(W), bias=b, **kw)
+
+
+# --------------------------------------------------------------------------- attention core
+def attention_fwd(ops, q, k, v, B, Lq, Lk, nh, hd, scale, kmask):
+    """softmax(scale * q k^T + mask) v per (batch, head).
+    q [B,Lq,nh*hd], k/v [B,Lk,nh*hd] (strided views ok) -> o [B,Lq,nh*hd] (TF32-clean), P."""
+    qh = q.reshape(B, Lq, nh, hd).permute(0, 2, 1, 3)            # [B,nh,Lq,hd]
+    khT = k.reshape(B, Lk, nh, hd).permute(0, 2, 3, 1)           # [B,nh,hd,Lk]
+    vh = v.reshape(B, Lk, nh, hd).permute(0, 2, 1, 3)            # [B,nh,Lk,hd]
+    P = ops.empty(B, nh, Lq, pad4(Lk))                           # row stride padded to 16 bytes for TMA
+    p = P[..., :Lk]
+    ops.matmul(qh, khT, out=p)
+    ops.softmax_(P, Lk, scale, kmask, rows_per_mask=nh * Lq)
+    o = ops.empty(B, Lq, nh * hd)
+    ops.matmul(p, vh, out=o.view(B, Lq, nh, hd).permute(0, 2, 1, 3), rnd=True)
+    return o, P
+
+
+def attention_bwd(ops, dO, q, k, v, P, B, Lq, Lk, nh, hd, scale, dq, dk, dv):
+    """dO [B,Lq,nh*hd] (TF32-clean).  Writes TF32-clean dq/dk/dv into the given [B,L,nh*hd] views."""
+    qh = q.reshape(B, Lq, nh, hd).permute(0, 2, 1, 3)
+    kh = k.reshape(B, Lk, nh, hd).permute(0, 2, 1, 3)
+    vhT = v.reshape(B, Lk, nh, hd).permute(0, 2, 3, 1)
+    dOh = dO.reshape(B, Lq, nh, hd).permute(0, 2, 1, 3)
+    p = P[..., :Lk]
+    dP = ops.empty(B, nh, Lq, pad4(Lk))
+    dp = dP[..., :Lk]
+    ops.matmul(dOh, vhT, out=dp)                                                    # dP = dO V^T
+    ops.matmul(T(p), dOh, out=dv.view(B, Lk, nh, hd).permute(0, 2, 1, 3), rnd=True)  # dV = P^T dO
+    ops.softmax_bwd_(P, dP, Lk, scale)                                              # dS (in dP)
+    ops.matmul(dp, kh, out=dq.view(B, Lq, nh, hd).permute(0, 2, 1, 3), rnd=True)     # dQ = dS K
+    ops.matmul(T(dp), qh, out=dk.view(B, Lk, nh, hd).permute(0, 2, 1, 3), rnd=True)  # dK = dS^T Q
+
+
+# --------------------------------------------------------------------------- gradient sink
+class GradSink:
+    """Writes weight gradients straight into the flat per-episode gradient buffer g [E, n]."""
+
+    def __init__(self, ops, pack, g):
+        self.ops, self.pack, self.g = ops, pack, g
+
+    def view(self, name):
+        return self.pack.view(self.g, name)
+
+    def linear(self, name, dy_r, x_r, dy_full=None):
+        """dW = dy^T x into `name.weight`, db = colsum(dy) into `name.bias`."""
+        w = self.view(name + ".weight")
+        E = w.shape[0]
+        self.ops.matmul(T(dy_r), x_r, out=w.reshape(E, w.shape[1], -1))
+        self.ops.colsum(dy_full if dy_full is not None else dy_r, out=self.view(name + ".bias"))
+
+    def norm(self, name):
+        return dict(dgamma=self.view(name + ".weight"), dbeta=self.view(name + ".bias"))
+
+
+# --------------------------------------------------------------------------- decoder layer
+class DecDims:
+    """E: episodes (weight groups of the activations), B: attention batches, Lq/Lk tokens per batch."""
+
+    def __init__(self, E, B, Lq, Lk, D, nh):
+        self.E, self.B, self.Lq, self.Lk, self.D, self.nh = E, B, Lq, Lk, D, nh
+        self.hd = D // nh
+        self.scale = 1.0 / (self.hd ** 0.5)
+        self.Q = B * Lq // E           # query rows per episode
+        self.R = B * Lk // E           # memory rows per episode
+
+
+def decoder_layer_fwd(ops, W, pre, dm, tgt, tgt_r, qpos, mem_pos_r, memory_r, kmask, need_cache=True):
+    """DETR post-norm decoder layer (reference detr_models/transformer.py:211-232).
+    tgt/tgt_r [E,Q,D]; qpos [Gw,Lq,D] added to the queries of every batch; mem_pos_r / memory_r
+    [1,E*R,D] TF32-clean keys-input (memory+pos) and values-input (memory).  -> t3, t3_r, cache."""
+    E, B, Lq, Lk, D, nh, hd, Q, R = dm.E, dm.B, dm.Lq, dm.Lk, dm.D, dm.nh, dm.hd, dm.Q, dm.R
+    sw, sb = W.w(pre + "self_attn.in_proj_weight"), W.p(pre + "self_attn.in_proj_bias")
+    cw, cb = W.w(pre + "multihead_attn.in_proj_weight"), W.p(pre + "multihead_attn.in_proj_bias")
+    # self attention among the Lq queries of each batch
+    qk_in = ops.add(tgt, qpos, rnd=True).view(1, E * Q, D)
+    qk = lin(ops, qk_in, sw[:, :2 * D], sb[:, :2 * D], rnd=True)
+    v = lin(ops, tgt_r.view(1, E * Q, D), sw[:, 2 * D:], sb[:, 2 * D:], rnd=True)
+    qk3, v3 = qk.view(B, Lq, 2 * D), v.view(B, Lq, D)
+    o, P = attention_fwd(ops, qk3[..., :D], qk3[..., D:], v3, B, Lq, Lq, nh, hd, dm.scale, None)
+    a1 = lin(ops, o.view(E, Q, D), W.w(pre + "self_attn.out_proj.weight"),
+             W.p(pre + "self_attn.out_proj.bias"), residual=tgt)
+    t1, t1_r, m1, r1 = ops.layernorm_fwd(a1.view(E * Q, D), W.p(pre + "norm1.weight"), W.p(pre + "norm1.bias"))
+    # cross attention into the Lk memory tokens of the batch
+    q_in = ops.add(t1.view(E, Q, D), qpos, rnd=True).view(1, E * Q, D)
+    qc = lin(ops, q_in, cw[:, :D], cb[:, :D], rnd=True).view(B, Lq, D)
+    kc = lin(ops, mem_pos_r, cw[:, D:2 * D], cb[:, D:2 * D], rnd=True).view(B, Lk, D)
+    vc = lin(ops, memory_r, cw[:, 2 * D:], cb[:, 2 * D:], rnd=True).view(B, Lk, D)
+    o2, P2 = attention_fwd(ops, qc, kc, vc, B, Lq, Lk, nh, hd, dm.scale, kmask)
+    a2 = lin(ops, o2.view(E, Q, D), W.w(pre + "multihead_attn.out_proj.weight"),
+             W.p(pre + "multihead_attn.out_proj.bias"), residual=t1.view(E, Q, D))
+    t2, t2_r, m2, r2 = ops.layernorm_fwd(a2.view(E * Q, D), W.p(pre + "norm2.weight"), W.p(pre + "norm2.bias"))
+    h = lin(ops, t2_r.view(E, Q, D), W.w(pre + "linear1.weight"), W.p(pre + "linear1.bias"), act="relu", rnd=True)
+    f = lin(ops, h, W.w(pre + "linear2.weight"), W.p(pre + "linear2.bias"), residual=t2.view(E, Q, D))
+    t3, t3_r, m3, r3 = ops.layernorm_fwd(f.view(E * Q, D), W.p(pre + "norm3.weight"), W.p(pre + "norm3.bias"))
+    cache = None
+    if need_cache:
+        cache = dict(qk3=qk3, v3=v3, P=P, o=o, a1=a1, m1=m1, r1=r1, qc=qc, kc=kc, vc=vc, P2=P2, o2=o2,
+                     a2=a2, m2=m2, r2=r2, t2_r=t2_r, h=h, f=f, m3=m3, r3=r3)
+    return t3.view(E, Q, D), t3_r.view(E, Q, D), cache
+
+
+def decoder_layer_bwd(ops, W, pre, dm, s, dt, sink, dqpos, dmp, dmem):
+    """dt [E*Q,D] = gradient of the layer output.  Returns the gradient of the layer input
+    [E*Q,D]; accumulates d(query_pos) into dqpos [E,Q,D] (if given), d(memory+pos) into dmp and
+    d(memory) into dmem (both [1,E*R,D]); writes weight gradients through `sink` (None = data
+    gradients only, as for the fusion network whose parameters are not adapted)."""
+    E, B, Lq, Lk, D, nh, hd, Q, R = dm.E, dm.B, dm.Lq, dm.Lk, dm.D, dm.nh, dm.hd, dm.Q, dm.R
+    sw = W.w(pre + "self_attn.in_proj_weight")
+    cw = W.w(pre + "multihead_attn.in_proj_weight")
+    nk = (lambda n: sink.norm(pre + n)) if sink is not None else (lambda n: {})
+    df, df_r = ops.layernorm_bwd(dt, s["f"].view(E * Q, D), s["m3"], s["r3"], W.p(pre + "norm3.weight"),
+                                 **nk("norm3"))
+    df3, df3_r = df.view(E, Q, D), df_r.view(E, Q, D)
+    dh = ops.matmul(df3_r, W.w(pre + "linear2.weight"), epi="relu_mask", aux=s["h"], rnd=True)
+    if sink is not None:
+        sink.linear(pre + "linear2", df3_r, s["h"], df3)
+        sink.linear(pre + "linear1", dh, s["t2_r"].view(E, Q, D))
+    dt2 = ops.matmul(dh, W.w(pre + "linear1.weight"), residual=df3)
+    da2, da2_r = ops.layernorm_bwd(dt2.view(E * Q, D), s["a2"].view(E * Q, D), s["m2"], s["r2"],
+                                   W.p(pre + "norm2.weight"), **nk("norm2"))
+    da2_3r = da2_r.view(E, Q, D)
+    if sink is not None:
+        sink.linear(pre + "multihead_attn.out_proj", da2_3r, s["o2"].view(E, Q, D), da2.view(E, Q, D))
+    dO2 = ops.matmul(da2_3r, W.w(pre + "multihead_attn.out_proj.weight"), rnd=True)
+    dqc, dkc, dvc = ops.empty(B, Lq, D), ops.empty(B, Lk, D), ops.empty(B, Lk, D)
+    attention_bwd(ops, dO2.view(B, Lq, D), s["qc"], s["kc"], s["vc"], s["P2"], B, Lq, Lk, nh, hd, dm.scale,
+                  dqc, dkc, dvc)
+    dqc1 = dqc.view(1, E * Q, D)
+    dt1 = ops.matmul(dqc1, cw[:, :D], residual=da2.view(1, E * Q, D))
+    if dqpos is not None:
+        ops.matmul(dqc1, cw[:, :D], out=dqpos.view(1, E * Q, D), accumulate=True)
+    ops.matmul(dkc.view(1, E * R, D), cw[:, D:2 * D], out=dmp, accumulate=True)
+    ops.matmul(dvc.view(1, E * R, D), cw[:, 2 * D:], out=dmem, accumulate=True)
+    da1, da1_r = ops.layernorm_bwd(dt1.view(E * Q, D), s["a1"].view(E * Q, D), s["m1"], s["r1"],
+                                   W.p(pre + "norm1.weight"), **nk("norm1"))
+    da1_3r = da1_r.view(E, Q, D)
+    if sink is not None:
+        sink.linear(pre + "self_attn.out_proj", da1_3r, s["o"].view(E, Q, D), da1.view(E, Q, D))
+    dO = ops.matmul(da1_3r, W.w(pre + "self_attn.out_proj.weight"), rnd=True)
+    dqk, dv = ops.empty(B, Lq, 2 * D), ops.empty(B, Lq, D)
+    attention_bwd(ops, dO.view(B, Lq, D), s["qk3"][..., :D], s["qk3"][..., D:], s["v3"], s["P"],
+                  B, Lq, Lq, nh, hd, dm.scale, dqk[..., :D], dqk[..., D:], dv)
+    dqk1 = dqk.view(1, E * Q, 2 * D)
+    dtg = ops.matmul(dqk1, sw[:, :2 * D], residual=da1.view(1, E * Q, D))
+    if dqpos is not None:
+        ops.matmul(dqk1, sw[:, :2 * D], out=dqpos.view(1, E * Q, D), accumulate=True)
+    ops.matmul(dv.view(1, E * Q, D), sw[:, 2 * D:], out=dtg, accumulate=True)
+    return dtg.view(E * Q, D)
+
+
+# --------------------------------------------------------------------------- MLP heads
+def mlp_fwd(ops, W, name, x_r, n_layers=3):
+    """DETR-style MLP (reference detr_models/detr.py:299-311): ReLU between layers, none after the
+    last.  x_r [E,R,K] TF32-clean -> (z [E,R,out] full fp32, hidden activations for the backward)."""
+    hid = []
+    h = x_r
+    for i in range(n_layers - 1):
+        h = lin(ops, h, W.w(f"{name}.layers.{i}.weight"), W.p(f"{name}.layers.{i}.bias"), act="relu", rnd=True)
+        hid.append(h)
+    z = lin(ops, h, W.w(f"{name}.layers.{n_layers - 1}.weight"), W.p(f"{name}.layers.{n_layers - 1}.bias"))
+    return z, hid
+
+
+def mlp_bwd(ops, W, name, dz_r, x_r, hid, sink=None, n_layers=3, **last_kw):
+    """dz_r [E,R,out] TF32-clean -> gradient wrt x (extra epilogue args via last_kw)."""
+    d = dz_r
+    for i in reversed(range(n_layers)):
+        inp = hid[i - 1] if i > 0 else x_r
+        if sink is not None:
+            sink.linear(f"{name}.layers.{i}", d, inp)
+        w = W.w(f"{name}.layers.{i}.weight")
+        if i > 0:
+            d = ops.matmul(d, w, epi="relu_mask", aux=hid[i - 1], rnd=True)
+        else:
+            d = ops.matmul(d, w, **last_kw)
+    return d

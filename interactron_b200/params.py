@@ -13,17 +13,16 @@ class ParamPack:
     """Names, shapes and offsets of a list of tensors inside a flat buffer."""
 
     def __init__(self, items):
-        self.names, self.shapes, self.offsets, self.sizes = [], {}, {}, {}
+        self.names, self.shapes, self.offsets, self.sizes, self.pads = [], {}, {}, {}, {}
         off = 0
         for name, t in items:
             n = t.numel()
-            if n % 4:
-                raise ValueError(f"{name}: numel {n} is not a multiple of 4 (TMA needs 16-byte aligned weights)")
             self.names.append(name)
             self.shapes[name] = tuple(t.shape)
             self.offsets[name] = off
             self.sizes[name] = n
-            off += n
+            self.pads[name] = (-n) % 4          # every tensor starts 16-byte aligned (TMA / float4)
+            off += n + self.pads[name]
         self.numel = off
 
     def __contains__(self, name):
@@ -31,7 +30,12 @@ class ParamPack:
 
     def pack(self, tensors, device=None, dtype=torch.float32):
         """Concatenate the (detached) tensors into a new flat [numel] buffer."""
-        flat = torch.cat([t.detach().reshape(-1).to(dtype) for t in tensors])
+        parts = []
+        for name, t in zip(self.names, tensors):
+            parts.append(t.detach().reshape(-1).to(dtype))
+            if self.pads[name]:
+                parts.append(torch.zeros(self.pads[name], dtype=dtype, device=t.device))
+        flat = torch.cat(parts)
         return flat.to(device) if device is not None else flat
 
     def view(self, flat, name):
