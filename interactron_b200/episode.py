@@ -1,0 +1,132 @@
+"""The inner loop: adapt on a 5-frame episode, then re-detect (reference
+models/interactron.py:31-59, models/interactron_random.py:27-55, utils/meta_utils.py).
+
+For E episodes at once (the reference handles one):
+  1. frozen backbone (PyTorch/cuDNN) on the E*S frames, once per episode (decision D1);
+  2. DETR transformer forward with the shared weights theta              (detr_t)
+  3. fusion forward -> learned loss = ||loss_decoder(...)||_2 per episode (fusion)
+  4. backward: d learned_loss / d theta for every episode                 (fusion + detr_t)
+  5. theta'_e = theta - clip(lr * g_e, +-0.01): ONE fused kernel over the flat buffer
+  6. DETR transformer forward with the per-episode fast weights theta'_e (grouped GEMMs).
+theta lives in one flat buffer, so the reference's clone/detach/set_parameters bookkeeping
+(utils/meta_utils.py:48-111) is pointer arithmetic here.
+"""
+import torch
+
+from . import detr_t, fusion
+from .backbone import run_backbone
+from .layers import GradSink
+from .params import ParamPack, Weights, detector_packs
+
+L_TOK = 361      # 19x19 feature map of a 300x300 frame
+
+
+class InnerLoop:
+    def __init__(self, ops, detector, fusion_mod, kind, lr, clip=0.01):
+        assert kind in ("A", "B") and (fusion_mod is not None or kind == "B")
+        self.ops, self.detector, self.fusion_mod, self.kind = ops, detector, fusion_mod, kind
+        self.lr, self.clip = float(lr), float(clip)
+        self.theta_pack, self.theta_params, self.psi_pack, self.psi_params = detector_packs(detector)
+        phi = list(fusion_mod.named_parameters()) if fusion_mod is not None else []
+        self.phi_pack, self.phi_params = ParamPack(phi), [p for _, p in phi]
+        self.refresh_weights()
+
+    # ------------------------------------------------------------------ weights
+    def refresh_weights(self):
+        """Pack theta / psi / phi into flat fp32 buffers + TF32-rounded twins (GEMM weights)."""
+        ops = self.ops
+        dev = ops.device
+        self.theta = self.theta_pack.pack(self.theta_params, device=dev).unsqueeze(0)
+        self.psi = self.psi_pack.pack(self.psi_params, device=dev).unsqueeze(0)
+        self.theta_r = ops.round_tf32(self.theta)
+        self.psi_r = ops.round_tf32(self.psi)
+        if self.phi_params:
+            self.phi = self.phi_pack.pack(self.phi_params, device=dev).unsqueeze(0)
+            self.phi_r = ops.round_tf32(self.phi)
+
+    def _det_weights(self, theta, theta_r):
+        return Weights((self.theta_pack, theta, theta_r), (self.psi_pack, self.psi, self.psi_r))
+
+    def _fusion_weights(self):
+        return Weights((self.phi_pack, self.phi, self.phi_r))
+
+    # ------------------------------------------------------------------ pieces
+    def features(self, frames, masks):
+        """frames [N,3,H,W], masks [N,H,W] (nonzero = padded) -> (src_r [N,L,2048] TF32-clean
+        token-major, pos [N*L,256], kmask uint8 [N,L], hw).  self.src keeps the unrounded features."""
+        ops = self.ops
+        src = run_backbone(self.detector.backbone[0].body, frames)          # [N,h,w,2048] channels-last
+        N, h, w, C = src.shape
+        self.src = src.reshape(N, h * w, C)
+        src_r = ops.round_tf32(self.src)
+        m = torch.nn.functional.interpolate(masks[None].float(), size=(h, w)).to(torch.bool)[0]
+        pos = ops.pos_embed_sine(m).reshape(N * h * w, -1)
+        kmask = m.reshape(N, h * w).to(torch.uint8).contiguous()
+        return src_r, pos, kmask, (h, w)
+
+    def detect(self, frames, masks, want_preds=False):
+        """Plain DETR forward with theta on N frames (no adaptation).  want_preds: also build the
+        TF32-clean prediction tokens [N*50, 1496] that fusion embeds (returned as out["preds"])."""
+        N = frames.shape[0]
+        src_r, pos, kmask, hw = self.features(frames, masks)
+        L = hw[0] * hw[1]
+        W = self._det_weights(self.theta, self.theta_r)
+        C = self.detector.class_embed.out_features
+        preds = self.ops.empty(N * detr_t.NQ, detr_t.D + C + 4) if want_preds else None
+        out, _ = detr_t.detr_t_forward(self.ops, W, src_r.view(1, N * L, -1), pos, kmask, 1, N, L,
+                                       preds=preds, need_cache=False)
+        out["preds"] = preds
+        return out, src_r, hw
+
+    # ------------------------------------------------------------------ the hot path
+    def adapt_detect(self, frames, masks, post_frames=(0,), want_trace=False):
+        """frames [E,S,3,H,W], masks [E,S,H,W] on the device -> dict with post-adapt
+        pred_logits [E,P,50,C], pred_boxes [E,P,50,4] (P = len(post_frames)) and features."""
+        ops = self.ops
+        E, S = frames.shape[:2]
+        src_r, pos, kmask, (h, w) = self.features(frames.flatten(0, 1), masks.flatten(0, 1))
+        L = h * w
+        C = self.detector.class_embed.out_features
+        # -- pre-adapt pass (shared theta) and learned loss
+        Wd = self._det_weights(self.theta, self.theta_r)
+        preds = ops.empty(E * S * detr_t.NQ, detr_t.D + C + 4)
+        pre, cache = detr_t.detr_t_forward(ops, Wd, src_r.view(E, S * L, -1), pos, kmask, E, S, L, preds=preds)
+        Wf = self._fusion_weights()
+        if self.kind == "A":
+            fout, fcache = fusion.fusion_a_forward(ops, Wf, pre["memory_r"], preds, E, S, L)
+            dmemory, dpreds = fusion.fusion_a_backward(ops, Wf, fcache)
+        else:
+            fout, fcache = fusion.fusion_b_forward(ops, Wf, pre["memory_r"], preds, E, S, L)
+            dmemory, dpreds = fusion.fusion_b_backward(ops, Wf, fcache)
+        # -- inner gradient g_e = d learned_loss_e / d theta
+        g = ops.empty(E, self.theta_pack.numel)
+        detr_t.detr_t_backward(ops, Wd, cache, GradSink(ops, self.theta_pack, g), dpreds=dpreds, dmemory=dmemory)
+        del cache, fcache
+        # -- fast weights
+        theta_p, theta_p_r = ops.sgd_clip_update(self.theta, g, self.lr, self.clip)
+        # -- post-adapt pass on the requested frames with per-episode weights
+        P = len(post_frames)
+        if P == S and tuple(post_frames) == tuple(range(S)):
+            src_p, pos_p, km_p, src_full = src_r.view(E, S * L, -1), pos, kmask, self.src
+        else:
+            idx = torch.tensor([e * S + f for e in range(E) for f in post_frames], device=src_r.device)
+            src_p = src_r.index_select(0, idx).view(E, P * L, -1)
+            src_full = self.src.index_select(0, idx)
+            pos_p = pos.view(E * S, L, -1).index_select(0, idx).reshape(E * P * L, -1)
+            km_p = kmask.index_select(0, idx)
+        Wp = self._det_weights(theta_p, theta_p_r)
+        post, _ = detr_t.detr_t_forward(ops, Wp, src_p, pos_p, km_p, E, P, L, need_cache=False)
+        out = {
+            "pred_logits": post["logits"].view(E, P, detr_t.NQ, C),
+            "pred_boxes": post["boxes"].view(E, P, detr_t.NQ, 4),
+            "box_features": post["hs"].view(E, P, detr_t.NQ, detr_t.D),
+            "embedded_memory_features": post["memory"].view(E, P, h, w, detr_t.D).permute(0, 1, 4, 2, 3),
+            "image_features": src_full.view(E, P, h, w, -1).permute(0, 1, 4, 2, 3),
+            "learned_loss": fout["learned_loss"],
+            "actions": fout["actions"],
+        }
+        if want_trace:
+            out["trace"] = dict(pre_logits=pre["logits"].view(E, S, detr_t.NQ, C),
+                                pre_boxes=pre["boxes"].view(E, S, detr_t.NQ, 4),
+                                loss_vec=fout["loss_vec"], g=g, theta_prime=theta_p)
+        return out

@@ -33,6 +33,10 @@ class FrozenBN(nn.Module):
         scale = self.weight * (self.running_var + eps).rsqrt()
         return scale, self.bias - self.running_mean * scale
 
+    def forward(self, x):
+        scale, shift = self.scale_shift()
+        return x * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+
 
 class _Body(nn.Module):
     """Holds the ResNet-50 (dilated last stage) trunk under the key `body`."""

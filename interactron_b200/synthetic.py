@@ -6,6 +6,7 @@ Everything is generated on the CPU generator so the values are identical on
 every box with the same torch build.
 """
 import math
+import zlib
 
 import torch
 
@@ -68,14 +69,17 @@ def _init_tensor(key, t, gen):
 
 
 def synthetic_state_dict(model, seed=WEIGHT_SEED):
-    """state_dict with every tensor drawn from a per-key seeded CPU generator."""
+    """state_dict with every tensor drawn from a CPU generator seeded by (seed, key name), so a
+    tensor gets the same values whichever model class holds it (`detector.*` of the adaptive
+    models == `model.*` of the plain DETR baseline).  `criterion.*` buffers are left untouched."""
     out = {}
-    for i, (key, t) in enumerate(model.state_dict().items()):
-        gen = torch.Generator(device="cpu").manual_seed(seed * 1_000_003 + i)
-        if not t.is_floating_point():
+    for key, t in model.state_dict().items():
+        if key.startswith("criterion.") or not t.is_floating_point():
             out[key] = t.clone()
             continue
-        out[key] = _init_tensor(key, t, gen).to(t.dtype).reshape(t.shape)
+        canon = "detector." + key[len("model."):] if key.startswith("model.") else key
+        gen = torch.Generator(device="cpu").manual_seed(seed * 1_000_003 + zlib.crc32(canon.encode()))
+        out[key] = _init_tensor(canon, t, gen).to(t.dtype).reshape(t.shape)
     return out
 
 
