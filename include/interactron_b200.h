@@ -47,6 +47,11 @@ typedef struct {
 } itn_operand_t;
 
 enum { ITN_ACT_NONE = 0, ITN_ACT_RELU = 1, ITN_ACT_GELU = 2 };
+/* ITN_PREC_TF32X3 (default, 0): error-compensated three-pass TF32 (A*B + A_lo*B + A*B_lo with the
+ * residual tiles produced in shared memory), ~fp32 accuracy; needed for the 1e-3 parity bar
+ * because the inner-loop gradient amplifies single-pass TF32 error to 1-10 %.
+ * ITN_PREC_TF32 (1): one tensor-core pass (operands truncated to 10 mantissa bits). */
+enum { ITN_PREC_TF32X3 = 0, ITN_PREC_TF32 = 1 };
 enum { ITN_EPI_NONE = 0, ITN_EPI_RELU_MASK = 1, ITN_EPI_GELU_GRAD = 2 };
 
 /* C[b0,b1] = epilogue( alpha * A[b0,b1] (MxK) * B[b0,b1]^T (NxK)^T ), batch = nb0*nb1.
@@ -79,6 +84,7 @@ typedef struct {
   int epi;
   int accumulate;
   int round_out;
+  int precision;
 } itn_gemm_desc_t;
 
 /* tcgen05/TMA path.  Requires 16-byte aligned operand bases and ld/sb* multiples

@@ -31,7 +31,7 @@ class GemmDesc(C.Structure):
         ("aux", C.c_void_p), ("ldaux", C.c_longlong), ("aux_sb0", C.c_longlong), ("aux_sb1", C.c_longlong),
         ("C2", C.c_void_p), ("ldc2", C.c_longlong), ("c2_sb0", C.c_longlong), ("c2_sb1", C.c_longlong),
         ("alpha", C.c_float), ("act", C.c_int), ("epi", C.c_int), ("accumulate", C.c_int),
-        ("round_out", C.c_int),
+        ("round_out", C.c_int), ("precision", C.c_int),
     ]
 
 

@@ -12,6 +12,15 @@
 // (dy W) and weight-grad (dy^T x) all run without materialising transposes.
 // Out-of-bounds rows/cols/K are zero-filled by TMA and masked in the epilogue,
 // so ragged sizes (N=1236, K=1496, M=250, ...) need no padding in HBM.
+//
+// Precision modes.  kind::tf32 truncates its fp32 operands to 10 mantissa bits; one pass
+// ("tf32") therefore carries ~1e-3 error per GEMM, which the inner-loop gradient amplifies to
+// 1-10 % (measured).  The default "tf32x3" mode is error-compensated: while the
+// raw tiles sit in shared memory, the four (otherwise idle) epilogue warps write the residual
+// tiles  x_lo = x - trunc_tf32(x)  next to them, and the issuer accumulates
+//     A*B  +  A_lo*B  +  A*B_lo        (the tensor core sees A, B as their truncated hi parts)
+// in TMEM, which restores ~fp32 accuracy (dropped terms are O(2^-20)) at 3 MMAs per k-step
+// and no extra HBM/L2 traffic.
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -76,23 +85,25 @@ __device__ __forceinline__ void epilogue_store(const GemmKParams& p, const EpiPt
   *c = p.round_out ? rn_tf32(v) : v;
 }
 
-template <int BN>
+template <int BN, bool X3>
 struct TileCfg {
-  static constexpr int kStages = (BN == 128) ? 3 : 4;
   static constexpr int kABytes = kBM * kBK * 4;
   static constexpr int kBBytes = BN * kBK * 4;
-  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kRawBytes = kABytes + kBBytes;          // what TMA delivers per stage
+  static constexpr int kStageBytes = X3 ? 2 * kRawBytes : kRawBytes;   // + residual (lo) tiles
+  static constexpr int kStages = X3 ? (BN == 256 ? 2 : (BN == 128 ? 3 : 4)) : (BN == 128 ? 3 : 4);
   static constexpr int kTmemCols = BN < 32 ? 32 : BN;
-  // stages + barriers (full, empty, tmem_full) + tmem ptr + 1024 alignment slack
-  static constexpr int kSmemBytes = kStages * kStageBytes + (2 * kStages + 1) * 8 + 16 + 1024;
+  // stages + barriers (full, split, empty, tmem_full) + tmem ptr + 1024 alignment slack
+  static constexpr int kSmemBytes = kStages * kStageBytes + (3 * kStages + 1) * 8 + 16 + 1024;
   static_assert(kStages * kStageBytes >= 4 * 32 * 33 * 4, "epilogue staging must fit in the ring");
+  static_assert(kSmemBytes <= 227 * 1024, "exceeds shared memory per CTA");
 };
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, bool X3>
 __global__ void __launch_bounds__(kThreads)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmKParams p) {
-  using Cfg = TileCfg<BN>;
+  using Cfg = TileCfg<BN, X3>;
   constexpr int STAGES = Cfg::kStages;
 
   extern __shared__ uint8_t smem_raw[];
@@ -100,7 +111,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
-  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* split_bar = full_bar + STAGES;
+  uint64_t* empty_bar = split_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
@@ -117,6 +129,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
+      mbar_init(&split_bar[s], 4);   // one arrival per splitter warp (tf32x3 mode)
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(tmem_full_bar, 1);
@@ -137,7 +150,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t ph = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&empty_bar[s], ph ^ 1);
-        mbar_expect_tx(&full_bar[s], Cfg::kStageBytes);
+        mbar_expect_tx(&full_bar[s], Cfg::kRawBytes);
         uint8_t* sa = smem + s * Cfg::kStageBytes;
         uint8_t* sb = sa + Cfg::kABytes;
         const int k0 = kb * kBK;
@@ -165,7 +178,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int s = 0;
       uint32_t ph = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&full_bar[s], ph);
+        mbar_wait(X3 ? &split_bar[s] : &full_bar[s], ph);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + s * Cfg::kStageBytes);
         const uint32_t sb = sa + Cfg::kABytes;
@@ -181,6 +194,13 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint64_t bd = B_MN ? umma_smem_desc(sb + k * 1024, kAtomBytes, 512, kLayoutSW128Base32)
                                    : umma_smem_desc(sb + k * 32, 16, 1024, kLayoutSW128);
           umma_tf32(tmem_base, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+          if (X3) {
+            // residual tiles live kRawBytes after their raw twins, same layout: the descriptor
+            // start address is in 16-byte units
+            constexpr uint64_t kLoOff = static_cast<uint64_t>(Cfg::kRawBytes >> 4);
+            umma_tf32(tmem_base, ad + kLoOff, bd, idesc, 1u);   // A_lo * B_hi
+            umma_tf32(tmem_base, ad, bd + kLoOff, idesc, 1u);   // A_hi * B_lo
+          }
         }
         umma_commit(&empty_bar[s]);  // frees the smem slot once the MMAs have read it
         if (++s == STAGES) { s = 0; ph ^= 1; }
@@ -191,6 +211,33 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ----------------------------------------------------------- epilogue
     const int ew = warp - 2;    // staging buffer index
     const int lg = warp & 3;    // TMEM lane group this warp may read: lanes [32*lg, 32*lg+32)
+    if (X3) {
+      // ------------------------------------------ residual splitter (tf32x3 mode)
+      // lo = x - trunc_tf32(x), element-wise on the raw stage bytes (layout-agnostic, so the
+      // swizzle is preserved), written kRawBytes further; then made visible to the async proxy.
+      int s = 0;
+      uint32_t ph = 0;
+      const int tid = threadIdx.x - 64;             // 0..127
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[s], ph);
+        float4* raw = reinterpret_cast<float4*>(smem + s * Cfg::kStageBytes);
+        float4* lo = reinterpret_cast<float4*>(smem + s * Cfg::kStageBytes + Cfg::kRawBytes);
+#pragma unroll 4
+        for (int i = tid; i < Cfg::kRawBytes / 16; i += 128) {
+          const float4 v = raw[i];
+          float4 r;
+          r.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+          r.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+          r.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+          r.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+          lo[i] = r;
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&split_bar[s]);
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+    }
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     // All MMAs have retired, so the operand ring is free: reuse it for the transpose.
@@ -355,12 +402,14 @@ static int validate(const itn_gemm_desc_t* d) {
   ITN_REQUIRE(d->epi == ITN_EPI_NONE || d->aux != nullptr, "gemm: epi mode %d needs aux", d->epi);
   ITN_REQUIRE(d->A.major == 0 || d->A.major == 1, "gemm: bad A.major");
   ITN_REQUIRE(d->B.major == 0 || d->B.major == 1, "gemm: bad B.major");
+  ITN_REQUIRE(d->precision == ITN_PREC_TF32X3 || d->precision == ITN_PREC_TF32,
+              "gemm: bad precision %d", d->precision);
   return ITN_OK;
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, bool X3>
 static int launch_tile(const itn_gemm_desc_t* d, cudaStream_t stream) {
-  using Cfg = TileCfg<BN>;
+  using Cfg = TileCfg<BN, X3>;
   GemmKParams p;
   fill_kparams(p, d);
   CUtensorMap tmA, tmB;
@@ -368,7 +417,7 @@ static int launch_tile(const itn_gemm_desc_t* d, cudaStream_t stream) {
   if (rc) return rc;
   rc = make_operand_map(&tmB, d->B, d->N, d->K, d->nb0, d->nb1, BN, &p.b_m0, &p.b_m1);
   if (rc) return rc;
-  auto kern = gemm_tf32_kernel<BN, A_MN, B_MN>;
+  auto kern = gemm_tf32_kernel<BN, A_MN, B_MN, X3>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
     cudaError_t e =
@@ -383,12 +432,19 @@ static int launch_tile(const itn_gemm_desc_t* d, cudaStream_t stream) {
   return check_launch("gemm_tf32_kernel");
 }
 
+template <int BN, bool X3>
+static int launch_major2(const itn_gemm_desc_t* d, cudaStream_t s) {
+  if (d->A.major == 0) {
+    return d->B.major == 0 ? launch_tile<BN, false, false, X3>(d, s)
+                           : launch_tile<BN, false, true, X3>(d, s);
+  }
+  return d->B.major == 0 ? launch_tile<BN, true, false, X3>(d, s)
+                         : launch_tile<BN, true, true, X3>(d, s);
+}
+
 template <int BN>
 static int launch_major(const itn_gemm_desc_t* d, cudaStream_t s) {
-  if (d->A.major == 0) {
-    return d->B.major == 0 ? launch_tile<BN, false, false>(d, s) : launch_tile<BN, false, true>(d, s);
-  }
-  return d->B.major == 0 ? launch_tile<BN, true, false>(d, s) : launch_tile<BN, true, true>(d, s);
+  return d->precision == ITN_PREC_TF32 ? launch_major2<BN, false>(d, s) : launch_major2<BN, true>(d, s);
 }
 
 static int pick_bn(const itn_gemm_desc_t* d) {

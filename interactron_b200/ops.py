@@ -16,6 +16,7 @@ import torch
 from . import _lib
 
 ACT = {None: 0, "none": 0, "relu": 1, "gelu": 2}
+PRECISION = {"tf32x3": 0, "tf32": 1}
 EPI = {None: 0, "none": 0, "relu_mask": 1, "gelu_grad": 2}
 
 
@@ -42,6 +43,11 @@ class CudaOps:
         self.lib = _lib.load()
         self.device = torch.device(device)
         self.force_simt = os.environ.get("ITN_FORCE_SIMT", "0") == "1"
+        # "tf32x3": error-compensated 3-pass TF32 (~fp32 accuracy, the parity mode, default);
+        # "tf32": single pass with TF32-clean (round-to-nearest at the producer) operands.
+        self.precision = os.environ.get("ITN_GEMM_PRECISION", "tf32x3")
+        if self.precision not in PRECISION:
+            raise ValueError(f"ITN_GEMM_PRECISION must be one of {sorted(PRECISION)}")
         self.n_tf32 = 0
         self.n_simt = 0
 
@@ -57,6 +63,11 @@ class CudaOps:
 
     def launch_count(self):
         return int(self.lib.itn_launch_count())
+
+    @property
+    def _clean(self):
+        """True when GEMM operands must be stored TF32-rounded (single-pass mode only)."""
+        return self.precision == "tf32"
 
     # ---------------------------------------------------------------- GEMM
     @staticmethod
@@ -149,7 +160,8 @@ class CudaOps:
         d.act = ACT[act]
         d.epi = EPI[epi]
         d.accumulate = 1 if accumulate else 0
-        d.round_out = 1 if rnd else 0
+        d.round_out = 1 if (rnd and self._clean) else 0
+        d.precision = PRECISION[self.precision]
         if not self.force_simt and self.lib.itn_gemm_tf32_supported(C.byref(d)):
             _lib.check(self.lib.itn_gemm_tf32(C.byref(d), self._stream()))
             self.n_tf32 += 1
@@ -168,12 +180,13 @@ class CudaOps:
         groups = g2.shape[0]
         assert x.is_contiguous() and g2.stride(1) == 1 and b2.stride(1) == 1
         assert groups == 1 or g2.stride(0) == b2.stride(0)
-        y, y_r = self.empty(rows, cols), self.empty(rows, cols)
+        y = self.empty(rows, cols)
+        y_r = self.empty(rows, cols) if self._clean else None
         mean, rstd = self.empty(rows), self.empty(rows)
         _lib.check(self.lib.itn_layernorm_fwd(_ptr(x), _ptr(g2), _ptr(b2), _ptr(y), _ptr(y_r), _ptr(mean),
                                               _ptr(rstd), rows, cols, groups, g2.stride(0) if groups > 1 else 0,
                                               eps, self._stream()))
-        return y, y_r, mean, rstd
+        return y, (y_r if y_r is not None else y), mean, rstd
 
     def layernorm_bwd(self, dy, x, mean, rstd, gamma, dgamma=None, dbeta=None):
         """-> dx, dx_r (TF32-rounded copy) [rows,D].  dgamma/dbeta: optional [G, D] views
@@ -184,7 +197,8 @@ class CudaOps:
         groups = g2.shape[0] if dgamma is None else dgamma.shape[0]
         assert dy.is_contiguous() and x.is_contiguous() and g2.stride(1) == 1
         assert g2.shape[0] in (1, groups)
-        dx, dx_r = self.empty(rows, cols), self.empty(rows, cols)
+        dx = self.empty(rows, cols)
+        dx_r = self.empty(rows, cols) if self._clean else None
         stride = 0
         if dgamma is not None:
             assert dgamma.shape == dbeta.shape == (groups, cols)
@@ -194,7 +208,7 @@ class CudaOps:
         _lib.check(self.lib.itn_layernorm_bwd(_ptr(dy), _ptr(x), _ptr(mean), _ptr(rstd), _ptr(g2), _ptr(dx),
                                               _ptr(dx_r), _ptr(dgamma), _ptr(dbeta), rows, cols, groups,
                                               gb_stride, stride, self._stream()))
-        return dx, dx_r
+        return dx, (dx_r if dx_r is not None else dx)
 
     def softmax_(self, s, cols, scale, key_mask=None, rows_per_mask=1):
         """In-place softmax over the first `cols` entries of the last dim of contiguous `s`
@@ -205,7 +219,7 @@ class CudaOps:
         if key_mask is not None:
             assert key_mask.dtype == torch.uint8 and key_mask.is_contiguous() and key_mask.shape[-1] == cols
         _lib.check(self.lib.itn_softmax_fwd(_ptr(s), rows, cols, ld, float(scale), _ptr(key_mask),
-                                            rows_per_mask, 1, self._stream()))
+                                            rows_per_mask, 1 if self._clean else 0, self._stream()))
         return s
 
     def softmax_bwd_(self, p, dp, cols, scale):
@@ -213,7 +227,8 @@ class CudaOps:
         assert p.is_contiguous() and dp.is_contiguous() and p.shape == dp.shape
         ld = p.shape[-1]
         rows = p.numel() // ld
-        _lib.check(self.lib.itn_softmax_bwd(_ptr(p), _ptr(dp), rows, cols, ld, float(scale), 1, self._stream()))
+        _lib.check(self.lib.itn_softmax_bwd(_ptr(p), _ptr(dp), rows, cols, ld, float(scale),
+                                            1 if self._clean else 0, self._stream()))
         return dp
 
     def colsum(self, x, out=None):
@@ -237,7 +252,8 @@ class CudaOps:
         assert a.is_contiguous()
         out = self.empty(a.shape)
         n = a.numel()
-        if b.dim() >= 2 and b.shape[0] == a.shape[0] and b.shape[0] > 1 and n != b.numel():
+        grouped = b.dim() >= 2 and b.shape[0] == a.shape[0] and b.shape[0] > 1
+        if grouped and (n != b.numel() or not b.is_contiguous()):
             G = a.shape[0]
             assert b[0].is_contiguous()          # blocks may sit G rows apart in a flat buffer
             b_elems, a_group, b_gs = b.numel() // G, n // G, b.stride(0)
@@ -245,8 +261,8 @@ class CudaOps:
             assert b.is_contiguous()
             b_elems, a_group, b_gs = b.numel(), n, 0
         assert n % b_elems == 0
-        _lib.check(self.lib.itn_add(_ptr(a), _ptr(b), _ptr(out), n, b_elems, a_group, b_gs, 1 if rnd else 0,
-                                    self._stream()))
+        _lib.check(self.lib.itn_add(_ptr(a), _ptr(b), _ptr(out), n, b_elems, a_group, b_gs,
+                                    1 if (rnd and self._clean) else 0, self._stream()))
         return out
 
     def copy2d_(self, dst, src, rnd=False):
@@ -254,11 +270,14 @@ class CudaOps:
         assert dst.shape == src.shape and dst.dim() == 2
         assert (dst.stride(1) == 1 and src.stride(1) == 1) or dst.shape[1] == 1
         _lib.check(self.lib.itn_copy2d(_ptr(src), src.stride(0), _ptr(dst), dst.stride(0), dst.shape[0],
-                                       dst.shape[1], 1 if rnd else 0, self._stream()))
+                                       dst.shape[1], 1 if (rnd and self._clean) else 0, self._stream()))
         return dst
 
     def round_tf32(self, x, out=None):
-        """TF32-rounded copy of contiguous x (out may alias x)."""
+        """TF32-rounded copy of contiguous x (out may alias x).  In tf32x3 mode operands are used
+        at full precision, so this is the identity (no launch)."""
+        if not self._clean:
+            return x
         assert x.is_contiguous()
         out = self.empty(x.shape) if out is None else out
         _lib.check(self.lib.itn_round_tf32(_ptr(x), _ptr(out), x.numel(), self._stream()))
@@ -289,10 +308,12 @@ class CudaOps:
         assert g.is_contiguous() and g.dim() == 2 and theta.is_contiguous()
         G, n = g.shape
         stride = 0 if theta.dim() == 1 or theta.shape[0] == 1 else n
-        out, out_r = self.empty(G, n), self.empty(G, n)
+        out = self.empty(G, n)
+        out_r = self.empty(G, n) if self._clean else None
         mask = torch.empty(G, n, dtype=torch.uint8, device=self.device) if want_mask else None
         _lib.check(self.lib.itn_sgd_clip_update(_ptr(theta), stride, _ptr(g), _ptr(out), _ptr(out_r), _ptr(mask),
                                                 G, n, float(lr), float(clip), self._stream()))
+        out_r = out if out_r is None else out_r
         return (out, out_r, mask) if want_mask else (out, out_r)
 
     def pos_embed_sine(self, mask, feats=128):
