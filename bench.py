@@ -1,0 +1,311 @@
+"""Benchmark of the Interactron inner-loop hot path (adapt on a 5-frame episode + re-detect).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--episodes E] [--workload NAME]
+    python bench.py --impl reference ...          # the reference's CPU path on the host cores
+
+Metric (BASELINE.json): Interactron episodes/s (inner-loop adapt+detect).  Workload =
+BASELINE.json configs[2], `interactron_random.yaml` predict(): seeded synthetic 5-frame 300x300
+episodes, random-init weights (`synthetic.py`).  A step = one predict() over E episodes per GPU.
+One process per GPU (torchrun for N > 1); episodes are sharded, the eval path has no collective
+(SURVEY.md section 8e), so scaling is weak.  Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "Interactron episodes/s (inner-loop adapt+detect)"
+WORKLOADS = {"interactron_random": ("interactron_random", "B"), "interactron": ("interactron", "A")}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks / throttle reasons with nvidia-smi during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "samples": len(sm)}
+
+
+def make_batch(E, first_id, pin):
+    from interactron_b200.synthetic import collate_episodes, synthetic_episode
+    data = collate_episodes([synthetic_episode(first_id + i, with_targets=False) for i in range(E)])
+    if pin:
+        data["frames"] = data["frames"].pin_memory()
+        data["masks"] = data["masks"].pin_memory()
+    return data
+
+
+# ---------------------------------------------------------------------------------- CPU arm
+def make_cpu_runner(workload):
+    """Reference CPU path on the host cores.  Uses the unmodified reference when it is present
+    (build container), else its pinned restatement oracle/port.py (GPU box).
+    -> (run(data), kind, cores)"""
+    import torch
+    import interactron_b200 as ib
+    from oracle import port
+    from oracle import reference_harness as rh
+    name, kind = WORKLOADS[workload]
+    torch.set_num_threads(os.cpu_count())
+    model = ib.build_model(ib.default_config(name, weights="synthetic").MODEL).eval()
+    if rh.reference_available():
+        ref = rh.build_reference_model(name, model.state_dict())
+        return (lambda d: ref.predict(d)), "reference", torch.get_num_threads()
+    sd, body = model.state_dict(), model.detector.backbone[0].body
+    lr = model.config.ADAPTIVE_LR
+    return (lambda d: port.predict(sd, body, d, kind, lr=lr)), "port", torch.get_num_threads()
+
+
+def time_cpu(run, n_episodes, first_id=0):
+    from interactron_b200.synthetic import synthetic_episode
+    eps = [synthetic_episode(first_id + i, with_targets=False) for i in range(n_episodes)]
+    t0 = time.perf_counter()
+    for d in eps:
+        run(d)
+    return time.perf_counter() - t0
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = max(1, args.cpu_episodes)
+    run, kind, cores = make_cpu_runner(args.workload)
+    step_times = []
+    for s in range(args.warmup + args.steps):
+        dt = time_cpu(run, n, first_id=10 * s)
+        if s >= args.warmup:
+            step_times.append(dt)
+    value = n * len(step_times) / sum(step_times)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "episodes/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(step_times) / len(step_times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}.yaml predict() = BASELINE configs[2] (inner-loop adapt+detect), "
+                               "reference algorithm on the host CPU",
+                   "episodes_per_step": n, "frames": 5, "resolution": 300, "mode": "D1 (backbone frozen)"},
+        "cpu_baseline": {"value": value, "unit": "episodes/s", "cores": cores, "kind": kind,
+                         "sample": f"{n} synthetic episode(s) per step, {args.steps} timed steps"},
+        "e2e": {"value": value, "unit": "episodes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------- GPU arm
+def gemm_roofline(loop, frames, masks, bf16_peak):
+    """One eager, instrumented step: CUDA-event pair around every tensor-core GEMM launch."""
+    import torch
+    ops = loop.ops
+    rec = []
+    orig = ops.matmul
+
+    def timed(a, b, **kw):
+        M, K = a.shape[-2], a.shape[-1]
+        N = b.shape[-1]
+        nb = 1
+        for x, y in zip(([1, 1] + list(a.shape[:-2]))[-2:], ([1, 1] + list(b.shape[:-2]))[-2:]):
+            nb *= max(x, y)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = orig(a, b, **kw)
+        e1.record()
+        rec.append((2.0 * M * N * K * nb, e0, e1))
+        return out
+
+    ops.matmul = timed
+    try:
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = ops.launch_count()
+        t0.record()
+        loop.adapt_detect(frames, masks, post_frames=(0,))
+        t1.record()
+        torch.cuda.synchronize()
+        launches = ops.launch_count() - l0
+    finally:
+        ops.matmul = orig
+    flops = sum(r[0] for r in rec)
+    ms = sum(r[1].elapsed_time(r[2]) for r in rec)
+    achieved = flops / (ms * 1e-3) / 1e12
+    peak = bf16_peak / 2.0          # kind::tf32 runs at half the bf16 rate
+    return {"bound": "tensor", "kernel": "gemm_tf32_kernel (tcgen05 kind::tf32, tf32x3 mode = 3 MMAs per k-step)",
+            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+            "gemm_launches_per_step": len(rec), "algorithmic_gflop_per_step": flops / 1e9,
+            "gemm_ms_per_step_eager": ms, "step_ms_eager": t0.elapsed_time(t1)}, launches
+
+
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback "
+                         "(use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import interactron_b200 as ib
+    name, _ = WORKLOADS[args.workload]
+    model = ib.build_model(ib.default_config(name, weights="synthetic").MODEL).to(f"cuda:{local}").eval()
+    loop = model._get_loop()
+    E = args.episodes
+    hbm_peak, bf16_peak, peak_src = load_peaks()
+
+    batches = [make_batch(E, 1000 * rank + 100 * i, pin=True) for i in range(2)]
+    dev_batches = [(b["frames"].cuda(non_blocking=True), b["masks"].cuda(non_blocking=True)) for b in batches]
+    torch.cuda.synchronize()
+
+    # instrumented eager step: per-launch GEMM timing (roofline) and launch count
+    loop.adapt_detect(*dev_batches[0], post_frames=(0,))
+    roof, launches_per_step = gemm_roofline(loop, *dev_batches[0], bf16_peak)
+    roof["peak_source"] = f"{peak_src} bf16 dense / 2"
+
+    keys = ("pred_logits", "pred_boxes", "image_features", "embedded_memory_features", "box_features")
+
+    def run(f, m):
+        out = loop.adapt_detect(f, m, post_frames=(0,))
+        return {k: out[k] for k in keys}
+
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput (`value`)
+    for i in range(args.warmup):
+        model._graphed("bench", run, *dev_batches[i % 2], clone=False)
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    ev = []
+    for i in range(args.steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        model._graphed("bench", run, *dev_batches[i % 2], clone=False)
+        e1.record()
+        ev.append((e0, e1))
+    barrier()
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+
+    # ---- end-to-end through the public API with host (pinned) inputs (`e2e`)
+    for i in range(max(1, args.warmup // 2)):
+        o = model.predict(batches[i % 2])
+        o["pred_logits"].cpu()
+    barrier()
+    ev2 = []
+    for i in range(args.steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        o = model.predict(batches[i % 2])
+        lg, bx = o["pred_logits"].cpu(), o["pred_boxes"].cpu()
+        e1.record()
+        ev2.append((e0, e1))
+    barrier()
+    sampler.stop_flag.set()
+    e2e_ms = sum(a.elapsed_time(b) for a, b in ev2)
+    h2d = batches[0]["frames"].numel() * 4 + batches[0]["masks"].numel() * 8
+    d2h = lg.numel() * 4 + bx.numel() * 4
+
+    t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = t.tolist()
+    if rank == 0:
+        total_eps = E * world * args.steps
+        cpu = None
+        if world == 1 and args.cpu_episodes > 0:
+            crun, kind, cores = make_cpu_runner(args.workload)
+            time_cpu(crun, 1, first_id=900)
+            dt = time_cpu(crun, args.cpu_episodes)
+            v = args.cpu_episodes / dt
+            cpu = {"value": v, "unit": "episodes/s", "cores": cores, "kind": kind,
+                   "sample": f"{args.cpu_episodes} synthetic episodes after 1 warm-up, {dt:.1f} s"}
+        line = {
+            "metric": METRIC, "value": total_eps / (dev_ms * 1e-3), "unit": "episodes/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "tf32x3 (fp32 storage; error-compensated 3-pass TF32 tensor-core GEMMs; fp32 cuDNN backbone)",
+            "data": "synthetic",
+            "config": {"workload": f"{args.workload}.yaml predict() = BASELINE configs[2] (inner-loop adapt+detect)",
+                       "episodes_per_step_per_gpu": E, "frames": 5, "resolution": 300,
+                       "mode": "D1 (backbone frozen, features once per episode)", "cuda_graph": True,
+                       "l2": "256 MiB buffer written between timed steps (L2 flush); per-step CUDA events"},
+            "e2e": {"value": total_eps / (e2e_ms * 1e-3), "unit": "episodes/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps,
+                    "api": "model.predict(data) with pinned host tensors; logits+boxes read back"},
+            "gpu_launches": launches_per_step * args.steps * 2,
+            "gpu_launches_per_step": launches_per_step,
+            "roofline": roof, "cpu_baseline": cpu, "clocks": sampler.summary(),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--episodes", type=int, default=8, help="episodes per step per GPU")
+    ap.add_argument("--workload", default="interactron_random", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-episodes", type=int, default=None,
+                    help="episodes in the bounded CPU-baseline sample (0 disables)")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.cpu_episodes is None:
+        args.cpu_episodes = 1 if args.impl == "reference" else 6
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

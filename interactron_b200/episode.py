@@ -29,20 +29,35 @@ class InnerLoop:
         self.theta_pack, self.theta_params, self.psi_pack, self.psi_params = detector_packs(detector)
         phi = list(fusion_mod.named_parameters()) if fusion_mod is not None else []
         self.phi_pack, self.phi_params = ParamPack(phi), [p for _, p in phi]
+        self.backbone_tf32 = False      # cuDNN convs in strict fp32: TF32 convs break the 1e-3 parity bar
+        self.theta = self.psi = self.phi = None
+        self._idx_cache = {}
         self.refresh_weights()
 
     # ------------------------------------------------------------------ weights
     def refresh_weights(self):
-        """Pack theta / psi / phi into flat fp32 buffers + TF32-rounded twins (GEMM weights)."""
+        """(Re)pack theta / psi / phi into the persistent flat fp32 buffers (+ TF32-rounded twins
+        in single-pass mode).  In place, so captured CUDA graphs keep reading valid addresses."""
         ops = self.ops
         dev = ops.device
-        self.theta = self.theta_pack.pack(self.theta_params, device=dev).unsqueeze(0)
-        self.psi = self.psi_pack.pack(self.psi_params, device=dev).unsqueeze(0)
-        self.theta_r = ops.round_tf32(self.theta)
-        self.psi_r = ops.round_tf32(self.psi)
+
+        def fill(buf, pack, params):
+            flat = pack.pack(params, device=dev)
+            if buf is None:
+                return flat.unsqueeze(0)
+            buf[0].copy_(flat)
+            return buf
+
+        self.theta = fill(self.theta, self.theta_pack, self.theta_params)
+        self.psi = fill(self.psi, self.psi_pack, self.psi_params)
+        if not ops._clean:
+            self.theta_r, self.psi_r = self.theta, self.psi
+        else:
+            self.theta_r = ops.round_tf32(self.theta, out=getattr(self, "theta_r", None))
+            self.psi_r = ops.round_tf32(self.psi, out=getattr(self, "psi_r", None))
         if self.phi_params:
-            self.phi = self.phi_pack.pack(self.phi_params, device=dev).unsqueeze(0)
-            self.phi_r = ops.round_tf32(self.phi)
+            self.phi = fill(self.phi, self.phi_pack, self.phi_params)
+            self.phi_r = self.phi if not ops._clean else ops.round_tf32(self.phi, out=getattr(self, "phi_r", None))
 
     def _det_weights(self, theta, theta_r):
         return Weights((self.theta_pack, theta, theta_r), (self.psi_pack, self.psi, self.psi_r))
@@ -55,7 +70,7 @@ class InnerLoop:
         """frames [N,3,H,W], masks [N,H,W] (nonzero = padded) -> (src_r [N,L,2048] TF32-clean
         token-major, pos [N*L,256], kmask uint8 [N,L], hw).  self.src keeps the unrounded features."""
         ops = self.ops
-        src = run_backbone(self.detector.backbone[0].body, frames)          # [N,h,w,2048] channels-last
+        src = run_backbone(self.detector.backbone[0].body, frames, self.backbone_tf32)   # [N,h,w,2048]
         N, h, w, C = src.shape
         self.src = src.reshape(N, h * w, C)
         src_r = ops.round_tf32(self.src)
@@ -109,7 +124,11 @@ class InnerLoop:
         if P == S and tuple(post_frames) == tuple(range(S)):
             src_p, pos_p, km_p, src_full = src_r.view(E, S * L, -1), pos, kmask, self.src
         else:
-            idx = torch.tensor([e * S + f for e in range(E) for f in post_frames], device=src_r.device)
+            key = (E, S, tuple(post_frames))
+            if key not in self._idx_cache:          # built once, outside any graph capture
+                self._idx_cache[key] = torch.tensor([e * S + f for e in range(E) for f in post_frames],
+                                                    device=src_r.device)
+            idx = self._idx_cache[key]
             src_p = src_r.index_select(0, idx).view(E, P * L, -1)
             src_full = self.src.index_select(0, idx)
             pos_p = pos.view(E * S, L, -1).index_select(0, idx).reshape(E * P * L, -1)

@@ -16,6 +16,8 @@ Extensions over the reference (a strict superset of its behaviour):
   * `config.WEIGHTS == "synthetic"` builds the deterministic random-init weights of
     `synthetic.synthetic_state_dict` instead of reading a checkpoint (none is shipped offline).
 """
+import os
+
 import torch
 from torch import nn
 
@@ -51,6 +53,9 @@ class _Base(nn.Module):
         self._ops = None
         self._loop = None
         self._loop_key = None
+        self._graphs = {}
+        self._bb_key = None
+        self.use_cuda_graph = os.environ.get("ITN_CUDA_GRAPH", "1") != "0"
 
     # -- reference surface ------------------------------------------------------------
     def eval(self):
@@ -138,9 +143,29 @@ class _Adaptive(_Base):
             raise NotImplementedError("train()-mode dropout inside predict() is not implemented; call eval()")
         loop = self._get_loop()
         frames, masks = self._frames_masks(data, loop.ops.device)
-        out = loop.adapt_detect(frames, masks, post_frames=(0,))
         keys = ("pred_logits", "pred_boxes", "image_features", "embedded_memory_features", "box_features")
-        return {k: out[k] for k in keys}
+
+        def run(f, m):
+            out = loop.adapt_detect(f, m, post_frames=(0,))
+            return {k: out[k] for k in keys}
+
+        if not (self.use_cuda_graph and frames.is_cuda):
+            return run(frames, masks)
+        return self._graphed("predict", run, frames, masks)
+
+    def _graphed(self, tag, fn, frames, masks, clone=True):
+        """Replay (capturing on first use) the CUDA graph of `fn` for this input geometry."""
+        from .graph import GraphedCall
+        bb = self._detector().backbone
+        bb_key = tuple(t.data_ptr() for t in list(bb.parameters()) + list(bb.buffers()))
+        if bb_key != self._bb_key:          # backbone tensors moved: captured conv launches are stale
+            self._graphs.clear()
+            self._bb_key = bb_key
+        key = (tag, tuple(frames.shape), tuple(masks.shape), self._loop.ops.precision, self._loop.backbone_tf32)
+        g = self._graphs.get(key)
+        if g is None:
+            g = self._graphs[key] = GraphedCall(fn, [frames, masks])
+        return g(frames, masks, clone=clone)
 
     def forward(self, data, train=True):
         raise NotImplementedError(

@@ -12,6 +12,8 @@ import torch.nn.functional as F
 
 class SimOps:
     name = "sim"
+    _clean = False      # exact arithmetic: no TF32-clean operand twins
+    precision = "sim"
 
     def __init__(self, dtype=torch.float32):
         self.dtype = dtype

@@ -1,0 +1,94 @@
+"""Pins the travelling CPU oracle (oracle/port.py) against (a) the UNMODIFIED reference run here
+and (b) the committed goldens the reference produced (tests/golden, tools/make_golden.py)."""
+import os
+
+import pytest
+import torch
+
+from oracle import port
+from oracle import reference_harness as rh
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def rel(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
+
+
+def _model(model_type):
+    import interactron_b200 as ib
+    name = {"detr": "single_frame_baseline", "detr_multiframe": "multi_frame_baseline"}.get(model_type, model_type)
+    return ib.build_model(ib.default_config(name, weights="synthetic").MODEL).eval()
+
+
+@pytest.mark.parametrize("model_type,kind", [("interactron_random", "B"), ("interactron", "A")])
+def test_port_matches_committed_reference_goldens(model_type, kind):
+    """Runs without /root/reference: golden vectors only."""
+    from interactron_b200.synthetic import synthetic_episode
+    m = _model(model_type)
+    gold = torch.load(os.path.join(GOLD, f"{model_type}_predict.pt"))
+    sd = m.state_dict()
+    assert port.fast_weight_names(sd) == ["detector." + n for n in gold["theta_names"]]
+    ep = 0
+    g = gold["episodes"][ep]
+    tr = {}
+    out = port.predict(sd, m.detector.backbone[0].body, synthetic_episode(ep), kind, lr=m.config.ADAPTIVE_LR,
+                       trace=tr)
+    assert rel(out["pred_logits"], g["pred_logits"]) < 1e-4
+    assert rel(out["pred_boxes"], g["pred_boxes"]) < 1e-4
+    assert rel(tr["learned_loss"], g["learned_loss"]) < 1e-5
+    assert rel(tr["loss_vec"], g["loss_vec"]) < 1e-5
+    gn = torch.stack([x.norm() for x in tr["grads"]])
+    assert ((gn - g["g_norms"]).abs() / g["g_norms"]).max().item() < 2e-3
+
+
+@pytest.mark.skipif(not rh.reference_available(), reason="reference checkout not present")
+def test_port_matches_live_reference():
+    from interactron_b200.synthetic import synthetic_episode
+    m = _model("interactron_random")
+    ref = rh.build_reference_model("interactron_random", m.state_dict())
+    data = synthetic_episode(5)
+    rt = rh.reference_predict_with_trace(ref, data)
+    tr = {}
+    out = port.predict(m.state_dict(), m.detector.backbone[0].body, data, "B", trace=tr)
+    for k in ("pred_logits", "pred_boxes", "box_features", "embedded_memory_features", "image_features"):
+        assert out[k].shape == rt["out"][k].shape
+        assert rel(out[k], rt["out"][k]) < 1e-4, k
+    g_ref = torch.cat([g.reshape(-1) for g in rt["grads"]])
+    g_port = torch.cat([g.reshape(-1) for g in tr["grads"]])
+    assert rel(g_port, g_ref) < 1e-3
+    assert rel(tr["pre"]["pred_logits"], rt["pre"]["pred_logits"][0]) < 1e-5
+
+
+def test_port_baselines_match_goldens():
+    from interactron_b200.synthetic import synthetic_episode
+    base = torch.load(os.path.join(GOLD, "baselines_predict.pt"))
+    m = _model("detr")
+    o = port.detr_predict(m.state_dict(), m.model.backbone[0].body, synthetic_episode(0, frames=1), pre="model.")
+    for k, v in base["detr_ep0_1frame"].items():
+        assert rel(o[k], v) < 1e-5, k
+    m = _model("detr_multiframe")
+    sd = m.state_dict()
+    src, mk = port.backbone_features(m.detector.backbone[0].body, synthetic_episode(0)["frames"][0],
+                                     synthetic_episode(0)["masks"][0])
+    with torch.no_grad():
+        det = port.detr_forward(sd, src, mk)
+        fo = port.fusion_a(sd, det, aux_heads=True)
+    assert rel(fo["pred_logits"].view(5, 50, -1), base["detr_multiframe_ep0"]["pred_logits"][0]) < 1e-5
+    assert rel(fo["pred_boxes"].view(5, 50, 4), base["detr_multiframe_ep0"]["pred_boxes"][0]) < 1e-5
+
+
+def test_port_matcher_cost_reproduces_reference_assignments():
+    """scipy LSAP on the port's cost matrix gives the reference HungarianMatcher's assignment."""
+    from scipy.optimize import linear_sum_assignment
+    gold = torch.load(os.path.join(GOLD, "matcher_assignments.pt"))
+    for seed, ref_idx in gold.items():
+        gen = torch.Generator().manual_seed(100 + seed)
+        logits = torch.randn(5, 50, 1236, generator=gen)
+        boxes = torch.rand(5, 50, 4, generator=gen) * 0.5 + 0.1
+        for f in range(5):
+            n = int(torch.randint(3, 9, (1,), generator=gen))
+            labels = torch.randint(1, 1235, (n,), generator=gen)
+            tb = torch.cat([torch.rand(n, 2, generator=gen) * 0.6 + 0.2, torch.rand(n, 2, generator=gen) * 0.3 + 0.05], 1)
+            i, j = linear_sum_assignment(port.hungarian_cost(logits[f], boxes[f], labels, tb).numpy())
+            assert torch.equal(torch.as_tensor(i), ref_idx[f][0]) and torch.equal(torch.as_tensor(j), ref_idx[f][1])

@@ -1,0 +1,180 @@
+"""GPU parity of the drop-in models against the reference goldens (tests/golden, produced by the
+unmodified reference on CPU, D1 mode) and against the travelling CPU oracle (oracle/port.py).
+
+Bar (BASELINE.json north_star): logits, boxes and adapted weights within 1e-3 relative L2;
+matcher assignments bit-exact.  Default precision: tf32x3 GEMMs, fp32 cuDNN backbone.
+"""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TOL = 1e-3
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def build(name):
+    import interactron_b200 as ib
+    return ib.build_model(ib.default_config(name, weights="synthetic").MODEL).cuda().eval()
+
+
+@pytest.fixture(scope="module")
+def rand_model():
+    return build("interactron_random")
+
+
+@pytest.fixture(scope="module")
+def full_model():
+    return build("interactron")
+
+
+@pytest.mark.parametrize("name", ["interactron_random", "interactron"])
+def test_adapt_detect_trace_matches_reference(name, rand_model, full_model):
+    from interactron_b200.synthetic import synthetic_episode
+    model = rand_model if name == "interactron_random" else full_model
+    gold = torch.load(os.path.join(GOLD, f"{name}_predict.pt"))
+    loop = model._get_loop()
+    assert loop.ops.precision == "tf32x3" and not loop.backbone_tf32
+    for ep, g in gold["episodes"].items():
+        d = synthetic_episode(ep)
+        out = loop.adapt_detect(d["frames"].cuda(), d["masks"].cuda(), post_frames=(0,), want_trace=True)
+        t = out["trace"]
+        assert rel(t["pre_logits"][0, 0], g["pre_logits_f0"]) < TOL
+        assert rel(t["pre_logits"][0, 4], g["pre_logits_f4"]) < TOL
+        assert rel(t["pre_boxes"][0], g["pre_boxes"]) < TOL
+        assert rel(t["loss_vec"][0], g["loss_vec"]) < TOL
+        assert rel(out["learned_loss"][0], g["learned_loss"]) < TOL
+        assert rel(out["actions"][0], g["actions"]) < TOL
+        names = gold["theta_names"]
+        assert names == loop.theta_pack.names
+        gn = torch.stack([loop.theta_pack.view(t["g"], n)[0].norm() for n in names]).cpu()
+        assert ((gn - g["g_norms"]).abs() / g["g_norms"]).max().item() < 5e-3
+        # adapted weights: every stored tensor within 1e-3, and all 157 norms
+        for n, (gr, tp) in g["small"].items():
+            assert rel(loop.theta_pack.view(t["theta_prime"], n)[0], tp) < TOL, n
+        tn = torch.stack([loop.theta_pack.view(t["theta_prime"], n)[0].double().norm() for n in names]).cpu()
+        assert ((tn - g["theta_prime_norms"]).abs() / g["theta_prime_norms"]).max().item() < 1e-5
+        assert rel(out["pred_logits"][0], g["pred_logits"][0]) < TOL
+        assert rel(out["pred_boxes"][0], g["pred_boxes"][0]) < TOL
+        assert rel(out["box_features"][0], g["box_features"][0]) < TOL
+
+
+def test_predict_public_api_graph_and_eager(rand_model):
+    """predict(data) with host tensors: CUDA-graph replay == eager launches, shapes as the reference."""
+    from interactron_b200.synthetic import synthetic_episode
+    gold = torch.load(os.path.join(GOLD, "interactron_random_predict.pt"))["episodes"]
+    m = rand_model
+    for use_graph in (False, True, True):
+        m.use_cuda_graph = use_graph
+        for ep in (0, 1):
+            o = m.predict(synthetic_episode(ep))
+            assert o["pred_logits"].shape == (1, 1, 50, 1236) and o["pred_boxes"].shape == (1, 1, 50, 4)
+            assert o["image_features"].shape == (1, 1, 2048, 19, 19)
+            assert o["embedded_memory_features"].shape == (1, 1, 256, 19, 19)
+            assert o["box_features"].shape == (1, 1, 50, 256)
+            assert rel(o["pred_logits"], gold[ep]["pred_logits"]) < TOL
+            assert rel(o["pred_boxes"], gold[ep]["pred_boxes"]) < TOL
+    assert any(k[0] == "predict" for k in m._graphs)
+
+
+def test_predict_batch_equals_single_and_is_deterministic(rand_model):
+    from interactron_b200.synthetic import collate_episodes, synthetic_episode
+    m = rand_model
+    eps = [synthetic_episode(i) for i in (0, 1, 2, 3)]
+    both = m.predict(collate_episodes(eps))
+    again = m.predict(collate_episodes(eps))
+    assert torch.equal(both["pred_logits"], again["pred_logits"])        # bit-identical replays
+    for i, e in enumerate(eps):
+        one = m.predict(e)
+        assert rel(both["pred_logits"][i], one["pred_logits"][0]) < 1e-4
+        assert rel(both["pred_boxes"][i], one["pred_boxes"][0]) < 1e-4
+
+
+def test_predict_leaves_parameters_intact_and_tracks_updates(rand_model):
+    from interactron_b200.synthetic import synthetic_episode
+    m = rand_model
+    before = {k: v.clone() for k, v in m.state_dict().items()}
+    d = synthetic_episode(0)
+    o1 = m.predict(d)
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, before[k]), k
+    # an in-place optimizer-style update must be picked up (flat buffers are re-packed)
+    p = m.detector.class_embed.bias
+    with torch.no_grad():
+        p.add_(0.5)
+    o2 = m.predict(d)
+    assert (o2["pred_logits"] - o1["pred_logits"]).abs().mean().item() > 0.1
+    with torch.no_grad():
+        p.sub_(0.5)
+    o3 = m.predict(d)
+    assert rel(o3["pred_logits"], o1["pred_logits"]) < 1e-5
+
+
+def test_live_cross_check_against_cpu_oracle(rand_model):
+    """Episode that is NOT in the goldens: CUDA path vs oracle/port.py run on the host."""
+    from oracle import port
+    from interactron_b200.synthetic import synthetic_episode
+    m = rand_model
+    d = synthetic_episode(11)
+    o = m.predict(d)
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    import copy
+    body = copy.deepcopy(m.detector.backbone[0].body).cpu()
+    ref = port.predict(sd, body, d, "B", lr=m.config.ADAPTIVE_LR)
+    assert rel(o["pred_logits"], ref["pred_logits"]) < TOL
+    assert rel(o["pred_boxes"], ref["pred_boxes"]) < TOL
+
+
+def test_policy_actions_match_reference(full_model):
+    from interactron_b200.synthetic import synthetic_episode
+    acts = torch.load(os.path.join(GOLD, "interactron_actions.pt"))
+    data = synthetic_episode(0)
+    for s in range(1, 5):
+        d = dict(data)
+        d["frames"], d["masks"] = data["frames"][:, :s], data["masks"][:, :s]
+        assert full_model.get_next_action(d) == acts[s]
+
+
+def test_baselines_match_reference():
+    from interactron_b200.synthetic import synthetic_episode
+    base = torch.load(os.path.join(GOLD, "baselines_predict.pt"))
+    o = build("single_frame_baseline").predict(synthetic_episode(0, frames=1))
+    for k, v in base["detr_ep0_1frame"].items():
+        assert o[k].shape == v.shape and rel(o[k], v) < TOL, k
+    o = build("multi_frame_baseline").predict(synthetic_episode(0))
+    for k, v in base["detr_multiframe_ep0"].items():
+        assert o[k].shape == v.shape and rel(o[k], v) < TOL, k
+
+
+def test_matcher_assignments_bit_exact():
+    """Cost matrix from the CUDA kernel -> scipy LSAP == the reference HungarianMatcher's indices."""
+    from scipy.optimize import linear_sum_assignment
+    from interactron_b200.ops import CudaOps
+    ops = CudaOps()
+    gold = torch.load(os.path.join(GOLD, "matcher_assignments.pt"))
+    for seed, ref_idx in gold.items():
+        gen = torch.Generator().manual_seed(100 + seed)
+        logits = torch.randn(5, 50, 1236, generator=gen)
+        boxes = torch.rand(5, 50, 4, generator=gen) * 0.5 + 0.1
+        labels, tboxes, off = [], [], [0]
+        for f in range(5):
+            n = int(torch.randint(3, 9, (1,), generator=gen))
+            labels.append(torch.randint(1, 1235, (n,), generator=gen))
+            tboxes.append(torch.cat([torch.rand(n, 2, generator=gen) * 0.6 + 0.2,
+                                     torch.rand(n, 2, generator=gen) * 0.3 + 0.05], 1))
+            off.append(off[-1] + n)
+        cost = ops.matcher_cost(logits.cuda(), boxes.cuda(), torch.cat(tboxes).cuda().contiguous(),
+                                torch.cat(labels).cuda(), torch.tensor(off, dtype=torch.int32).cuda(),
+                                1.0, 5.0, 2.0).cpu()
+        for f in range(5):
+            n = off[f + 1] - off[f]
+            c = cost[50 * off[f]:50 * off[f + 1]].view(50, n)
+            i, j = linear_sum_assignment(c.numpy())
+            assert torch.equal(torch.as_tensor(i), ref_idx[f][0]) and torch.equal(torch.as_tensor(j), ref_idx[f][1])

@@ -14,7 +14,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 import interactron_b200 as ib  # noqa: E402
-from interactron_b200.backbone import set_backbone_precision  # noqa: E402
 from interactron_b200.synthetic import collate_episodes, synthetic_episode  # noqa: E402
 
 G = os.path.join(ROOT, "tests", "golden")
@@ -29,7 +28,6 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--tf32-backbone", action="store_true")
     args = ap.parse_args()
-    set_backbone_precision(args.tf32_backbone)
     torch.backends.cuda.matmul.allow_tf32 = False
     print("backbone conv precision:", "tf32" if args.tf32_backbone else "fp32")
     for mt in ("interactron_random", "interactron"):
@@ -37,6 +35,7 @@ def main():
         cfg = ib.default_config(mt, weights="synthetic")
         model = ib.build_model(cfg.MODEL).cuda().eval()
         loop = model._get_loop()
+        loop.backbone_tf32 = args.tf32_backbone
         for ep, g in gold["episodes"].items():
             data = synthetic_episode(ep)
             t0 = time.time()
