@@ -1,23 +1,27 @@
 // Batched TF32 GEMM on tcgen05 tensor cores (sm_100a), operands staged by TMA,
-// accumulator in TMEM, fused epilogue.  See include/interactron_b200.h
+// accumulators in TMEM, fused epilogue.  See include/interactron_b200.h
 // (itn_gemm_tf32) for the contract and the reference call sites it replaces.
 //
-// CTA = 192 threads: warp 0 TMA producer, warp 1 TMEM owner + MMA issuer (one
-// elected lane issues tcgen05.mma.kind::tf32 128xBNx8), warps 2-5 epilogue
-// (TMEM -> registers -> per-warp smem transpose -> coalesced global stores).
-// One CTA produces one 128 x BN tile of one batch entry; the K loop runs over a
-// STAGES-deep ring of {A tile, B tile} filled with 128-byte-swizzled TMA boxes whose
-// inner extent is 32 floats (= one 128-byte swizzle row).  Both operand majors
-// are supported through the UMMA descriptors, so forward (x W^T), data-grad
-// (dy W) and weight-grad (dy^T x) all run without materialising transposes.
+// Persistent, warp-specialised kernel: one CTA per SM loops over the 128 x BN output tiles
+// (n fastest, so concurrently running CTAs share A tiles in L2).  Roles:
+//   warp 0      TMA producer: fills a STAGES-deep ring of {A tile, B tile} with 128-byte
+//               swizzled boxes whose inner extent is 32 floats; runs ahead across tiles.
+//   warp 1      TMEM owner + MMA issuer: one lane issues tcgen05.mma.kind::tf32 128xBNx8 into
+//               one of TWO TMEM accumulators, so tile i+1 is computed while tile i drains.
+//   warps 2-5   (tf32x3 mode only) residual splitters, see "Precision modes".
+//   last 4      epilogue: TMEM -> registers -> per-warp smem transpose -> coalesced global
+//               stores, with bias / activation / mask / residual / accumulate fused and the
+//               auxiliary global loads of a row block issued together (latency hidden).
+// Both operand majors are supported through the UMMA descriptors, so forward (x W^T),
+// data-grad (dy W) and weight-grad (dy^T x) all run without materialising transposes.
 // Out-of-bounds rows/cols/K are zero-filled by TMA and masked in the epilogue,
 // so ragged sizes (N=1236, K=1496, M=250, ...) need no padding in HBM.
 //
 // Precision modes.  kind::tf32 truncates its fp32 operands to 10 mantissa bits; one pass
 // ("tf32") therefore carries ~1e-3 error per GEMM, which the inner-loop gradient amplifies to
 // 1-10 % (measured).  The default "tf32x3" mode is error-compensated: while the
-// raw tiles sit in shared memory, the four (otherwise idle) epilogue warps write the residual
-// tiles  x_lo = x - trunc_tf32(x)  next to them, and the issuer accumulates
+// raw tiles sit in shared memory, four splitter warps write the residual tiles
+// x_lo = x - trunc_tf32(x)  next to them, and the issuer accumulates
 //     A*B  +  A_lo*B  +  A*B_lo        (the tensor core sees A, B as their truncated hi parts)
 // in TMEM, which restores ~fp32 accuracy (dropped terms are O(2^-20)) at 3 MMAs per k-step
 // and no extra HBM/L2 traffic.
@@ -34,11 +38,11 @@ namespace itn {
 constexpr int kBM = 128;
 constexpr int kBK = 32;                    // floats per k-block = 128 B swizzle row
 constexpr int kAtomBytes = 32 * kBK * 4;   // one 32(mn) x 32(k) MN-major box = 4096 B
-constexpr int kThreads = 192;
 
 struct GemmKParams {
   int M, N, K;
   int nb1;
+  int tiles_m, tiles_n, num_tiles;
   int a_m0, a_m1, b_m0, b_m1;  // 0 when the operand is broadcast over that batch dim
   float* C;              long long ldc,   c_sb0,    c_sb1;
   const float* bias;     long long        bias_sb0, bias_sb1;
@@ -85,43 +89,59 @@ __device__ __forceinline__ void epilogue_store(const GemmKParams& p, const EpiPt
   *c = p.round_out ? rn_tf32(v) : v;
 }
 
+__device__ __forceinline__ float epilogue_math(const GemmKParams& p, float acc, float bias_v,
+                                               float auxv, float resv, float cinv, float* pre) {
+  float v = p.alpha * acc + bias_v;
+  *pre = v;
+  if (p.act == ITN_ACT_RELU) v = fmaxf(v, 0.0f);
+  else if (p.act == ITN_ACT_GELU) v = gelu_erf(v);
+  if (p.epi == ITN_EPI_RELU_MASK) v = auxv > 0.0f ? v : 0.0f;
+  else if (p.epi == ITN_EPI_GELU_GRAD) v *= gelu_erf_grad(auxv);
+  v += resv + cinv;
+  return p.round_out ? rn_tf32(v) : v;
+}
+
 template <int BN, bool X3>
 struct TileCfg {
   static constexpr int kABytes = kBM * kBK * 4;
   static constexpr int kBBytes = BN * kBK * 4;
   static constexpr int kRawBytes = kABytes + kBBytes;          // what TMA delivers per stage
   static constexpr int kStageBytes = X3 ? 2 * kRawBytes : kRawBytes;   // + residual (lo) tiles
-  static constexpr int kStages = X3 ? (BN == 256 ? 2 : (BN == 128 ? 3 : 4)) : (BN == 128 ? 3 : 4);
-  static constexpr int kTmemCols = BN < 32 ? 32 : BN;
-  // stages + barriers (full, split, empty, tmem_full) + tmem ptr + 1024 alignment slack
-  static constexpr int kSmemBytes = kStages * kStageBytes + (3 * kStages + 1) * 8 + 16 + 1024;
-  static_assert(kStages * kStageBytes >= 4 * 32 * 33 * 4, "epilogue staging must fit in the ring");
+  static constexpr int kStagingBytes = 4 * 32 * 33 * 4;        // per-warp transpose buffers
+  static constexpr int kBudget = 227 * 1024 - kStagingBytes - 1024 - 512;
+  static constexpr int kMaxStages = kBudget / kStageBytes;
+  static constexpr int kStages = kMaxStages > 8 ? 8 : kMaxStages;
+  static constexpr int kAccCols = BN < 32 ? 32 : BN;
+  static constexpr int kTmemCols = 2 * kAccCols;               // two accumulators (double buffer)
+  static constexpr int kThreads = X3 ? 320 : 192;
+  static constexpr int kEpiWarp0 = X3 ? 6 : 2;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + (3 * kStages + 4) * 8 + 16 + 1024;
+  static_assert(kStages >= 2, "need at least a double-buffered operand ring");
   static_assert(kSmemBytes <= 227 * 1024, "exceeds shared memory per CTA");
+  static_assert(kSmemBytes > 114 * 1024, "one CTA per SM is assumed (TMEM is allocated in full)");
 };
 
 template <int BN, bool A_MN, bool B_MN, bool X3>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(TileCfg<BN, X3>::kThreads, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmKParams p) {
   using Cfg = TileCfg<BN, X3>;
   constexpr int STAGES = Cfg::kStages;
 
   extern __shared__ uint8_t smem_raw[];
-  // SWIZZLE_128B atoms need 1024-byte aligned tiles.
+  // 128-byte swizzle atoms need 1024-byte aligned tiles.
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
+  float* staging = reinterpret_cast<float*>(smem + STAGES * Cfg::kStageBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes + Cfg::kStagingBytes);
   uint64_t* split_bar = full_bar + STAGES;
   uint64_t* empty_bar = split_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tfull_bar = empty_bar + STAGES;      // [2] accumulator ready for the epilogue
+  uint64_t* tempty_bar = tfull_bar + 2;          // [2] accumulator drained
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN;
-  const int m0 = blockIdx.y * kBM;
-  const int b0 = blockIdx.z / p.nb1;
-  const int b1 = blockIdx.z % p.nb1;
   const int num_kb = (p.K + kBK - 1) / kBK;
 
   if (threadIdx.x == 0) {
@@ -129,10 +149,13 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&split_bar[s], 4);   // one arrival per splitter warp (tf32x3 mode)
+      mbar_init(&split_bar[s], 4);   // one arrival per splitter warp
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 4);  // one arrival per epilogue warp
+    }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_ptr_smem);
@@ -144,31 +167,39 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0) {
     // ------------------------------------------------------- TMA producer
     if (lane == 0) {
-      const int a_c0 = b0 * p.a_m0, a_c1 = b1 * p.a_m1;
-      const int b_c0 = b0 * p.b_m0, b_c1 = b1 * p.b_m1;
       int s = 0;
       uint32_t ph = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        mbar_expect_tx(&full_bar[s], Cfg::kRawBytes);
-        uint8_t* sa = smem + s * Cfg::kStageBytes;
-        uint8_t* sb = sa + Cfg::kABytes;
-        const int k0 = kb * kBK;
-        if (!A_MN) {
-          tma_load_4d(sa, &tmA, &full_bar[s], k0, m0, a_c1, a_c0);
-        } else {
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int nb = tile % p.tiles_n;
+        const int t2 = tile / p.tiles_n;
+        const int mb = t2 % p.tiles_m;
+        const int z = t2 / p.tiles_m;
+        const int b0 = z / p.nb1, b1 = z % p.nb1;
+        const int m0 = mb * kBM, n0 = nb * BN;
+        const int a_c0 = b0 * p.a_m0, a_c1 = b1 * p.a_m1;
+        const int b_c0 = b0 * p.b_m0, b_c1 = b1 * p.b_m1;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_expect_tx(&full_bar[s], Cfg::kRawBytes);
+          uint8_t* sa = smem + s * Cfg::kStageBytes;
+          uint8_t* sb = sa + Cfg::kABytes;
+          const int k0 = kb * kBK;
+          if (!A_MN) {
+            tma_load_4d(sa, &tmA, &full_bar[s], k0, m0, a_c1, a_c0);
+          } else {
 #pragma unroll
-          for (int j = 0; j < kBM / 32; ++j)
-            tma_load_4d(sa + j * kAtomBytes, &tmA, &full_bar[s], m0 + 32 * j, k0, a_c1, a_c0);
-        }
-        if (!B_MN) {
-          tma_load_4d(sb, &tmB, &full_bar[s], k0, n0, b_c1, b_c0);
-        } else {
+            for (int j = 0; j < kBM / 32; ++j)
+              tma_load_4d(sa + j * kAtomBytes, &tmA, &full_bar[s], m0 + 32 * j, k0, a_c1, a_c0);
+          }
+          if (!B_MN) {
+            tma_load_4d(sb, &tmB, &full_bar[s], k0, n0, b_c1, b_c0);
+          } else {
 #pragma unroll
-          for (int j = 0; j < BN / 32; ++j)
-            tma_load_4d(sb + j * kAtomBytes, &tmB, &full_bar[s], n0 + 32 * j, k0, b_c1, b_c0);
+            for (int j = 0; j < BN / 32; ++j)
+              tma_load_4d(sb + j * kAtomBytes, &tmB, &full_bar[s], n0 + 32 * j, k0, b_c1, b_c0);
+          }
+          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
-        if (++s == STAGES) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -177,52 +208,58 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       constexpr uint32_t idesc = umma_idesc_tf32(kBM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       int s = 0;
       uint32_t ph = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(X3 ? &split_bar[s] : &full_bar[s], ph);
+      int acc = 0;
+      uint32_t acc_ph = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_ph ^ 1);     // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + s * Cfg::kStageBytes);
-        const uint32_t sb = sa + Cfg::kABytes;
+        const uint32_t tacc = tmem_base + acc * Cfg::kAccCols;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(X3 ? &split_bar[s] : &full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * Cfg::kStageBytes);
+          const uint32_t sb = sa + Cfg::kABytes;
 #pragma unroll
-        for (int k = 0; k < kBK / 8; ++k) {
-          // K-major (SWIZZLE_128B): rows of 32 floats, 8-row groups 1024 B apart (SBO); the
-          //   k-th MMA starts 8 floats = 32 B further along the swizzled row.
-          // MN-major (SWIZZLE_128B_BASE32B): k-rows of 32 mn-floats, 4-row swizzle atoms 512 B
-          //   apart (SBO), 32-wide mn blocks one TMA box = 4096 B apart (LBO); the k-th MMA
-          //   starts 8 k-rows = 1024 B further.
-          const uint64_t ad = A_MN ? umma_smem_desc(sa + k * 1024, kAtomBytes, 512, kLayoutSW128Base32)
-                                   : umma_smem_desc(sa + k * 32, 16, 1024, kLayoutSW128);
-          const uint64_t bd = B_MN ? umma_smem_desc(sb + k * 1024, kAtomBytes, 512, kLayoutSW128Base32)
-                                   : umma_smem_desc(sb + k * 32, 16, 1024, kLayoutSW128);
-          umma_tf32(tmem_base, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
-          if (X3) {
-            // residual tiles live kRawBytes after their raw twins, same layout: the descriptor
-            // start address is in 16-byte units
-            constexpr uint64_t kLoOff = static_cast<uint64_t>(Cfg::kRawBytes >> 4);
-            umma_tf32(tmem_base, ad + kLoOff, bd, idesc, 1u);   // A_lo * B_hi
-            umma_tf32(tmem_base, ad, bd + kLoOff, idesc, 1u);   // A_hi * B_lo
+          for (int k = 0; k < kBK / 8; ++k) {
+            // K-major (SWIZZLE_128B): rows of 32 floats, 8-row groups 1024 B apart (SBO); the
+            //   k-th MMA starts 8 floats = 32 B further along the swizzled row.
+            // MN-major (SWIZZLE_128B_BASE32B): k-rows of 32 mn-floats, 4-row swizzle atoms 512 B
+            //   apart (SBO), 32-wide mn blocks one TMA box = 4096 B apart (LBO); the k-th MMA
+            //   starts 8 k-rows = 1024 B further.
+            const uint64_t ad = A_MN ? umma_smem_desc(sa + k * 1024, kAtomBytes, 512, kLayoutSW128Base32)
+                                     : umma_smem_desc(sa + k * 32, 16, 1024, kLayoutSW128);
+            const uint64_t bd = B_MN ? umma_smem_desc(sb + k * 1024, kAtomBytes, 512, kLayoutSW128Base32)
+                                     : umma_smem_desc(sb + k * 32, 16, 1024, kLayoutSW128);
+            umma_tf32(tacc, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (X3) {
+              // residual tiles live kRawBytes after their raw twins, same layout: the descriptor
+              // start address is in 16-byte units
+              constexpr uint64_t kLoOff = static_cast<uint64_t>(Cfg::kRawBytes >> 4);
+              umma_tf32(tacc, ad + kLoOff, bd, idesc, 1u);   // A_lo * B_hi
+              umma_tf32(tacc, ad, bd + kLoOff, idesc, 1u);   // A_hi * B_lo
+            }
           }
+          umma_commit(&empty_bar[s]);  // frees the smem slot once the MMAs have read it
+          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
-        umma_commit(&empty_bar[s]);  // frees the smem slot once the MMAs have read it
-        if (++s == STAGES) { s = 0; ph ^= 1; }
+        umma_commit(&tfull_bar[acc]);  // accumulator complete
+        acc ^= 1;
+        if (acc == 0) acc_ph ^= 1;
       }
-      umma_commit(tmem_full_bar);  // accumulator complete
     }
-  } else {
-    // ----------------------------------------------------------- epilogue
-    const int ew = warp - 2;    // staging buffer index
-    const int lg = warp & 3;    // TMEM lane group this warp may read: lanes [32*lg, 32*lg+32)
-    if (X3) {
-      // ------------------------------------------ residual splitter (tf32x3 mode)
-      // lo = x - trunc_tf32(x), element-wise on the raw stage bytes (layout-agnostic, so the
-      // swizzle is preserved), written kRawBytes further; then made visible to the async proxy.
-      int s = 0;
-      uint32_t ph = 0;
-      const int tid = threadIdx.x - 64;             // 0..127
+  } else if (X3 && warp < Cfg::kEpiWarp0) {
+    // ------------------------------------------------ residual splitters (tf32x3 mode)
+    // lo = x - trunc_tf32(x), element-wise on the raw stage bytes (layout-agnostic, so the
+    // swizzle is preserved), written kRawBytes further; then made visible to the async proxy.
+    int s = 0;
+    uint32_t ph = 0;
+    const int tid = threadIdx.x - 64;               // 0..127
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&full_bar[s], ph);
-        float4* raw = reinterpret_cast<float4*>(smem + s * Cfg::kStageBytes);
+        const float4* raw = reinterpret_cast<const float4*>(smem + s * Cfg::kStageBytes);
         float4* lo = reinterpret_cast<float4*>(smem + s * Cfg::kStageBytes + Cfg::kRawBytes);
-#pragma unroll 4
+#pragma unroll 8
         for (int i = tid; i < Cfg::kRawBytes / 16; i += 128) {
           const float4 v = raw[i];
           float4 r;
@@ -238,36 +275,87 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (++s == STAGES) { s = 0; ph ^= 1; }
       }
     }
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    // All MMAs have retired, so the operand ring is free: reuse it for the transpose.
-    float* st = reinterpret_cast<float*>(smem) + ew * (32 * 33);
-    const EpiPtrs e = make_epi_ptrs(p, b0, b1);
-    const int row_base = m0 + lg * 32;
-    if (row_base < p.M) {
-      for (int c = 0; c < BN / 32; ++c) {
+  } else if (warp >= Cfg::kEpiWarp0) {
+    // ----------------------------------------------------------- epilogue
+    const int lg = warp & 3;    // TMEM lane group this warp may read: lanes [32*lg, 32*lg+32)
+    float* st = staging + (warp - Cfg::kEpiWarp0) * (32 * 33);
+    int acc = 0;
+    uint32_t acc_ph = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int nb = tile % p.tiles_n;
+      const int t2 = tile / p.tiles_n;
+      const int mb = t2 % p.tiles_m;
+      const int z = t2 / p.tiles_m;
+      const int n0 = nb * BN;
+      const int row_base = mb * kBM + lg * 32;
+      const EpiPtrs e = make_epi_ptrs(p, z / p.nb1, z % p.nb1);
+      mbar_wait(&tfull_bar[acc], acc_ph);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + acc * Cfg::kAccCols + (static_cast<uint32_t>(lg * 32) << 16);
+      const int rmax = min(32, p.M - row_base);       // <= 0: this warp's rows are all padding
+      constexpr int kChunks = BN / 32;
+      const int nchunks = min(kChunks, (p.N - n0 + 31) / 32);   // live 32-column chunks (>= 1)
+      if (rmax <= 0) {
+        // nothing to store: hand the accumulator straight back to the issuer
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      }
+#pragma unroll 1
+      for (int c = 0; c < nchunks && rmax > 0; ++c) {
         const int col0 = n0 + c * 32;
-        if (col0 >= p.N) break;
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + c * 32, v);
-        tmem_ld_wait();
+        {
+          uint32_t v[32];
+          tmem_ld_32x32(tacc + c * 32, v);
+          tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) st[lane * 33 + j] = __uint_as_float(v[j]);
+          for (int j = 0; j < 32; ++j) st[lane * 33 + j] = __uint_as_float(v[j]);
+        }
+        if (c == nchunks - 1) {
+          // last chunk of this tile is out of TMEM: hand the accumulator back to the issuer
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        }
         __syncwarp();
         const int col = col0 + lane;
-        const bool col_ok = col < p.N;
-        const float bias_v = (e.bias && col_ok) ? e.bias[col] : 0.0f;
-        const int rmax = min(32, p.M - row_base);
-        if (col_ok) {
-          for (int r = 0; r < rmax; ++r)
-            epilogue_store(p, e, row_base + r, col, st[r * 33 + lane], bias_v);
+        if (col < p.N) {
+          const float bias_v = e.bias ? e.bias[col] : 0.0f;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            // 16 rows at a time: issue every auxiliary load first, then do the math and store
+            float accv[16], auxv[16], resv[16], cinv[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int r = h * 16 + i;
+              const long long row = row_base + r;
+              const bool ok = r < rmax;
+              accv[i] = st[r * 33 + lane];
+              auxv[i] = (ok && e.aux) ? e.aux[row * p.ldaux + col] : 0.0f;
+              resv[i] = (ok && e.residual) ? e.residual[row * p.ldr + col] : 0.0f;
+              cinv[i] = (ok && p.accumulate) ? e.C[row * p.ldc + col] : 0.0f;
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int r = h * 16 + i;
+              if (r < rmax) {
+                const long long row = row_base + r;
+                float pre;
+                const float o = epilogue_math(p, accv[i], bias_v, auxv[i], resv[i], cinv[i], &pre);
+                if (e.C2) e.C2[row * p.ldc2 + col] = pre;
+                e.C[row * p.ldc + col] = o;
+              }
+            }
+          }
         }
         __syncwarp();
       }
+      acc ^= 1;
+      if (acc == 0) acc_ph ^= 1;
     }
-    tc_fence_before();
   }
 
+  tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
@@ -381,6 +469,7 @@ static int make_operand_map(CUtensorMap* tm, const itn_operand_t& o, int rows, i
 static void fill_kparams(GemmKParams& p, const itn_gemm_desc_t* d) {
   p.M = d->M; p.N = d->N; p.K = d->K;
   p.nb1 = d->nb1 < 1 ? 1 : d->nb1;
+  p.tiles_m = p.tiles_n = p.num_tiles = 0;
   p.a_m0 = p.a_m1 = p.b_m0 = p.b_m1 = 0;
   p.C = d->C; p.ldc = d->ldc; p.c_sb0 = d->c_sb0; p.c_sb1 = d->c_sb1;
   p.bias = d->bias; p.bias_sb0 = d->bias_sb0; p.bias_sb1 = d->bias_sb1;
@@ -397,8 +486,7 @@ static int validate(const itn_gemm_desc_t* d) {
               d->N, d->K);
   ITN_REQUIRE(d->A.ptr && d->B.ptr && d->C, "gemm: null A/B/C");
   ITN_REQUIRE(d->nb0 >= 1 && d->nb1 >= 1, "gemm: batch counts must be >= 1");
-  ITN_REQUIRE((long long)d->nb0 * d->nb1 <= 65535, "gemm: batch %d x %d exceeds gridDim.z", d->nb0,
-              d->nb1);
+  ITN_REQUIRE((long long)d->nb0 * d->nb1 <= 65535, "gemm: batch %d x %d too large", d->nb0, d->nb1);
   ITN_REQUIRE(d->epi == ITN_EPI_NONE || d->aux != nullptr, "gemm: epi mode %d needs aux", d->epi);
   ITN_REQUIRE(d->A.major == 0 || d->A.major == 1, "gemm: bad A.major");
   ITN_REQUIRE(d->B.major == 0 || d->B.major == 1, "gemm: bad B.major");
@@ -407,11 +495,27 @@ static int validate(const itn_gemm_desc_t* d) {
   return ITN_OK;
 }
 
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
 template <int BN, bool A_MN, bool B_MN, bool X3>
 static int launch_tile(const itn_gemm_desc_t* d, cudaStream_t stream) {
   using Cfg = TileCfg<BN, X3>;
   GemmKParams p;
   fill_kparams(p, d);
+  p.tiles_m = (d->M + kBM - 1) / kBM;
+  p.tiles_n = (d->N + BN - 1) / BN;
+  const long long nt = (long long)p.tiles_m * p.tiles_n * d->nb0 * d->nb1;
+  if (nt > 0x7fffffffLL) return set_error(ITN_ERR_ARG, "gemm: too many tiles");
+  p.num_tiles = (int)nt;
   CUtensorMap tmA, tmB;
   int rc = make_operand_map(&tmA, d->A, d->M, d->K, d->nb0, d->nb1, kBM, &p.a_m0, &p.a_m1);
   if (rc) return rc;
@@ -427,8 +531,8 @@ static int launch_tile(const itn_gemm_desc_t* d, cudaStream_t stream) {
                        cudaGetErrorString(e));
     attr_set = true;
   }
-  dim3 grid((d->N + BN - 1) / BN, (d->M + kBM - 1) / kBM, d->nb0 * d->nb1);
-  kern<<<grid, kThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
+  const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();   // persistent: <= 1 CTA per SM
+  kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
   return check_launch("gemm_tf32_kernel");
 }
 
@@ -447,6 +551,9 @@ static int launch_major(const itn_gemm_desc_t* d, cudaStream_t s) {
   return d->precision == ITN_PREC_TF32 ? launch_major2<BN, false>(d, s) : launch_major2<BN, true>(d, s);
 }
 
+// Tile width: the widest tile that still yields at least one tile per SM (wide tiles re-read
+// less from L2: 48 KB of operands per 128x256x32 step vs 32 KB per 128x128x32); small problems
+// fall back to 64-wide tiles to spread over more SMs.
 static int pick_bn(const itn_gemm_desc_t* d) {
   if (d->N <= 32) return 32;
   if (d->N <= 64) return 64;
@@ -455,9 +562,9 @@ static int pick_bn(const itn_gemm_desc_t* d) {
   const int cand[3] = {256, 128, 64};
   for (int i = 0; i < 3; ++i) {
     const int bn = cand[i];
-    if (bn > 64 && d->N < bn && d->N <= bn / 2) continue;
-    const long long ctas = tiles_m * ((d->N + bn - 1) / bn) * batch;
-    if (ctas >= 120) return bn;
+    if (bn > 64 && d->N <= bn / 2) continue;
+    const long long tiles = tiles_m * ((d->N + bn - 1) / bn) * batch;
+    if (tiles >= sm_count()) return bn;
   }
   return 64;
 }

@@ -133,8 +133,9 @@ def run_group(group):
         for (M, N, K, batch) in [(8 * 1805, 256, 2048, ()), (8 * 1805, 2048, 256, ()), (8 * 1805, 256, 256, ()),
                                  (8 * 2060, 2048, 512, ()), (8192, 8192, 2048, ()), (361, 361, 32, (320,)),
                                  (2060, 2060, 64, (64,)), (2000, 512, 512, ())]:
-            for bn in ("64", "128", "256"):
+            for bn, prec in (("128", "tf32"), ("256", "tf32"), ("64", "tf32x3"), ("128", "tf32x3"), ("256", "tf32x3")):
                 os.environ["ITN_GEMM_BN"] = bn
+                ops.precision = prec
                 a = torch.randn(*batch, M, K, device=dev)
                 w = torch.randn(*batch, N, K, device=dev)
                 out = torch.empty(*batch, M, N, device=dev)
@@ -165,7 +166,7 @@ def run_group(group):
                 torch.cuda.synchronize()
                 ms2 = e0.elapsed_time(e1) / iters
                 tf2 = 2.0 * M * N * K * nb / ms2 / 1e9
-                print(f"  perf M={M} N={N} K={K} batch={batch} BN={bn}: {ms*1e3:8.1f} us {tf:8.1f} TF/s"
+                print(f"  perf M={M} N={N} K={K} batch={batch} BN={bn} {prec:6s}: {ms*1e3:8.1f} us {tf:8.1f} TF/s"
                       f"   | cuBLAS tf32 {ms2*1e3:8.1f} us {tf2:8.1f} TF/s", flush=True)
         os.environ["ITN_GEMM_BN"] = "0"
 
