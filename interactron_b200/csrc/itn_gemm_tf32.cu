@@ -89,16 +89,78 @@ __device__ __forceinline__ void epilogue_store(const GemmKParams& p, const EpiPt
   *c = p.round_out ? rn_tf32(v) : v;
 }
 
-__device__ __forceinline__ float epilogue_math(const GemmKParams& p, float acc, float bias_v,
-                                               float auxv, float resv, float cinv, float* pre) {
-  float v = p.alpha * acc + bias_v;
-  *pre = v;
-  if (p.act == ITN_ACT_RELU) v = fmaxf(v, 0.0f);
-  else if (p.act == ITN_ACT_GELU) v = gelu_erf(v);
-  if (p.epi == ITN_EPI_RELU_MASK) v = auxv > 0.0f ? v : 0.0f;
-  else if (p.epi == ITN_EPI_GELU_GRAD) v *= gelu_erf_grad(auxv);
-  v += resv + cinv;
-  return p.round_out ? rn_tf32(v) : v;
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == ITN_ACT_RELU) return fmaxf(v, 0.0f);
+  if (act == ITN_ACT_GELU) return gelu_erf(v);
+  return v;
+}
+
+// Writes one transposed 32x32 accumulator chunk (st[r*33 + lane] = row r, this lane's column)
+// to global memory with the fused epilogue.  Lean on purpose: pointers are advanced by the row
+// stride instead of being recomputed, and the common case (no aux / residual / accumulate /
+// second output) has no loads at all; the general case issues the loads of 8 rows together.
+__device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, const EpiPtrs& e,
+                                               const float* st, int lane, int row_base, int rmax,
+                                               int col) {
+  const float bias_v = e.bias ? e.bias[col] : 0.0f;
+  float* cp = e.C + (long long)row_base * p.ldc + col;
+  const float alpha = p.alpha;
+  const int act = p.act;
+  const bool rnd = p.round_out != 0;
+  const bool simple = !e.aux && !e.residual && !e.C2 && !p.accumulate;
+  if (simple) {
+    // act / rounding are hoisted out of the row loops (warp-uniform), rows fully unrolled
+    if (act == ITN_ACT_GELU) {
+#pragma unroll 4
+      for (int r = 0; r < rmax; ++r) {
+        const float v = gelu_erf(fmaf(alpha, st[r * 33 + lane], bias_v));
+        cp[(long long)r * p.ldc] = rnd ? rn_tf32(v) : v;
+      }
+    } else if (rmax == 32 && !rnd) {
+      const float lo = act == ITN_ACT_RELU ? 0.0f : -INFINITY;
+#pragma unroll
+      for (int r = 0; r < 32; ++r)
+        cp[(long long)r * p.ldc] = fmaxf(fmaf(alpha, st[r * 33 + lane], bias_v), lo);
+    } else {
+      const float lo = act == ITN_ACT_RELU ? 0.0f : -INFINITY;
+#pragma unroll 4
+      for (int r = 0; r < rmax; ++r) {
+        const float v = fmaxf(fmaf(alpha, st[r * 33 + lane], bias_v), lo);
+        cp[(long long)r * p.ldc] = rnd ? rn_tf32(v) : v;
+      }
+    }
+    return;
+  }
+  const float* ap = e.aux ? e.aux + (long long)row_base * p.ldaux + col : nullptr;
+  const float* rp = e.residual ? e.residual + (long long)row_base * p.ldr + col : nullptr;
+  float* c2p = e.C2 ? e.C2 + (long long)row_base * p.ldc2 + col : nullptr;
+  const bool acc = p.accumulate != 0;
+  const int epi = p.epi;
+  for (int r0 = 0; r0 < rmax; r0 += 8) {
+    float av[8], xv[8], rv[8], cv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = r0 + i;
+      const bool ok = r < rmax;
+      av[i] = st[r * 33 + lane];
+      xv[i] = (ok && ap) ? ap[(long long)r * p.ldaux] : 0.0f;
+      rv[i] = (ok && rp) ? rp[(long long)r * p.ldr] : 0.0f;
+      cv[i] = (ok && acc) ? cp[(long long)r * p.ldc] : 0.0f;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = r0 + i;
+      if (r < rmax) {
+        float v = fmaf(alpha, av[i], bias_v);
+        if (c2p) c2p[(long long)r * p.ldc2] = v;
+        v = apply_act(v, act);
+        if (epi == ITN_EPI_RELU_MASK) v = xv[i] > 0.0f ? v : 0.0f;
+        else if (epi == ITN_EPI_GELU_GRAD) v *= gelu_erf_grad(xv[i]);
+        v += rv[i] + cv[i];
+        cp[(long long)r * p.ldc] = rnd ? rn_tf32(v) : v;
+      }
+    }
+  }
 }
 
 template <int BN, bool X3>
@@ -319,35 +381,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         __syncwarp();
         const int col = col0 + lane;
-        if (col < p.N) {
-          const float bias_v = e.bias ? e.bias[col] : 0.0f;
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            // 16 rows at a time: issue every auxiliary load first, then do the math and store
-            float accv[16], auxv[16], resv[16], cinv[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const int r = h * 16 + i;
-              const long long row = row_base + r;
-              const bool ok = r < rmax;
-              accv[i] = st[r * 33 + lane];
-              auxv[i] = (ok && e.aux) ? e.aux[row * p.ldaux + col] : 0.0f;
-              resv[i] = (ok && e.residual) ? e.residual[row * p.ldr + col] : 0.0f;
-              cinv[i] = (ok && p.accumulate) ? e.C[row * p.ldc + col] : 0.0f;
-            }
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const int r = h * 16 + i;
-              if (r < rmax) {
-                const long long row = row_base + r;
-                float pre;
-                const float o = epilogue_math(p, accv[i], bias_v, auxv[i], resv[i], cinv[i], &pre);
-                if (e.C2) e.C2[row * p.ldc2 + col] = pre;
-                e.C[row * p.ldc + col] = o;
-              }
-            }
-          }
-        }
+        if (col < p.N) epilogue_chunk(p, e, st, lane, row_base, rmax, col);
         __syncwarp();
       }
       acc ^= 1;
