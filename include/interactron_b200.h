@@ -146,6 +146,11 @@ int itn_add(const float* a, const float* b, float* out, long long n,
 /* Strided 2-D copy: dst[r*ldd + c] = src[r*lds + c]; optional TF32 rounding. */
 int itn_copy2d(const float* src, long long lds, float* dst, long long ldd,
                long long rows, int cols, int round_out, void* stream);
+/* Batched 2-D transpose: dst[g][c][r] = src[g][r][c] (src [groups, rows, cols], group strides in
+ * elements).  Builds the W^T twins of the weights so that data-gradient GEMMs (dy W) read both
+ * operands K-major: MN-major fp32 operands run ~4x slower through the tensor core. */
+int itn_transpose(const float* src, float* dst, int groups, int rows, int cols,
+                  long long src_group_stride, long long dst_group_stride, void* stream);
 /* dst = rn_tf32(src) (dst may equal src): makes weights / inputs TF32-clean. */
 int itn_round_tf32(const float* src, float* dst, long long n, void* stream);
 /* y = sigmoid(x)   (detr.py:72 `.sigmoid()`). */

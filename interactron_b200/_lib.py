@@ -51,6 +51,7 @@ SIGNATURES = {
     "itn_colsum": (_I, [_P, _P, _I, _LL, _I, _LL, _LL, _P]),
     "itn_add": (_I, [_P, _P, _P, _LL, _LL, _LL, _LL, _I, _P]),
     "itn_copy2d": (_I, [_P, _LL, _P, _LL, _LL, _I, _I, _P]),
+    "itn_transpose": (_I, [_P, _P, _I, _I, _I, _LL, _LL, _P]),
     "itn_round_tf32": (_I, [_P, _P, _LL, _P]),
     "itn_sigmoid_fwd": (_I, [_P, _P, _LL, _P]),
     "itn_sigmoid_bwd": (_I, [_P, _P, _P, _LL, _P]),

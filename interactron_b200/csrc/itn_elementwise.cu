@@ -96,6 +96,28 @@ copy2d_kernel(const float* __restrict__ src, long long lds, float* __restrict__ 
   }
 }
 
+// 32x32 tiles through padded shared memory: coalesced reads and writes.
+__global__ void __launch_bounds__(256)
+transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols,
+                 long long sgs, long long dgs) {
+  __shared__ float t[32][33];
+  const float* s = src + blockIdx.z * sgs;
+  float* d = dst + blockIdx.z * dgs;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    const int r = r0 + ty + i, c = c0 + tx;
+    if (r < rows && c < cols) t[ty + i][tx] = s[(long long)r * cols + c];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    const int c = c0 + ty + i, r = r0 + tx;
+    if (r < rows && c < cols) d[(long long)c * rows + r] = t[tx][ty + i];
+  }
+}
+
 __global__ void __launch_bounds__(256)
 round_tf32_kernel(const float* __restrict__ src, float* __restrict__ dst, long long n) {
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -231,6 +253,16 @@ extern "C" int itn_copy2d(const float* src, long long lds, float* dst, long long
   copy2d_kernel<<<grid_for(rows * cols, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       src, lds, dst, ldd, rows, cols, round_out);
   return check_launch("copy2d_kernel");
+}
+
+extern "C" int itn_transpose(const float* src, float* dst, int groups, int rows, int cols,
+                             long long src_group_stride, long long dst_group_stride, void* stream) {
+  ITN_REQUIRE(src && dst && groups > 0 && rows > 0 && cols > 0, "transpose: bad arguments");
+  ITN_REQUIRE(groups <= 65535, "transpose: too many groups");
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32, groups);
+  transpose_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, dst, rows, cols,
+                                                                        src_group_stride, dst_group_stride);
+  return check_launch("transpose_kernel");
 }
 
 extern "C" int itn_round_tf32(const float* src, float* dst, long long n, void* stream) {

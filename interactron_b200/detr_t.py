@@ -124,7 +124,7 @@ def detr_t_backward(ops, W, cache, sink, dpreds=None, dmemory=None, dlogits=None
     dz = ops.round_tf32(dz, out=dz)
     dhs_t = mlp_bwd(ops, W, "bbox_embed", dz, hs_r, cache["bb_hid"], sink, residual=dhs_in)
     sink.linear("class_embed", dlogits_r, hs_r)
-    ops.matmul(dlogits_r, W.w("class_embed.weight"), out=dhs_t, accumulate=True)
+    ops.matmul(dlogits_r, W.bwd("class_embed.weight"), out=dhs_t, accumulate=True)
     dt, _ = ops.layernorm_bwd(dhs_t.view(E * Q, D), cache["tgt_last"].view(E * Q, D), cache["mh"], cache["rh"],
                               W.p("transformer.decoder.norm.weight"),
                               dgamma=sink.view("transformer.decoder.norm.weight"),
@@ -147,26 +147,26 @@ def detr_t_backward(ops, W, cache, sink, dpreds=None, dmemory=None, dlogits=None
     for i in reversed(range(N_ENC)):
         pre = f"transformer.encoder.layers.{i}."
         s = cache["enc"][i]
-        ipw = W.w(pre + "self_attn.in_proj_weight")
+        ip_name = pre + "self_attn.in_proj_weight"
         df, df_r = ops.layernorm_bwd(dx, s["f"].view(E * R, D), s["m2"], s["r2"], W.p(pre + "norm2.weight"),
                                      dgamma=sink.view(pre + "norm2.weight"), dbeta=sink.view(pre + "norm2.bias"))
         df3, df3_r = df.view(E, R, D), df_r.view(E, R, D)
         sink.linear(pre + "linear2", df3_r, s["h"], df3)
-        dh = ops.matmul(df3_r, W.w(pre + "linear2.weight"), epi="relu_mask", aux=s["h"], rnd=True)
+        dh = ops.matmul(df3_r, W.bwd(pre + "linear2.weight"), epi="relu_mask", aux=s["h"], rnd=True)
         sink.linear(pre + "linear1", dh, s["x1_r"].view(E, R, D))
-        dx1 = ops.matmul(dh, W.w(pre + "linear1.weight"), residual=df3)
+        dx1 = ops.matmul(dh, W.bwd(pre + "linear1.weight"), residual=df3)
         da, da_r = ops.layernorm_bwd(dx1.view(E * R, D), s["a"].view(E * R, D), s["m1"], s["r1"],
                                      W.p(pre + "norm1.weight"), dgamma=sink.view(pre + "norm1.weight"),
                                      dbeta=sink.view(pre + "norm1.bias"))
         da3, da3_r = da.view(E, R, D), da_r.view(E, R, D)
         sink.linear(pre + "self_attn.out_proj", da3_r, s["o"].view(E, R, D), da3)
-        dO = ops.matmul(da3_r, W.w(pre + "self_attn.out_proj.weight"), rnd=True)
+        dO = ops.matmul(da3_r, W.bwd(pre + "self_attn.out_proj.weight"), rnd=True)
         dqk, dv = ops.empty(B, L, 2 * D), ops.empty(B, L, D)
         attention_bwd(ops, dO.view(B, L, D), s["qk3"][..., :D], s["qk3"][..., D:], s["v3"], s["P"],
                       B, L, L, H, HD, SCALE, dqk[..., :D], dqk[..., D:], dv)
-        dxi = ops.matmul(dqk.view(1, E * R, 2 * D), ipw[:, :2 * D], residual=da.view(1, E * R, D))
+        dxi = ops.matmul(dqk.view(1, E * R, 2 * D), W.bwd(ip_name, 0, 2 * D), residual=da.view(1, E * R, D))
         last = i == 0
-        ops.matmul(dv.view(1, E * R, D), ipw[:, 2 * D:], out=dxi, accumulate=True, rnd=last)
+        ops.matmul(dv.view(1, E * R, D), W.bwd(ip_name, 2 * D, 3 * D), out=dxi, accumulate=True, rnd=last)
         dx = dxi.view(E * R, D)
 
     # input_proj ----------------------------------------------------------------------

@@ -31,6 +31,7 @@ class InnerLoop:
         self.phi_pack, self.phi_params = ParamPack(phi), [p for _, p in phi]
         self.backbone_tf32 = False      # cuDNN convs in strict fp32: TF32 convs break the 1e-3 parity bar
         self.theta = self.psi = self.phi = None
+        self.theta_t = self.psi_t = self.phi_t = None
         self._idx_cache = {}
         self.refresh_weights()
 
@@ -58,12 +59,23 @@ class InnerLoop:
         if self.phi_params:
             self.phi = fill(self.phi, self.phi_pack, self.phi_params)
             self.phi_r = self.phi if not ops._clean else ops.round_tf32(self.phi, out=getattr(self, "phi_r", None))
+        # W^T twins of the shared weights for the data-gradient GEMMs (K-major operands are ~4x
+        # faster than MN-major ones through the fp32/tf32 tensor-core path)
+        for nm, pack in (("theta", self.theta_pack), ("psi", self.psi_pack), ("phi", self.phi_pack)):
+            src = getattr(self, nm + "_r", None) if getattr(self, nm, None) is not None else None
+            if src is None:
+                continue
+            dst = getattr(self, nm + "_t", None)
+            if dst is None:
+                dst = ops.zeros(*src.shape)
+                setattr(self, nm + "_t", dst)
+            pack.transpose_into(ops, src, dst)
 
-    def _det_weights(self, theta, theta_r):
-        return Weights((self.theta_pack, theta, theta_r), (self.psi_pack, self.psi, self.psi_r))
+    def _det_weights(self, theta, theta_r, theta_t=None):
+        return Weights((self.theta_pack, theta, theta_r, theta_t), (self.psi_pack, self.psi, self.psi_r, self.psi_t))
 
     def _fusion_weights(self):
-        return Weights((self.phi_pack, self.phi, self.phi_r))
+        return Weights((self.phi_pack, self.phi, self.phi_r, self.phi_t))
 
     # ------------------------------------------------------------------ pieces
     def features(self, frames, masks):
@@ -103,7 +115,7 @@ class InnerLoop:
         L = h * w
         C = self.detector.class_embed.out_features
         # -- pre-adapt pass (shared theta) and learned loss
-        Wd = self._det_weights(self.theta, self.theta_r)
+        Wd = self._det_weights(self.theta, self.theta_r, self.theta_t)
         preds = ops.empty(E * S * detr_t.NQ, detr_t.D + C + 4)
         pre, cache = detr_t.detr_t_forward(ops, Wd, src_r.view(E, S * L, -1), pos, kmask, E, S, L, preds=preds)
         Wf = self._fusion_weights()

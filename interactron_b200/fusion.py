@@ -82,9 +82,9 @@ def fusion_b_backward(ops, W, cache):
         dt = decoder_layer_bwd(ops, W, f"transformer.layers.{j}.", dm, cache["layers"][j], dt, None, None,
                                dmp, dmem)
     dmem_tot = ops.add(dmem.view(E * R, DF), dmp.view(E * R, DF), rnd=True).view(1, E * R, DF)
-    dmemory = ops.matmul(dmem_tot, W.w("img_feature_embedding.weight")).view(E, R, -1)
+    dmemory = ops.matmul(dmem_tot, W.bwd("img_feature_embedding.weight")).view(E, R, -1)
     dtp = ops.copy2d_(ops.empty(E, Qp * DF), dt.view(E, Q * DF)[:, :Qp * DF], rnd=True).view(1, E * Qp, DF)
-    dpreds = ops.matmul(dtp, W.w("prediction_embedding.weight"), rnd=True).view(E * Qp, -1)
+    dpreds = ops.matmul(dtp, W.bwd("prediction_embedding.weight"), rnd=True).view(E * Qp, -1)
     return dmemory, dpreds
 
 
@@ -157,7 +157,7 @@ def fusion_a_backward(ops, W, cache):
     HD = DF // NH
     dz = ops.round_tf32(cache["dlv"].view(E, Qp, 1))
     dyp = mlp_bwd(ops, W, "loss_decoder", dz, cache["yp_r"], cache["lhid"], rnd=True)  # d(head out) [E,Qp,512]
-    dyp_in = ops.matmul(dyp, W.w("model.head.weight"))                                  # d(ln_f out)
+    dyp_in = ops.matmul(dyp, W.bwd("model.head.weight"))                                  # d(ln_f out)
     dyf = ops.zeros(E, Tn, DF)
     ops.copy2d_(dyf.view(E, Tn * DF)[:, R * DF:(R + Qp) * DF], dyp_in.view(E, Qp * DF))
     dx, _ = ops.layernorm_bwd(dyf.view(E * Tn, DF), cache["x_last"].view(E * Tn, DF), cache["mf"], cache["rf"],
@@ -166,13 +166,13 @@ def fusion_a_backward(ops, W, cache):
         pre = f"model.blocks.{i}."
         s = cache["layers"][i]
         dx_r = ops.round_tf32(dx).view(1, E * Tn, DF)
-        du = ops.matmul(dx_r, W.w(pre + "mlp.2.weight"), epi="gelu_grad", aux=s["upre"], rnd=True)
-        dh2 = ops.matmul(du, W.w(pre + "mlp.0.weight"))
+        du = ops.matmul(dx_r, W.bwd(pre + "mlp.2.weight"), epi="gelu_grad", aux=s["upre"], rnd=True)
+        dh2 = ops.matmul(du, W.bwd(pre + "mlp.0.weight"))
         dx1, dx1_r = ops.layernorm_bwd(dh2.view(E * Tn, DF), s["x1"].view(E * Tn, DF), s["m2"], s["r2"],
                                        W.p(pre + "ln2.weight"))
         dx1 = ops.add(dx1, dx)                                                          # + residual path
         dx1_r = ops.round_tf32(dx1).view(1, E * Tn, DF)
-        dO = ops.matmul(dx1_r, W.w(pre + "attn.proj.weight"), rnd=True)
+        dO = ops.matmul(dx1_r, W.bwd(pre + "attn.proj.weight"), rnd=True)
         dq, dk, dv = ops.empty(E, Tn, DF), ops.empty(E, Tn, DF), ops.empty(E, Tn, DF)
         attention_bwd(ops, dO.view(E, Tn, DF), s["q"], s["k"], s["v"], s["P"], E, Tn, Tn, NH, HD,
                       1.0 / (HD ** 0.5), dq, dk, dv)
@@ -184,7 +184,7 @@ def fusion_a_backward(ops, W, cache):
         dx = ops.add(dxa, dx1)
     dseq = dx.view(E, Tn * DF)
     dimg = ops.copy2d_(ops.empty(E, R * DF), dseq[:, :R * DF], rnd=True).view(1, E * R, DF)
-    dmemory = ops.matmul(dimg, W.w("img_feature_embedding.weight")).view(E, R, -1)
+    dmemory = ops.matmul(dimg, W.bwd("img_feature_embedding.weight")).view(E, R, -1)
     dpe = ops.copy2d_(ops.empty(E, Qp * DF), dseq[:, R * DF:(R + Qp) * DF], rnd=True).view(1, E * Qp, DF)
-    dpreds = ops.matmul(dpe, W.w("prediction_embedding.weight"), rnd=True).view(E * Qp, -1)
+    dpreds = ops.matmul(dpe, W.bwd("prediction_embedding.weight"), rnd=True).view(E * Qp, -1)
     return dmemory, dpreds

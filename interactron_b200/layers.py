@@ -127,46 +127,45 @@ def decoder_layer_bwd(ops, W, pre, dm, s, dt, sink, dqpos, dmp, dmem):
     d(memory) into dmem (both [1,E*R,D]); writes weight gradients through `sink` (None = data
     gradients only, as for the fusion network whose parameters are not adapted)."""
     E, B, Lq, Lk, D, nh, hd, Q, R = dm.E, dm.B, dm.Lq, dm.Lk, dm.D, dm.nh, dm.hd, dm.Q, dm.R
-    sw = W.w(pre + "self_attn.in_proj_weight")
-    cw = W.w(pre + "multihead_attn.in_proj_weight")
+    sa_w, ca_w = pre + "self_attn.in_proj_weight", pre + "multihead_attn.in_proj_weight"
     nk = (lambda n: sink.norm(pre + n)) if sink is not None else (lambda n: {})
     df, df_r = ops.layernorm_bwd(dt, s["f"].view(E * Q, D), s["m3"], s["r3"], W.p(pre + "norm3.weight"),
                                  **nk("norm3"))
     df3, df3_r = df.view(E, Q, D), df_r.view(E, Q, D)
-    dh = ops.matmul(df3_r, W.w(pre + "linear2.weight"), epi="relu_mask", aux=s["h"], rnd=True)
+    dh = ops.matmul(df3_r, W.bwd(pre + "linear2.weight"), epi="relu_mask", aux=s["h"], rnd=True)
     if sink is not None:
         sink.linear(pre + "linear2", df3_r, s["h"], df3)
         sink.linear(pre + "linear1", dh, s["t2_r"].view(E, Q, D))
-    dt2 = ops.matmul(dh, W.w(pre + "linear1.weight"), residual=df3)
+    dt2 = ops.matmul(dh, W.bwd(pre + "linear1.weight"), residual=df3)
     da2, da2_r = ops.layernorm_bwd(dt2.view(E * Q, D), s["a2"].view(E * Q, D), s["m2"], s["r2"],
                                    W.p(pre + "norm2.weight"), **nk("norm2"))
     da2_3r = da2_r.view(E, Q, D)
     if sink is not None:
         sink.linear(pre + "multihead_attn.out_proj", da2_3r, s["o2"].view(E, Q, D), da2.view(E, Q, D))
-    dO2 = ops.matmul(da2_3r, W.w(pre + "multihead_attn.out_proj.weight"), rnd=True)
+    dO2 = ops.matmul(da2_3r, W.bwd(pre + "multihead_attn.out_proj.weight"), rnd=True)
     dqc, dkc, dvc = ops.empty(B, Lq, D), ops.empty(B, Lk, D), ops.empty(B, Lk, D)
     attention_bwd(ops, dO2.view(B, Lq, D), s["qc"], s["kc"], s["vc"], s["P2"], B, Lq, Lk, nh, hd, dm.scale,
                   dqc, dkc, dvc)
     dqc1 = dqc.view(1, E * Q, D)
-    dt1 = ops.matmul(dqc1, cw[:, :D], residual=da2.view(1, E * Q, D))
+    dt1 = ops.matmul(dqc1, W.bwd(ca_w, 0, D), residual=da2.view(1, E * Q, D))
     if dqpos is not None:
-        ops.matmul(dqc1, cw[:, :D], out=dqpos.view(1, E * Q, D), accumulate=True)
-    ops.matmul(dkc.view(1, E * R, D), cw[:, D:2 * D], out=dmp, accumulate=True)
-    ops.matmul(dvc.view(1, E * R, D), cw[:, 2 * D:], out=dmem, accumulate=True)
+        ops.matmul(dqc1, W.bwd(ca_w, 0, D), out=dqpos.view(1, E * Q, D), accumulate=True)
+    ops.matmul(dkc.view(1, E * R, D), W.bwd(ca_w, D, 2 * D), out=dmp, accumulate=True)
+    ops.matmul(dvc.view(1, E * R, D), W.bwd(ca_w, 2 * D, 3 * D), out=dmem, accumulate=True)
     da1, da1_r = ops.layernorm_bwd(dt1.view(E * Q, D), s["a1"].view(E * Q, D), s["m1"], s["r1"],
                                    W.p(pre + "norm1.weight"), **nk("norm1"))
     da1_3r = da1_r.view(E, Q, D)
     if sink is not None:
         sink.linear(pre + "self_attn.out_proj", da1_3r, s["o"].view(E, Q, D), da1.view(E, Q, D))
-    dO = ops.matmul(da1_3r, W.w(pre + "self_attn.out_proj.weight"), rnd=True)
+    dO = ops.matmul(da1_3r, W.bwd(pre + "self_attn.out_proj.weight"), rnd=True)
     dqk, dv = ops.empty(B, Lq, 2 * D), ops.empty(B, Lq, D)
     attention_bwd(ops, dO.view(B, Lq, D), s["qk3"][..., :D], s["qk3"][..., D:], s["v3"], s["P"],
                   B, Lq, Lq, nh, hd, dm.scale, dqk[..., :D], dqk[..., D:], dv)
     dqk1 = dqk.view(1, E * Q, 2 * D)
-    dtg = ops.matmul(dqk1, sw[:, :2 * D], residual=da1.view(1, E * Q, D))
+    dtg = ops.matmul(dqk1, W.bwd(sa_w, 0, 2 * D), residual=da1.view(1, E * Q, D))
     if dqpos is not None:
-        ops.matmul(dqk1, sw[:, :2 * D], out=dqpos.view(1, E * Q, D), accumulate=True)
-    ops.matmul(dv.view(1, E * Q, D), sw[:, 2 * D:], out=dtg, accumulate=True)
+        ops.matmul(dqk1, W.bwd(sa_w, 0, 2 * D), out=dqpos.view(1, E * Q, D), accumulate=True)
+    ops.matmul(dv.view(1, E * Q, D), W.bwd(sa_w, 2 * D, 3 * D), out=dtg, accumulate=True)
     return dtg.view(E * Q, D)
 
 
@@ -190,7 +189,7 @@ def mlp_bwd(ops, W, name, dz_r, x_r, hid, sink=None, n_layers=3, **last_kw):
         inp = hid[i - 1] if i > 0 else x_r
         if sink is not None:
             sink.linear(f"{name}.layers.{i}", d, inp)
-        w = W.w(f"{name}.layers.{i}.weight")
+        w = W.bwd(f"{name}.layers.{i}.weight")
         if i > 0:
             d = ops.matmul(d, w, epi="relu_mask", aux=hid[i - 1], rnd=True)
         else:

@@ -273,6 +273,14 @@ class CudaOps:
                                        dst.shape[1], 1 if (rnd and self._clean) else 0, self._stream()))
         return dst
 
+    def transpose_(self, dst, src):
+        """dst [G, C, R] = src [G, R, C] transposed per group (inner dims contiguous)."""
+        G, R, Cc = src.shape
+        assert dst.shape == (G, Cc, R) and src[0].is_contiguous() and dst[0].is_contiguous()
+        _lib.check(self.lib.itn_transpose(_ptr(src), _ptr(dst), G, R, Cc, src.stride(0) if G > 1 else 0,
+                                          dst.stride(0) if G > 1 else 0, self._stream()))
+        return dst
+
     def round_tf32(self, x, out=None):
         """TF32-rounded copy of contiguous x (out may alias x).  In tf32x3 mode operands are used
         at full precision, so this is the identity (no launch)."""

@@ -46,31 +46,67 @@ class ParamPack:
     def unpack(self, flat):
         return {n: self.view(flat, n) for n in self.names}
 
+    def matrix_shape(self, name):
+        """(N_out, K_in) of a >= 2-D weight (trailing dims flattened, e.g. the 1x1 conv)."""
+        shp = self.shapes[name]
+        k = 1
+        for d in shp[1:]:
+            k *= d
+        return shp[0], k
+
+    def view_t(self, flat_t, name):
+        """flat_t [..., numel] -> W^T view [..., K_in, N_out] of the transposed twin buffer."""
+        off, n = self.offsets[name], self.sizes[name]
+        N, K = self.matrix_shape(name)
+        return flat_t[..., off:off + n].reshape(*flat_t.shape[:-1], K, N)
+
+    def transpose_into(self, ops, flat, flat_t):
+        """Fill flat_t with the per-tensor transposes of every >= 2-D tensor of flat ([G, numel])."""
+        for name in self.names:
+            if len(self.shapes[name]) < 2:
+                continue
+            N, K = self.matrix_shape(name)
+            src = self.view(flat, name).reshape(flat.shape[0], N, K)
+            ops.transpose_(self.view_t(flat_t, name), src)
+        return flat_t
+
 
 class Weights:
-    """Named weight views over one or more (pack, flat, flat_rounded) triples.
+    """Named weight views over one or more (pack, flat, flat_rounded[, flat_transposed]) tuples.
 
-    `p(name)` is the full-precision tensor (biases, LayerNorm affines, embeddings);
-    `w(name)` the TF32-rounded twin that the tensor cores read.  Every view has a
-    leading group dim G (1 = shared by all episodes, E = one fast-weight set per episode).
-    """
+    `p(name)`   full-precision tensor (biases, LayerNorm affines, embeddings);
+    `w(name)`   GEMM weight [G, N_out, K_in...] (TF32-rounded twin in single-pass mode);
+    `bwd(name)` the b-operand [G, N_out, K_in] of a data-gradient GEMM `dy @ W`, served from the
+                transposed twin W^T when there is one so the tensor core reads it K-major.
+    Every view has a leading group dim G (1 = shared by all episodes, E = per-episode theta')."""
 
-    def __init__(self, *triples):
-        self.triples = triples
+    def __init__(self, *tuples):
+        self.tuples = [t if len(t) == 4 else (*t, None) for t in tuples]
 
     def _find(self, name):
-        for pack, flat, flat_r in self.triples:
-            if name in pack:
-                return pack, flat, flat_r
+        for t in self.tuples:
+            if name in t[0]:
+                return t
         raise KeyError(name)
 
     def p(self, name):
-        pack, flat, _ = self._find(name)
+        pack, flat, _, _ = self._find(name)
         return pack.view(flat, name)
 
     def w(self, name):
-        pack, _, flat_r = self._find(name)
+        pack, _, flat_r, _ = self._find(name)
         return pack.view(flat_r, name)
+
+    def bwd(self, name, lo=None, hi=None):
+        pack, _, flat_r, flat_t = self._find(name)
+        if flat_t is not None:
+            wt = pack.view_t(flat_t, name)
+            if lo is not None:
+                wt = wt[..., lo:hi]
+            return wt.transpose(-1, -2)
+        N, K = pack.matrix_shape(name)
+        w = pack.view(flat_r, name).reshape(flat_r.shape[0], N, K)
+        return w[..., lo:hi, :] if lo is not None else w
 
 
 def detector_packs(detector):

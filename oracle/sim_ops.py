@@ -128,6 +128,11 @@ class SimOps:
         dst.copy_(src)
         return dst
 
+    def transpose_(self, dst, src):
+        self.calls += 1
+        dst.copy_(src.transpose(-1, -2))
+        return dst
+
     def round_tf32(self, x, out=None):
         self.calls += 1
         if out is None:
