@@ -53,11 +53,13 @@ enum { ITN_ACT_NONE = 0, ITN_ACT_RELU = 1, ITN_ACT_GELU = 2 };
  * ITN_PREC_TF32 (1): one tensor-core pass (operands truncated to 10 mantissa bits). */
 enum { ITN_PREC_TF32X3 = 0, ITN_PREC_TF32 = 1 };
 enum { ITN_EPI_NONE = 0, ITN_EPI_RELU_MASK = 1, ITN_EPI_GELU_GRAD = 2 };
+/* act_pos: 0 = activation right after the bias (default), 1 = after residual/accumulate
+ * (ResNet bottleneck: relu(conv(x) + identity)). */
 
 /* C[b0,b1] = epilogue( alpha * A[b0,b1] (MxK) * B[b0,b1]^T (NxK)^T ), batch = nb0*nb1.
  * Epilogue order per element:  v = alpha*acc; v += bias[n]; if (C2) C2 = v;
- * v = act(v); epi (RELU_MASK: v = aux>0 ? v : 0; GELU_GRAD: v *= gelu'(aux));
- * v += residual; if (accumulate) v += C; if (round_out) v = rn_tf32(v); C = v.
+ * v = act(v) [act_pos 0]; epi (RELU_MASK: v = aux>0 ? v : 0; GELU_GRAD: v *= gelu'(aux));
+ * v += residual; if (accumulate) v += C; v = act(v) [act_pos 1]; if (round_out) v = rn_tf32(v); C = v.
  * tcgen05 kind::tf32 TRUNCATES its fp32 operands to 10 mantissa bits, which biases
  * every product by about -4e-4 per operand.  The path therefore keeps every tensor
  * that feeds a GEMM already rounded-to-nearest to TF32 ("TF32-clean"): producers
@@ -85,6 +87,7 @@ typedef struct {
   int accumulate;
   int round_out;
   int precision;
+  int act_pos;
 } itn_gemm_desc_t;
 
 /* tcgen05/TMA path.  Requires 16-byte aligned operand bases and ld/sb* multiples
@@ -178,6 +181,18 @@ int itn_sgd_clip_update(const float* theta, long long theta_stride, const float*
  * mask uint8 [frames,h,w] (1 = padded) -> pos [frames, h*w, 2*feats] token-major. */
 int itn_pos_embed_sine(const unsigned char* mask, float* pos, int frames, int h,
                        int w, int feats, void* stream);
+
+/* ------------------------------------------------------------ frozen trunk --- */
+/* Channels-last im2col: dst[(n,ho,wo)][(ky*kw+kx)*C + c] = src[n][ho*stride-pad+ky*dil][wo*stride-pad+kx*dil][c]
+ * (zero outside the image); dst row stride ld >= kh*kw*C, extra columns are zeroed.  With the BN-folded
+ * weights reshaped to [Cout, kh*kw*Cin] every convolution of the frozen ResNet-50 trunk
+ * (reference models/detr_models/backbone.py:57-92, torchvision resnet50) becomes one
+ * itn_gemm_tf32 with bias / ReLU / residual fused (k=1,stride=2 is the strided 1x1 gather). */
+int itn_im2col_nhwc(const float* src, float* dst, int N, int H, int W, int C, int kh, int kw,
+                    int stride, int pad, int dil, int Ho, int Wo, long long ld, void* stream);
+/* 3x3 stride-2 pad-1 max pooling, channels-last (C multiple of 4). */
+int itn_maxpool3x3s2_nhwc(const float* src, float* dst, int N, int H, int W, int C, int Ho, int Wo,
+                          void* stream);
 
 /* ------------------------------------------------------ matcher/criterion --- */
 /* HungarianMatcher cost matrix (detr_models/matcher.py:53-71, util/box_ops.py:8-58):

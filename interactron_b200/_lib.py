@@ -31,7 +31,7 @@ class GemmDesc(C.Structure):
         ("aux", C.c_void_p), ("ldaux", C.c_longlong), ("aux_sb0", C.c_longlong), ("aux_sb1", C.c_longlong),
         ("C2", C.c_void_p), ("ldc2", C.c_longlong), ("c2_sb0", C.c_longlong), ("c2_sb1", C.c_longlong),
         ("alpha", C.c_float), ("act", C.c_int), ("epi", C.c_int), ("accumulate", C.c_int),
-        ("round_out", C.c_int), ("precision", C.c_int),
+        ("round_out", C.c_int), ("precision", C.c_int), ("act_pos", C.c_int),
     ]
 
 
@@ -58,6 +58,8 @@ SIGNATURES = {
     "itn_l2norm_fwd_bwd": (_I, [_P, _P, _P, _I, _I, _P]),
     "itn_sgd_clip_update": (_I, [_P, _LL, _P, _P, _P, _P, _I, _LL, _F, _F, _P]),
     "itn_pos_embed_sine": (_I, [_P, _P, _I, _I, _I, _I, _P]),
+    "itn_im2col_nhwc": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _LL, _P]),
+    "itn_maxpool3x3s2_nhwc": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "itn_matcher_cost": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _F, _P]),
 }
 

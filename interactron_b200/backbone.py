@@ -1,12 +1,18 @@
-"""Frozen ResNet-50-DC5 trunk, executed through PyTorch/cuDNN (decision D1, SURVEY.md section 8a row D1:
-the backbone is not a fast weight, so its features are computed once per episode and reused by
-the pre- and post-adaptation passes).  This is the only arithmetic on the path that is a library
-call; everything downstream of `src` runs in the hand-written kernels.
+"""Frozen ResNet-50-DC5 trunk (decision D1, SURVEY.md section 8a row D1: the backbone is not a fast
+weight, so its features are computed once per episode and reused by the pre- and post-adaptation
+passes; reference models/detr_models/backbone.py:57-92 + torchvision resnet50).
 
 Because the trunk is frozen, the FrozenBatchNorm affine of every convolution is folded into the
-convolution's weight and bias once (reference models/detr_models/backbone.py:44-54 applies it as
-separate element-wise ops), and conv + bias + ReLU (+ residual) run as cuDNN's fused
-ConvolutionBiasActivation: 53 convolutions, no element-wise kernels in between.
+convolution's weight and bias once (the reference applies it as separate element-wise ops,
+backbone.py:44-54).  Two executors:
+
+  GemmTrunk   (default) channels-last activations; every convolution is ONE tf32x3 tensor-core GEMM
+              of our own kernel with bias / ReLU / residual fused in the epilogue: 1x1 convolutions
+              read the activation matrix [N*H*W, Cin] directly, kxk ones (and the strided 1x1
+              down-samples) go through a channels-last im2col gather first.  fp32-accurate
+              (error-compensated TF32), ~3-4x faster than cuDNN's fp32 convolutions on B200.
+  FoldedTrunk cuDNN fused ConvolutionBiasActivation in strict fp32 (NCHW) or TF32 (channels-last);
+              kept as a cross-check (`ITN_BACKBONE=cudnn`) and for the TF32-backbone ablation.
 """
 import torch
 import torch.nn.functional as F
@@ -76,11 +82,87 @@ class FoldedTrunk:
         return x
 
 
+class GemmTrunk:
+    """The trunk as im2col + GEMM on the hand-written kernels (see module docstring)."""
+
+    def __init__(self, body, ops):
+        self.body, self.ops = body, ops
+        self.key = None
+        self.layers = None
+
+    _key = FoldedTrunk._key
+
+    def _prep(self, conv, bn):
+        """-> dict(w [Cout, ld] with columns (ky, kx, cin) matching im2col, bias, geometry)."""
+        w, b = FoldedTrunk._fold(conv, bn)
+        co, ci, kh, kw = w.shape
+        k = kh * kw * ci
+        ld = (k + 3) // 4 * 4
+        wm = torch.zeros(co, ld, dtype=w.dtype, device=w.device)
+        wm[:, :k] = w.permute(0, 2, 3, 1).reshape(co, k)
+        wm = self.ops.round_tf32(wm.to(self.ops.device).contiguous())
+        return dict(w=wm, b=b.to(self.ops.device), kh=kh, kw=kw, stride=conv.stride[0], pad=conv.padding[0],
+                    dil=conv.dilation[0], cout=co)
+
+    def refresh(self):
+        key = self._key()
+        if key == self.key:
+            return
+        b = self.body
+        with torch.no_grad():
+            stem = self._prep(b.conv1, b.bn1)
+            blocks = []
+            for name in ("layer1", "layer2", "layer3", "layer4"):
+                for blk in getattr(b, name):
+                    blocks.append(dict(
+                        a=self._prep(blk.conv1, blk.bn1), b=self._prep(blk.conv2, blk.bn2),
+                        c=self._prep(blk.conv3, blk.bn3),
+                        down=self._prep(blk.downsample[0], blk.downsample[1]) if blk.downsample is not None else None))
+        self.layers = (stem, blocks)
+        self.key = key
+
+    def _conv(self, x, L, act="relu", residual=None):
+        """x [N,H,W,Cin] channels-last -> [N,Ho,Wo,Cout]; bias (+ residual) + ReLU fused in the GEMM."""
+        ops = self.ops
+        N, H, W, Cin = x.shape
+        if L["kh"] == 1 and L["stride"] == 1:
+            a, Ho, Wo = x.view(N * H * W, Cin), H, W
+        else:
+            a, Ho, Wo = ops.im2col_nhwc(x, L["kh"], L["kw"], L["stride"], L["pad"], L["dil"])
+        res = residual.view(N * Ho * Wo, L["cout"]) if residual is not None else None
+        y = ops.matmul(a, L["w"].t(), bias=L["b"], act=act, residual=res, act_after_residual=res is not None)
+        return y.view(N, Ho, Wo, L["cout"])
+
+    def forward(self, frames):
+        """frames [N,3,H,W] -> [N,h,w,2048] channels-last features."""
+        self.refresh()
+        stem, blocks = self.layers
+        x = frames.permute(0, 2, 3, 1).contiguous()
+        x = self._conv(x, stem)
+        x = self.ops.maxpool3x3s2_nhwc(x)
+        for blk in blocks:
+            idt = x if blk["down"] is None else self._conv(x, blk["down"], act=None)
+            o = self._conv(x, blk["a"])
+            o = self._conv(o, blk["b"])
+            x = self._conv(o, blk["c"], residual=idt)
+        return x
+
+
 _TRUNKS = {}
 
 
+def run_backbone_gemm(body, frames, ops):
+    """The default executor: our own kernels end to end (see GemmTrunk)."""
+    key = (id(body), id(ops))
+    trunk = _TRUNKS.get(key)
+    if trunk is None or trunk.body is not body:
+        trunk = _TRUNKS[key] = GemmTrunk(body, ops)
+    with torch.no_grad():
+        return trunk.forward(frames)
+
+
 def run_backbone(body, frames, tf32=False):
-    """frames [N,3,H,W] -> token-major features [N,h,w,2048] (fp32, contiguous).
+    """cuDNN executor.  frames [N,3,H,W] -> token-major features [N,h,w,2048] (fp32, contiguous).
     tf32=False keeps cuDNN in strict fp32: with TF32 convolutions the features move by ~4e-4,
     which the adaptation step amplifies to ~1.6e-2 on the re-detected logits (measured,
     profiles/README.md) — outside the 1e-3 parity bar.  fp32 runs in NCHW: cuDNN's fp32

@@ -50,7 +50,7 @@ struct GemmKParams {
   const float* aux;      long long ldaux, aux_sb0,  aux_sb1;
   float* C2;             long long ldc2,  c2_sb0,   c2_sb1;
   float alpha;
-  int act, epi, accumulate, round_out;
+  int act, epi, accumulate, round_out, act_pos;
 };
 
 // Per-batch-entry epilogue pointers.
@@ -76,8 +76,10 @@ __device__ __forceinline__ void epilogue_store(const GemmKParams& p, const EpiPt
                                                int col, float acc, float bias_v) {
   float v = p.alpha * acc + bias_v;
   if (e.C2) e.C2[(long long)row * p.ldc2 + col] = v;
-  if (p.act == ITN_ACT_RELU) v = fmaxf(v, 0.0f);
-  else if (p.act == ITN_ACT_GELU) v = gelu_erf(v);
+  if (p.act_pos == 0) {
+    if (p.act == ITN_ACT_RELU) v = fmaxf(v, 0.0f);
+    else if (p.act == ITN_ACT_GELU) v = gelu_erf(v);
+  }
   if (p.epi == ITN_EPI_RELU_MASK) {
     v = e.aux[(long long)row * p.ldaux + col] > 0.0f ? v : 0.0f;
   } else if (p.epi == ITN_EPI_GELU_GRAD) {
@@ -86,6 +88,10 @@ __device__ __forceinline__ void epilogue_store(const GemmKParams& p, const EpiPt
   if (e.residual) v += e.residual[(long long)row * p.ldr + col];
   float* c = e.C + (long long)row * p.ldc + col;
   if (p.accumulate) v += *c;
+  if (p.act_pos == 1) {
+    if (p.act == ITN_ACT_RELU) v = fmaxf(v, 0.0f);
+    else if (p.act == ITN_ACT_GELU) v = gelu_erf(v);
+  }
   *c = p.round_out ? rn_tf32(v) : v;
 }
 
@@ -135,6 +141,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, const EpiPt
   const float* rp = e.residual ? e.residual + (long long)row_base * p.ldr + col : nullptr;
   float* c2p = e.C2 ? e.C2 + (long long)row_base * p.ldc2 + col : nullptr;
   const bool acc = p.accumulate != 0;
+  const bool act_late = p.act_pos == 1;
   const int epi = p.epi;
   for (int r0 = 0; r0 < rmax; r0 += 8) {
     float av[8], xv[8], rv[8], cv[8];
@@ -153,10 +160,11 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, const EpiPt
       if (r < rmax) {
         float v = fmaf(alpha, av[i], bias_v);
         if (c2p) c2p[(long long)r * p.ldc2] = v;
-        v = apply_act(v, act);
+        if (!act_late) v = apply_act(v, act);
         if (epi == ITN_EPI_RELU_MASK) v = xv[i] > 0.0f ? v : 0.0f;
         else if (epi == ITN_EPI_GELU_GRAD) v *= gelu_erf_grad(xv[i]);
         v += rv[i] + cv[i];
+        if (act_late) v = apply_act(v, act);
         cp[(long long)r * p.ldc] = rnd ? rn_tf32(v) : v;
       }
     }
@@ -512,6 +520,7 @@ static void fill_kparams(GemmKParams& p, const itn_gemm_desc_t* d) {
   p.C2 = d->C2; p.ldc2 = d->ldc2; p.c2_sb0 = d->c2_sb0; p.c2_sb1 = d->c2_sb1;
   p.alpha = d->alpha; p.act = d->act; p.epi = d->epi; p.accumulate = d->accumulate;
   p.round_out = d->round_out;
+  p.act_pos = d->act_pos;
 }
 
 static int validate(const itn_gemm_desc_t* d) {

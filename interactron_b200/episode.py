@@ -11,10 +11,13 @@ For E episodes at once (the reference handles one):
 theta lives in one flat buffer, so the reference's clone/detach/set_parameters bookkeeping
 (utils/meta_utils.py:48-111) is pointer arithmetic here.
 """
+import os
+
 import torch
 
 from . import detr_t, fusion
-from .backbone import run_backbone
+
+from .backbone import run_backbone, run_backbone_gemm
 from .layers import GradSink
 from .params import ParamPack, Weights, detector_packs
 
@@ -29,7 +32,9 @@ class InnerLoop:
         self.theta_pack, self.theta_params, self.psi_pack, self.psi_params = detector_packs(detector)
         phi = list(fusion_mod.named_parameters()) if fusion_mod is not None else []
         self.phi_pack, self.phi_params = ParamPack(phi), [p for _, p in phi]
-        self.backbone_tf32 = False      # cuDNN convs in strict fp32: TF32 convs break the 1e-3 parity bar
+        # "gemm": the trunk on our own im2col + tf32x3 GEMM kernels (default); "cudnn": cuDNN convolutions
+        self.backbone_impl = os.environ.get("ITN_BACKBONE", "gemm")
+        self.backbone_tf32 = False      # cuDNN executor only: TF32 convs break the 1e-3 parity bar
         self.theta = self.psi = self.phi = None
         self.theta_t = self.psi_t = self.phi_t = None
         self._idx_cache = {}
@@ -82,7 +87,11 @@ class InnerLoop:
         """frames [N,3,H,W], masks [N,H,W] (nonzero = padded) -> (src_r [N,L,2048] TF32-clean
         token-major, pos [N*L,256], kmask uint8 [N,L], hw).  self.src keeps the unrounded features."""
         ops = self.ops
-        src = run_backbone(self.detector.backbone[0].body, frames, self.backbone_tf32)   # [N,h,w,2048]
+        body = self.detector.backbone[0].body
+        if self.backbone_impl == "gemm":
+            src = run_backbone_gemm(body, frames, ops)                                    # [N,h,w,2048]
+        else:
+            src = run_backbone(body, frames, self.backbone_tf32)
         N, h, w, C = src.shape
         self.src = src.reshape(N, h * w, C)
         src_r = ops.round_tf32(self.src)

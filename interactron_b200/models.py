@@ -161,7 +161,8 @@ class _Adaptive(_Base):
         if bb_key != self._bb_key:          # backbone tensors moved: captured conv launches are stale
             self._graphs.clear()
             self._bb_key = bb_key
-        key = (tag, tuple(frames.shape), tuple(masks.shape), self._loop.ops.precision, self._loop.backbone_tf32)
+        key = (tag, tuple(frames.shape), tuple(masks.shape), self._loop.ops.precision, self._loop.backbone_tf32,
+               self._loop.backbone_impl)
         g = self._graphs.get(key)
         if g is None:
             g = self._graphs[key] = GraphedCall(fn, [frames, masks])

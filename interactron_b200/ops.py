@@ -104,7 +104,7 @@ class CudaOps:
         return op, t4
 
     def matmul(self, a, b, *, bias=None, act=None, residual=None, out=None, out_pre=None,
-               alpha=1.0, accumulate=False, epi=None, aux=None, rnd=False):
+               alpha=1.0, accumulate=False, epi=None, aux=None, rnd=False, act_after_residual=False):
         """out = epilogue(alpha * a @ b), a [..,M,K], b [..,K,N]; see itn_gemm_desc_t.
         rnd: store `out` rounded to TF32 (set when `out` only feeds further GEMMs)."""
         rank = max(a.dim(), b.dim(), 2)
@@ -162,6 +162,7 @@ class CudaOps:
         d.accumulate = 1 if accumulate else 0
         d.round_out = 1 if (rnd and self._clean) else 0
         d.precision = PRECISION[self.precision]
+        d.act_pos = 1 if act_after_residual else 0
         if not self.force_simt and self.lib.itn_gemm_tf32_supported(C.byref(d)):
             _lib.check(self.lib.itn_gemm_tf32(C.byref(d), self._stream()))
             self.n_tf32 += 1
@@ -323,6 +324,26 @@ class CudaOps:
                                                 G, n, float(lr), float(clip), self._stream()))
         out_r = out if out_r is None else out_r
         return (out, out_r, mask) if want_mask else (out, out_r)
+
+    def im2col_nhwc(self, x, kh, kw, stride, pad, dil):
+        """x [N,H,W,C] channels-last -> ([N*Ho*Wo, ld] patch matrix, Ho, Wo); ld = kh*kw*C rounded up to 4."""
+        assert x.is_contiguous() and x.dim() == 4
+        N, H, W, Cc = x.shape
+        Ho = (H + 2 * pad - dil * (kh - 1) - 1) // stride + 1
+        Wo = (W + 2 * pad - dil * (kw - 1) - 1) // stride + 1
+        ld = (kh * kw * Cc + 3) // 4 * 4
+        out = self.empty(N * Ho * Wo, ld)
+        _lib.check(self.lib.itn_im2col_nhwc(_ptr(x), _ptr(out), N, H, W, Cc, kh, kw, stride, pad, dil, Ho, Wo, ld,
+                                            self._stream()))
+        return out, Ho, Wo
+
+    def maxpool3x3s2_nhwc(self, x):
+        assert x.is_contiguous() and x.dim() == 4
+        N, H, W, Cc = x.shape
+        Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+        out = self.empty(N, Ho, Wo, Cc)
+        _lib.check(self.lib.itn_maxpool3x3s2_nhwc(_ptr(x), _ptr(out), N, H, W, Cc, Ho, Wo, self._stream()))
+        return out
 
     def pos_embed_sine(self, mask, feats=128):
         """mask [F,h,w] bool/uint8 (1 = padded) -> [F, h*w, 2*feats]."""

@@ -32,13 +32,16 @@ class SimOps:
         return self.calls
 
     def matmul(self, a, b, *, bias=None, act=None, residual=None, out=None, out_pre=None,
-               alpha=1.0, accumulate=False, epi=None, aux=None, rnd=False):
+               alpha=1.0, accumulate=False, epi=None, aux=None, rnd=False, act_after_residual=False):
         self.calls += 1
         v = alpha * torch.matmul(a, b)
         if bias is not None:
             v = v + bias.unsqueeze(-2)
         if out_pre is not None:
             out_pre.copy_(v.reshape(out_pre.shape) if v.numel() == out_pre.numel() else v)
+        late_act = act if act_after_residual else None
+        if act_after_residual:
+            act = None
         if act == "relu":
             v = torch.relu(v)
         elif act == "gelu":
@@ -52,12 +55,15 @@ class SimOps:
             v = v * (cdf + x * pdf)
         if residual is not None:
             v = v + residual
+        if accumulate:
+            v = v + out.reshape(v.shape)
+        if late_act == "relu":
+            v = torch.relu(v)
+        elif late_act == "gelu":
+            v = F.gelu(v)
         if out is None:
             return v.contiguous()
-        if accumulate:
-            out.add_(v.reshape(out.shape) if v.shape != out.shape else v)
-        else:
-            out.copy_(v.reshape(out.shape) if v.shape != out.shape else v)
+        out.copy_(v.reshape(out.shape) if v.shape != out.shape else v)
         return out
 
     def layernorm_fwd(self, x, gamma, beta, eps=1e-5):
@@ -162,6 +168,22 @@ class SimOps:
         if want_mask:
             return out, out, (step.abs() <= clip).to(torch.uint8)
         return out, out
+
+    def im2col_nhwc(self, x, kh, kw, stride, pad, dil):
+        self.calls += 1
+        N, H, W, Cc = x.shape
+        Ho = (H + 2 * pad - dil * (kh - 1) - 1) // stride + 1
+        Wo = (W + 2 * pad - dil * (kw - 1) - 1) // stride + 1
+        cols = F.unfold(x.permute(0, 3, 1, 2), (kh, kw), dilation=dil, padding=pad, stride=stride)  # [N, C*kh*kw, L]
+        cols = cols.view(N, Cc, kh * kw, Ho * Wo).permute(0, 3, 2, 1).reshape(N * Ho * Wo, kh * kw * Cc)
+        ld = (kh * kw * Cc + 3) // 4 * 4
+        out = torch.zeros(N * Ho * Wo, ld, dtype=x.dtype)
+        out[:, :kh * kw * Cc] = cols
+        return out, Ho, Wo
+
+    def maxpool3x3s2_nhwc(self, x):
+        self.calls += 1
+        return F.max_pool2d(x.permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1).contiguous()
 
     def pos_embed_sine(self, mask, feats=128):
         self.calls += 1

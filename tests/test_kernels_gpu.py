@@ -339,3 +339,48 @@ def test_matcher_cost_block_diagonal(ops):
         blk = cost[Q * o: Q * (o + n)].view(Q, n)
         assert (blk - Cfull[f, :, o:o + n]).abs().max().item() < 1e-5
         o += n
+
+
+@pytest.mark.parametrize("geom", [(7, 2, 3, 1, 3, 30), (3, 1, 1, 1, 64, 19), (3, 2, 1, 1, 128, 38),
+                                  (3, 1, 2, 2, 512, 19), (1, 2, 0, 1, 256, 38)])
+def test_im2col_nhwc_matches_unfold(ops3, geom):
+    """k, stride, pad, dilation, channels, size: the conv geometries of the ResNet-50-DC5 trunk."""
+    k, stride, pad, dil, Cc, S = geom
+    gen = torch.Generator(device="cuda").manual_seed(k * 100 + Cc)
+    x = torch.randn(3, S, S, Cc, generator=gen, device="cuda")
+    cols, Ho, Wo = ops3.im2col_nhwc(x, k, k, stride, pad, dil)
+    ref = torch.nn.functional.unfold(x.permute(0, 3, 1, 2), (k, k), dilation=dil, padding=pad, stride=stride)
+    ref = ref.view(3, Cc, k * k, Ho * Wo).permute(0, 3, 2, 1).reshape(3 * Ho * Wo, k * k * Cc)
+    assert cols.shape[1] % 4 == 0 and torch.equal(cols[:, :k * k * Cc], ref)
+    assert cols[:, k * k * Cc:].abs().sum() == 0
+
+
+def test_maxpool_and_conv_as_gemm(ops3):
+    gen = torch.Generator(device="cuda").manual_seed(21)
+    x = torch.randn(2, 37, 37, 64, generator=gen, device="cuda")
+    ref = torch.nn.functional.max_pool2d(x.permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1)
+    assert torch.equal(ops3.maxpool3x3s2_nhwc(x), ref)
+    # 3x3 dilated conv + bias + residual + ReLU-after-residual as one im2col + GEMM
+    w = torch.randn(96, 64, 3, 3, generator=gen, device="cuda") * 0.05
+    b = torch.randn(96, generator=gen, device="cuda")
+    z = torch.randn(2, 37, 37, 96, generator=gen, device="cuda")
+    cols, Ho, Wo = ops3.im2col_nhwc(x, 3, 3, 1, 2, 2)
+    wm = w.permute(0, 2, 3, 1).reshape(96, -1).contiguous()
+    y = ops3.matmul(cols, wm.t(), bias=b, act="relu", residual=z.view(-1, 96), act_after_residual=True)
+    ref = torch.relu(torch.nn.functional.conv2d(x.permute(0, 3, 1, 2).double(), w.double(), b.double(), 1, 2, 2)
+                     .permute(0, 2, 3, 1) + z.double())
+    assert rel(y.view(2, Ho, Wo, 96), ref) < X3_TOL
+
+
+def test_gemm_trunk_matches_cudnn_fp32():
+    """The im2col+GEMM trunk against cuDNN strict-fp32 convolutions on the same folded weights."""
+    import interactron_b200 as ib
+    from interactron_b200.backbone import run_backbone, run_backbone_gemm
+    from interactron_b200.ops import CudaOps
+    m = ib.build_model(ib.default_config("single_frame_baseline", weights="synthetic").MODEL).cuda().eval()
+    body = m.model.backbone[0].body
+    x = torch.randn(3, 3, 300, 300, generator=torch.Generator(device="cuda").manual_seed(2), device="cuda")
+    a = run_backbone_gemm(body, x, CudaOps())
+    b = run_backbone(body, x, tf32=False)
+    assert a.shape == b.shape == (3, 19, 19, 2048)
+    assert rel(a, b) < 2e-5
