@@ -92,9 +92,13 @@ class GemmTrunk:
 
     _key = FoldedTrunk._key
 
-    def _prep(self, conv, bn):
-        """-> dict(w [Cout, ld] with columns (ky, kx, cin) matching im2col, bias, geometry)."""
+    def _prep(self, conv, bn, pad_cin=0):
+        """-> dict(w [Cout, ld] with columns (ky, kx, cin) matching im2col, bias, geometry).
+        pad_cin: zero input channels appended (the RGB stem runs with 4 channels so that the
+        im2col gather moves 16-byte vectors)."""
         w, b = FoldedTrunk._fold(conv, bn)
+        if pad_cin:
+            w = F.pad(w, (0, 0, 0, 0, 0, pad_cin))
         co, ci, kh, kw = w.shape
         k = kh * kw * ci
         ld = (k + 3) // 4 * 4
@@ -110,7 +114,7 @@ class GemmTrunk:
             return
         b = self.body
         with torch.no_grad():
-            stem = self._prep(b.conv1, b.bn1)
+            stem = self._prep(b.conv1, b.bn1, pad_cin=1)
             blocks = []
             for name in ("layer1", "layer2", "layer3", "layer4"):
                 for blk in getattr(b, name):
@@ -137,7 +141,7 @@ class GemmTrunk:
         """frames [N,3,H,W] -> [N,h,w,2048] channels-last features."""
         self.refresh()
         stem, blocks = self.layers
-        x = frames.permute(0, 2, 3, 1).contiguous()
+        x = F.pad(frames.permute(0, 2, 3, 1), (0, 1)).contiguous()      # NHWC, RGB + one zero channel
         x = self._conv(x, stem)
         x = self.ops.maxpool3x3s2_nhwc(x)
         for blk in blocks:

@@ -101,19 +101,25 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   return v;
 }
 
+// Which operand of the general epilogue is streamed through the register prefetch pipeline.
+enum { XS_NONE = 0, XS_AUX = 1, XS_RESIDUAL = 2, XS_CIN = 3 };
+
 // Writes one transposed 32x32 accumulator chunk (st[r*33 + lane] = row r, this lane's column)
-// to global memory with the fused epilogue.  Lean on purpose: pointers are advanced by the row
-// stride instead of being recomputed, and the common case (no aux / residual / accumulate /
-// second output) has no loads at all; the general case issues the loads of 8 rows together.
+// to global memory with the fused epilogue.  Lean on purpose: pointers advance by the row
+// stride; the common case (no aux / residual / accumulate / second output) has no loads at
+// all; in the general case the ONE streamed operand (aux, residual or the accumulate input)
+// arrives in registers `xs`, prefetched a whole chunk ahead by the caller, so its HBM/L2
+// latency overlaps the TMEM read-out and the math of the previous chunk.  A second streamed
+// operand (rare) is loaded in place.
 __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, const EpiPtrs& e,
                                                const float* st, int lane, int row_base, int rmax,
-                                               int col) {
+                                               int col, const float (&xs)[32], int xmode) {
   const float bias_v = e.bias ? e.bias[col] : 0.0f;
   float* cp = e.C + (long long)row_base * p.ldc + col;
   const float alpha = p.alpha;
   const int act = p.act;
   const bool rnd = p.round_out != 0;
-  const bool simple = !e.aux && !e.residual && !e.C2 && !p.accumulate;
+  const bool simple = xmode == XS_NONE && !e.C2;
   if (simple) {
     // act / rounding are hoisted out of the row loops (warp-uniform), rows fully unrolled
     if (act == ITN_ACT_GELU) {
@@ -137,36 +143,29 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, const EpiPt
     }
     return;
   }
-  const float* ap = e.aux ? e.aux + (long long)row_base * p.ldaux + col : nullptr;
-  const float* rp = e.residual ? e.residual + (long long)row_base * p.ldr + col : nullptr;
+  // operands that are NOT the prefetched stream are read in place (rare)
+  const float* ap = (e.aux && xmode != XS_AUX) ? e.aux + (long long)row_base * p.ldaux + col : nullptr;
+  const float* rp = (e.residual && xmode != XS_RESIDUAL) ? e.residual + (long long)row_base * p.ldr + col : nullptr;
+  const bool acc_inplace = p.accumulate != 0 && xmode != XS_CIN;
   float* c2p = e.C2 ? e.C2 + (long long)row_base * p.ldc2 + col : nullptr;
-  const bool acc = p.accumulate != 0;
   const bool act_late = p.act_pos == 1;
   const int epi = p.epi;
-  for (int r0 = 0; r0 < rmax; r0 += 8) {
-    float av[8], xv[8], rv[8], cv[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int r = r0 + i;
-      const bool ok = r < rmax;
-      av[i] = st[r * 33 + lane];
-      xv[i] = (ok && ap) ? ap[(long long)r * p.ldaux] : 0.0f;
-      rv[i] = (ok && rp) ? rp[(long long)r * p.ldr] : 0.0f;
-      cv[i] = (ok && acc) ? cp[(long long)r * p.ldc] : 0.0f;
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int r = r0 + i;
-      if (r < rmax) {
-        float v = fmaf(alpha, av[i], bias_v);
-        if (c2p) c2p[(long long)r * p.ldc2] = v;
-        if (!act_late) v = apply_act(v, act);
-        if (epi == ITN_EPI_RELU_MASK) v = xv[i] > 0.0f ? v : 0.0f;
-        else if (epi == ITN_EPI_GELU_GRAD) v *= gelu_erf_grad(xv[i]);
-        v += rv[i] + cv[i];
-        if (act_late) v = apply_act(v, act);
-        cp[(long long)r * p.ldc] = rnd ? rn_tf32(v) : v;
+  for (int r = 0; r < 32; ++r) {
+    if (r < rmax) {
+      float v = fmaf(alpha, st[r * 33 + lane], bias_v);
+      if (c2p) c2p[(long long)r * p.ldc2] = v;
+      if (!act_late) v = apply_act(v, act);
+      if (epi != ITN_EPI_NONE) {
+        const float a = xmode == XS_AUX ? xs[r] : ap[(long long)r * p.ldaux];
+        if (epi == ITN_EPI_RELU_MASK) v = a > 0.0f ? v : 0.0f;
+        else v *= gelu_erf_grad(a);
       }
+      if (xmode == XS_RESIDUAL || xmode == XS_CIN) v += xs[r];
+      if (rp) v += rp[(long long)r * p.ldr];
+      if (acc_inplace) v += cp[(long long)r * p.ldc];
+      if (act_late) v = apply_act(v, act);
+      cp[(long long)r * p.ldc] = rnd ? rn_tf32(v) : v;
     }
   }
 }
@@ -359,12 +358,29 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int n0 = nb * BN;
       const int row_base = mb * kBM + lg * 32;
       const EpiPtrs e = make_epi_ptrs(p, z / p.nb1, z % p.nb1);
-      mbar_wait(&tfull_bar[acc], acc_ph);
-      tc_fence_after();
-      const uint32_t tacc = tmem_base + acc * Cfg::kAccCols + (static_cast<uint32_t>(lg * 32) << 16);
       const int rmax = min(32, p.M - row_base);       // <= 0: this warp's rows are all padding
       constexpr int kChunks = BN / 32;
       const int nchunks = min(kChunks, (p.N - n0 + 31) / 32);   // live 32-column chunks (>= 1)
+      // the streamed epilogue operand (at most one is pipelined through registers)
+      const float* xsp = nullptr;
+      long long ldx = 0;
+      int xmode = XS_NONE;
+      if (e.aux) { xsp = e.aux; ldx = p.ldaux; xmode = XS_AUX; }
+      else if (e.residual) { xsp = e.residual; ldx = p.ldr; xmode = XS_RESIDUAL; }
+      else if (p.accumulate) { xsp = e.C; ldx = p.ldc; xmode = XS_CIN; }
+      float cur[32], nxt[32];
+      auto prefetch = [&](float (&buf)[32], int c) {
+        const int col = n0 + c * 32 + lane;
+        const bool ok = col < p.N;
+        const float* src = xsp + (long long)row_base * ldx + col;
+#pragma unroll
+        for (int r = 0; r < 32; ++r) buf[r] = (ok && r < rmax) ? src[(long long)r * ldx] : 0.0f;
+      };
+      // chunk 0 of the stream is fetched while the tensor core is still working on this tile
+      if (xsp && rmax > 0) prefetch(cur, 0);
+      mbar_wait(&tfull_bar[acc], acc_ph);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + acc * Cfg::kAccCols + (static_cast<uint32_t>(lg * 32) << 16);
       if (rmax <= 0) {
         // nothing to store: hand the accumulator straight back to the issuer
         tc_fence_before();
@@ -374,6 +390,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll 1
       for (int c = 0; c < nchunks && rmax > 0; ++c) {
         const int col0 = n0 + c * 32;
+        if (xsp && c + 1 < nchunks) prefetch(nxt, c + 1);
         {
           uint32_t v[32];
           tmem_ld_32x32(tacc + c * 32, v);
@@ -389,8 +406,12 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         __syncwarp();
         const int col = col0 + lane;
-        if (col < p.N) epilogue_chunk(p, e, st, lane, row_base, rmax, col);
+        if (col < p.N) epilogue_chunk(p, e, st, lane, row_base, rmax, col, cur, xmode);
         __syncwarp();
+        if (xsp) {
+#pragma unroll
+          for (int r = 0; r < 32; ++r) cur[r] = nxt[r];
+        }
       }
       acc ^= 1;
       if (acc == 0) acc_ph ^= 1;

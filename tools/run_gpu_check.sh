@@ -1,10 +1,8 @@
 set -x
-timeout 900 python -m pytest tests -q -m gpu --timeout 600 -x > gpurun_out/pytest_gpu.log 2>&1
+timeout 900 python -m pytest tests -q -m gpu --timeout 600 > gpurun_out/pytest_gpu.log 2>&1
 tail -4 gpurun_out/pytest_gpu.log
 timeout 900 python bench.py --steps 10 --warmup 3 --cpu-episodes 0 > gpurun_out/bench_e8.log 2>&1
 tail -1 gpurun_out/bench_e8.log | cut -c1-300
-ITN_BACKBONE=cudnn timeout 900 python bench.py --steps 10 --warmup 3 --cpu-episodes 0 > gpurun_out/bench_e8_cudnn.log 2>&1
-tail -1 gpurun_out/bench_e8_cudnn.log | cut -c1-300
 timeout 900 python bench.py --steps 6 --warmup 3 --cpu-episodes 0 --episodes 32 > gpurun_out/bench_e32.log 2>&1
 tail -1 gpurun_out/bench_e32.log | cut -c1-300
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_e8.csv python tools/profile_step.py 8 interactron_random 2 > gpurun_out/profile_step.log 2>&1
