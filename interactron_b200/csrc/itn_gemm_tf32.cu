@@ -51,6 +51,7 @@ struct GemmKParams {
   float* C2;             long long ldc2,  c2_sb0,   c2_sb1;
   float alpha;
   int act, epi, accumulate, round_out, act_pos;
+  int variant;   // epilogue_variant(...)
 };
 
 // Per-batch-entry epilogue pointers.
@@ -101,73 +102,110 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   return v;
 }
 
-// Which operand of the general epilogue is streamed through the register prefetch pipeline.
+// Which operand of the general epilogue is streamed through the register prefetch.
 enum { XS_NONE = 0, XS_AUX = 1, XS_RESIDUAL = 2, XS_CIN = 3 };
 
-// Writes one transposed 32x32 accumulator chunk (st[r*33 + lane] = row r, this lane's column)
-// to global memory with the fused epilogue.  Lean on purpose: pointers advance by the row
-// stride; the common case (no aux / residual / accumulate / second output) has no loads at
-// all; in the general case the ONE streamed operand (aux, residual or the accumulate input)
-// arrives in registers `xs`, prefetched a whole chunk ahead by the caller, so its HBM/L2
-// latency overlaps the TMEM read-out and the math of the previous chunk.  A second streamed
-// operand (rare) is loaded in place.
-__device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, const EpiPtrs& e,
-                                               const float* st, int lane, int row_base, int rmax,
-                                               int col, const float (&xs)[32], int xmode) {
+// Epilogue variants.  Every fused combination the path uses gets its own branch-free,
+// compile-time specialised row loop (a single generic loop with run-time flags measured 6-7x
+// slower: the 32-row unrolled body with a dozen warp-uniform branches per element thrashes the
+// instruction cache).  EV_GENERIC keeps the full contract for anything else.
+enum {
+  EV_SIMPLE = 0,        // bias + {none, relu, gelu}
+  EV_RESIDUAL,          // + residual
+  EV_RESIDUAL_RELU,     // relu(bias + acc + residual)            (ResNet bottleneck output)
+  EV_ACCUMULATE,        // C += acc                               (gradient accumulation)
+  EV_RELU_MASK,         // acc * (aux > 0)                        (d ReLU)
+  EV_GELU_GRAD,         // acc * gelu'(aux)                       (d GELU)
+  EV_PRE,               // C = C2 = bias + acc                    (rounded + full copies)
+  EV_PRE_GELU,          // C2 = bias + acc, C = gelu(C2)
+  EV_GENERIC
+};
+
+__host__ __device__ inline int epilogue_variant(bool aux, bool residual, bool c2, int act, int epi,
+                                                int accumulate, int act_pos) {
+  const int extras = (aux ? 1 : 0) + (residual ? 1 : 0) + (accumulate ? 1 : 0);
+  if (extras == 0 && !c2) return EV_SIMPLE;
+  if (extras == 0 && c2 && epi == ITN_EPI_NONE) {
+    if (act == ITN_ACT_NONE) return EV_PRE;
+    if (act == ITN_ACT_GELU && act_pos == 0) return EV_PRE_GELU;
+    return EV_GENERIC;
+  }
+  if (c2 || extras != 1) return EV_GENERIC;
+  if (residual && epi == ITN_EPI_NONE) {
+    if (act == ITN_ACT_NONE) return EV_RESIDUAL;
+    if (act == ITN_ACT_RELU && act_pos == 1) return EV_RESIDUAL_RELU;
+    return EV_GENERIC;
+  }
+  if (accumulate && epi == ITN_EPI_NONE && act == ITN_ACT_NONE) return EV_ACCUMULATE;
+  if (aux && act == ITN_ACT_NONE) {
+    if (epi == ITN_EPI_RELU_MASK) return EV_RELU_MASK;
+    if (epi == ITN_EPI_GELU_GRAD) return EV_GELU_GRAD;
+  }
+  return EV_GENERIC;
+}
+
+// One transposed 32x32 accumulator chunk (st[r*33 + lane] = row r, this lane's column) -> global
+// memory.  `xs` holds the streamed operand of this chunk (prefetched by the caller).
+template <int EV>
+__device__ __forceinline__ void epilogue_rows(const GemmKParams& p, const EpiPtrs& e, const float* st,
+                                              int lane, int row_base, int rmax, int col,
+                                              const float (&xs)[32]) {
+  const float bias_v = e.bias ? e.bias[col] : 0.0f;
+  const float alpha = p.alpha;
+  const bool rnd = p.round_out != 0;
+  float* cp = e.C + (long long)row_base * p.ldc + col;
+  float* c2p = (EV == EV_PRE || EV == EV_PRE_GELU) ? e.C2 + (long long)row_base * p.ldc2 + col : nullptr;
+#pragma unroll
+  for (int r = 0; r < 32; ++r) {
+    if (r < rmax) {
+      float v = fmaf(alpha, st[r * 33 + lane], bias_v);
+      if (EV == EV_PRE || EV == EV_PRE_GELU) c2p[(long long)r * p.ldc2] = v;
+      if (EV == EV_PRE_GELU) v = gelu_erf(v);
+      if (EV == EV_RESIDUAL || EV == EV_RESIDUAL_RELU || EV == EV_ACCUMULATE) v += xs[r];
+      if (EV == EV_RESIDUAL_RELU) v = fmaxf(v, 0.0f);
+      if (EV == EV_RELU_MASK) v = xs[r] > 0.0f ? v : 0.0f;
+      if (EV == EV_GELU_GRAD) v *= gelu_erf_grad(xs[r]);
+      cp[(long long)r * p.ldc] = rnd ? rn_tf32(v) : v;
+    }
+  }
+}
+
+__device__ __forceinline__ void epilogue_simple(const GemmKParams& p, const EpiPtrs& e, const float* st,
+                                                int lane, int row_base, int rmax, int col) {
   const float bias_v = e.bias ? e.bias[col] : 0.0f;
   float* cp = e.C + (long long)row_base * p.ldc + col;
   const float alpha = p.alpha;
   const int act = p.act;
   const bool rnd = p.round_out != 0;
-  const bool simple = xmode == XS_NONE && !e.C2;
-  if (simple) {
-    // act / rounding are hoisted out of the row loops (warp-uniform), rows fully unrolled
-    if (act == ITN_ACT_GELU) {
+  // act / rounding are hoisted out of the row loops (warp-uniform)
+  if (act == ITN_ACT_GELU) {
 #pragma unroll 4
-      for (int r = 0; r < rmax; ++r) {
-        const float v = gelu_erf(fmaf(alpha, st[r * 33 + lane], bias_v));
-        cp[(long long)r * p.ldc] = rnd ? rn_tf32(v) : v;
-      }
-    } else if (rmax == 32 && !rnd) {
-      const float lo = act == ITN_ACT_RELU ? 0.0f : -INFINITY;
-#pragma unroll
-      for (int r = 0; r < 32; ++r)
-        cp[(long long)r * p.ldc] = fmaxf(fmaf(alpha, st[r * 33 + lane], bias_v), lo);
-    } else {
-      const float lo = act == ITN_ACT_RELU ? 0.0f : -INFINITY;
-#pragma unroll 4
-      for (int r = 0; r < rmax; ++r) {
-        const float v = fmaxf(fmaf(alpha, st[r * 33 + lane], bias_v), lo);
-        cp[(long long)r * p.ldc] = rnd ? rn_tf32(v) : v;
-      }
+    for (int r = 0; r < rmax; ++r) {
+      const float v = gelu_erf(fmaf(alpha, st[r * 33 + lane], bias_v));
+      cp[(long long)r * p.ldc] = rnd ? rn_tf32(v) : v;
     }
-    return;
-  }
-  // operands that are NOT the prefetched stream are read in place (rare)
-  const float* ap = (e.aux && xmode != XS_AUX) ? e.aux + (long long)row_base * p.ldaux + col : nullptr;
-  const float* rp = (e.residual && xmode != XS_RESIDUAL) ? e.residual + (long long)row_base * p.ldr + col : nullptr;
-  const bool acc_inplace = p.accumulate != 0 && xmode != XS_CIN;
-  float* c2p = e.C2 ? e.C2 + (long long)row_base * p.ldc2 + col : nullptr;
-  const bool act_late = p.act_pos == 1;
-  const int epi = p.epi;
+  } else if (rmax == 32 && !rnd) {
+    const float lo = act == ITN_ACT_RELU ? 0.0f : -INFINITY;
 #pragma unroll
-  for (int r = 0; r < 32; ++r) {
-    if (r < rmax) {
-      float v = fmaf(alpha, st[r * 33 + lane], bias_v);
-      if (c2p) c2p[(long long)r * p.ldc2] = v;
-      if (!act_late) v = apply_act(v, act);
-      if (epi != ITN_EPI_NONE) {
-        const float a = xmode == XS_AUX ? xs[r] : ap[(long long)r * p.ldaux];
-        if (epi == ITN_EPI_RELU_MASK) v = a > 0.0f ? v : 0.0f;
-        else v *= gelu_erf_grad(a);
-      }
-      if (xmode == XS_RESIDUAL || xmode == XS_CIN) v += xs[r];
-      if (rp) v += rp[(long long)r * p.ldr];
-      if (acc_inplace) v += cp[(long long)r * p.ldc];
-      if (act_late) v = apply_act(v, act);
+    for (int r = 0; r < 32; ++r)
+      cp[(long long)r * p.ldc] = fmaxf(fmaf(alpha, st[r * 33 + lane], bias_v), lo);
+  } else {
+    const float lo = act == ITN_ACT_RELU ? 0.0f : -INFINITY;
+#pragma unroll 4
+    for (int r = 0; r < rmax; ++r) {
+      const float v = fmaxf(fmaf(alpha, st[r * 33 + lane], bias_v), lo);
       cp[(long long)r * p.ldc] = rnd ? rn_tf32(v) : v;
     }
   }
+}
+
+// Full contract with run-time flags; compact (not unrolled) on purpose.  Rarely taken.
+__device__ __noinline__ void epilogue_generic(const GemmKParams& p, const EpiPtrs& e, const float* st,
+                                              int lane, int row_base, int rmax, int col) {
+  const float bias_v = e.bias ? e.bias[col] : 0.0f;
+#pragma unroll 1
+  for (int r = 0; r < rmax; ++r)
+    epilogue_store(p, e, row_base + r, col, st[r * 33 + lane], bias_v);
 }
 
 template <int BN, bool X3>
@@ -361,23 +399,23 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int rmax = min(32, p.M - row_base);       // <= 0: this warp's rows are all padding
       constexpr int kChunks = BN / 32;
       const int nchunks = min(kChunks, (p.N - n0 + 31) / 32);   // live 32-column chunks (>= 1)
-      // the streamed epilogue operand (at most one is pipelined through registers)
+      // the streamed epilogue operand of the specialised variants (prefetched into registers)
+      const int ev = p.variant;
       const float* xsp = nullptr;
       long long ldx = 0;
-      int xmode = XS_NONE;
-      if (e.aux) { xsp = e.aux; ldx = p.ldaux; xmode = XS_AUX; }
-      else if (e.residual) { xsp = e.residual; ldx = p.ldr; xmode = XS_RESIDUAL; }
-      else if (p.accumulate) { xsp = e.C; ldx = p.ldc; xmode = XS_CIN; }
-      float cur[32], nxt[32];
-      auto prefetch = [&](float (&buf)[32], int c) {
+      if (ev == EV_RELU_MASK || ev == EV_GELU_GRAD) { xsp = e.aux; ldx = p.ldaux; }
+      else if (ev == EV_RESIDUAL || ev == EV_RESIDUAL_RELU) { xsp = e.residual; ldx = p.ldr; }
+      else if (ev == EV_ACCUMULATE) { xsp = e.C; ldx = p.ldc; }
+      float xs[32];
+      auto prefetch = [&](int c) {
         const int col = n0 + c * 32 + lane;
         const bool ok = col < p.N;
         const float* src = xsp + (long long)row_base * ldx + col;
 #pragma unroll
-        for (int r = 0; r < 32; ++r) buf[r] = (ok && r < rmax) ? src[(long long)r * ldx] : 0.0f;
+        for (int r = 0; r < 32; ++r) xs[r] = (ok && r < rmax) ? src[(long long)r * ldx] : 0.0f;
       };
       // chunk 0 of the stream is fetched while the tensor core is still working on this tile
-      if (xsp && rmax > 0) prefetch(cur, 0);
+      if (xsp && rmax > 0) prefetch(0);
       mbar_wait(&tfull_bar[acc], acc_ph);
       tc_fence_after();
       const uint32_t tacc = tmem_base + acc * Cfg::kAccCols + (static_cast<uint32_t>(lg * 32) << 16);
@@ -390,7 +428,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll 1
       for (int c = 0; c < nchunks && rmax > 0; ++c) {
         const int col0 = n0 + c * 32;
-        if (xsp && c + 1 < nchunks) prefetch(nxt, c + 1);
+        if (xsp && c > 0) prefetch(c);      // latency overlaps the TMEM read-out + transpose below
         {
           uint32_t v[32];
           tmem_ld_32x32(tacc + c * 32, v);
@@ -406,12 +444,20 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         __syncwarp();
         const int col = col0 + lane;
-        if (col < p.N) epilogue_chunk(p, e, st, lane, row_base, rmax, col, cur, xmode);
-        __syncwarp();
-        if (xsp) {
-#pragma unroll
-          for (int r = 0; r < 32; ++r) cur[r] = nxt[r];
+        if (col < p.N) {
+          switch (ev) {
+            case EV_SIMPLE: epilogue_simple(p, e, st, lane, row_base, rmax, col); break;
+            case EV_RESIDUAL: epilogue_rows<EV_RESIDUAL>(p, e, st, lane, row_base, rmax, col, xs); break;
+            case EV_RESIDUAL_RELU: epilogue_rows<EV_RESIDUAL_RELU>(p, e, st, lane, row_base, rmax, col, xs); break;
+            case EV_ACCUMULATE: epilogue_rows<EV_ACCUMULATE>(p, e, st, lane, row_base, rmax, col, xs); break;
+            case EV_RELU_MASK: epilogue_rows<EV_RELU_MASK>(p, e, st, lane, row_base, rmax, col, xs); break;
+            case EV_GELU_GRAD: epilogue_rows<EV_GELU_GRAD>(p, e, st, lane, row_base, rmax, col, xs); break;
+            case EV_PRE: epilogue_rows<EV_PRE>(p, e, st, lane, row_base, rmax, col, xs); break;
+            case EV_PRE_GELU: epilogue_rows<EV_PRE_GELU>(p, e, st, lane, row_base, rmax, col, xs); break;
+            default: epilogue_generic(p, e, st, lane, row_base, rmax, col); break;
+          }
         }
+        __syncwarp();
       }
       acc ^= 1;
       if (acc == 0) acc_ph ^= 1;
@@ -542,6 +588,8 @@ static void fill_kparams(GemmKParams& p, const itn_gemm_desc_t* d) {
   p.alpha = d->alpha; p.act = d->act; p.epi = d->epi; p.accumulate = d->accumulate;
   p.round_out = d->round_out;
   p.act_pos = d->act_pos;
+  p.variant = epilogue_variant(d->aux != nullptr, d->residual != nullptr, d->C2 != nullptr, d->act, d->epi,
+                               d->accumulate, d->act_pos);
 }
 
 static int validate(const itn_gemm_desc_t* d) {

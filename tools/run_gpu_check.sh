@@ -1,4 +1,5 @@
 set -x
+python tools/gemm_epi_bench.py 225000 256 64 2>&1 | head -10
 timeout 900 python -m pytest tests -q -m gpu --timeout 600 > gpurun_out/pytest_gpu.log 2>&1
 tail -4 gpurun_out/pytest_gpu.log
 timeout 900 python bench.py --steps 10 --warmup 3 --cpu-episodes 0 > gpurun_out/bench_e8.log 2>&1
