@@ -35,6 +35,18 @@
 
 namespace itn {
 
+// Optional in-kernel timeline (debug builds only: `make trace`): CTA 0 stamps clock64() at the
+// hand-off points of every role so pipeline bubbles can be read off directly.
+#ifdef ITN_TRACE
+__device__ long long* g_trace = nullptr;
+#define ITN_TRACE_AT(slot, idx)                                                        \
+  do {                                                                                 \
+    if (blockIdx.x == 0 && g_trace != nullptr && (idx) < 1024) g_trace[(slot) * 1024 + (idx)] = clock64(); \
+  } while (0)
+#else
+#define ITN_TRACE_AT(slot, idx) do { } while (0)
+#endif
+
 constexpr int kBM = 128;
 constexpr int kBK = 32;                    // floats per k-block = 128 B swizzle row
 constexpr int kAtomBytes = 32 * kBK * 4;   // one 32(mn) x 32(k) MN-major box = 4096 B
@@ -52,6 +64,8 @@ struct GemmKParams {
   float alpha;
   int act, epi, accumulate, round_out, act_pos;
   int variant;   // epilogue_variant(...)
+  int vec;       // 1: 128-bit epilogue path is legal (alignment / N % 4 checked on the host)
+  int dbg;       // ITN_TRACE builds only: 1 = skip global stores, 2 = skip TMEM read, 4 = skip smem transpose
 };
 
 // Per-batch-entry epilogue pointers.
@@ -146,27 +160,30 @@ __host__ __device__ inline int epilogue_variant(bool aux, bool residual, bool c2
 
 // One transposed 32x32 accumulator chunk (st[r*33 + lane] = row r, this lane's column) -> global
 // memory.  `xs` holds the streamed operand of this chunk (prefetched by the caller).
+// Scalar (32-bit) variants for outputs whose rows are not 16-byte aligned or N % 4 != 0 (e.g. the
+// attention score matrices): compact loops, the streamed operand is read in place.
 template <int EV>
 __device__ __forceinline__ void epilogue_rows(const GemmKParams& p, const EpiPtrs& e, const float* st,
                                               int lane, int row_base, int rmax, int col,
-                                              const float (&xs)[32]) {
+                                              const float* xsp, long long ldx) {
   const float bias_v = e.bias ? e.bias[col] : 0.0f;
   const float alpha = p.alpha;
   const bool rnd = p.round_out != 0;
-  float* cp = e.C + (long long)row_base * p.ldc + col;
-  float* c2p = (EV == EV_PRE || EV == EV_PRE_GELU) ? e.C2 + (long long)row_base * p.ldc2 + col : nullptr;
-#pragma unroll
-  for (int r = 0; r < 32; ++r) {
-    if (r < rmax) {
-      float v = fmaf(alpha, st[r * 33 + lane], bias_v);
-      if (EV == EV_PRE || EV == EV_PRE_GELU) c2p[(long long)r * p.ldc2] = v;
-      if (EV == EV_PRE_GELU) v = gelu_erf(v);
-      if (EV == EV_RESIDUAL || EV == EV_RESIDUAL_RELU || EV == EV_ACCUMULATE) v += xs[r];
-      if (EV == EV_RESIDUAL_RELU) v = fmaxf(v, 0.0f);
-      if (EV == EV_RELU_MASK) v = xs[r] > 0.0f ? v : 0.0f;
-      if (EV == EV_GELU_GRAD) v *= gelu_erf_grad(xs[r]);
-      cp[(long long)r * p.ldc] = rnd ? rn_tf32(v) : v;
-    }
+  const long long ldc = p.ldc, ldc2 = p.ldc2;
+  float* cp = e.C + (long long)row_base * ldc + col;
+  float* c2p = (EV == EV_PRE || EV == EV_PRE_GELU) ? e.C2 + (long long)row_base * ldc2 + col : nullptr;
+  const float* xp = xsp ? xsp + (long long)row_base * ldx + col : nullptr;
+  const float* sp = st + lane;
+#pragma unroll 4
+  for (int r = 0; r < rmax; ++r) {
+    float v = fmaf(alpha, sp[r * 33], bias_v);
+    if (EV == EV_PRE || EV == EV_PRE_GELU) c2p[r * ldc2] = v;
+    if (EV == EV_PRE_GELU) v = gelu_erf(v);
+    if (EV == EV_RESIDUAL || EV == EV_RESIDUAL_RELU || EV == EV_ACCUMULATE) v += xp[r * ldx];
+    if (EV == EV_RESIDUAL_RELU) v = fmaxf(v, 0.0f);
+    if (EV == EV_RELU_MASK) v = xp[r * ldx] > 0.0f ? v : 0.0f;
+    if (EV == EV_GELU_GRAD) v *= gelu_erf_grad(xp[r * ldx]);
+    cp[r * ldc] = rnd ? rn_tf32(v) : v;
   }
 }
 
@@ -199,8 +216,72 @@ __device__ __forceinline__ void epilogue_simple(const GemmKParams& p, const EpiP
   }
 }
 
+// ---- 128-bit variants.  Staging pitch 36 floats: thread t stores its accumulator row t as 8 float4
+// (conflict-free per quarter-warp), then lane (q = lane/8, c = lane%8) owns columns 4c..4c+3 of rows
+// 4i+q: every warp-wide global access covers 4 rows x 128 contiguous bytes.  Needs 16-byte aligned
+// rows (ld % 4 == 0) and N % 4 == 0 for C and the streamed operand (GemmKParams::vec).
+__device__ __forceinline__ float4 f4_fma(float a, float4 x, float4 b) {
+  return make_float4(fmaf(a, x.x, b.x), fmaf(a, x.y, b.y), fmaf(a, x.z, b.z), fmaf(a, x.w, b.w));
+}
+__device__ __forceinline__ float4 f4_add(float4 a, float4 b) {
+  return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+}
+__device__ __forceinline__ float4 f4_max(float4 a, float lo) {
+  return make_float4(fmaxf(a.x, lo), fmaxf(a.y, lo), fmaxf(a.z, lo), fmaxf(a.w, lo));
+}
+__device__ __forceinline__ float4 f4_rnd(float4 a) {
+  return make_float4(rn_tf32(a.x), rn_tf32(a.y), rn_tf32(a.z), rn_tf32(a.w));
+}
+
+template <int EV, bool FULL, bool RND>
+__device__ __forceinline__ void epilogue_rows_v4(const GemmKParams& p, const EpiPtrs& e, const float4* st4,
+                                                 int lane, int row_base, int rmax, int col,
+                                                 const float4 (&xs)[8]) {
+  const int q = lane >> 3, c = lane & 7;
+  const float4 bias_v = e.bias ? *reinterpret_cast<const float4*>(e.bias + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float alpha = p.alpha;
+  const int act = p.act;
+  const float lo = (EV == EV_SIMPLE && act == ITN_ACT_RELU) ? 0.0f : -INFINITY;
+  const bool gelu = EV == EV_PRE_GELU || (EV == EV_SIMPLE && act == ITN_ACT_GELU);
+  const long long step = 4 * p.ldc, step2 = 4 * p.ldc2;
+  float* cp = e.C + (long long)(row_base + q) * p.ldc + col;
+#ifdef ITN_TRACE
+  // dbg 8: same instruction stream, but every chunk overwrites one L2-resident 16 KB window per CTA
+  if (p.dbg & 8) cp = e.C + (long long)(blockIdx.x * 128 + (row_base & 127) + q) * p.ldc + (col & 31);
+#endif
+  float* c2p = (EV == EV_PRE || EV == EV_PRE_GELU) ? e.C2 + (long long)(row_base + q) * p.ldc2 + col : nullptr;
+  const float4* sp = st4 + q * 9 + c;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (FULL || 4 * i + q < rmax) {
+      float4 v = f4_fma(alpha, sp[i * 36], bias_v);
+      if (EV == EV_PRE || EV == EV_PRE_GELU) *reinterpret_cast<float4*>(c2p + i * step2) = v;
+      if (gelu) v = make_float4(gelu_erf(v.x), gelu_erf(v.y), gelu_erf(v.z), gelu_erf(v.w));
+      if (EV == EV_SIMPLE) v = f4_max(v, lo);
+      if (EV == EV_RESIDUAL || EV == EV_RESIDUAL_RELU || EV == EV_ACCUMULATE) v = f4_add(v, xs[i]);
+      if (EV == EV_RESIDUAL_RELU) v = f4_max(v, 0.0f);
+      if (EV == EV_RELU_MASK)
+        v = make_float4(xs[i].x > 0.f ? v.x : 0.f, xs[i].y > 0.f ? v.y : 0.f, xs[i].z > 0.f ? v.z : 0.f,
+                        xs[i].w > 0.f ? v.w : 0.f);
+      if (EV == EV_GELU_GRAD)
+        v = make_float4(v.x * gelu_erf_grad(xs[i].x), v.y * gelu_erf_grad(xs[i].y),
+                        v.z * gelu_erf_grad(xs[i].z), v.w * gelu_erf_grad(xs[i].w));
+      *reinterpret_cast<float4*>(cp + i * step) = RND ? f4_rnd(v) : v;
+    }
+  }
+}
+
+// warp-uniform dispatch on (full row block, rounding) so the common case has no per-row predicates
+template <int EV>
+__device__ __forceinline__ void epilogue_v4(const GemmKParams& p, const EpiPtrs& e, const float4* st4, int lane,
+                                            int row_base, int rmax, int col, const float4 (&xs)[8]) {
+  if (p.round_out) epilogue_rows_v4<EV, false, true>(p, e, st4, lane, row_base, rmax, col, xs);
+  else if (rmax == 32) epilogue_rows_v4<EV, true, false>(p, e, st4, lane, row_base, rmax, col, xs);
+  else epilogue_rows_v4<EV, false, false>(p, e, st4, lane, row_base, rmax, col, xs);
+}
+
 // Full contract with run-time flags; compact (not unrolled) on purpose.  Rarely taken.
-__device__ __noinline__ void epilogue_generic(const GemmKParams& p, const EpiPtrs& e, const float* st,
+__device__ __forceinline__ void epilogue_generic(const GemmKParams& p, const EpiPtrs& e, const float* st,
                                               int lane, int row_base, int rmax, int col) {
   const float bias_v = e.bias ? e.bias[col] : 0.0f;
 #pragma unroll 1
@@ -214,7 +295,7 @@ struct TileCfg {
   static constexpr int kBBytes = BN * kBK * 4;
   static constexpr int kRawBytes = kABytes + kBBytes;          // what TMA delivers per stage
   static constexpr int kStageBytes = X3 ? 2 * kRawBytes : kRawBytes;   // + residual (lo) tiles
-  static constexpr int kStagingBytes = 4 * 32 * 33 * 4;        // per-warp transpose buffers
+  static constexpr int kStagingBytes = 4 * 32 * 36 * 4;        // per-warp transpose buffers (pitch 36)
   static constexpr int kBudget = 227 * 1024 - kStagingBytes - 1024 - 512;
   static constexpr int kMaxStages = kBudget / kStageBytes;
   static constexpr int kStages = kMaxStages > 8 ? 8 : kMaxStages;
@@ -231,14 +312,17 @@ struct TileCfg {
 template <int BN, bool A_MN, bool B_MN, bool X3>
 __global__ void __launch_bounds__(TileCfg<BN, X3>::kThreads, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const GemmKParams p) {
+                 const __grid_constant__ GemmKParams p) {
+  // p is __grid_constant__: it is read straight from the constant bank even where its address is
+  // taken (a by-value copy lands on the local-memory stack and turns every p.ld* into an LDL).
   using Cfg = TileCfg<BN, X3>;
   constexpr int STAGES = Cfg::kStages;
 
   extern __shared__ uint8_t smem_raw[];
-  // 128-byte swizzle atoms need 1024-byte aligned tiles.
-  uint8_t* smem = reinterpret_cast<uint8_t*>(
-      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  // 128-byte swizzle atoms need 1024-byte aligned tiles.  The alignment is applied as an OFFSET
+  // on the __shared__ array so the compiler keeps the shared address space (rounding through
+  // uintptr_t turns every staging / splitter access into a generic LD/ST: measured 4x slower).
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   float* staging = reinterpret_cast<float*>(smem + STAGES * Cfg::kStageBytes);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes + Cfg::kStagingBytes);
   uint64_t* split_bar = full_bar + STAGES;
@@ -276,6 +360,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
+      int gk = 0;   // running k-block counter (trace index)
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const int nb = tile % p.tiles_n;
         const int t2 = tile / p.tiles_n;
@@ -285,8 +370,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int m0 = mb * kBM, n0 = nb * BN;
         const int a_c0 = b0 * p.a_m0, a_c1 = b1 * p.a_m1;
         const int b_c0 = b0 * p.b_m0, b_c1 = b1 * p.b_m1;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = 0; kb < num_kb; ++kb, ++gk) {
           mbar_wait(&empty_bar[s], ph ^ 1);
+          ITN_TRACE_AT(0, gk);
           mbar_expect_tx(&full_bar[s], Cfg::kRawBytes);
           uint8_t* sa = smem + s * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
@@ -317,12 +403,15 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t ph = 0;
       int acc = 0;
       uint32_t acc_ph = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      int gk = 0, gt = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++gt) {
         mbar_wait(&tempty_bar[acc], acc_ph ^ 1);     // epilogue has drained this accumulator
+        ITN_TRACE_AT(7, gt);
         tc_fence_after();
         const uint32_t tacc = tmem_base + acc * Cfg::kAccCols;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = 0; kb < num_kb; ++kb, ++gk) {
           mbar_wait(X3 ? &split_bar[s] : &full_bar[s], ph);
+          ITN_TRACE_AT(3, gk);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * Cfg::kStageBytes);
           const uint32_t sb = sa + Cfg::kABytes;
@@ -347,6 +436,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
           umma_commit(&empty_bar[s]);  // frees the smem slot once the MMAs have read it
+          ITN_TRACE_AT(4, gk);
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
         umma_commit(&tfull_bar[acc]);  // accumulator complete
@@ -361,9 +451,11 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int s = 0;
     uint32_t ph = 0;
     const int tid = threadIdx.x - 64;               // 0..127
+    int gk = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      for (int kb = 0; kb < num_kb; ++kb) {
+      for (int kb = 0; kb < num_kb; ++kb, ++gk) {
         mbar_wait(&full_bar[s], ph);
+        if (tid == 0) ITN_TRACE_AT(1, gk);
         const float4* raw = reinterpret_cast<const float4*>(smem + s * Cfg::kStageBytes);
         float4* lo = reinterpret_cast<float4*>(smem + s * Cfg::kStageBytes + Cfg::kRawBytes);
 #pragma unroll 8
@@ -378,6 +470,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         fence_proxy_async();
         __syncwarp();
+        if (tid == 0) ITN_TRACE_AT(2, gk);
         if (lane == 0) mbar_arrive(&split_bar[s]);
         if (++s == STAGES) { s = 0; ph ^= 1; }
       }
@@ -385,10 +478,13 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp >= Cfg::kEpiWarp0) {
     // ----------------------------------------------------------- epilogue
     const int lg = warp & 3;    // TMEM lane group this warp may read: lanes [32*lg, 32*lg+32)
-    float* st = staging + (warp - Cfg::kEpiWarp0) * (32 * 33);
+    float* st = staging + (warp - Cfg::kEpiWarp0) * (32 * 36);
+    float4* st4 = reinterpret_cast<float4*>(st);
+    const bool vec = p.vec != 0;
     int acc = 0;
     uint32_t acc_ph = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    int gt = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++gt) {
       const int nb = tile % p.tiles_n;
       const int t2 = tile / p.tiles_n;
       const int mb = t2 % p.tiles_m;
@@ -406,17 +502,20 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (ev == EV_RELU_MASK || ev == EV_GELU_GRAD) { xsp = e.aux; ldx = p.ldaux; }
       else if (ev == EV_RESIDUAL || ev == EV_RESIDUAL_RELU) { xsp = e.residual; ldx = p.ldr; }
       else if (ev == EV_ACCUMULATE) { xsp = e.C; ldx = p.ldc; }
-      float xs[32];
-      auto prefetch = [&](int c) {
-        const int col = n0 + c * 32 + lane;
+      float4 xs4[8];
+      auto prefetch = [&](int c) {     // 128-bit path only: 8 row-vectors of this lane's 4 columns
+        const int col = n0 + c * 32 + (lane & 7) * 4;
         const bool ok = col < p.N;
-        const float* src = xsp + (long long)row_base * ldx + col;
+        const float* src = xsp + (long long)(row_base + (lane >> 3)) * ldx + col;
 #pragma unroll
-        for (int r = 0; r < 32; ++r) xs[r] = (ok && r < rmax) ? src[(long long)r * ldx] : 0.0f;
+        for (int i = 0; i < 8; ++i)
+          xs4[i] = (ok && 4 * i + (lane >> 3) < rmax) ? *reinterpret_cast<const float4*>(src + (long long)(4 * i) * ldx)
+                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
       };
       // chunk 0 of the stream is fetched while the tensor core is still working on this tile
-      if (xsp && rmax > 0) prefetch(0);
+      if (vec && xsp && rmax > 0) prefetch(0);
       mbar_wait(&tfull_bar[acc], acc_ph);
+      if (warp == Cfg::kEpiWarp0 && lane == 0) ITN_TRACE_AT(5, gt);
       tc_fence_after();
       const uint32_t tacc = tmem_base + acc * Cfg::kAccCols + (static_cast<uint32_t>(lg * 32) << 16);
       if (rmax <= 0) {
@@ -428,13 +527,41 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll 1
       for (int c = 0; c < nchunks && rmax > 0; ++c) {
         const int col0 = n0 + c * 32;
-        if (xsp && c > 0) prefetch(c);      // latency overlaps the TMEM read-out + transpose below
+        if (vec && xsp && c > 0) prefetch(c);      // latency overlaps the TMEM read-out + transpose below
+#ifdef ITN_TRACE
+        const long long tp0 = clock64();
+        long long tp1 = 0, tp2 = 0;
+#endif
         {
           uint32_t v[32];
-          tmem_ld_32x32(tacc + c * 32, v);
-          tmem_ld_wait();
+#ifdef ITN_TRACE
+          if (p.dbg & 2) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) st[lane * 33 + j] = __uint_as_float(v[j]);
+            for (int j = 0; j < 32; ++j) v[j] = j + lane;
+          } else
+#endif
+          {
+            tmem_ld_32x32(tacc + c * 32, v);
+            tmem_ld_wait();
+          }
+#ifdef ITN_TRACE
+          tp1 = clock64();
+          if (p.dbg & 4) {
+            float sum = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sum += __uint_as_float(v[j]);
+            if (sum == 123.456f) st[0] = sum;
+          } else
+#endif
+          if (vec) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              st4[lane * 9 + j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                              __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) st[lane * 33 + j] = __uint_as_float(v[j]);
+          }
         }
         if (c == nchunks - 1) {
           // last chunk of this tile is out of TMEM: hand the accumulator back to the issuer
@@ -443,22 +570,55 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (lane == 0) mbar_arrive(&tempty_bar[acc]);
         }
         __syncwarp();
-        const int col = col0 + lane;
-        if (col < p.N) {
-          switch (ev) {
-            case EV_SIMPLE: epilogue_simple(p, e, st, lane, row_base, rmax, col); break;
-            case EV_RESIDUAL: epilogue_rows<EV_RESIDUAL>(p, e, st, lane, row_base, rmax, col, xs); break;
-            case EV_RESIDUAL_RELU: epilogue_rows<EV_RESIDUAL_RELU>(p, e, st, lane, row_base, rmax, col, xs); break;
-            case EV_ACCUMULATE: epilogue_rows<EV_ACCUMULATE>(p, e, st, lane, row_base, rmax, col, xs); break;
-            case EV_RELU_MASK: epilogue_rows<EV_RELU_MASK>(p, e, st, lane, row_base, rmax, col, xs); break;
-            case EV_GELU_GRAD: epilogue_rows<EV_GELU_GRAD>(p, e, st, lane, row_base, rmax, col, xs); break;
-            case EV_PRE: epilogue_rows<EV_PRE>(p, e, st, lane, row_base, rmax, col, xs); break;
-            case EV_PRE_GELU: epilogue_rows<EV_PRE_GELU>(p, e, st, lane, row_base, rmax, col, xs); break;
-            default: epilogue_generic(p, e, st, lane, row_base, rmax, col); break;
+#ifdef ITN_TRACE
+        tp2 = clock64();
+#endif
+        if (vec) {
+          const int col = col0 + (lane & 7) * 4;
+#ifdef ITN_TRACE
+          if (col < p.N && !(p.dbg & 1)) {
+#else
+          if (col < p.N) {
+#endif
+            switch (ev) {
+              case EV_SIMPLE: epilogue_v4<EV_SIMPLE>(p, e, st4, lane, row_base, rmax, col, xs4); break;
+              case EV_RESIDUAL: epilogue_v4<EV_RESIDUAL>(p, e, st4, lane, row_base, rmax, col, xs4); break;
+              case EV_RESIDUAL_RELU: epilogue_v4<EV_RESIDUAL_RELU>(p, e, st4, lane, row_base, rmax, col, xs4); break;
+              case EV_ACCUMULATE: epilogue_v4<EV_ACCUMULATE>(p, e, st4, lane, row_base, rmax, col, xs4); break;
+              case EV_RELU_MASK: epilogue_v4<EV_RELU_MASK>(p, e, st4, lane, row_base, rmax, col, xs4); break;
+              case EV_GELU_GRAD: epilogue_v4<EV_GELU_GRAD>(p, e, st4, lane, row_base, rmax, col, xs4); break;
+              case EV_PRE: epilogue_v4<EV_PRE>(p, e, st4, lane, row_base, rmax, col, xs4); break;
+              default: epilogue_v4<EV_PRE_GELU>(p, e, st4, lane, row_base, rmax, col, xs4); break;
+            }
+          }
+        } else {
+          const int col = col0 + lane;
+          if (col < p.N) {
+            switch (ev) {
+              case EV_SIMPLE: epilogue_simple(p, e, st, lane, row_base, rmax, col); break;
+              case EV_RESIDUAL: epilogue_rows<EV_RESIDUAL>(p, e, st, lane, row_base, rmax, col, xsp, ldx); break;
+              case EV_RESIDUAL_RELU: epilogue_rows<EV_RESIDUAL_RELU>(p, e, st, lane, row_base, rmax, col, xsp, ldx); break;
+              case EV_ACCUMULATE: epilogue_rows<EV_ACCUMULATE>(p, e, st, lane, row_base, rmax, col, xsp, ldx); break;
+              case EV_RELU_MASK: epilogue_rows<EV_RELU_MASK>(p, e, st, lane, row_base, rmax, col, xsp, ldx); break;
+              case EV_GELU_GRAD: epilogue_rows<EV_GELU_GRAD>(p, e, st, lane, row_base, rmax, col, xsp, ldx); break;
+              case EV_PRE: epilogue_rows<EV_PRE>(p, e, st, lane, row_base, rmax, col, xsp, ldx); break;
+              case EV_PRE_GELU: epilogue_rows<EV_PRE_GELU>(p, e, st, lane, row_base, rmax, col, xsp, ldx); break;
+              default: epilogue_generic(p, e, st, lane, row_base, rmax, col); break;
+            }
           }
         }
         __syncwarp();
+#ifdef ITN_TRACE
+        if (warp == Cfg::kEpiWarp0 && lane == 0 && blockIdx.x == 0 && g_trace != nullptr) {
+          const long long tp3 = clock64();
+          g_trace[8 * 1024 + 0] += tp1 - tp0;   // TMEM read
+          g_trace[8 * 1024 + 1] += tp2 - tp1;   // smem transpose + hand-back
+          g_trace[8 * 1024 + 2] += tp3 - tp2;   // math + global stores
+          g_trace[8 * 1024 + 3] += 1;
+        }
+#endif
       }
+      if (warp == Cfg::kEpiWarp0 && lane == 0) ITN_TRACE_AT(6, gt);
       acc ^= 1;
       if (acc == 0) acc_ph ^= 1;
     }
@@ -590,6 +750,15 @@ static void fill_kparams(GemmKParams& p, const itn_gemm_desc_t* d) {
   p.act_pos = d->act_pos;
   p.variant = epilogue_variant(d->aux != nullptr, d->residual != nullptr, d->C2 != nullptr, d->act, d->epi,
                                d->accumulate, d->act_pos);
+  auto al = [](const void* ptr, long long ld, long long s0, long long s1) {
+    return ptr == nullptr || (((reinterpret_cast<uintptr_t>(ptr) & 15) == 0) && (ld % 4 == 0) && (s0 % 4 == 0) &&
+                              (s1 % 4 == 0));
+  };
+  p.vec = (p.variant != EV_GENERIC) && (d->N % 4 == 0) && al(d->C, d->ldc, d->c_sb0, d->c_sb1) &&
+          al(d->bias, 4, d->bias_sb0, d->bias_sb1) && al(d->residual, d->ldr, d->r_sb0, d->r_sb1) &&
+          al(d->aux, d->ldaux, d->aux_sb0, d->aux_sb1) && al(d->C2, d->ldc2, d->c2_sb0, d->c2_sb1);
+  if (getenv("ITN_GEMM_NOVEC")) p.vec = 0;
+  p.dbg = getenv("ITN_GEMM_DBG") ? atoi(getenv("ITN_GEMM_DBG")) : 0;
 }
 
 static int validate(const itn_gemm_desc_t* d) {
@@ -682,6 +851,12 @@ static int pick_bn(const itn_gemm_desc_t* d) {
 }
 
 }  // namespace itn
+
+#ifdef ITN_TRACE
+extern "C" int itn_debug_set_trace(long long* buf) {
+  return cudaMemcpyToSymbol(itn::g_trace, &buf, sizeof(buf)) == cudaSuccess ? 0 : -2;
+}
+#endif
 
 extern "C" int itn_gemm_tf32_supported(const itn_gemm_desc_t* d) {
   if (!d || d->M <= 0 || d->N <= 0 || d->K <= 0) return 0;
