@@ -268,11 +268,12 @@ def run_gpu_arm(args):
             "metric": METRIC, "value": total_eps / (dev_ms * 1e-3), "unit": "episodes/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "tf32x3 (fp32 storage; error-compensated 3-pass TF32 tensor-core GEMMs; fp32 cuDNN backbone)",
+            "dtype": "tf32x3 (fp32 storage; error-compensated 3-pass TF32 tcgen05 GEMMs, backbone convolutions included)",
             "data": "synthetic",
             "config": {"workload": f"{args.workload}.yaml predict() = BASELINE configs[2] (inner-loop adapt+detect)",
                        "episodes_per_step_per_gpu": E, "frames": 5, "resolution": 300,
                        "mode": "D1 (backbone frozen, features once per episode)", "cuda_graph": True,
+                       "backbone": loop.backbone_impl + (" (our im2col + tf32x3 GEMM kernels)" if loop.backbone_impl == "gemm" else " (cuDNN fp32)"),
                        "l2": "256 MiB buffer written between timed steps (L2 flush); per-step CUDA events"},
             "e2e": {"value": total_eps / (e2e_ms * 1e-3), "unit": "episodes/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps,

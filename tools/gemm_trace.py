@@ -38,6 +38,8 @@ if ph[3]:
     print(f"epilogue warp 0 of CTA 0: {int(ph[3])} chunks; cycles per chunk: TMEM read {ph[0]/ph[3]:.0f}, "
           f"transpose {ph[1]/ph[3]:.0f}, math+stores {ph[2]/ph[3]:.0f}")
 nkb = (K + 31) // 32
+import signal
+signal.signal(signal.SIGPIPE, signal.SIG_DFL)
 names = ["tma_issue", "split_start", "split_done", "mma_ready", "mma_issued"]
 print(f"M={M} N={N} K={K} {prec}: k-blocks per tile {nkb}; times in SM cycles since first event")
 print("kb   " + " ".join(f"{n:>12s}" for n in names))
