@@ -88,6 +88,9 @@ typedef struct {
   int round_out;
   int precision;
   int act_pos;
+  int c_pad;        /* 1: columns [N, round_up(N,4)) of every C row belong to C and may be overwritten
+                       (with zeros): lets N % 4 != 0 outputs such as attention scores use 128-bit stores.
+                       Honoured only for bias-free plain epilogues; otherwise ignored. */
 } itn_gemm_desc_t;
 
 /* tcgen05/TMA path.  Requires 16-byte aligned operand bases and ld/sb* multiples
@@ -206,6 +209,28 @@ int itn_matcher_cost(const float* logits, const float* boxes, const float* tgt_b
                      const long long* tgt_labels, const int* tgt_off, float* cost,
                      int frames, int queries, int classes, float w_class,
                      float w_bbox, float w_giou, void* stream);
+
+/* SetCriterion.forward (detr_models/detr.py:220-265) given the Hungarian assignment, for `groups`
+ * independent criterion calls of frames_per_group frames each (one group = one episode's frames, as
+ * models/interactron.py:117,131 call it).  logits [groups*frames,Q,classes], boxes [..,Q,4] cxcywh;
+ * targets concatenated over all frames (frame f owns [tgt_off[f], tgt_off[f+1])); the matches are
+ * (match_row = global row index frame*Q + query, match_tgt = global target index) pairs, group g
+ * owning [match_off[g], match_off[g+1]).  Per group:
+ *   losses[g] = { loss_ce   weighted CE, weights 1 and background_c on the last class (:111-126),
+ *                 class_error  100 - top-1 accuracy on the matched rows (:130-131; 100 if none),
+ *                 cardinality_error  mean_f |#(argmax != no-object) - T_f| (:134-146),
+ *                 loss_bbox  sum L1 / num_boxes,  loss_giou  sum (1 - GIoU) / num_boxes (:148-167) },
+ * num_boxes = max(targets in the group, 1) (:238-242).  If dlogits / dboxes are non-null they receive
+ * the gradient of w_ce*loss_ce + w_bbox*loss_bbox + w_giou*loss_giou (what .backward() feeds the
+ * detector at models/interactron.py:121-123,133).  scratch: itn_criterion_scratch_bytes() bytes,
+ * 16-byte aligned.  Deterministic (fixed-order reductions). */
+long long itn_criterion_scratch_bytes(int rows, int n_match, int groups);
+int itn_criterion(const float* logits, const float* boxes, const float* tgt_boxes,
+                  const long long* tgt_labels, const int* tgt_off, const int* match_row,
+                  const int* match_tgt, const int* match_off, int n_match, int groups,
+                  int frames_per_group, int queries, int classes, float background_c, float w_ce,
+                  float w_bbox, float w_giou, float* losses, float* dlogits, float* dboxes,
+                  void* scratch, void* stream);
 
 #ifdef __cplusplus
 }

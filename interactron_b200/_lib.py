@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libinteractron_b200.so")
+# ITN_LIB: load another build of the same ABI (the trace / experiment builds of csrc/Makefile)
+LIB_PATH = os.environ.get("ITN_LIB") or os.path.join(_HERE, "libinteractron_b200.so")
 
 
 class ItnError(RuntimeError):
@@ -31,7 +32,7 @@ class GemmDesc(C.Structure):
         ("aux", C.c_void_p), ("ldaux", C.c_longlong), ("aux_sb0", C.c_longlong), ("aux_sb1", C.c_longlong),
         ("C2", C.c_void_p), ("ldc2", C.c_longlong), ("c2_sb0", C.c_longlong), ("c2_sb1", C.c_longlong),
         ("alpha", C.c_float), ("act", C.c_int), ("epi", C.c_int), ("accumulate", C.c_int),
-        ("round_out", C.c_int), ("precision", C.c_int), ("act_pos", C.c_int),
+        ("round_out", C.c_int), ("precision", C.c_int), ("act_pos", C.c_int), ("c_pad", C.c_int),
     ]
 
 
@@ -61,6 +62,8 @@ SIGNATURES = {
     "itn_im2col_nhwc": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _LL, _P]),
     "itn_maxpool3x3s2_nhwc": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "itn_matcher_cost": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _F, _P]),
+    "itn_criterion_scratch_bytes": (_LL, [_I, _I, _I]),
+    "itn_criterion": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _F, _F, _F, _P, _P, _P, _P, _P]),
 }
 
 _lib = None

@@ -24,6 +24,35 @@ inline int check_launch(const char* what) {
   return ITN_OK;
 }
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------
+// Every kernel of the library is launched with the programmatic-stream-serialization attribute
+// and starts with pdl_wait() (prerequisite grids complete + their writes visible) followed by
+// pdl_trigger() (the next grid in the stream may be scheduled: its CTAs become resident on idle
+// SMs and run their own prologue up to pdl_wait()).  A step is ~1300 short launches; this hides
+// the grid-to-grid launch latency and the GEMM prologue (barrier init, TMEM allocation, tensor-map
+// fetch) behind the tail of the previous kernel.  Opt-in with ITN_PDL=1 (without the attribute the
+// device instructions are no-ops); see pdl_enabled() for the measurement that keeps it off.
+bool pdl_enabled();
+
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <class... KArgs, class... Args>
+inline void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                   Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 #define ITN_REQUIRE(cond, ...)                              \
   do {                                                      \
     if (!(cond)) return itn::set_error(ITN_ERR_ARG, __VA_ARGS__); \

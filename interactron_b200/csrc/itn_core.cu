@@ -1,4 +1,5 @@
 // Error reporting, version, launch accounting for the C ABI.
+#include <cstdlib>
 #include <cstring>
 
 #include "itn_common.cuh"
@@ -14,6 +15,16 @@ int set_error(int code, const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
   return code;
+}
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    // Off by default: inside a captured CUDA graph the kernel-to-kernel gap is already ~1 us and
+    // co-resident early CTAs cost slightly more than they hide (measured 264 vs 268 episodes/s).
+    const char* e = std::getenv("ITN_PDL");
+    return e && e[0] == '1';
+  }();
+  return on;
 }
 
 }  // namespace itn

@@ -21,6 +21,8 @@ sgd_clip_update_kernel(const float* __restrict__ theta, long long theta_stride,
                        const float* __restrict__ g, float* __restrict__ out,
                        float* __restrict__ out_r, unsigned char* __restrict__ mask, long long n,
                        float lr, float clip) {
+  pdl_wait();
+  pdl_trigger();
   const int grp = blockIdx.y;
   const float* th = theta + grp * theta_stride;
   const float* gg = g + (long long)grp * n;
@@ -67,6 +69,8 @@ __global__ void __launch_bounds__(256)
 add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
            long long n, long long b_elems, long long a_group, long long b_group_stride,
            int round_out) {
+  pdl_wait();
+  pdl_trigger();
   // all of n, b_elems, a_group, b_group_stride are multiples of 4 and pointers 16-byte aligned
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long n4 = n >> 2;
@@ -86,6 +90,8 @@ add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __re
 __global__ void __launch_bounds__(256)
 copy2d_kernel(const float* __restrict__ src, long long lds, float* __restrict__ dst, long long ldd,
               long long rows, int cols, int round_out) {
+  pdl_wait();
+  pdl_trigger();
   const long long total = rows * cols;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
@@ -100,6 +106,8 @@ copy2d_kernel(const float* __restrict__ src, long long lds, float* __restrict__ 
 __global__ void __launch_bounds__(256)
 transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols,
                  long long sgs, long long dgs) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float t[32][33];
   const float* s = src + blockIdx.z * sgs;
   float* d = dst + blockIdx.z * dgs;
@@ -120,6 +128,8 @@ transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int row
 
 __global__ void __launch_bounds__(256)
 round_tf32_kernel(const float* __restrict__ src, float* __restrict__ dst, long long n) {
+  pdl_wait();
+  pdl_trigger();
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long n4 = n >> 2;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -133,6 +143,8 @@ round_tf32_kernel(const float* __restrict__ src, float* __restrict__ dst, long l
 
 __global__ void __launch_bounds__(256)
 sigmoid_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long long n) {
+  pdl_wait();
+  pdl_trigger();
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
     y[i] = 1.0f / (1.0f + expf(-x[i]));
@@ -141,6 +153,8 @@ sigmoid_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long long
 __global__ void __launch_bounds__(256)
 sigmoid_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y,
                    float* __restrict__ dx, long long n) {
+  pdl_wait();
+  pdl_trigger();
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const float s = y[i];
@@ -152,6 +166,8 @@ sigmoid_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y,
 __global__ void __launch_bounds__(256)
 l2norm_fwd_bwd_kernel(const float* __restrict__ x, float* __restrict__ loss,
                       float* __restrict__ dx, int n) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float sm[8];
   const float* xg = x + (long long)blockIdx.x * n;
   float a = 0.f;
@@ -177,6 +193,8 @@ l2norm_fwd_bwd_kernel(const float* __restrict__ x, float* __restrict__ loss,
 __global__ void __launch_bounds__(256)
 pos_embed_sine_kernel(const unsigned char* __restrict__ mask, float* __restrict__ pos, int h, int w,
                       int feats) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float sh[];
   float* ye = sh;            // [h*w]
   float* xe = sh + h * w;    // [h*w]
@@ -229,7 +247,7 @@ extern "C" int itn_sgd_clip_update(const float* theta, long long theta_stride, c
   ITN_REQUIRE(!clip_mask || ((uintptr_t)clip_mask & 3) == 0, "sgd_clip_update: mask must be 4-byte aligned");
   ITN_REQUIRE(!theta_out_r || ((uintptr_t)theta_out_r & 15) == 0, "sgd_clip_update: theta_out_r must be 16-byte aligned");
   dim3 grid(grid_for(n >> 2, 256, 8), groups);
-  sgd_clip_update_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch(sgd_clip_update_kernel, grid, 256, 0, static_cast<cudaStream_t>(stream), 
       theta, theta_stride, g, theta_out, theta_out_r, clip_mask, n, lr, clip);
   return check_launch("sgd_clip_update_kernel");
 }
@@ -242,7 +260,7 @@ extern "C" int itn_add(const float* a, const float* b, float* out, long long n, 
   ITN_REQUIRE(((n | b_elems | a_group | b_group_stride) & 3) == 0,
               "add: n, b_elems, a_group, b_group_stride must be multiples of 4");
   ITN_REQUIRE(a_group % b_elems == 0, "add: a_group must be a multiple of b_elems");
-  add_kernel<<<grid_for(n >> 2, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch(add_kernel, grid_for(n >> 2, 256), 256, 0, static_cast<cudaStream_t>(stream), 
       a, b, out, n, b_elems, a_group, b_group_stride, round_out);
   return check_launch("add_kernel");
 }
@@ -250,7 +268,7 @@ extern "C" int itn_add(const float* a, const float* b, float* out, long long n, 
 extern "C" int itn_copy2d(const float* src, long long lds, float* dst, long long ldd, long long rows,
                           int cols, int round_out, void* stream) {
   ITN_REQUIRE(src && dst && rows > 0 && cols > 0, "copy2d: bad arguments");
-  copy2d_kernel<<<grid_for(rows * cols, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch(copy2d_kernel, grid_for(rows * cols, 256), 256, 0, static_cast<cudaStream_t>(stream), 
       src, lds, dst, ldd, rows, cols, round_out);
   return check_launch("copy2d_kernel");
 }
@@ -260,7 +278,7 @@ extern "C" int itn_transpose(const float* src, float* dst, int groups, int rows,
   ITN_REQUIRE(src && dst && groups > 0 && rows > 0 && cols > 0, "transpose: bad arguments");
   ITN_REQUIRE(groups <= 65535, "transpose: too many groups");
   dim3 grid((cols + 31) / 32, (rows + 31) / 32, groups);
-  transpose_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, dst, rows, cols,
+  launch(transpose_kernel, grid, 256, 0, static_cast<cudaStream_t>(stream), src, dst, rows, cols,
                                                                         src_group_stride, dst_group_stride);
   return check_launch("transpose_kernel");
 }
@@ -268,27 +286,27 @@ extern "C" int itn_transpose(const float* src, float* dst, int groups, int rows,
 extern "C" int itn_round_tf32(const float* src, float* dst, long long n, void* stream) {
   ITN_REQUIRE(src && dst && n > 0, "round_tf32: bad arguments");
   ITN_REQUIRE((((uintptr_t)src | (uintptr_t)dst) & 15) == 0, "round_tf32: pointers must be 16-byte aligned");
-  round_tf32_kernel<<<grid_for(n >> 2, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, dst, n);
+  launch(round_tf32_kernel, grid_for(n >> 2, 256), 256, 0, static_cast<cudaStream_t>(stream), src, dst, n);
   return check_launch("round_tf32_kernel");
 }
 
 extern "C" int itn_sigmoid_fwd(const float* x, float* y, long long n, void* stream) {
   ITN_REQUIRE(x && y && n > 0, "sigmoid_fwd: bad arguments");
-  sigmoid_fwd_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, n);
+  launch(sigmoid_fwd_kernel, grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream), x, y, n);
   return check_launch("sigmoid_fwd_kernel");
 }
 
 extern "C" int itn_sigmoid_bwd(const float* dy, const float* y, float* dx, long long n,
                                void* stream) {
   ITN_REQUIRE(dy && y && dx && n > 0, "sigmoid_bwd: bad arguments");
-  sigmoid_bwd_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(dy, y, dx, n);
+  launch(sigmoid_bwd_kernel, grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream), dy, y, dx, n);
   return check_launch("sigmoid_bwd_kernel");
 }
 
 extern "C" int itn_l2norm_fwd_bwd(const float* x, float* loss, float* dx, int groups, int n,
                                   void* stream) {
   ITN_REQUIRE(x && groups > 0 && n > 0, "l2norm_fwd_bwd: bad arguments");
-  l2norm_fwd_bwd_kernel<<<groups, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, loss, dx, n);
+  launch(l2norm_fwd_bwd_kernel, groups, 256, 0, static_cast<cudaStream_t>(stream), x, loss, dx, n);
   return check_launch("l2norm_fwd_bwd_kernel");
 }
 
@@ -297,6 +315,6 @@ extern "C" int itn_pos_embed_sine(const unsigned char* mask, float* pos, int fra
   ITN_REQUIRE(mask && pos && frames > 0 && h > 0 && w > 0 && feats > 0, "pos_embed_sine: bad arguments");
   const size_t smem = 2ull * h * w * sizeof(float);
   ITN_REQUIRE(smem <= 48 * 1024, "pos_embed_sine: feature map %dx%d too large", h, w);
-  pos_embed_sine_kernel<<<frames, 256, smem, static_cast<cudaStream_t>(stream)>>>(mask, pos, h, w, feats);
+  launch(pos_embed_sine_kernel, frames, 256, smem, static_cast<cudaStream_t>(stream), mask, pos, h, w, feats);
   return check_launch("pos_embed_sine_kernel");
 }

@@ -10,6 +10,8 @@ matcher_cost_kernel(const float* __restrict__ logits, const float* __restrict__ 
                     const float* __restrict__ tgt_boxes, const long long* __restrict__ tgt_labels,
                     const int* __restrict__ tgt_off, float* __restrict__ cost, int frames,
                     int queries, int classes, float w_class, float w_bbox, float w_giou) {
+  pdl_wait();
+  pdl_trigger();
   const int wq = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (wq >= frames * queries) return;
   const int lane = threadIdx.x & 31;
@@ -61,7 +63,7 @@ extern "C" int itn_matcher_cost(const float* logits, const float* boxes, const f
   ITN_REQUIRE((((uintptr_t)boxes | (uintptr_t)tgt_boxes) & 15) == 0,
               "matcher_cost: boxes must be 16-byte aligned");
   const int warps = frames * queries;
-  itn::matcher_cost_kernel<<<(warps + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  itn::launch(itn::matcher_cost_kernel, (warps + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream), 
       logits, boxes, tgt_boxes, tgt_labels, tgt_off, cost, frames, queries, classes, w_class,
       w_bbox, w_giou);
   return itn::check_launch("matcher_cost_kernel");

@@ -13,6 +13,8 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
                      const float* __restrict__ beta, float* __restrict__ y,
                      float* __restrict__ y_r, float* __restrict__ mean_out, float* __restrict__ rstd_out, long long rows,
                      long long rows_per_group, long long gb_stride, float eps) {
+  pdl_wait();
+  pdl_trigger();
   constexpr int cols = VPL * 128;
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -63,6 +65,8 @@ layernorm_bwd_dx_kernel(const float* __restrict__ dy, const float* __restrict__ 
                         const float* __restrict__ gamma, float* __restrict__ dx,
                         float* __restrict__ dx_r, long long rows, long long rows_per_group,
                         long long gb_stride) {
+  pdl_wait();
+  pdl_trigger();
   constexpr int cols = VPL * 128;
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -106,6 +110,8 @@ layernorm_bwd_gb_kernel(const float* __restrict__ dy, const float* __restrict__ 
                         const float* __restrict__ mean, const float* __restrict__ rstd,
                         float* __restrict__ dgamma, float* __restrict__ dbeta,
                         long long rows_per_group, int cols, long long dgb_stride) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float sg[32][33];
   __shared__ float sb[32][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
@@ -142,6 +148,8 @@ __global__ void __launch_bounds__(256)
 softmax_fwd_kernel(float* __restrict__ s, long long rows, int cols, long long ld, float scale,
                    const unsigned char* __restrict__ key_mask, long long rows_per_mask,
                    int round_out) {
+  pdl_wait();
+  pdl_trigger();
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -172,6 +180,8 @@ softmax_fwd_kernel(float* __restrict__ s, long long rows, int cols, long long ld
 __global__ void __launch_bounds__(256)
 softmax_bwd_kernel(const float* __restrict__ p, float* __restrict__ dp, long long rows, int cols,
                    long long ld, float scale, int round_out) {
+  pdl_wait();
+  pdl_trigger();
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -186,10 +196,126 @@ softmax_bwd_kernel(const float* __restrict__ p, float* __restrict__ dp, long lon
   }
 }
 
+// Register-resident variants: a warp keeps its whole row (<= 128*NV columns) in registers as NV
+// float4 per lane, so every element is read from memory once with all loads in flight at
+// once, and written once (the generic kernels above re-read the row and carry a serial exp chain
+// in the online pass: 2.4 TB/s on the 361-column encoder rows, profiles/README.md).
+// Requires 16-byte aligned rows (ld % 4 == 0) that own their padding up to a multiple of 4 columns;
+// the pad columns are written as zeros.
+template <int NV>
+__global__ void __launch_bounds__(256)
+softmax_fwd_reg_kernel(float* __restrict__ s, long long rows, int cols, long long ld, float scale,
+                       const unsigned char* __restrict__ key_mask, long long rows_per_mask,
+                       int round_out) {
+  pdl_wait();
+  pdl_trigger();
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  float4* r4 = reinterpret_cast<float4*>(s + row * ld);
+  const unsigned char* mk = key_mask ? key_mask + (row / rows_per_mask) * cols : nullptr;
+  const int nvec = (cols + 3) >> 2;
+  float v[NV][4];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int j = lane + 32 * i;
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (j < nvec) t = r4[j];
+    v[i][0] = t.x; v[i][1] = t.y; v[i][2] = t.z; v[i][3] = t.w;
+  }
+  float m = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c0 = 4 * (lane + 32 * i);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = c0 + k;
+      const bool live = c < cols && !(mk && mk[c]);
+      v[i][k] = live ? v[i][k] * scale : -INFINITY;
+      m = fmaxf(m, v[i][k]);
+    }
+  }
+  m = warp_max(m);
+  float l = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      v[i][k] = __expf(v[i][k] - m);      // exp(-inf) = 0 for masked / pad columns
+      l += v[i][k];
+    }
+  }
+  const float inv = 1.0f / warp_sum(l);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int j = lane + 32 * i;
+    if (j < nvec) {
+      float4 o = make_float4(v[i][0] * inv, v[i][1] * inv, v[i][2] * inv, v[i][3] * inv);
+      if (round_out) o = make_float4(rn_tf32(o.x), rn_tf32(o.y), rn_tf32(o.z), rn_tf32(o.w));
+      r4[j] = o;
+    }
+  }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(256)
+softmax_bwd_reg_kernel(const float* __restrict__ p, float* __restrict__ dp, long long rows, int cols,
+                       long long ld, float scale, int round_out) {
+  pdl_wait();
+  pdl_trigger();
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float4* p4 = reinterpret_cast<const float4*>(p + row * ld);
+  float4* d4 = reinterpret_cast<float4*>(dp + row * ld);
+  const int nvec = (cols + 3) >> 2;
+  float pv[NV][4], dv[NV][4];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int j = lane + 32 * i;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (j < nvec) {
+      a = p4[j];
+      b = d4[j];
+    }
+    pv[i][0] = a.x; pv[i][1] = a.y; pv[i][2] = a.z; pv[i][3] = a.w;
+    dv[i][0] = b.x; dv[i][1] = b.y; dv[i][2] = b.z; dv[i][3] = b.w;
+  }
+  float acc = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c0 = 4 * (lane + 32 * i);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (c0 + k >= cols) pv[i][k] = 0.f, dv[i][k] = 0.f;    // pad columns of the last chunk
+      acc = fmaf(pv[i][k], dv[i][k], acc);
+    }
+  }
+  const float dot = warp_sum(acc);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int j = lane + 32 * i;
+    if (j < nvec) {
+      float4 o = make_float4(scale * pv[i][0] * (dv[i][0] - dot), scale * pv[i][1] * (dv[i][1] - dot),
+                             scale * pv[i][2] * (dv[i][2] - dot), scale * pv[i][3] * (dv[i][3] - dot));
+      if (round_out) o = make_float4(rn_tf32(o.x), rn_tf32(o.y), rn_tf32(o.z), rn_tf32(o.w));
+      d4[j] = o;
+    }
+  }
+}
+
+// rows the register-resident kernels can take: 16-byte aligned, padding owned by the row
+static inline bool softmax_rows_vectorisable(const void* a, const void* b, int cols, long long ld) {
+  return (ld % 4) == 0 && ld >= ((cols + 3) / 4) * 4 && cols <= 128 * 20 &&
+         (((uintptr_t)a | (uintptr_t)b) & 15) == 0;
+}
+
 // ------------------------------------------------------------------- colsum
 __global__ void __launch_bounds__(1024)
 colsum_kernel(const float* __restrict__ x, float* __restrict__ out, long long rows, int cols,
               long long ld, long long out_stride) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float sm[32][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   const int g = blockIdx.y;
@@ -221,10 +347,10 @@ extern "C" int itn_layernorm_fwd(const float* x, const float* gamma, const float
   const unsigned grid = (unsigned)((rows + 7) / 8);
   const long long rpg = rows / groups;
   switch (cols) {
-    case 128: layernorm_fwd_kernel<1><<<grid, 256, 0, s>>>(x, gamma, beta, y, y_r, mean, rstd, rows, rpg, gb_stride, eps); break;
-    case 256: layernorm_fwd_kernel<2><<<grid, 256, 0, s>>>(x, gamma, beta, y, y_r, mean, rstd, rows, rpg, gb_stride, eps); break;
-    case 512: layernorm_fwd_kernel<4><<<grid, 256, 0, s>>>(x, gamma, beta, y, y_r, mean, rstd, rows, rpg, gb_stride, eps); break;
-    case 1024: layernorm_fwd_kernel<8><<<grid, 256, 0, s>>>(x, gamma, beta, y, y_r, mean, rstd, rows, rpg, gb_stride, eps); break;
+    case 128: launch(layernorm_fwd_kernel<1>, grid, 256, 0, s, x, gamma, beta, y, y_r, mean, rstd, rows, rpg, gb_stride, eps); break;
+    case 256: launch(layernorm_fwd_kernel<2>, grid, 256, 0, s, x, gamma, beta, y, y_r, mean, rstd, rows, rpg, gb_stride, eps); break;
+    case 512: launch(layernorm_fwd_kernel<4>, grid, 256, 0, s, x, gamma, beta, y, y_r, mean, rstd, rows, rpg, gb_stride, eps); break;
+    case 1024: launch(layernorm_fwd_kernel<8>, grid, 256, 0, s, x, gamma, beta, y, y_r, mean, rstd, rows, rpg, gb_stride, eps); break;
     default: return set_error(ITN_ERR_UNSUPPORTED, "layernorm_fwd: cols must be 128/256/512/1024, got %d", cols);
   }
   return check_launch("layernorm_fwd_kernel");
@@ -241,17 +367,17 @@ extern "C" int itn_layernorm_bwd(const float* dy, const float* x, const float* m
   const unsigned grid = (unsigned)((rows + 7) / 8);
   const long long rpg = rows / groups;
   switch (cols) {
-    case 128: layernorm_bwd_dx_kernel<1><<<grid, 256, 0, s>>>(dy, x, mean, rstd, gamma, dx, dx_r, rows, rpg, gb_stride); break;
-    case 256: layernorm_bwd_dx_kernel<2><<<grid, 256, 0, s>>>(dy, x, mean, rstd, gamma, dx, dx_r, rows, rpg, gb_stride); break;
-    case 512: layernorm_bwd_dx_kernel<4><<<grid, 256, 0, s>>>(dy, x, mean, rstd, gamma, dx, dx_r, rows, rpg, gb_stride); break;
-    case 1024: layernorm_bwd_dx_kernel<8><<<grid, 256, 0, s>>>(dy, x, mean, rstd, gamma, dx, dx_r, rows, rpg, gb_stride); break;
+    case 128: launch(layernorm_bwd_dx_kernel<1>, grid, 256, 0, s, dy, x, mean, rstd, gamma, dx, dx_r, rows, rpg, gb_stride); break;
+    case 256: launch(layernorm_bwd_dx_kernel<2>, grid, 256, 0, s, dy, x, mean, rstd, gamma, dx, dx_r, rows, rpg, gb_stride); break;
+    case 512: launch(layernorm_bwd_dx_kernel<4>, grid, 256, 0, s, dy, x, mean, rstd, gamma, dx, dx_r, rows, rpg, gb_stride); break;
+    case 1024: launch(layernorm_bwd_dx_kernel<8>, grid, 256, 0, s, dy, x, mean, rstd, gamma, dx, dx_r, rows, rpg, gb_stride); break;
     default: return set_error(ITN_ERR_UNSUPPORTED, "layernorm_bwd: cols must be 128/256/512/1024, got %d", cols);
   }
   int rc = check_launch("layernorm_bwd_dx_kernel");
   if (rc) return rc;
   if (dgamma || dbeta) {
     dim3 g2((cols + 31) / 32, groups);
-    layernorm_bwd_gb_kernel<<<g2, dim3(32, 32), 0, s>>>(dy, x, mean, rstd, dgamma, dbeta, rpg, cols, dgb_stride);
+    launch(layernorm_bwd_gb_kernel, g2, dim3(32, 32), 0, s, dy, x, mean, rstd, dgamma, dbeta, rpg, cols, dgb_stride);
     rc = check_launch("layernorm_bwd_gb_kernel");
   }
   return rc;
@@ -262,16 +388,42 @@ extern "C" int itn_softmax_fwd(float* sc, long long rows, int cols, long long ld
                                int round_out, void* stream) {
   ITN_REQUIRE(sc && rows > 0 && cols > 0 && ld >= cols, "softmax_fwd: bad arguments");
   ITN_REQUIRE(!key_mask || rows_per_mask > 0, "softmax_fwd: rows_per_mask must be > 0 with a mask");
-  softmax_fwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      sc, rows, cols, ld, scale, key_mask, rows_per_mask, round_out);
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (softmax_rows_vectorisable(sc, nullptr, cols, ld)) {
+#define ITN_SOFTMAX_FWD(NV) launch(softmax_fwd_reg_kernel<NV>, grid, 256, 0, st, sc, rows, cols, ld, scale, key_mask, rows_per_mask, round_out)
+    if (cols <= 128) ITN_SOFTMAX_FWD(1);
+    else if (cols <= 256) ITN_SOFTMAX_FWD(2);
+    else if (cols <= 384) ITN_SOFTMAX_FWD(3);
+    else if (cols <= 512) ITN_SOFTMAX_FWD(4);
+    else if (cols <= 1024) ITN_SOFTMAX_FWD(8);
+    else if (cols <= 2048) ITN_SOFTMAX_FWD(16);
+    else ITN_SOFTMAX_FWD(20);
+#undef ITN_SOFTMAX_FWD
+    return check_launch("softmax_fwd_reg_kernel");
+  }
+  launch(softmax_fwd_kernel, grid, 256, 0, st, sc, rows, cols, ld, scale, key_mask, rows_per_mask, round_out);
   return check_launch("softmax_fwd_kernel");
 }
 
 extern "C" int itn_softmax_bwd(const float* p, float* dp, long long rows, int cols, long long ld,
                                float scale, int round_out, void* stream) {
   ITN_REQUIRE(p && dp && rows > 0 && cols > 0 && ld >= cols, "softmax_bwd: bad arguments");
-  softmax_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      p, dp, rows, cols, ld, scale, round_out);
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (softmax_rows_vectorisable(p, dp, cols, ld)) {
+#define ITN_SOFTMAX_BWD(NV) launch(softmax_bwd_reg_kernel<NV>, grid, 256, 0, st, p, dp, rows, cols, ld, scale, round_out)
+    if (cols <= 128) ITN_SOFTMAX_BWD(1);
+    else if (cols <= 256) ITN_SOFTMAX_BWD(2);
+    else if (cols <= 384) ITN_SOFTMAX_BWD(3);
+    else if (cols <= 512) ITN_SOFTMAX_BWD(4);
+    else if (cols <= 1024) ITN_SOFTMAX_BWD(8);
+    else if (cols <= 2048) ITN_SOFTMAX_BWD(16);
+    else ITN_SOFTMAX_BWD(20);
+#undef ITN_SOFTMAX_BWD
+    return check_launch("softmax_bwd_reg_kernel");
+  }
+  launch(softmax_bwd_kernel, grid, 256, 0, st, p, dp, rows, cols, ld, scale, round_out);
   return check_launch("softmax_bwd_kernel");
 }
 
@@ -279,6 +431,6 @@ extern "C" int itn_colsum(const float* x, float* out, int groups, long long rows
                           long long ld, long long out_stride, void* stream) {
   ITN_REQUIRE(x && out && groups > 0 && rows > 0 && cols > 0 && ld >= cols, "colsum: bad arguments");
   dim3 grid((cols + 31) / 32, groups);
-  colsum_kernel<<<grid, dim3(32, 32), 0, static_cast<cudaStream_t>(stream)>>>(x, out, rows, cols, ld, out_stride);
+  launch(colsum_kernel, grid, dim3(32, 32), 0, static_cast<cudaStream_t>(stream), x, out, rows, cols, ld, out_stride);
   return check_launch("colsum_kernel");
 }

@@ -30,7 +30,7 @@ def attention_fwd(ops, q, k, v, B, Lq, Lk, nh, hd, scale, kmask):
     vh = v.reshape(B, Lk, nh, hd).permute(0, 2, 1, 3)            # [B,nh,Lk,hd]
     P = ops.empty(B, nh, Lq, pad4(Lk))                           # row stride padded to 16 bytes for TMA
     p = P[..., :Lk]
-    ops.matmul(qh, khT, out=p)
+    ops.matmul(qh, khT, out=p, out_pad=True)
     ops.softmax_(P, Lk, scale, kmask, rows_per_mask=nh * Lq)
     o = ops.empty(B, Lq, nh * hd)
     ops.matmul(p, vh, out=o.view(B, Lq, nh, hd).permute(0, 2, 1, 3), rnd=True)
@@ -46,7 +46,7 @@ def attention_bwd(ops, dO, q, k, v, P, B, Lq, Lk, nh, hd, scale, dq, dk, dv):
     p = P[..., :Lk]
     dP = ops.empty(B, nh, Lq, pad4(Lk))
     dp = dP[..., :Lk]
-    ops.matmul(dOh, vhT, out=dp)                                                    # dP = dO V^T
+    ops.matmul(dOh, vhT, out=dp, out_pad=True)                                                    # dP = dO V^T
     ops.matmul(T(p), dOh, out=dv.view(B, Lk, nh, hd).permute(0, 2, 1, 3), rnd=True)  # dV = P^T dO
     ops.softmax_bwd_(P, dP, Lk, scale)                                              # dS (in dP)
     ops.matmul(dp, kh, out=dq.view(B, Lq, nh, hd).permute(0, 2, 1, 3), rnd=True)     # dQ = dS K

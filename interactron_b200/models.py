@@ -22,18 +22,8 @@ import torch
 from torch import nn
 
 from . import modules as M
+from .criterion import build_criterion
 from .synthetic import synthetic_state_dict
-
-
-class _CriterionState(nn.Module):
-    """Carries the `criterion.empty_weight` buffer that reference checkpoints contain
-    (reference models/detr_models/detr.py:104-106)."""
-
-    def __init__(self, num_classes, eos_coef=0.1):
-        super().__init__()
-        w = torch.ones(num_classes + 1)
-        w[-1] = eos_coef
-        self.register_buffer("empty_weight", w)
 
 
 def _load_detector_weights(detector, config, full_model):
@@ -122,7 +112,7 @@ class _Adaptive(_Base):
     def __init__(self, config, fusion_cls, kind):
         super().__init__()
         self.detector = M.DetectorHolder(config.NUM_CLASSES)
-        self.criterion = _CriterionState(config.NUM_CLASSES)
+        self.criterion = build_criterion(config)
         self.postprocessor = {}
         self.fusion = fusion_cls(config)
         self.config = config
@@ -206,7 +196,7 @@ class detr(_Base):
     def __init__(self, config):
         super().__init__()
         self.model = M.DetectorHolder(config.NUM_CLASSES)
-        self.criterion = _CriterionState(config.NUM_CLASSES)
+        self.criterion = build_criterion(config)
         self.postprocessor = {}
         self.config = config
         self._kind = "B"
@@ -251,7 +241,7 @@ class detr_multiframe(_Base):
     def __init__(self, config):
         super().__init__()
         self.detector = M.DetectorHolder(config.NUM_CLASSES)
-        self.criterion = _CriterionState(config.NUM_CLASSES)
+        self.criterion = build_criterion(config)
         self.postprocessor = {}
         self.fusion = M.FusionAHolder(config)
         self.config = config

@@ -104,9 +104,12 @@ class CudaOps:
         return op, t4
 
     def matmul(self, a, b, *, bias=None, act=None, residual=None, out=None, out_pre=None,
-               alpha=1.0, accumulate=False, epi=None, aux=None, rnd=False, act_after_residual=False):
+               alpha=1.0, accumulate=False, epi=None, aux=None, rnd=False, act_after_residual=False,
+               out_pad=False):
         """out = epilogue(alpha * a @ b), a [..,M,K], b [..,K,N]; see itn_gemm_desc_t.
-        rnd: store `out` rounded to TF32 (set when `out` only feeds further GEMMs)."""
+        rnd: store `out` rounded to TF32 (set when `out` only feeds further GEMMs).
+        out_pad: `out` is a [..., :N] view of rows padded to a multiple of 4 columns and the pad may
+        be overwritten with zeros (attention score matrices): enables 128-bit stores for N % 4 != 0."""
         rank = max(a.dim(), b.dim(), 2)
         a4, b4 = _as4d(a), _as4d(b)
         M, K = a4.shape[2], a4.shape[3]
@@ -163,6 +166,7 @@ class CudaOps:
         d.round_out = 1 if (rnd and self._clean) else 0
         d.precision = PRECISION[self.precision]
         d.act_pos = 1 if act_after_residual else 0
+        d.c_pad = 1 if out_pad else 0
         if not self.force_simt and self.lib.itn_gemm_tf32_supported(C.byref(d)):
             _lib.check(self.lib.itn_gemm_tf32(C.byref(d), self._stream()))
             self.n_tf32 += 1
@@ -363,3 +367,25 @@ class CudaOps:
                                              _ptr(tgt_off), _ptr(cost), F_, Q, Cn, float(w_class),
                                              float(w_bbox), float(w_giou), self._stream()))
         return cost
+
+    def criterion(self, logits, boxes, tgt_boxes, tgt_labels, tgt_off, match_row, match_tgt, match_off,
+                  groups, background_c, weights=(1.0, 1.0, 1.0), want_grad=False):
+        """SetCriterion on the device (see itn_criterion): logits [groups*F,Q,C], boxes [groups*F,Q,4].
+        -> losses [groups,5] (loss_ce, class_error, cardinality_error, loss_bbox, loss_giou)
+        and, with want_grad, d(w_ce*ce + w_bbox*bbox + w_giou*giou)/d(logits, boxes)."""
+        Fn, Q, Cn = logits.shape
+        assert Fn % groups == 0 and logits.is_contiguous() and boxes.is_contiguous()
+        n_match = int(match_row.numel())
+        rows = Fn * Q
+        nbytes = self.lib.itn_criterion_scratch_bytes(rows, n_match, groups)
+        scratch = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        losses = self.empty(groups, 5)
+        dl = self.empty(Fn, Q, Cn) if want_grad else None
+        db = self.empty(Fn, Q, 4) if want_grad else None
+        _lib.check(self.lib.itn_criterion(
+            _ptr(logits), _ptr(boxes), _ptr(tgt_boxes) if n_match else None, _ptr(tgt_labels) if n_match else None,
+            _ptr(tgt_off), _ptr(match_row) if n_match else None, _ptr(match_tgt) if n_match else None,
+            _ptr(match_off), n_match, groups, Fn // groups, Q, Cn, float(background_c), float(weights[0]),
+            float(weights[1]), float(weights[2]), _ptr(losses), _ptr(dl) if want_grad else None,
+            _ptr(db) if want_grad else None, _ptr(scratch), self._stream()))
+        return (losses, dl, db) if want_grad else losses

@@ -242,3 +242,64 @@ def hungarian_cost(logits, boxes, tgt_labels, tgt_boxes, w_class=1.0, w_bbox=5.0
     areac = whc[..., 0] * whc[..., 1]
     giou = inter / union - (areac - union) / areac
     return w_bbox * torch.cdist(boxes, tgt_boxes, p=1) - w_class * prob[:, tgt_labels] - w_giou * giou
+
+
+def _xyxy(b):
+    cx, cy, w, h = b.unbind(-1)
+    return torch.stack((cx - 0.5 * w, cy - 0.5 * h, cx + 0.5 * w, cy + 0.5 * h), -1)
+
+
+def hungarian_match(logits, boxes, targets, w_class=1.0, w_bbox=5.0, w_giou=2.0):
+    """reference models/detr_models/matcher.py:32-77: per-frame LSAP on the cost matrix ->
+    [(index_i, index_j)] int64."""
+    from scipy.optimize import linear_sum_assignment
+    out = []
+    for f, t in enumerate(targets):
+        if t["labels"].numel() == 0:
+            e = torch.zeros(0, dtype=torch.int64)
+            out.append((e, e))
+            continue
+        c = hungarian_cost(logits[f].detach(), boxes[f].detach(), t["labels"], t["boxes"], w_class, w_bbox, w_giou)
+        i, j = linear_sum_assignment(c.numpy())
+        out.append((torch.as_tensor(i, dtype=torch.int64), torch.as_tensor(j, dtype=torch.int64)))
+    return out
+
+
+def set_criterion(logits, boxes, targets, indices, background_c=0.1):
+    """reference models/detr_models/detr.py:220-265 with losses = labels, boxes, cardinality
+    (:111-167), given the matcher's indices.  logits [F,Q,C], boxes [F,Q,4] -> dict of 0-dim tensors
+    (differentiable wrt logits / boxes)."""
+    F_, Q, C = logits.shape
+    bi = torch.cat([torch.full_like(i, f) for f, (i, _) in enumerate(indices)])
+    si = torch.cat([i for i, _ in indices])
+    tco = torch.cat([t["labels"][j] for t, (_, j) in zip(targets, indices)])
+    tc = torch.full((F_, Q), C - 1, dtype=torch.int64)
+    tc[bi, si] = tco                                                            # :118-122
+    w = torch.ones(C, dtype=logits.dtype)
+    w[-1] = background_c                                                        # :124-125
+    logp = torch.log_softmax(logits, -1)
+    nll = -logp.gather(-1, tc[..., None])[..., 0]
+    loss_ce = (w[tc] * nll).sum() / w[tc].sum()                                 # F.cross_entropy(weight) :126
+    if tco.numel():
+        class_error = 100 - 100.0 * (logits[bi, si].argmax(-1) == tco).float().mean()   # :131, misc.py:431-446
+    else:
+        class_error = torch.tensor(100.0)
+    lens = torch.tensor([float(t["labels"].numel()) for t in targets])
+    card = (logits.argmax(-1) != C - 1).sum(1).float()
+    cardinality_error = (card - lens).abs().mean()                              # :143-145
+    num_boxes = max(float(lens.sum()), 1.0)                                     # :238-242 (single process)
+    src = boxes[bi, si]
+    tgt = torch.cat([t["boxes"][j] for t, (_, j) in zip(targets, indices)], 0)
+    loss_bbox = (src - tgt).abs().sum() / num_boxes                             # :157-160
+    a, t = _xyxy(src), _xyxy(tgt)
+    area_a = (a[:, 2] - a[:, 0]) * (a[:, 3] - a[:, 1])
+    area_t = (t[:, 2] - t[:, 0]) * (t[:, 3] - t[:, 1])
+    wh = (torch.min(a[:, 2:], t[:, 2:]) - torch.max(a[:, :2], t[:, :2])).clamp(min=0)
+    inter = wh[:, 0] * wh[:, 1]
+    union = area_a + area_t - inter
+    whc = (torch.max(a[:, 2:], t[:, 2:]) - torch.min(a[:, :2], t[:, :2])).clamp(min=0)
+    areac = whc[:, 0] * whc[:, 1]
+    giou = inter / union - (areac - union) / areac                              # util/box_ops.py:38-58 (diagonal)
+    loss_giou = (1 - giou).sum() / num_boxes                                    # :162-165
+    return {"loss_ce": loss_ce, "class_error": class_error, "loss_bbox": loss_bbox, "loss_giou": loss_giou,
+            "cardinality_error": cardinality_error}

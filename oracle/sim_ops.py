@@ -32,7 +32,8 @@ class SimOps:
         return self.calls
 
     def matmul(self, a, b, *, bias=None, act=None, residual=None, out=None, out_pre=None,
-               alpha=1.0, accumulate=False, epi=None, aux=None, rnd=False, act_after_residual=False):
+               alpha=1.0, accumulate=False, epi=None, aux=None, rnd=False, act_after_residual=False,
+               out_pad=False):
         self.calls += 1
         v = alpha * torch.matmul(a, b)
         if bias is not None:

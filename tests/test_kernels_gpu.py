@@ -228,6 +228,37 @@ def test_softmax_fwd_bwd(ops, cols):
     assert rel(ds[:, :cols], ref_ds) < 4e-4
 
 
+@pytest.mark.parametrize("Lq,Lk,hd", [(361, 361, 32), (50, 361, 32), (255, 1805, 64)])
+def test_gemm_padded_score_rows_vector_store(ops3, Lq, Lk, hd):
+    ops = ops3
+    """Attention scores: N % 4 != 0 written with 128-bit stores into rows that own their padding
+    (itn_gemm_desc_t.c_pad); must equal the scalar-store result and leave zeros in the pad."""
+    gen = torch.Generator(device="cuda").manual_seed(Lq + Lk)
+    q = torch.randn(2, 3, Lq, hd, generator=gen, device="cuda")
+    k = torch.randn(2, 3, Lk, hd, generator=gen, device="cuda")
+    ld = (Lk + 3) // 4 * 4
+    P0 = torch.full((2, 3, Lq, ld), 7.0, device="cuda")
+    P1 = torch.full((2, 3, Lq, ld), 7.0, device="cuda")
+    ops.matmul(q, k.transpose(-1, -2), out=P0[..., :Lk], alpha=0.25)
+    ops.matmul(q, k.transpose(-1, -2), out=P1[..., :Lk], alpha=0.25, out_pad=True)
+    assert torch.equal(P0[..., :Lk], P1[..., :Lk])
+    assert (P0[..., Lk:] == 7.0).all() and (P1[..., Lk:] == 0.0).all()
+    assert rel(P1[..., :Lk], 0.25 * q.double() @ k.double().transpose(-1, -2)) < X3_TOL
+
+
+def test_softmax_unpadded_rows_take_generic_path(ops):
+    """ld = 361 (rows not 16-byte aligned): the register-resident kernels do not apply."""
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    s = torch.randn(40, 361, generator=gen, device="cuda") * 2
+    dp = torch.randn(40, 361, generator=gen, device="cuda")
+    ref = torch.softmax(s.double() * 0.5, -1)
+    p = ops.softmax_(s.clone(), 361, 0.5)
+    assert rel(p, ref) < 4e-4
+    ds = ops.softmax_bwd_(p, dp.clone(), 361, 0.5)
+    pd = p.double()
+    assert rel(ds, 0.5 * pd * (dp.double() - (pd * dp.double()).sum(-1, keepdim=True))) < 4e-4
+
+
 def test_softmax_key_mask(ops):
     gen = torch.Generator(device="cuda").manual_seed(1)
     B, H, L, Lk = 2, 4, 50, 361

@@ -15,25 +15,28 @@ from interactron_b200.ops import CudaOps  # noqa: E402
 
 M, N, K = (int(x) for x in sys.argv[1:4])
 prec = sys.argv[4] if len(sys.argv) > 4 else "tf32x3"
-if len(sys.argv) > 5:
+if len(sys.argv) > 5 and sys.argv[5] != "0":
     os.environ["ITN_GEMM_BN"] = sys.argv[5]
+pad = len(sys.argv) > 6 and sys.argv[6] == "pad"     # rows padded to 4 columns, 128-bit stores (c_pad)
 ops = CudaOps()
 ops.precision = prec
 ops.lib.itn_debug_set_trace.argtypes = [C.c_void_p]
 a = torch.randn(M, K, device="cuda")
 w = torch.randn(N, K, device="cuda")
-out = torch.empty(M, N, device="cuda")
+out = torch.empty(M, (N + 3) // 4 * 4 if pad else N, device="cuda")[:, :N]
 for _ in range(3):
-    ops.matmul(a, w.t(), out=out)
+    ops.matmul(a, w.t(), out=out, out_pad=pad)
 torch.cuda.synchronize()
 buf = torch.zeros(9, 1024, dtype=torch.int64, device="cuda")
 assert ops.lib.itn_debug_set_trace(C.c_void_p(buf.data_ptr())) == 0
-ops.matmul(a, w.t(), out=out)
+ops.matmul(a, w.t(), out=out, out_pad=pad)
 torch.cuda.synchronize()
 t = buf.cpu()
 ph = t[8, :4].tolist()
+marks = t[8, 8:11].tolist()
 t[8] = 0
-t0 = int(t[t > 0].min())
+t0 = int(marks[0]) if marks[0] else int(t[t > 0].min())
+print(f"CTA 0: entry 0, prologue done {marks[1] - t0}, all roles done {marks[2] - t0} (SM cycles)")
 if ph[3]:
     print(f"epilogue warp 0 of CTA 0: {int(ph[3])} chunks; cycles per chunk: TMEM read {ph[0]/ph[3]:.0f}, "
           f"transpose {ph[1]/ph[3]:.0f}, math+stores {ph[2]/ph[3]:.0f}")

@@ -114,6 +114,33 @@ def matcher():
     print("matcher done")
 
 
+def criterion():
+    """Reference SetCriterion (+ autograd of ce + 5*giou + 2*bbox, models/interactron.py:121-122) on
+    oracle/cases.criterion_case inputs."""
+    rh._load()
+    from models.detr_models.detr import SetCriterion
+    from models.detr_models.matcher import HungarianMatcher
+    from oracle.cases import criterion_case
+    crit = SetCriterion(1235, matcher=HungarianMatcher(1, 5, 2), weight_dict={"loss_ce": 1, "loss_bbox": 5, "loss_giou": 2},
+                        eos_coef=0.1, losses=["labels", "boxes", "cardinality"])
+    gold = {}
+    for seed in (0, 1, 2):
+        for frames in (5, 1):
+            logits, boxes, targets = criterion_case(seed, frames)
+            logits.requires_grad_(True)
+            boxes.requires_grad_(True)
+            out = crit({"pred_logits": logits, "pred_boxes": boxes}, targets, background_c=0.1)
+            total = out["loss_ce"] + 5 * out["loss_giou"] + 2 * out["loss_bbox"]
+            dl, db = torch.autograd.grad(total, (logits, boxes))
+            idx = crit.matcher({"pred_logits": logits.detach(), "pred_boxes": boxes.detach()}, targets)
+            gold[(seed, frames)] = {
+                "losses": {k: v.detach().clone() for k, v in out.items()}, "keys": list(out.keys()),
+                "indices": [(i.clone(), j.clone()) for i, j in idx], "dboxes": db.clone(),
+                "dlogits_cols": dl[..., ::97].clone(), "dlogits_abs_rowsum": dl.abs().sum(-1).clone()}
+    torch.save(gold, os.path.join(OUT, "criterion.pt"))
+    print("criterion done", {k: {n: round(float(x), 5) for n, x in v["losses"].items()} for k, v in gold.items()})
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
@@ -122,3 +149,4 @@ if __name__ == "__main__":
     baselines()
     policy()
     matcher()
+    criterion()
