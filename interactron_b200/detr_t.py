@@ -16,8 +16,8 @@ the `_r` twins of LayerNorm outputs); residual streams and gradients accumulate 
 """
 import math
 
-from .layers import (DecDims, GradSink, T, attention_bwd, attention_fwd, decoder_layer_bwd,  # noqa: F401
-                     decoder_layer_fwd, lin, mlp_bwd, mlp_fwd)
+from .layers import (DecDims, GradSink, MultiSink, NullSink, T, attention_bwd, attention_fwd,  # noqa: F401
+                     decoder_layer_bwd, decoder_layer_fwd, lin, mlp_bwd, mlp_fwd)
 
 D, H, HD, FFN, NQ = 256, 8, 32, 2048, 50
 N_ENC, N_DEC = 6, 6
@@ -101,12 +101,14 @@ def detr_t_forward(ops, W, src_r, pos, kmask, E, Fe, L, preds=None, need_cache=T
 
 # --------------------------------------------------------------------------- backward
 def detr_t_backward(ops, W, cache, sink, dpreds=None, dmemory=None, dlogits=None, dboxes=None, dhs=None):
-    """Back-propagates into the flat gradient buffer behind `sink` (all 157 fast weights).
+    """Back-propagates into the flat gradient buffer(s) behind `sink`: the 157 fast weights on the
+    inner loop (per-episode GradSink over theta); in the meta-training step also / only the shared
+    `in_proj_*` parameters psi (reference models/interactron.py:123,134 - they stay live Parameters).
 
     Upstream gradients: either `dpreds` [E*Fe*50, 1496] (TF32-clean gradient of the fusion
     prediction tokens = cat(d box_features, d logits, d boxes)) and `dmemory` [E, Fe*L, 256]
     (gradient of the encoder memory from fusion), or explicit dlogits/dboxes/dhs.
-    in_proj_* receive no gradient here (they are not fast weights); the backbone is frozen (D1).
+    The backbone is frozen (D1).
     """
     E, Fe, L = cache["E"], cache["Fe"], cache["L"]
     R, Q, B = Fe * L, Fe * NQ, E * Fe
@@ -126,9 +128,7 @@ def detr_t_backward(ops, W, cache, sink, dpreds=None, dmemory=None, dlogits=None
     sink.linear("class_embed", dlogits_r, hs_r)
     ops.matmul(dlogits_r, W.bwd("class_embed.weight"), out=dhs_t, accumulate=True)
     dt, _ = ops.layernorm_bwd(dhs_t.view(E * Q, D), cache["tgt_last"].view(E * Q, D), cache["mh"], cache["rh"],
-                              W.p("transformer.decoder.norm.weight"),
-                              dgamma=sink.view("transformer.decoder.norm.weight"),
-                              dbeta=sink.view("transformer.decoder.norm.bias"))
+                              W.p("transformer.decoder.norm.weight"), **sink.norm("transformer.decoder.norm"))
 
     # decoder -------------------------------------------------------------------------
     dmem = dmemory.contiguous() if dmemory is not None else ops.zeros(E, R, D)         # accumulates
@@ -139,7 +139,7 @@ def detr_t_backward(ops, W, cache, sink, dpreds=None, dmemory=None, dlogits=None
         dt = decoder_layer_bwd(ops, W, f"transformer.decoder.layers.{j}.", dm, cache["dec"][j], dt, sink,
                                dqpos, dmp, dmem.view(1, E * R, D))
     # query_embed gradient: sum the per-frame query_pos gradients of each episode
-    ops.colsum(dqpos.view(E, Fe, NQ * D), out=sink.view("query_embed.weight").reshape(E, NQ * D))
+    sink.colsum("query_embed.weight", dqpos.view(E, Fe, NQ * D))
     # gradient of memory = decoder V paths (dmem) + K paths through memory+pos (dmp) [+ fusion]
     dx = ops.add(dmem.view(E * R, D), dmp.view(E * R, D))
 
@@ -147,23 +147,25 @@ def detr_t_backward(ops, W, cache, sink, dpreds=None, dmemory=None, dlogits=None
     for i in reversed(range(N_ENC)):
         pre = f"transformer.encoder.layers.{i}."
         s = cache["enc"][i]
-        ip_name = pre + "self_attn.in_proj_weight"
+        ip_name, ip_bias = pre + "self_attn.in_proj_weight", pre + "self_attn.in_proj_bias"
         df, df_r = ops.layernorm_bwd(dx, s["f"].view(E * R, D), s["m2"], s["r2"], W.p(pre + "norm2.weight"),
-                                     dgamma=sink.view(pre + "norm2.weight"), dbeta=sink.view(pre + "norm2.bias"))
+                                     **sink.norm(pre + "norm2"))
         df3, df3_r = df.view(E, R, D), df_r.view(E, R, D)
         sink.linear(pre + "linear2", df3_r, s["h"], df3)
         dh = ops.matmul(df3_r, W.bwd(pre + "linear2.weight"), epi="relu_mask", aux=s["h"], rnd=True)
         sink.linear(pre + "linear1", dh, s["x1_r"].view(E, R, D))
         dx1 = ops.matmul(dh, W.bwd(pre + "linear1.weight"), residual=df3)
         da, da_r = ops.layernorm_bwd(dx1.view(E * R, D), s["a"].view(E * R, D), s["m1"], s["r1"],
-                                     W.p(pre + "norm1.weight"), dgamma=sink.view(pre + "norm1.weight"),
-                                     dbeta=sink.view(pre + "norm1.bias"))
+                                     W.p(pre + "norm1.weight"), **sink.norm(pre + "norm1"))
         da3, da3_r = da.view(E, R, D), da_r.view(E, R, D)
         sink.linear(pre + "self_attn.out_proj", da3_r, s["o"].view(E, R, D), da3)
         dO = ops.matmul(da3_r, W.bwd(pre + "self_attn.out_proj.weight"), rnd=True)
         dqk, dv = ops.empty(B, L, 2 * D), ops.empty(B, L, D)
         attention_bwd(ops, dO.view(B, L, D), s["qk3"][..., :D], s["qk3"][..., D:], s["v3"], s["P"],
                       B, L, L, H, HD, SCALE, dqk[..., :D], dqk[..., D:], dv)
+        if sink.wants(ip_name):
+            sink.rows(ip_name, ip_bias, 0, 2 * D, dqk.view(1, E * R, 2 * D), s["qk_in"])
+            sink.rows(ip_name, ip_bias, 2 * D, 3 * D, dv.view(1, E * R, D), s["x_r"].view(1, E * R, D))
         dxi = ops.matmul(dqk.view(1, E * R, 2 * D), W.bwd(ip_name, 0, 2 * D), residual=da.view(1, E * R, D))
         last = i == 0
         ops.matmul(dv.view(1, E * R, D), W.bwd(ip_name, 2 * D, 3 * D), out=dxi, accumulate=True, rnd=last)
@@ -171,6 +173,4 @@ def detr_t_backward(ops, W, cache, sink, dpreds=None, dmemory=None, dlogits=None
 
     # input_proj ----------------------------------------------------------------------
     dx3 = dx.view(E, R, D)                                            # TF32-clean (rounded by the last GEMM)
-    wv = sink.view("input_proj.weight")
-    ops.matmul(T(dx3), cache["src_r"], out=wv.reshape(E, D, -1))
-    ops.colsum(dx3, out=sink.view("input_proj.bias"))
+    sink.linear("input_proj", dx3, cache["src_r"])

@@ -13,7 +13,8 @@ tokens `preds` [E*S*50, 1496] = cat(box_features, logits, boxes).  Only *data* g
 needed on the inner loop (the fusion parameters phi are not adapted): `backward` returns
 d memory and d preds for detr_t.detr_t_backward.
 """
-from .layers import DecDims, T, attention_bwd, attention_fwd, decoder_layer_bwd, decoder_layer_fwd, lin, mlp_bwd, mlp_fwd
+from .layers import (DecDims, NullSink, T, attention_bwd, attention_fwd, decoder_layer_bwd,  # noqa: F401
+                     decoder_layer_fwd, lin, mlp_bwd, mlp_fwd)
 
 DF, NH, NP, NA = 512, 8, 50, 5          # width, heads, predictions per frame, action tokens
 N_LAYERS = 4
@@ -57,33 +58,45 @@ def fusion_b_forward(ops, W, memory_r, preds, E, S, L, need_cache=True):
     yp_r = ops.copy2d_(ops.empty(E, Qp * DF), y_r.view(E, Q * DF)[:, :Qp * DF]).view(E, Qp, DF)
     ya_r = ops.copy2d_(ops.empty(E, 4 * DF), y_r.view(E, Q * DF)[:, Qp * DF:(Qp + 4) * DF]).view(E, 4, DF)
     lv, norm, dlv, lhid = _learned_loss(ops, W, yp_r, E, S, need_cache)
-    actions, _ = mlp_fwd(ops, W, "action_decoder", ya_r)
+    actions, ahid = mlp_fwd(ops, W, "action_decoder", ya_r)
     out = dict(loss_vec=lv, learned_loss=norm, actions=actions)
     cache = None
     if need_cache:
-        cache = dict(layers=caches, x_last=x, my=my, ry=ry, yp_r=yp_r, dlv=dlv, lhid=lhid, E=E, S=S, L=L)
+        cache = dict(layers=caches, x_last=x, my=my, ry=ry, yp_r=yp_r, dlv=dlv, lhid=lhid, E=E, S=S, L=L,
+                     ya_r=ya_r, ahid=ahid, memory_r=memory_r, preds=preds)
     return out, cache
 
 
-def fusion_b_backward(ops, W, cache):
-    """Gradient of sum_e learned_loss[e] wrt the inputs: -> (dmemory [E,S*L,256] fp32,
-    dpreds [E*S*50,1496] TF32-clean)."""
+def fusion_b_backward(ops, W, cache, sink=None, dactions=None):
+    """Gradient of sum_e learned_loss[e] (+ <dactions, actions> when given) wrt the inputs:
+    -> (dmemory [E,S*L,256] fp32, dpreds [E*S*50,1496] TF32-clean).  `sink` (default: none, the
+    inner loop) receives the gradients of the fusion parameters phi (meta-training step)."""
     E, S, L = cache["E"], cache["S"], cache["L"]
     R, Qp, Q = S * L, S * NP, S * NP + NA
+    sink = sink if sink is not None else NullSink()
     dz = ops.round_tf32(cache["dlv"].view(E, Qp, 1))
-    dyp = mlp_bwd(ops, W, "loss_decoder", dz, cache["yp_r"], cache["lhid"])            # [E,Qp,512]
+    dyp = mlp_bwd(ops, W, "loss_decoder", dz, cache["yp_r"], cache["lhid"], sink)      # [E,Qp,512]
     dy = ops.zeros(E, Q, DF)
     ops.copy2d_(dy.view(E, Q * DF)[:, :Qp * DF], dyp.view(E, Qp * DF))
+    if dactions is not None:
+        dya = mlp_bwd(ops, W, "action_decoder", dactions, cache["ya_r"], cache["ahid"], sink)   # [E,4,512]
+        ops.copy2d_(dy.view(E, Q * DF)[:, Qp * DF:(Qp + 4) * DF], dya.view(E, 4 * DF))
     dt, _ = ops.layernorm_bwd(dy.view(E * Q, DF), cache["x_last"].view(E * Q, DF), cache["my"], cache["ry"],
-                              W.p("transformer.norm.weight"))
+                              W.p("transformer.norm.weight"), **sink.norm("transformer.norm"))
     dm = DecDims(E, E, Q, R, DF, NH)
     dmp, dmem = ops.zeros(1, E * R, DF), ops.zeros(1, E * R, DF)
+    dqpos = ops.zeros(E, Q, DF) if sink.wants("query_embed") else None
     for j in reversed(range(N_LAYERS)):
-        dt = decoder_layer_bwd(ops, W, f"transformer.layers.{j}.", dm, cache["layers"][j], dt, None, None,
+        dt = decoder_layer_bwd(ops, W, f"transformer.layers.{j}.", dm, cache["layers"][j], dt, sink, dqpos,
                                dmp, dmem)
+    if dqpos is not None:
+        sink.colsum("query_embed", dqpos.view(E, 1, Q * DF))
+    sink.colsum("action_tokens", dt.view(1, E, Q * DF)[:, :, Qp * DF:])
     dmem_tot = ops.add(dmem.view(E * R, DF), dmp.view(E * R, DF), rnd=True).view(1, E * R, DF)
+    sink.linear("img_feature_embedding", dmem_tot, cache["memory_r"].view(1, E * R, -1))
     dmemory = ops.matmul(dmem_tot, W.bwd("img_feature_embedding.weight")).view(E, R, -1)
     dtp = ops.copy2d_(ops.empty(E, Qp * DF), dt.view(E, Q * DF)[:, :Qp * DF], rnd=True).view(1, E * Qp, DF)
+    sink.linear("prediction_embedding", dtp, cache["preds"].view(1, E * Qp, -1))
     dpreds = ops.matmul(dtp, W.bwd("prediction_embedding.weight"), rnd=True).view(E * Qp, -1)
     return dmemory, dpreds
 
@@ -122,7 +135,8 @@ def fusion_a_forward(ops, W, memory_r, preds, E, S, L, need_cache=True, want_aux
                 out_pre=upre, rnd=True)
         x2 = lin(ops, u, W.w(pre + "mlp.2.weight"), W.p(pre + "mlp.2.bias"), residual=x1)
         if need_cache:
-            caches.append(dict(x=x, m1=m1, r1=r1, q=q, k=k, v=v, P=P, x1=x1, m2=m2, r2=r2, upre=upre))
+            caches.append(dict(x=x, m1=m1, r1=r1, q=q, k=k, v=v, P=P, x1=x1, m2=m2, r2=r2, upre=upre,
+                               h_r=h_r, o=o, h2_r=h2_r, u=u))
         x = x2
     yf, yf_r, mf, rf = ops.layernorm_fwd(x.view(E * Tn, DF), W.p("model.ln_f.weight"), W.p("model.ln_f.bias"))
     yf_r = yf_r.view(E, Tn, DF)
@@ -133,7 +147,7 @@ def fusion_a_forward(ops, W, memory_r, preds, E, S, L, need_cache=True, want_aux
     yp_r = lin(ops, yp_in, hw, rnd=True)
     ya_r = lin(ops, ya_in, hw, rnd=True)
     lv, norm, dlv, lhid = _learned_loss(ops, W, yp_r, E, S, need_cache)
-    actions, _ = mlp_fwd(ops, W, "action_decoder", ya_r)
+    actions, ahid = mlp_fwd(ops, W, "action_decoder", ya_r)
     out = dict(loss_vec=lv, learned_loss=norm, actions=actions)
     if want_aux_heads:
         # direct-supervision heads, used by the detr_multiframe baseline only
@@ -144,47 +158,66 @@ def fusion_a_forward(ops, W, memory_r, preds, E, S, L, need_cache=True, want_aux
     cache = None
     if need_cache:
         cache = dict(layers=caches, x_last=x, mf=mf, rf=rf, yp_in=yp_in, yp_r=yp_r, dlv=dlv, lhid=lhid,
-                     E=E, S=S, L=L)
+                     E=E, S=S, L=L, ya_in=ya_in, ya_r=ya_r, ahid=ahid, memory_r=memory_r, preds=preds)
     return out, cache
 
 
-def fusion_a_backward(ops, W, cache):
-    """Gradient of sum_e learned_loss[e] wrt the inputs: -> (dmemory [E,S*L,256] fp32,
-    dpreds [E*S*50,1496] TF32-clean)."""
+def fusion_a_backward(ops, W, cache, sink=None, dactions=None):
+    """Gradient of sum_e learned_loss[e] (+ <dactions, actions> when given) wrt the inputs:
+    -> (dmemory [E,S*L,256] fp32, dpreds [E*S*50,1496] TF32-clean).  `sink` (default: none, the
+    inner loop) receives the gradients of the fusion parameters phi (meta-training step)."""
     E, S, L = cache["E"], cache["S"], cache["L"]
     R, Qp = S * L, S * NP
     Tn = R + Qp + NA
     HD = DF // NH
+    sink = sink if sink is not None else NullSink()
     dz = ops.round_tf32(cache["dlv"].view(E, Qp, 1))
-    dyp = mlp_bwd(ops, W, "loss_decoder", dz, cache["yp_r"], cache["lhid"], rnd=True)  # d(head out) [E,Qp,512]
+    dyp = mlp_bwd(ops, W, "loss_decoder", dz, cache["yp_r"], cache["lhid"], sink, rnd=True)  # d(head out) [E,Qp,512]
+    sink.linear("model.head", dyp, cache["yp_in"])
     dyp_in = ops.matmul(dyp, W.bwd("model.head.weight"))                                  # d(ln_f out)
     dyf = ops.zeros(E, Tn, DF)
     ops.copy2d_(dyf.view(E, Tn * DF)[:, R * DF:(R + Qp) * DF], dyp_in.view(E, Qp * DF))
+    if dactions is not None:
+        dya = mlp_bwd(ops, W, "action_decoder", dactions, cache["ya_r"], cache["ahid"], sink, rnd=True)
+        sink.linear("model.head", dya, cache["ya_in"], accumulate=True)
+        dya_in = ops.matmul(dya, W.bwd("model.head.weight"))
+        ops.copy2d_(dyf.view(E, Tn * DF)[:, (R + Qp) * DF:(R + Qp + 4) * DF], dya_in.view(E, 4 * DF))
     dx, _ = ops.layernorm_bwd(dyf.view(E * Tn, DF), cache["x_last"].view(E * Tn, DF), cache["mf"], cache["rf"],
-                              W.p("model.ln_f.weight"))
+                              W.p("model.ln_f.weight"), **sink.norm("model.ln_f"))
     for i in reversed(range(N_LAYERS)):
         pre = f"model.blocks.{i}."
         s = cache["layers"][i]
         dx_r = ops.round_tf32(dx).view(1, E * Tn, DF)
+        sink.linear(pre + "mlp.2", dx_r, s["u"])
         du = ops.matmul(dx_r, W.bwd(pre + "mlp.2.weight"), epi="gelu_grad", aux=s["upre"], rnd=True)
+        sink.linear(pre + "mlp.0", du, s["h2_r"].view(1, E * Tn, DF))
         dh2 = ops.matmul(du, W.bwd(pre + "mlp.0.weight"))
         dx1, dx1_r = ops.layernorm_bwd(dh2.view(E * Tn, DF), s["x1"].view(E * Tn, DF), s["m2"], s["r2"],
-                                       W.p(pre + "ln2.weight"))
+                                       W.p(pre + "ln2.weight"), **sink.norm(pre + "ln2"))
         dx1 = ops.add(dx1, dx)                                                          # + residual path
         dx1_r = ops.round_tf32(dx1).view(1, E * Tn, DF)
+        sink.linear(pre + "attn.proj", dx1_r, s["o"].view(1, E * Tn, DF))
         dO = ops.matmul(dx1_r, W.bwd(pre + "attn.proj.weight"), rnd=True)
         dq, dk, dv = ops.empty(E, Tn, DF), ops.empty(E, Tn, DF), ops.empty(E, Tn, DF)
         attention_bwd(ops, dO.view(E, Tn, DF), s["q"], s["k"], s["v"], s["P"], E, Tn, Tn, NH, HD,
                       1.0 / (HD ** 0.5), dq, dk, dv)
+        for nm, d_ in (("query", dq), ("key", dk), ("value", dv)):
+            sink.linear(pre + "attn." + nm, d_.view(1, E * Tn, DF), s["h_r"])
         dh = ops.matmul(dq.view(1, E * Tn, DF), W.w(pre + "attn.query.weight"))
         ops.matmul(dk.view(1, E * Tn, DF), W.w(pre + "attn.key.weight"), out=dh, accumulate=True)
         ops.matmul(dv.view(1, E * Tn, DF), W.w(pre + "attn.value.weight"), out=dh, accumulate=True)
         dxa, _ = ops.layernorm_bwd(dh.view(E * Tn, DF), s["x"].view(E * Tn, DF), s["m1"], s["r1"],
-                                   W.p(pre + "ln1.weight"))
+                                   W.p(pre + "ln1.weight"), **sink.norm(pre + "ln1"))
         dx = ops.add(dxa, dx1)
     dseq = dx.view(E, Tn * DF)
+    if sink.wants("model.seq_pos_embed"):
+        assert Tn * DF == W.p("model.seq_pos_embed").numel(), "phi gradients need the full 5-frame sequence"
+        sink.colsum("model.seq_pos_embed", dx.view(1, E, Tn * DF))
+    sink.colsum("action_tokens", dx.view(1, E, Tn * DF)[:, :, (R + Qp) * DF:])
     dimg = ops.copy2d_(ops.empty(E, R * DF), dseq[:, :R * DF], rnd=True).view(1, E * R, DF)
+    sink.linear("img_feature_embedding", dimg, cache["memory_r"].view(1, E * R, -1))
     dmemory = ops.matmul(dimg, W.bwd("img_feature_embedding.weight")).view(E, R, -1)
     dpe = ops.copy2d_(ops.empty(E, Qp * DF), dseq[:, R * DF:(R + Qp) * DF], rnd=True).view(1, E * Qp, DF)
+    sink.linear("prediction_embedding", dpe, cache["preds"].view(1, E * Qp, -1))
     dpreds = ops.matmul(dpe, W.bwd("prediction_embedding.weight"), rnd=True).view(E * Qp, -1)
     return dmemory, dpreds

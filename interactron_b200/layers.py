@@ -53,25 +53,121 @@ def attention_bwd(ops, dO, q, k, v, P, B, Lq, Lk, nh, hd, scale, dq, dk, dv):
     ops.matmul(T(dp), qh, out=dk.view(B, Lk, nh, hd).permute(0, 2, 1, 3), rnd=True)  # dK = dS^T Q
 
 
-# --------------------------------------------------------------------------- gradient sink
-class GradSink:
-    """Writes weight gradients straight into the flat per-episode gradient buffer g [E, n]."""
+# --------------------------------------------------------------------------- gradient sinks
+class NullSink:
+    """Data gradients only (the inner loop never needs d/d phi of the fusion network)."""
 
-    def __init__(self, ops, pack, g):
-        self.ops, self.pack, self.g = ops, pack, g
+    def wants(self, name):
+        return False
+
+    def linear(self, name, dy_r, x_r, dy_full=None, accumulate=False):
+        pass
+
+    def rows(self, name_w, name_b, lo, hi, dy, x):
+        pass
+
+    def norm(self, name):
+        return {}
+
+    def colsum(self, name, x):
+        pass
+
+    def copy(self, name, x):
+        pass
+
+
+class GradSink(NullSink):
+    """Writes weight gradients straight into a flat gradient buffer laid out by `pack`.
+
+    per-episode (default): g [E, n], one gradient per episode - the inner gradient of the fast
+    weights theta (reference models/interactron.py:51-52).
+    shared=True: g [1, n], the gradient summed over the episodes of the step - what `.backward()`
+    accumulates on parameters every episode shares (in_proj_* and the fusion network in the
+    meta-training step, reference models/interactron.py:123,134).  Activations [E, rows, .] are
+    then read as one [1, E*rows, .] matrix.
+    Names outside `pack` are ignored, so sinks over disjoint packs compose with MultiSink."""
+
+    def __init__(self, ops, pack, g, shared=False):
+        self.ops, self.pack, self.g, self.shared = ops, pack, g, shared
+
+    def wants(self, name):
+        return name in self.pack
 
     def view(self, name):
         return self.pack.view(self.g, name)
 
-    def linear(self, name, dy_r, x_r, dy_full=None):
-        """dW = dy^T x into `name.weight`, db = colsum(dy) into `name.bias`."""
+    def _flat(self, t):
+        return t.reshape(1, -1, t.shape[-1]) if self.shared else t
+
+    def linear(self, name, dy_r, x_r, dy_full=None, accumulate=False):
+        """dW = dy^T x into `name.weight`, db = colsum(dy) into `name.bias` (if there is one).
+        accumulate: second use of a bias-free weight in the same pass (fusion A's `model.head`)."""
+        if not self.wants(name + ".weight"):
+            return
         w = self.view(name + ".weight")
-        E = w.shape[0]
-        self.ops.matmul(T(dy_r), x_r, out=w.reshape(E, w.shape[1], -1))
-        self.ops.colsum(dy_full if dy_full is not None else dy_r, out=self.view(name + ".bias"))
+        self.ops.matmul(T(self._flat(dy_r)), self._flat(x_r), out=w.reshape(w.shape[0], w.shape[1], -1),
+                        accumulate=accumulate)
+        if self.wants(name + ".bias"):
+            assert not accumulate
+            self.ops.colsum(self._flat(dy_full if dy_full is not None else dy_r), out=self.view(name + ".bias"))
+
+    def rows(self, name_w, name_b, lo, hi, dy, x):
+        """Rows [lo, hi) of a packed projection (nn.MultiheadAttention.in_proj_*)."""
+        if not self.wants(name_w):
+            return
+        self.ops.matmul(T(self._flat(dy)), self._flat(x), out=self.view(name_w)[:, lo:hi])
+        self.ops.colsum(self._flat(dy), out=self.view(name_b)[:, lo:hi])
 
     def norm(self, name):
+        if not self.wants(name + ".weight"):
+            return {}
         return dict(dgamma=self.view(name + ".weight"), dbeta=self.view(name + ".bias"))
+
+    def colsum(self, name, x):
+        """x [G, rows, cols] summed over rows into parameter `name` (numel = cols per group)."""
+        if not self.wants(name):
+            return
+        if self.shared:
+            x = x.reshape(1, -1, x.shape[-1])
+        v = self.view(name)
+        self.ops.colsum(x, out=v.reshape(v.shape[0], -1))
+
+    def copy(self, name, x):
+        """x [G, numel] is the gradient of parameter `name` itself."""
+        if not self.wants(name):
+            return
+        v = self.view(name)
+        self.ops.copy2d_(v.reshape(v.shape[0], -1), x)
+
+
+class MultiSink(NullSink):
+    def __init__(self, *sinks):
+        self.sinks = [s for s in sinks if s is not None]
+
+    def wants(self, name):
+        return any(s.wants(name) for s in self.sinks)
+
+    def linear(self, name, dy_r, x_r, dy_full=None, accumulate=False):
+        for s in self.sinks:
+            s.linear(name, dy_r, x_r, dy_full, accumulate)
+
+    def rows(self, name_w, name_b, lo, hi, dy, x):
+        for s in self.sinks:
+            s.rows(name_w, name_b, lo, hi, dy, x)
+
+    def norm(self, name):
+        for s in self.sinks:
+            if s.wants(name + ".weight"):
+                return s.norm(name)
+        return {}
+
+    def colsum(self, name, x):
+        for s in self.sinks:
+            s.colsum(name, x)
+
+    def copy(self, name, x):
+        for s in self.sinks:
+            s.copy(name, x)
 
 
 # --------------------------------------------------------------------------- decoder layer
@@ -117,36 +213,41 @@ def decoder_layer_fwd(ops, W, pre, dm, tgt, tgt_r, qpos, mem_pos_r, memory_r, km
     cache = None
     if need_cache:
         cache = dict(qk3=qk3, v3=v3, P=P, o=o, a1=a1, m1=m1, r1=r1, qc=qc, kc=kc, vc=vc, P2=P2, o2=o2,
-                     a2=a2, m2=m2, r2=r2, t2_r=t2_r, h=h, f=f, m3=m3, r3=r3)
+                     a2=a2, m2=m2, r2=r2, t2_r=t2_r, h=h, f=f, m3=m3, r3=r3,
+                     qk_in=qk_in, tgt_r=tgt_r, q_in=q_in, mem_pos_r=mem_pos_r, memory_r=memory_r)
     return t3.view(E, Q, D), t3_r.view(E, Q, D), cache
 
 
 def decoder_layer_bwd(ops, W, pre, dm, s, dt, sink, dqpos, dmp, dmem):
     """dt [E*Q,D] = gradient of the layer output.  Returns the gradient of the layer input
     [E*Q,D]; accumulates d(query_pos) into dqpos [E,Q,D] (if given), d(memory+pos) into dmp and
-    d(memory) into dmem (both [1,E*R,D]); writes weight gradients through `sink` (None = data
-    gradients only, as for the fusion network whose parameters are not adapted)."""
+    d(memory) into dmem (both [1,E*R,D]); writes weight gradients through `sink` (NullSink = data
+    gradients only, as for the fusion network on the inner loop, whose parameters are not adapted)."""
     E, B, Lq, Lk, D, nh, hd, Q, R = dm.E, dm.B, dm.Lq, dm.Lk, dm.D, dm.nh, dm.hd, dm.Q, dm.R
     sa_w, ca_w = pre + "self_attn.in_proj_weight", pre + "multihead_attn.in_proj_weight"
-    nk = (lambda n: sink.norm(pre + n)) if sink is not None else (lambda n: {})
+    sa_b, ca_b = pre + "self_attn.in_proj_bias", pre + "multihead_attn.in_proj_bias"
+    sink = sink if sink is not None else NullSink()
+    nk = lambda n: sink.norm(pre + n)
     df, df_r = ops.layernorm_bwd(dt, s["f"].view(E * Q, D), s["m3"], s["r3"], W.p(pre + "norm3.weight"),
                                  **nk("norm3"))
     df3, df3_r = df.view(E, Q, D), df_r.view(E, Q, D)
     dh = ops.matmul(df3_r, W.bwd(pre + "linear2.weight"), epi="relu_mask", aux=s["h"], rnd=True)
-    if sink is not None:
-        sink.linear(pre + "linear2", df3_r, s["h"], df3)
-        sink.linear(pre + "linear1", dh, s["t2_r"].view(E, Q, D))
+    sink.linear(pre + "linear2", df3_r, s["h"], df3)
+    sink.linear(pre + "linear1", dh, s["t2_r"].view(E, Q, D))
     dt2 = ops.matmul(dh, W.bwd(pre + "linear1.weight"), residual=df3)
     da2, da2_r = ops.layernorm_bwd(dt2.view(E * Q, D), s["a2"].view(E * Q, D), s["m2"], s["r2"],
                                    W.p(pre + "norm2.weight"), **nk("norm2"))
     da2_3r = da2_r.view(E, Q, D)
-    if sink is not None:
-        sink.linear(pre + "multihead_attn.out_proj", da2_3r, s["o2"].view(E, Q, D), da2.view(E, Q, D))
+    sink.linear(pre + "multihead_attn.out_proj", da2_3r, s["o2"].view(E, Q, D), da2.view(E, Q, D))
     dO2 = ops.matmul(da2_3r, W.bwd(pre + "multihead_attn.out_proj.weight"), rnd=True)
     dqc, dkc, dvc = ops.empty(B, Lq, D), ops.empty(B, Lk, D), ops.empty(B, Lk, D)
     attention_bwd(ops, dO2.view(B, Lq, D), s["qc"], s["kc"], s["vc"], s["P2"], B, Lq, Lk, nh, hd, dm.scale,
                   dqc, dkc, dvc)
     dqc1 = dqc.view(1, E * Q, D)
+    if sink.wants(ca_w):
+        sink.rows(ca_w, ca_b, 0, D, dqc1, s["q_in"])
+        sink.rows(ca_w, ca_b, D, 2 * D, dkc.view(1, E * R, D), s["mem_pos_r"])
+        sink.rows(ca_w, ca_b, 2 * D, 3 * D, dvc.view(1, E * R, D), s["memory_r"])
     dt1 = ops.matmul(dqc1, W.bwd(ca_w, 0, D), residual=da2.view(1, E * Q, D))
     if dqpos is not None:
         ops.matmul(dqc1, W.bwd(ca_w, 0, D), out=dqpos.view(1, E * Q, D), accumulate=True)
@@ -155,13 +256,15 @@ def decoder_layer_bwd(ops, W, pre, dm, s, dt, sink, dqpos, dmp, dmem):
     da1, da1_r = ops.layernorm_bwd(dt1.view(E * Q, D), s["a1"].view(E * Q, D), s["m1"], s["r1"],
                                    W.p(pre + "norm1.weight"), **nk("norm1"))
     da1_3r = da1_r.view(E, Q, D)
-    if sink is not None:
-        sink.linear(pre + "self_attn.out_proj", da1_3r, s["o"].view(E, Q, D), da1.view(E, Q, D))
+    sink.linear(pre + "self_attn.out_proj", da1_3r, s["o"].view(E, Q, D), da1.view(E, Q, D))
     dO = ops.matmul(da1_3r, W.bwd(pre + "self_attn.out_proj.weight"), rnd=True)
     dqk, dv = ops.empty(B, Lq, 2 * D), ops.empty(B, Lq, D)
     attention_bwd(ops, dO.view(B, Lq, D), s["qk3"][..., :D], s["qk3"][..., D:], s["v3"], s["P"],
                   B, Lq, Lq, nh, hd, dm.scale, dqk[..., :D], dqk[..., D:], dv)
     dqk1 = dqk.view(1, E * Q, 2 * D)
+    if sink.wants(sa_w):
+        sink.rows(sa_w, sa_b, 0, 2 * D, dqk1, s["qk_in"])
+        sink.rows(sa_w, sa_b, 2 * D, 3 * D, dv.view(1, E * Q, D), s["tgt_r"].view(1, E * Q, D))
     dtg = ops.matmul(dqk1, W.bwd(sa_w, 0, 2 * D), residual=da1.view(1, E * Q, D))
     if dqpos is not None:
         ops.matmul(dqk1, W.bwd(sa_w, 0, 2 * D), out=dqpos.view(1, E * Q, D), accumulate=True)
@@ -185,10 +288,10 @@ def mlp_fwd(ops, W, name, x_r, n_layers=3):
 def mlp_bwd(ops, W, name, dz_r, x_r, hid, sink=None, n_layers=3, **last_kw):
     """dz_r [E,R,out] TF32-clean -> gradient wrt x (extra epilogue args via last_kw)."""
     d = dz_r
+    sink = sink if sink is not None else NullSink()
     for i in reversed(range(n_layers)):
         inp = hid[i - 1] if i > 0 else x_r
-        if sink is not None:
-            sink.linear(f"{name}.layers.{i}", d, inp)
+        sink.linear(f"{name}.layers.{i}", d, inp)
         w = W.bwd(f"{name}.layers.{i}.weight")
         if i > 0:
             d = ops.matmul(d, w, epi="relu_mask", aux=hid[i - 1], rnd=True)

@@ -60,7 +60,7 @@ def test_detr_t_forward_backward_matches_reference_autograd(setup):
     wl, wb, wh, wm = wl.double(), wb.double(), wh.double(), wm.double()
     loss = ((out["pred_logits"] * wl).sum() + (out["pred_boxes"] * wb).sum() + (out["box_features"] * wh).sum()
             + (out["embedded_memory_features"] * wm).sum())
-    g_ref = torch.autograd.grad(loss, theta_ref)
+    g_ref = torch.autograd.grad(loss, theta_ref, retain_graph=True)
 
     ops = SimOps(torch.float64)
     tp, tparams, pp, pparams = detector_packs(holder.detector)
@@ -85,7 +85,9 @@ def test_detr_t_forward_backward_matches_reference_autograd(setup):
     assert rel(preds, cat_ref) < 1e-10
 
     g = ops.zeros(1, tp.numel)
-    sink = detr_t.GradSink(ops, tp, g)
+    gpsi = ops.zeros(1, pp.numel)
+    # theta per episode + the shared in_proj_* parameters (meta-training step) through one MultiSink
+    sink = detr_t.MultiSink(detr_t.GradSink(ops, tp, g), detr_t.GradSink(ops, pp, gpsi, shared=True))
     dpreds = torch.cat((wh, wl, wb), -1).reshape(Fe * 50, 1496).contiguous()
     dmem = wm.flatten(2).transpose(1, 2).reshape(1, Fe * L, 256).contiguous()
     detr_t.detr_t_backward(ops, W, cache, sink, dpreds=dpreds, dmemory=dmem)
@@ -99,3 +101,6 @@ def test_detr_t_forward_backward_matches_reference_autograd(setup):
     errs.sort(reverse=True)
     print("worst theta-grad rel errs", errs[:8])
     assert worst < 1e-9, errs[:8]
+    g_psi_ref = torch.autograd.grad(loss, [named[n] for n in pp.names])
+    for name, gr in zip(pp.names, g_psi_ref):
+        assert rel(pp.view(gpsi, name)[0], gr) < 1e-9, name

@@ -123,3 +123,45 @@ def test_fusion_a_partial_sequence_and_aux_heads():
     assert rel(out["actions"][0], o["actions"]) < 1e-10
     assert rel(out["pred_boxes"].view(S, 50, 4), o["pred_boxes"]) < 1e-10
     assert rel(out["pred_logits"].view(S, 50, 1236), o["pred_logits"]) < 1e-10
+
+
+@pytest.mark.parametrize("model_type,E", [("interactron_random", 2), ("interactron", 1)])
+def test_fusion_parameter_gradients(model_type, E):
+    """phi gradients of sum_e (learned_loss_e + <wa_e, actions_e>) summed over the episodes, as
+    `.backward()` accumulates them in the meta-training step (reference models/interactron.py:118-123)."""
+    from interactron_b200 import fusion
+    from interactron_b200.layers import GradSink
+    ref, W = _build(model_type)
+    pack = W.tuples[0][0]
+    S = 5
+    mem, bf, lg, bx = _inputs(E, S, 11)
+    wa = torch.randn(E, 4, 4, generator=torch.Generator().manual_seed(5), dtype=torch.float64)
+    torch.set_default_dtype(torch.float64)
+    try:
+        total = 0
+        for e in range(E):
+            o = ref({"embedded_memory_features": mem[e:e + 1], "box_features": bf[e:e + 1],
+                     "pred_logits": lg[e:e + 1], "pred_boxes": bx[e:e + 1]})
+            total = total + torch.norm(o["loss"]) + (o["actions"] * wa[e]).sum()
+    finally:
+        torch.set_default_dtype(torch.float32)
+    named = dict(ref.named_parameters())
+    live = [n for n in pack.names if named[n].requires_grad]
+    g_ref = torch.autograd.grad(total, [named[n] for n in live], allow_unused=True)
+    ops = SimOps(torch.float64)
+    memory_r, preds = _mine_inputs(mem, bf, lg, bx)
+    fwd = fusion.fusion_a_forward if model_type == "interactron" else fusion.fusion_b_forward
+    bwd = fusion.fusion_a_backward if model_type == "interactron" else fusion.fusion_b_backward
+    out, cache = fwd(ops, W, memory_r, preds, E, S, 361)
+    gphi = ops.zeros(1, pack.numel)
+    bwd(ops, W, cache, sink=GradSink(ops, pack, gphi, shared=True), dactions=wa.clone())
+    n_checked = 0
+    for name, gr in zip(live, g_ref):
+        mine = pack.view(gphi, name)[0]
+        if gr is None:
+            assert float(mine.abs().max()) == 0.0, name
+            continue
+        # key biases have an exactly-zero gradient (softmax shift invariance): absolute floor
+        assert float((mine - gr).norm()) <= 1e-9 * float(gr.norm()) + 1e-13, name
+        n_checked += 1
+    assert n_checked > 60
