@@ -161,6 +161,120 @@ class SimOps:
         nrm = x.norm(dim=1)
         return nrm, x / nrm[:, None]
 
+    # ---- tangent (forward-mode) rules used by interactron_b200.dual.DualOps --------------------
+    @staticmethod
+    def _z(t, like):
+        return torch.zeros_like(like) if t is None else t
+
+    def mask_mul_(self, y, ref):
+        self.calls += 1
+        y.mul_((ref > 0).to(y.dtype).reshape(y.shape))
+        return y
+
+    def gelu_grad_dual(self, raw, raw_dot, aux, aux_dot, out=None):
+        """y = raw * gelu'(aux);  y_dot = raw_dot * gelu'(aux) + raw * gelu''(aux) * aux_dot."""
+        self.calls += 1
+        x = aux.reshape(raw.shape)
+        cdf = 0.5 * (1 + torch.erf(x * 0.7071067811865476))
+        pdf = torch.exp(-0.5 * x * x) * 0.3989422804014327
+        g1 = cdf + x * pdf
+        y = raw * g1
+        if out is not None:
+            out.copy_(y)
+            y = out
+        if raw_dot is None and aux_dot is None:
+            return y, None
+        yd = torch.zeros_like(raw)
+        if raw_dot is not None:
+            yd = yd + raw_dot * g1
+        if aux_dot is not None:
+            yd = yd + raw * pdf * (2 - x * x) * aux_dot.reshape(raw.shape)
+        return y, yd
+
+    def layernorm_fwd_jvp(self, x, x_dot, mean, rstd, gamma, gamma_dot, beta_dot):
+        self.calls += 1
+        rows, cols = x.shape
+        xh = (x - mean[:, None]) * rstd[:, None]
+        g2 = gamma.reshape(-1, cols)
+        G = g2.shape[0]
+        yd = torch.zeros_like(x)
+        if x_dot is not None:
+            xc = x_dot - x_dot.mean(-1, keepdim=True)
+            m = (xh * xc).mean(-1, keepdim=True)
+            xhd = rstd[:, None] * (xc - xh * m)
+            yd = yd + (xhd.view(G, -1, cols) * g2[:, None]).reshape(rows, cols)
+        if gamma_dot is not None:
+            gd = gamma_dot.reshape(-1, cols)
+            yd = yd + (xh.view(gd.shape[0], -1, cols) * gd[:, None]).reshape(rows, cols)
+        if beta_dot is not None:
+            bd = beta_dot.reshape(-1, cols)
+            yd = (yd.view(bd.shape[0], -1, cols) + bd[:, None]).reshape(rows, cols)
+        return yd
+
+    def layernorm_bwd_jvp(self, dy, dy_dot, x, x_dot, mean, rstd, gamma, gamma_dot, dgamma_dot=None, dbeta_dot=None):
+        self.calls += 1
+        rows, cols = x.shape
+        r = rstd[:, None]
+        xh = (x - mean[:, None]) * r
+        g2 = gamma.reshape(-1, cols)
+        G = g2.shape[0]
+        dy_dot = self._z(dy_dot, dy)
+        u = (dy.view(G, -1, cols) * g2[:, None]).reshape(rows, cols)
+        ud = (dy_dot.view(G, -1, cols) * g2[:, None]).reshape(rows, cols)
+        if gamma_dot is not None:
+            gd = gamma_dot.reshape(-1, cols)
+            ud = ud + (dy.view(gd.shape[0], -1, cols) * gd[:, None]).reshape(rows, cols)
+        a = u.mean(-1, keepdim=True)
+        b = (u * xh).mean(-1, keepdim=True)
+        dx = r * (u - a - xh * b)
+        if x_dot is not None:
+            xc = x_dot - x_dot.mean(-1, keepdim=True)
+            m = (xh * xc).mean(-1, keepdim=True)
+            xhd = r * (xc - xh * m)
+        else:
+            m = torch.zeros_like(a)
+            xhd = torch.zeros_like(x)
+        ad = ud.mean(-1, keepdim=True)
+        bd = (ud * xh + u * xhd).mean(-1, keepdim=True)
+        dxd = -r * m * dx + r * (ud - ad - xhd * b - xh * bd)
+        if dgamma_dot is not None:
+            Gd = dgamma_dot.shape[0]
+            dgamma_dot.copy_((dy_dot * xh + dy * xhd).view(Gd, -1, cols).sum(1))
+            dbeta_dot.copy_(dy_dot.view(Gd, -1, cols).sum(1))
+        return dxd
+
+    def softmax_bwd_jvp_(self, p, p_dot, dp, dp_dot, cols, scale):
+        """dp <- dS = scale*p*(dp - sum p dp);  dp_dot <- d/d(eps) of the same."""
+        self.calls += 1
+        ld = p.shape[-1]
+        pv = p.reshape(-1, ld)[:, :cols]
+        dv = dp.reshape(-1, ld)[:, :cols].clone()
+        dd = dp_dot.reshape(-1, ld)[:, :cols].clone()
+        r = (pv * dv).sum(-1, keepdim=True)
+        rd = (pv * dd).sum(-1, keepdim=True)
+        out_d = pv * (dd - rd)
+        if p_dot is not None:
+            pd = p_dot.reshape(-1, ld)[:, :cols]
+            rd2 = (pd * dv).sum(-1, keepdim=True)
+            out_d = out_d + pd * (dv - r) - pv * rd2
+        dp.reshape(-1, ld)[:, :cols] = scale * pv * (dv - r)
+        dp_dot.reshape(-1, ld)[:, :cols] = scale * out_d
+        return dp
+
+    def sigmoid_bwd_jvp(self, dy, dy_dot, y, y_dot):
+        self.calls += 1
+        out = torch.zeros_like(y)
+        if dy_dot is not None:
+            out = out + dy_dot * y * (1 - y)
+        if y_dot is not None:
+            out = out + dy * (1 - 2 * y) * y_dot
+        return out
+
+    def l2norm_jvp(self, x_dot, nrm, d):
+        self.calls += 1
+        nd = (d * x_dot).sum(1)
+        return nd, (x_dot - d * nd[:, None]) / nrm[:, None]
+
     def sgd_clip_update(self, theta, g, lr, clip=0.01, want_mask=False):
         self.calls += 1
         th = theta if theta.dim() == 2 else theta[None]
