@@ -31,7 +31,7 @@ def _ops_for(t):
 _OPS = {}
 
 
-def _pack_targets(targets, device):
+def _pack_targets(targets, device, dtype=torch.float32):
     """list of {"labels": [T_f], "boxes": [T_f,4]} -> concatenated labels/boxes + int32 offsets."""
     sizes = [int(t["labels"].numel()) for t in targets]
     off = [0]
@@ -39,10 +39,10 @@ def _pack_targets(targets, device):
         off.append(off[-1] + n)
     if off[-1]:
         labels = torch.cat([t["labels"].reshape(-1) for t in targets]).to(device=device, dtype=torch.int64)
-        boxes = torch.cat([t["boxes"].reshape(-1, 4) for t in targets]).to(device=device, dtype=torch.float32)
+        boxes = torch.cat([t["boxes"].reshape(-1, 4) for t in targets]).to(device=device, dtype=dtype)
     else:
         labels = torch.zeros(0, dtype=torch.int64, device=device)
-        boxes = torch.zeros(0, 4, dtype=torch.float32, device=device)
+        boxes = torch.zeros(0, 4, dtype=dtype, device=device)
     return labels.contiguous(), boxes.contiguous(), torch.tensor(off, dtype=torch.int32, device=device), sizes, off
 
 
@@ -51,15 +51,17 @@ class HungarianMatcher(nn.Module):
         super().__init__()
         assert cost_class != 0 or cost_bbox != 0 or cost_giou != 0, "all costs cant be 0"
         self.cost_class, self.cost_bbox, self.cost_giou = cost_class, cost_bbox, cost_giou
+        self._ops_override = None       # tests only: the torch simulation of the kernel interface
 
     @torch.no_grad()
     def forward(self, outputs, targets):
         """-> [(index_i int64, index_j int64)] per frame, as matcher.py:75-77."""
-        logits = outputs["pred_logits"].detach().float().contiguous()
-        boxes = outputs["pred_boxes"].detach().float().contiguous()
+        dt = torch.float32 if self._ops_override is None else outputs["pred_logits"].dtype
+        logits = outputs["pred_logits"].detach().to(dt).contiguous()
+        boxes = outputs["pred_boxes"].detach().to(dt).contiguous()
         Fn, Q = logits.shape[:2]
-        ops = _ops_for(logits)
-        labels, tboxes, off_t, sizes, off = _pack_targets(targets, logits.device)
+        ops = self._ops_override or _ops_for(logits)
+        labels, tboxes, off_t, sizes, off = _pack_targets(targets, logits.device, logits.dtype)
         if off[-1] == 0:
             e = torch.zeros(0, dtype=torch.int64)
             return [(e, e) for _ in range(Fn)]
@@ -88,20 +90,22 @@ class SetCriterion(nn.Module):
         w = torch.ones(num_classes + 1)
         w[-1] = eos_coef
         self.register_buffer("empty_weight", w)
+        self._ops_override = None       # tests only: the torch simulation of the kernel interface
 
     def _run(self, outputs, targets, indices, background_c, groups, weights, want_grad):
         logits = outputs["pred_logits"]
         boxes = outputs["pred_boxes"]
         lead = logits.shape[:-2]
-        logits = logits.detach().float().reshape(-1, *logits.shape[-2:]).contiguous()
-        boxes = boxes.detach().float().reshape(-1, *boxes.shape[-2:]).contiguous()
+        dt = torch.float32 if self._ops_override is None else logits.dtype
+        logits = logits.detach().to(dt).reshape(-1, *logits.shape[-2:]).contiguous()
+        boxes = boxes.detach().to(dt).reshape(-1, *boxes.shape[-2:]).contiguous()
         Fn, Q, Cn = logits.shape
         if Cn != self.num_classes + 1:
             raise ValueError(f"pred_logits has {Cn} classes, criterion built for {self.num_classes}+1")
         if len(targets) != Fn or len(indices) != Fn or Fn % groups:
             raise ValueError("targets / indices must have one entry per frame")
-        ops = _ops_for(logits)
-        labels, tboxes, off_t, sizes, off = _pack_targets(targets, logits.device)
+        ops = self._ops_override or _ops_for(logits)
+        labels, tboxes, off_t, sizes, off = _pack_targets(targets, logits.device, logits.dtype)
         rows, tg, moff = [], [], [0]
         per_group = Fn // groups
         for f, (i, j) in enumerate(indices):
@@ -134,6 +138,11 @@ class SetCriterion(nn.Module):
         order = {"labels": ("loss_ce", "class_error"), "boxes": ("loss_bbox", "loss_giou"),
                  "cardinality": ("cardinality_error",)}
         return {k: d[k] for name in self.losses for k in order[name]}
+
+    def group_losses(self, outputs, targets, background_c=0.1, groups=1, detector_out=None):
+        """`groups` independent criterion calls in one launch sequence -> [groups, 5] (LOSS_KEYS order)."""
+        indices = self._indices(outputs, targets, detector_out)
+        return self._run(outputs, targets, indices, background_c, groups, (1.0, 1.0, 1.0), False)
 
     def loss_and_grad(self, outputs, targets, background_c=0.1, groups=1, weights=(1.0, 2.0, 5.0),
                       detector_out=None):

@@ -48,7 +48,7 @@ class InnerLoop:
         dev = ops.device
 
         def fill(buf, pack, params):
-            flat = pack.pack(params, device=dev)
+            flat = pack.pack(params, device=dev, dtype=getattr(ops, "dtype", torch.float32))
             if buf is None:
                 return flat.unsqueeze(0)
             buf[0].copy_(flat)

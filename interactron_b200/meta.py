@@ -1,0 +1,208 @@
+"""The meta-training step: `interactron.forward(data)` / `interactron_random.forward(data)`
+(reference models/interactron.py:61-151, models/interactron_random.py:57-136; BASELINE config 5).
+
+Per episode the reference does (theta = fast weights, psi = in_proj_*, phi = fusion):
+  supervisor  g = d l(theta, psi, phi)/d theta with create_graph, theta' = theta - clip(lr*g),
+              L_sup = criterion(detector_theta'(5 frames)) [+ CE(actions, best path)], backward:
+              grads on phi and psi only (theta was detached), through theta' -> g (second order).
+  detector    theta'' = clone(theta) - clip(lr * g.detach()), L_det = criterion(detector_theta''(1
+              random frame)), backward: first-order grads on theta (identity Jacobian) and psi.
+Gradients are *summed* over the episodes of the batch into `.grad`; the caller never calls backward.
+
+Here, for all E episodes of the batch at once (every arithmetic step in the sm_100a kernels):
+  1. pre-adapt forward + backward -> g [E,n]                         (the predict() path, cached)
+  2. theta' and the clip mask in one kernel; W^T twins of theta'
+  3. post-adapt forward on the 5 frames with per-episode theta'; matcher + criterion (+ gradient)
+  4. its backward -> dL_sup/dtheta' [E,n] and the direct psi gradient
+  5. v = -lr * mask * dL_sup/dtheta'; ONE dual-number pass of step 1 with theta-tangent v
+     (interactron_b200/dual.py): the tangents of the phi / psi gradients are the second-order
+     meta-gradients, and the policy loss's first-order gradient rides along as a tangent seed
+  6. 1-frame post-adapt forward/backward for the detector loss (theta'' == theta' numerically)
+The reference's train()-mode dropout (p=0.1) is NOT applied: the step is the reference's
+`forward()` in eval() mode, which is also the mode every parity statement is made in.
+"""
+import random
+
+import torch
+import torch.nn.functional as F
+
+from . import detr_t, fusion
+from .dual import Dual, DualOps, DualWeights
+from .layers import GradSink, MultiSink
+
+LOSS_W = (1.0, 2.0, 5.0)            # ce + 2*bbox + 5*giou  (reference models/interactron.py:121-122,133)
+
+
+class PathStorage:
+    """Trie of action paths keeping, at every node, the first action of the cheapest path seen
+    through it (reference utils/storage_utils.py:4-50: Node/Edge/PathStorage)."""
+
+    def __init__(self):
+        self.root = {"cost": float("inf"), "action": None, "next": {}}
+
+    def add_path(self, path, cost):
+        node = self.root
+        for a in path:
+            a = int(a)
+            if cost < node["cost"]:
+                node["cost"], node["action"] = cost, a
+            node = node["next"].setdefault(a, {"cost": float("inf"), "action": None, "next": {}})
+
+    def get_label(self, path):
+        out, node = [], self.root
+        for a in path:
+            out.append(node["action"])
+            node = node["next"][int(a)]
+        return out
+
+
+def _targets(data, E, S):
+    return [{"labels": data["category_ids"][e][f], "boxes": data["boxes"][e][f]} for e in range(E) for f in range(S)]
+
+
+def meta_step(model, data, ridx=None):
+    """-> (predictions, losses, flat_grads) with flat_grads = {"theta","psi","phi": [1,n] buffers laid
+    out by the loop's packs} holding this batch's summed meta-gradients (not yet added to .grad)."""
+    loop = model._get_loop()
+    ops = loop.ops
+    if ops._clean:
+        raise RuntimeError("the meta-training step needs the fp32-accurate GEMM mode (ITN_GEMM_PRECISION=tf32x3)")
+    crit = model.criterion
+    dev = ops.device
+    frames = data["frames"].to(dev, non_blocking=True)
+    masks = data["masks"].to(dev, non_blocking=True)
+    E, S = frames.shape[:2]
+    assert S == 5, "the meta-training step is defined on full 5-frame episodes"
+    lr, clip = loop.lr, loop.clip
+    C = loop.detector.class_embed.out_features
+    NQ, D = detr_t.NQ, detr_t.D
+    tpk, ppk, fpk = loop.theta_pack, loop.psi_pack, loop.phi_pack
+    kind = loop.kind
+    f_fwd = fusion.fusion_a_forward if kind == "A" else fusion.fusion_b_forward
+    f_bwd = fusion.fusion_a_backward if kind == "A" else fusion.fusion_b_backward
+
+    # 1. pre-adapt pass, learned loss, inner gradient ------------------------------------------
+    src_r, pos, kmask, (h, w) = loop.features(frames.flatten(0, 1), masks.flatten(0, 1))
+    L = h * w
+    src3 = src_r.view(E, S * L, -1)
+    Wd = loop._det_weights(loop.theta, loop.theta_r, loop.theta_t)
+    Wf = loop._fusion_weights()
+    preds = ops.empty(E * S * NQ, D + C + 4)
+    pre, cache = detr_t.detr_t_forward(ops, Wd, src3, pos, kmask, E, S, L, preds=preds)
+    fout, fcache = f_fwd(ops, Wf, pre["memory_r"], preds, E, S, L)
+    dmemory, dpreds = f_bwd(ops, Wf, fcache)
+    g = ops.empty(E, tpk.numel)
+    detr_t.detr_t_backward(ops, Wd, cache, GradSink(ops, tpk, g), dpreds=dpreds, dmemory=dmemory)
+    del cache, fcache, dmemory, dpreds
+
+    # 2. fast weights + clip mask -----------------------------------------------------------------
+    theta_p, theta_p_r, cmask = ops.sgd_clip_update(loop.theta, g, lr, clip, want_mask=True)
+    theta_p_t = tpk.transpose_into(ops, theta_p, ops.zeros(E, tpk.numel))
+    Wp = loop._det_weights(theta_p, theta_p_r, theta_p_t)
+
+    # 3. post-adapt pass on the 5 frames, supervisor loss ---------------------------------------
+    post, pcache = detr_t.detr_t_forward(ops, Wp, src3, pos, kmask, E, S, L)
+    targets = _targets(data, E, S)
+    outs = {"pred_logits": post["logits"].view(E * S, NQ, C), "pred_boxes": post["boxes"].view(E * S, NQ, 4)}
+    sup_l, dlog, dbox = crit.loss_and_grad(outs, targets, background_c=0.1, groups=E, weights=LOSS_W)
+    sup_host = sup_l.cpu()                                                        # [E,5]
+    sup = {k: sup_host[:, i] for i, k in enumerate(("loss_ce", "class_error", "cardinality_error", "loss_bbox",
+                                                      "loss_giou"))}
+    dact = None
+    if kind == "A":
+        # lowest-loss policy labels (reference models/interactron.py:105-118)
+        f0 = {"pred_logits": post["logits"].view(E, S, NQ, C)[:, 0].contiguous(),
+              "pred_boxes": post["boxes"].view(E, S, NQ, 4)[:, 0].contiguous()}
+        t0 = [targets[e * S] for e in range(E)]
+        gt = crit.group_losses(f0, t0, background_c=0.1, groups=E).cpu()
+        rew = gt[:, 0] + 5 * gt[:, 4] + 2 * gt[:, 3]
+        best = []
+        for e in range(E):
+            iip = data["initial_image_path"][e]
+            store = model.path_storage.setdefault(iip, PathStorage())
+            path = [int(a) for a in data["actions"][e][:4]]
+            store.add_path(path, float(rew[e]))
+            best.append(store.get_label(path))
+        best = torch.tensor(best, dtype=torch.long, device=dev)                     # [E,4]
+        # 16 logits per episode: CE over the 4 action heads and its gradient
+        logp = F.log_softmax(fout["actions"].view(E, 4, 4), dim=-1)
+        loss_path = -logp.gather(-1, best[..., None]).squeeze(-1).mean(-1)            # [E]
+        dact = (logp.exp() - F.one_hot(best, 4).to(logp.dtype)) / 4.0
+        sup["loss_path"] = loss_path.cpu()
+        sup["policy_reward"] = rew
+
+    # 4. backward of the post-adapt pass: dL_sup/dtheta' per episode, direct psi gradient ----------
+    g_sup = ops.empty(E, tpk.numel)
+    gpsi = ops.zeros(1, ppk.numel)
+    detr_t.detr_t_backward(ops, Wp, pcache, MultiSink(GradSink(ops, tpk, g_sup), GradSink(ops, ppk, gpsi, shared=True)),
+                           dlogits=dlog.view(E, S * NQ, C), dboxes=dbox.view(E, S * NQ, 4))
+    del pcache
+
+    # 5. second order: one dual pass of step 1 along v = -lr * mask * dL_sup/dtheta' ---------------
+    v = ops.mul_mask_u8(g_sup, cmask, -lr)
+    v_t = tpk.transpose_into(ops, v, ops.zeros(E, tpk.numel))
+    dops = DualOps(ops)
+    DWd = DualWeights((tpk, loop.theta, loop.theta_t, v, v_t), (ppk, loop.psi, loop.psi_t, None, None))
+    DWf = DualWeights((fpk, loop.phi, loop.phi_t, None, None))
+    preds2 = dops.empty(E * S * NQ, D + C + 4)
+    pre2, cache2 = detr_t.detr_t_forward(dops, DWd, src3, pos, kmask, E, S, L, preds=preds2)
+    _, fcache2 = f_fwd(dops, DWf, pre2["memory_r"], preds2, E, S, L)
+    gphi2 = dops.zeros(1, fpk.numel)
+    gpsi2 = dops.zeros(1, ppk.numel)
+    seed = None if dact is None else Dual(ops.zeros(E, 4, 4), dact.contiguous())
+    dmem2, dpreds2 = f_bwd(dops, DWf, fcache2, sink=GradSink(dops, fpk, gphi2, shared=True), dactions=seed)
+    detr_t.detr_t_backward(dops, DWd, cache2, GradSink(dops, ppk, gpsi2, shared=True), dpreds=dpreds2, dmemory=dmem2)
+    del cache2, fcache2
+
+    # 6. detector loss on one random frame per episode (first order) ------------------------------
+    if ridx is None:
+        ridx = [random.randint(0, 4) for _ in range(E)]                     # reference :129, one draw per task
+    idx = torch.tensor([e * S + int(r) for e, r in enumerate(ridx)], device=dev)
+    src1 = src_r.index_select(0, idx).view(E, L, -1)
+    pos1 = pos.view(E * S, L, -1).index_select(0, idx).reshape(E * L, -1)
+    km1 = kmask.index_select(0, idx)
+    post1, c1 = detr_t.detr_t_forward(ops, Wp, src1, pos1, km1, E, 1, L)
+    t1 = [targets[e * S + int(r)] for e, r in enumerate(ridx)]
+    o1 = {"pred_logits": post1["logits"].view(E, NQ, C), "pred_boxes": post1["boxes"].view(E, NQ, 4)}
+    det_l, dlog1, dbox1 = crit.loss_and_grad(o1, t1, background_c=0.1, groups=E, weights=LOSS_W)
+    det_host = det_l.cpu()
+    g_det = ops.empty(E, tpk.numel)
+    gpsi1 = ops.zeros(1, ppk.numel)
+    detr_t.detr_t_backward(ops, Wp, c1, MultiSink(GradSink(ops, tpk, g_det), GradSink(ops, ppk, gpsi1, shared=True)),
+                           dlogits=dlog1.view(E, NQ, C), dboxes=dbox1.view(E, NQ, 4))
+
+    # the batch's meta-gradients, summed over episodes --------------------------------------------
+    g_theta = ops.colsum(g_det.view(1, E, tpk.numel))
+    g_psi = ops.add(ops.add(gpsi, gpsi2.t), gpsi1)
+    flat = {"theta": g_theta, "psi": g_psi, "phi": gphi2.t}
+
+    det = {k: det_host[:, i] for i, k in enumerate(("loss_ce", "class_error", "cardinality_error", "loss_bbox",
+                                                      "loss_giou"))}
+    order = ("loss_ce", "class_error", "loss_bbox", "loss_giou", "cardinality_error")
+    losses = {k.replace("loss", "loss_detector"): det[k].mean().to(dev) for k in order}
+    sup_order = order + (("loss_path", "policy_reward") if kind == "A" else ())
+    losses.update({k.replace("loss", "loss_supervisor"): sup[k].mean().to(dev) for k in sup_order})
+    predictions = {"pred_logits": post1["logits"].view(E, 1, NQ, C), "pred_boxes": post1["boxes"].view(E, 1, NQ, 4)}
+    return predictions, losses, flat
+
+
+# fusion parameters the loss never reaches: their .grad stays None, as in the reference
+UNUSED_PHI = {"A": ("model.pos_emb", "box_decoder.", "logit_decoder."),
+              "B": ("pos_embed", "box_decoder.", "logit_decoder.", "action_decoder.")}
+
+
+def accumulate_grads(model, flat):
+    """Add the flat meta-gradients to `.grad` of the detector / fusion Parameters (sum semantics of
+    repeated `.backward()` calls; a Parameter whose grad is None receives a view of the flat buffer)."""
+    loop = model._get_loop()
+    for key, pack, params in (("theta", loop.theta_pack, loop.theta_params), ("psi", loop.psi_pack, loop.psi_params),
+                              ("phi", loop.phi_pack, loop.phi_params)):
+        buf = flat[key]
+        for name, p in zip(pack.names, params):
+            if not p.requires_grad or (key == "phi" and name.startswith(UNUSED_PHI[loop.kind])):
+                continue
+            gv = pack.view(buf, name)[0]
+            if p.grad is None:
+                p.grad = gv
+            else:
+                p.grad.add_(gv)

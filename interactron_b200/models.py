@@ -158,10 +158,19 @@ class _Adaptive(_Base):
             g = self._graphs[key] = GraphedCall(fn, [frames, masks])
         return g(frames, masks, clone=clone)
 
-    def forward(self, data, train=True):
-        raise NotImplementedError(
-            "the meta-training step (second-order MAML gradients, BASELINE config 5) is not built yet; "
-            "only the inner-loop adapt+detect path (predict / get_next_action) runs on the B200 kernels")
+    def forward(self, data, train=True, ridx=None):
+        """Meta-training step (reference models/interactron.py:61-151, interactron_random.py:57-136):
+        -> (predictions, losses) and, as in the reference, the side effect of *accumulating* the
+        batch's summed meta-gradients on `.grad` of the detector and fusion Parameters (second-order
+        supervisor gradients on fusion + in_proj_*, first-order detector gradients on the fast
+        weights).  `train` is ignored, as in the reference.  `ridx` (extension): the per-episode frame
+        of the detector loss; default = the reference's `random.randint(0, 4)` draw per episode.
+        Dropout is not applied (the reference's forward in eval() mode); see meta.py."""
+        from . import meta
+        predictions, losses, flat = meta.meta_step(self, data, ridx)
+        self.last_meta_grads = flat                       # flat [1,n] buffers: what a trainer all-reduces
+        meta.accumulate_grads(self, flat)
+        return predictions, losses
 
 
 class interactron_random(_Adaptive):

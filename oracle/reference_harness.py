@@ -143,3 +143,23 @@ def reference_predict_with_trace(model, data):
     trace["out"] = {k: v.detach().clone() for k, v in out.items()}
     del mu
     return trace
+
+
+def reference_forward_with_grads(model, data, ridx):
+    """model(data) (the meta-training step, reference models/interactron.py:61-151) with the
+    `random.randint(0, 4)` draws replaced by `ridx` (one per episode).  Returns (predictions, losses,
+    {parameter name: grad or None}); the model's .grad fields are cleared afterwards."""
+    _load()
+    import random
+    draws = list(ridx)
+    real = random.randint
+    random.randint = lambda a, b: draws.pop(0)
+    try:
+        model.zero_grad(set_to_none=True)
+        preds, losses = model(data)
+    finally:
+        random.randint = real
+    grads = {n: (None if p.grad is None else p.grad.detach().clone()) for n, p in model.named_parameters()}
+    model.zero_grad(set_to_none=True)
+    return ({k: v.detach().clone() for k, v in preds.items()}, {k: v.detach().clone() for k, v in losses.items()},
+            grads)

@@ -275,6 +275,54 @@ class SimOps:
         nd = (d * x_dot).sum(1)
         return nd, (x_dot - d * nd[:, None]) / nrm[:, None]
 
+    def mul_mask_u8(self, x, mask, scale=1.0):
+        self.calls += 1
+        return x * mask.to(x.dtype) * scale
+
+    def matcher_cost(self, logits, boxes, tgt_boxes, tgt_labels, tgt_off, w_class, w_bbox, w_giou):
+        from . import port
+        self.calls += 1
+        off = tgt_off.tolist()
+        parts = []
+        for f in range(logits.shape[0]):
+            lo, hi = off[f], off[f + 1]
+            if hi > lo:
+                parts.append(port.hungarian_cost(logits[f], boxes[f], tgt_labels[lo:hi], tgt_boxes[lo:hi],
+                                                 w_class, w_bbox, w_giou).reshape(-1))
+        return torch.cat(parts) if parts else torch.zeros(1)
+
+    def criterion(self, logits, boxes, tgt_boxes, tgt_labels, tgt_off, match_row, match_tgt, match_off,
+                  groups, background_c, weights=(1.0, 1.0, 1.0), want_grad=False):
+        from . import port
+        self.calls += 1
+        Fn, Q, Cn = logits.shape
+        per = Fn // groups
+        off, moff = tgt_off.tolist(), match_off.tolist()
+        lg = logits.detach().clone().requires_grad_(want_grad)
+        bx = boxes.detach().clone().requires_grad_(want_grad)
+        rows_all, tg_all = match_row.tolist(), match_tgt.tolist()
+        losses = []
+        total = 0
+        for gi in range(groups):
+            fr = range(gi * per, (gi + 1) * per)
+            targets = [{"labels": tgt_labels[off[f]:off[f + 1]], "boxes": tgt_boxes[off[f]:off[f + 1]]} for f in fr]
+            idx = [([], []) for _ in fr]
+            for r, t in zip(rows_all[moff[gi]:moff[gi + 1]], tg_all[moff[gi]:moff[gi + 1]]):
+                f = r // Q
+                idx[f - gi * per][0].append(r - f * Q)
+                idx[f - gi * per][1].append(t - off[f])
+            idx = [(torch.tensor(i, dtype=torch.int64), torch.tensor(j, dtype=torch.int64)) for i, j in idx]
+            out = port.set_criterion(lg[gi * per:(gi + 1) * per], bx[gi * per:(gi + 1) * per], targets, idx,
+                                     background_c)
+            losses.append(torch.stack([out[k].detach().to(logits.dtype) for k in
+                                       ("loss_ce", "class_error", "cardinality_error", "loss_bbox", "loss_giou")]))
+            total = total + weights[0] * out["loss_ce"] + weights[1] * out["loss_bbox"] + weights[2] * out["loss_giou"]
+        losses = torch.stack(losses)
+        if not want_grad:
+            return losses
+        dl, db = torch.autograd.grad(total, (lg, bx))
+        return losses, dl, db
+
     def sgd_clip_update(self, theta, g, lr, clip=0.01, want_mask=False):
         self.calls += 1
         th = theta if theta.dim() == 2 else theta[None]
