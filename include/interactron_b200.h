@@ -232,6 +232,46 @@ int itn_criterion(const float* logits, const float* boxes, const float* tgt_boxe
                   float w_bbox, float w_giou, float* losses, float* dlogits, float* dboxes,
                   void* scratch, void* stream);
 
+/* ----------------------------------------- meta-training step (second order) --- */
+/* Tangent (forward-mode) companions of the kernels above.  The reference differentiates the inner
+ * gradient a second time (`create_graph=True` at models/interactron.py:98-99, then
+ * `supervisor_loss.backward()` at :123); here the same numbers come from ONE dual-number re-run of the
+ * inner forward+backward along v = -lr * clip_mask * dL_sup/dtheta' (interactron_b200/dual.py), which
+ * needs, besides GEMMs, the tangent rules below.  A null "*_dot" input means a zero tangent. */
+/* y_dot of LayerNorm: gamma [groups, cols] (row stride g_stride), gamma_dot / beta_dot
+ * [groups_dot, cols] (row stride d_stride; per-episode tangents of a shared affine). */
+int itn_layernorm_fwd_jvp(const float* x, const float* x_dot, const float* mean, const float* rstd,
+                          const float* gamma, const float* gamma_dot, const float* beta_dot,
+                          float* y_dot, long long rows, int cols, int groups, long long g_stride,
+                          int groups_dot, long long d_stride, void* stream);
+/* dx_dot of the LayerNorm backward; gterm (may be NULL, [rows, cols]) receives
+ * dy_dot*xhat + dy*xhat_dot whose column sums are the tangent of dgamma. */
+int itn_layernorm_bwd_jvp(const float* dy, const float* dy_dot, const float* x, const float* x_dot,
+                          const float* mean, const float* rstd, const float* gamma,
+                          const float* gamma_dot, float* dx_dot, float* gterm, long long rows, int cols,
+                          int groups, long long g_stride, int groups_dot, long long d_stride,
+                          void* stream);
+/* Softmax backward on dual numbers, in place: dp <- dS, dp_dot <- dS_dot (rows 16-byte aligned and
+ * padded to a multiple of 4 columns, as the attention score buffers are). */
+int itn_softmax_bwd_jvp(const float* p, const float* p_dot, float* dp, float* dp_dot, long long rows,
+                        int cols, long long ld, float scale, void* stream);
+/* y *= (ref > 0): tangent of ReLU / of the ReLU-mask backward epilogue. */
+int itn_mask_mul(float* y, const float* ref, long long n, void* stream);
+/* out = scale * x * mask (mask uint8 from itn_sgd_clip_update): the derivative of the clipped SGD step
+ * wrt g applied to dL/dtheta' (utils/meta_utils.py:141: lr inside the clip band, 0 outside). */
+int itn_mul_mask_u8(const float* x, const unsigned char* mask, float scale, float* out, long long n,
+                    void* stream);
+/* y = raw * gelu'(aux); y_dot = raw_dot * gelu'(aux) + raw * gelu''(aux) * aux_dot (exact-erf GELU,
+ * models/gpt.py:70).  y_dot may be NULL. */
+int itn_gelu_grad_dual(const float* raw, const float* raw_dot, const float* aux, const float* aux_dot,
+                       float* y, float* y_dot, long long n, void* stream);
+/* out = dy_dot*y*(1-y) + dy*(1-2y)*y_dot: tangent of itn_sigmoid_bwd. */
+int itn_sigmoid_bwd_jvp(const float* dy, const float* dy_dot, const float* y, const float* y_dot,
+                        float* out, long long n, void* stream);
+/* Tangent of itn_l2norm_fwd_bwd: n_dot[g] = <d_g, x_dot_g>, d_dot_g = (x_dot_g - d_g*n_dot[g]) / nrm[g]. */
+int itn_l2norm_jvp(const float* x_dot, const float* nrm, const float* d, float* n_dot, float* d_dot,
+                   int groups, int n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

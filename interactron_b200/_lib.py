@@ -63,6 +63,14 @@ SIGNATURES = {
     "itn_maxpool3x3s2_nhwc": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "itn_matcher_cost": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _F, _P]),
     "itn_criterion_scratch_bytes": (_LL, [_I, _I, _I]),
+    "itn_layernorm_fwd_jvp": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _LL, _I, _I, _LL, _I, _LL, _P]),
+    "itn_layernorm_bwd_jvp": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _LL, _I, _I, _LL, _I, _LL, _P]),
+    "itn_softmax_bwd_jvp": (_I, [_P, _P, _P, _P, _LL, _I, _LL, _F, _P]),
+    "itn_mask_mul": (_I, [_P, _P, _LL, _P]),
+    "itn_mul_mask_u8": (_I, [_P, _P, _F, _P, _LL, _P]),
+    "itn_gelu_grad_dual": (_I, [_P, _P, _P, _P, _P, _P, _LL, _P]),
+    "itn_sigmoid_bwd_jvp": (_I, [_P, _P, _P, _P, _P, _LL, _P]),
+    "itn_l2norm_jvp": (_I, [_P, _P, _P, _P, _P, _I, _I, _P]),
     "itn_criterion": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _F, _F, _F, _P, _P, _P, _P, _P]),
 }
 

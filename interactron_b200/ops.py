@@ -329,6 +329,95 @@ class CudaOps:
         out_r = out if out_r is None else out_r
         return (out, out_r, mask) if want_mask else (out, out_r)
 
+    # ---------------------------------------- tangent rules (meta-training step, dual.py)
+    @staticmethod
+    def _gb(t, cols):
+        """[G, cols] view of an affine parameter (row stride arbitrary) -> (tensor, groups, stride)."""
+        if t is None:
+            return None, 1, 0
+        t2 = t.reshape(-1, cols)
+        assert t2.stride(1) == 1
+        return t2, t2.shape[0], (t2.stride(0) if t2.shape[0] > 1 else 0)
+
+    def layernorm_fwd_jvp(self, x, x_dot, mean, rstd, gamma, gamma_dot, beta_dot):
+        rows, cols = x.shape
+        assert x.is_contiguous() and (x_dot is None or x_dot.is_contiguous())
+        g2, G, gs = self._gb(gamma, cols)
+        gd, Gd, ds = self._gb(gamma_dot, cols)
+        bd, Gb, bs = self._gb(beta_dot, cols)
+        if gd is not None and bd is not None:
+            assert Gd == Gb and ds == bs
+        elif bd is not None:
+            Gd, ds = Gb, bs
+        y_dot = self.empty(rows, cols)
+        _lib.check(self.lib.itn_layernorm_fwd_jvp(_ptr(x), _ptr(x_dot), _ptr(mean), _ptr(rstd), _ptr(g2), _ptr(gd),
+                                                  _ptr(bd), _ptr(y_dot), rows, cols, G, gs, Gd, ds, self._stream()))
+        return y_dot
+
+    def layernorm_bwd_jvp(self, dy, dy_dot, x, x_dot, mean, rstd, gamma, gamma_dot, dgamma_dot=None, dbeta_dot=None):
+        rows, cols = x.shape
+        assert dy.is_contiguous() and x.is_contiguous()
+        assert (dy_dot is None or dy_dot.is_contiguous()) and (x_dot is None or x_dot.is_contiguous())
+        g2, G, gs = self._gb(gamma, cols)
+        gd, Gd, ds = self._gb(gamma_dot, cols)
+        dx_dot = self.empty(rows, cols)
+        gterm = self.empty(rows, cols) if dgamma_dot is not None else None
+        _lib.check(self.lib.itn_layernorm_bwd_jvp(_ptr(dy), _ptr(dy_dot), _ptr(x), _ptr(x_dot), _ptr(mean), _ptr(rstd),
+                                                  _ptr(g2), _ptr(gd), _ptr(dx_dot), _ptr(gterm), rows, cols, G, gs,
+                                                  Gd, ds, self._stream()))
+        if dgamma_dot is not None:
+            Gn = dgamma_dot.shape[0]
+            self.colsum(gterm.view(Gn, rows // Gn, cols), out=dgamma_dot)
+            if dy_dot is not None:
+                self.colsum(dy_dot.view(Gn, rows // Gn, cols), out=dbeta_dot)
+        return dx_dot
+
+    def softmax_bwd_jvp_(self, p, p_dot, dp, dp_dot, cols, scale):
+        assert p.is_contiguous() and dp.is_contiguous() and dp_dot.is_contiguous() and p.shape == dp.shape
+        assert p_dot is None or (p_dot.is_contiguous() and p_dot.shape == p.shape)
+        ld = p.shape[-1]
+        rows = p.numel() // ld
+        _lib.check(self.lib.itn_softmax_bwd_jvp(_ptr(p), _ptr(p_dot), _ptr(dp), _ptr(dp_dot), rows, cols, ld,
+                                                float(scale), self._stream()))
+        return dp
+
+    def mask_mul_(self, y, ref):
+        assert y.is_contiguous() and ref.is_contiguous() and y.numel() == ref.numel()
+        _lib.check(self.lib.itn_mask_mul(_ptr(y), _ptr(ref), y.numel(), self._stream()))
+        return y
+
+    def mul_mask_u8(self, x, mask, scale=1.0):
+        assert x.is_contiguous() and mask.is_contiguous() and mask.dtype == torch.uint8 and mask.numel() == x.numel()
+        out = self.empty(x.shape)
+        _lib.check(self.lib.itn_mul_mask_u8(_ptr(x), _ptr(mask), float(scale), _ptr(out), x.numel(), self._stream()))
+        return out
+
+    def gelu_grad_dual(self, raw, raw_dot, aux, aux_dot, out=None):
+        assert raw.is_contiguous() and aux.is_contiguous() and raw.numel() == aux.numel()
+        for t in (raw_dot, aux_dot, out):
+            assert t is None or (t.is_contiguous() and t.numel() == raw.numel())
+        y = self.empty(raw.shape) if out is None else out
+        y_dot = self.empty(raw.shape) if (raw_dot is not None or aux_dot is not None) else None
+        _lib.check(self.lib.itn_gelu_grad_dual(_ptr(raw), _ptr(raw_dot), _ptr(aux), _ptr(aux_dot), _ptr(y), _ptr(y_dot),
+                                               raw.numel(), self._stream()))
+        return y, y_dot
+
+    def sigmoid_bwd_jvp(self, dy, dy_dot, y, y_dot):
+        for t in (dy, dy_dot, y, y_dot):
+            assert t is None or t.is_contiguous()
+        out = self.empty(y.shape)
+        _lib.check(self.lib.itn_sigmoid_bwd_jvp(_ptr(dy), _ptr(dy_dot), _ptr(y), _ptr(y_dot), _ptr(out), y.numel(),
+                                                self._stream()))
+        return out
+
+    def l2norm_jvp(self, x_dot, nrm, d):
+        assert x_dot.is_contiguous() and d.is_contiguous() and x_dot.dim() == 2
+        G, n = x_dot.shape
+        n_dot, d_dot = self.empty(G), self.empty(G, n)
+        _lib.check(self.lib.itn_l2norm_jvp(_ptr(x_dot), _ptr(nrm), _ptr(d), _ptr(n_dot), _ptr(d_dot), G, n,
+                                           self._stream()))
+        return n_dot, d_dot
+
     def im2col_nhwc(self, x, kh, kw, stride, pad, dil):
         """x [N,H,W,C] channels-last -> ([N*Ho*Wo, ld] patch matrix, Ho, Wo); ld = kh*kw*C rounded up to 4."""
         assert x.is_contiguous() and x.dim() == 4
