@@ -290,13 +290,106 @@ def run_gpu_arm(args):
         dist.destroy_process_group()
 
 
+def run_meta_arm(args):
+    """BASELINE configs[4]: the meta-training step `forward(data)` (second-order MAML gradients), the
+    batch's episodes sharded over the ranks and the flat meta-gradient all-reduced (SUM) with NCCL.
+    Not the driver's headline line (that is the predict() workload); run with --workload meta_*."""
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import interactron_b200 as ib
+    from interactron_b200.synthetic import collate_episodes, synthetic_episode
+    name = args.workload[len("meta_"):]
+    model = ib.build_model(ib.default_config(name, weights="synthetic").MODEL).to(f"cuda:{local}").eval()
+    E = args.episodes
+    ops = model._get_ops()
+    batches = []
+    for i in range(2):
+        d = collate_episodes([synthetic_episode(1000 * rank + 100 * i + e) for e in range(E)])
+        d["frames"], d["masks"] = d["frames"].pin_memory(), d["masks"].pin_memory()
+        batches.append(d)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(i):
+        model.zero_grad(set_to_none=True)
+        _, losses = model(batches[i % 2], ridx=[(i + e) % 5 for e in range(E)])
+        return float(losses["loss_supervisor_ce"])          # D2H read of the step's result
+
+    for i in range(args.warmup):
+        step(i)
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    l0 = ops.launch_count()
+    ev = []
+    for i in range(args.steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step(i)
+        e1.record()
+        ev.append((e0, e1))
+    barrier()
+    sampler.stop_flag.set()
+    launches = ops.launch_count() - l0
+    ms = torch.tensor([sum(a.elapsed_time(b) for a, b in ev)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms)
+    if rank == 0:
+        n_flat = model.last_meta_grads["all"].numel()
+        cpu = None
+        if world == 1 and args.cpu_episodes > 0:
+            from oracle import reference_harness as rh
+            if rh.reference_available():
+                torch.set_num_threads(os.cpu_count())
+                ref = rh.build_reference_model(name, {k: v.cpu() for k, v in model.state_dict().items()})
+                d1 = collate_episodes([synthetic_episode(7)])
+                t0 = time.perf_counter()
+                rh.reference_forward_with_grads(ref, d1, [2])
+                dt = time.perf_counter() - t0
+                cpu = {"value": 1.0 / dt, "unit": "episodes/s", "cores": torch.get_num_threads(), "kind": "reference",
+                       "sample": f"1 episode of the reference forward(), {dt:.1f} s"}
+        v = E * world * args.steps / (ms * 1e-3)
+        print(json.dumps({
+            "metric": "Interactron episodes/s (meta-training step, second-order MAML)", "value": v,
+            "unit": "episodes/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "tf32x3", "data": "synthetic",
+            "config": {"workload": f"{name}.yaml forward() = BASELINE configs[4] (meta-training step), eval-mode "
+                                   "numerics (no dropout), D1", "episodes_per_step_per_gpu": E,
+                       "allreduce_elems": n_flat if world > 1 else 0, "cuda_graph": False,
+                       "l2": "256 MiB buffer written between timed steps"},
+            "e2e": {"value": v, "unit": "episodes/s", "h2d_bytes_per_step": batches[0]["frames"].numel() * 4 +
+                    batches[0]["masks"].numel() * 8, "d2h_bytes_per_step": 4,
+                    "api": "model(data) with pinned host frames; grads left on .grad; one loss read back"},
+            "gpu_launches": launches, "gpu_launches_per_step": launches // args.steps, "roofline": None,
+            "cpu_baseline": cpu, "clocks": sampler.summary()}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--episodes", type=int, default=32, help="episodes per step per GPU")
-    ap.add_argument("--workload", default="interactron_random", choices=sorted(WORKLOADS))
+    ap.add_argument("--episodes", type=int, default=None, help="episodes per step per GPU (default 32; 2 for meta_*)")
+    ap.add_argument("--workload", default="interactron_random",
+                    choices=sorted(WORKLOADS) + ["meta_" + w for w in sorted(WORKLOADS)])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-episodes", type=int, default=None,
                     help="episodes in the bounded CPU-baseline sample (0 disables)")
@@ -304,8 +397,15 @@ def main():
     if args.warmup < 3:
         args.warmup = 3
     if args.cpu_episodes is None:
-        args.cpu_episodes = 1 if args.impl == "reference" else 6
-    if args.impl == "reference":
+        args.cpu_episodes = 1 if args.impl == "reference" else 40       # ~10 s of host time
+    meta = args.workload.startswith("meta_")
+    if args.episodes is None:
+        args.episodes = 2 if meta else 32
+    if meta and args.impl == "b200":
+        run_meta_arm(args)
+    elif args.impl == "reference":
+        if meta:
+            raise SystemExit("--impl reference times the predict() workloads; meta_* reports its CPU baseline inline")
         run_reference_arm(args)
     else:
         run_gpu_arm(args)

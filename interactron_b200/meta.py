@@ -26,7 +26,7 @@ import random
 import torch
 import torch.nn.functional as F
 
-from . import detr_t, fusion
+from . import detr_t, fusion, parallel
 from .dual import Dual, DualOps, DualWeights
 from .layers import GradSink, MultiSink
 
@@ -61,8 +61,9 @@ def _targets(data, E, S):
 
 
 def meta_step(model, data, ridx=None):
-    """-> (predictions, losses, flat_grads) with flat_grads = {"theta","psi","phi": [1,n] buffers laid
-    out by the loop's packs} holding this batch's summed meta-gradients (not yet added to .grad)."""
+    """-> (predictions, losses, flat_grads): flat_grads["all"] is ONE [1, n_theta+n_psi+n_phi] buffer
+    with this rank's summed meta-gradients (not yet added to .grad; "theta"/"psi"/"phi" are its views,
+    laid out by the loop's packs)."""
     loop = model._get_loop()
     ops = loop.ops
     if ops._clean:
@@ -116,13 +117,17 @@ def meta_step(model, data, ridx=None):
         t0 = [targets[e * S] for e in range(E)]
         gt = crit.group_losses(f0, t0, background_c=0.1, groups=E).cpu()
         rew = gt[:, 0] + 5 * gt[:, 4] + 2 * gt[:, 3]
-        best = []
-        for e in range(E):
-            iip = data["initial_image_path"][e]
+        # the trie is process state fed by every episode of the (global) batch: replay all ranks' episodes
+        # in global order, keep the labels of our own
+        mine = [(data["initial_image_path"][e], [int(a) for a in data["actions"][e][:4]], float(rew[e]))
+                for e in range(E)]
+        rank = parallel.world()[0]
+        best = [None] * E
+        for r_, j, (iip, path, cost) in parallel.exchange_in_order(mine):
             store = model.path_storage.setdefault(iip, PathStorage())
-            path = [int(a) for a in data["actions"][e][:4]]
-            store.add_path(path, float(rew[e]))
-            best.append(store.get_label(path))
+            store.add_path(path, cost)
+            if r_ == rank:
+                best[j] = store.get_label(path)
         best = torch.tensor(best, dtype=torch.long, device=dev)                     # [E,4]
         # 16 logits per episode: CE over the 4 action heads and its gradient
         logp = F.log_softmax(fout["actions"].view(E, 4, 4), dim=-1)
@@ -147,7 +152,10 @@ def meta_step(model, data, ridx=None):
     preds2 = dops.empty(E * S * NQ, D + C + 4)
     pre2, cache2 = detr_t.detr_t_forward(dops, DWd, src3, pos, kmask, E, S, L, preds=preds2)
     _, fcache2 = f_fwd(dops, DWf, pre2["memory_r"], preds2, E, S, L)
-    gphi2 = dops.zeros(1, fpk.numel)
+    # the step's meta-gradient: ONE flat buffer [theta | psi | phi] (what gets all-reduced)
+    n_t, n_p, n_f = tpk.numel, ppk.numel, fpk.numel
+    G = ops.zeros(1, n_t + n_p + n_f)
+    gphi2 = Dual(ops.zeros(1, n_f), G[:, n_t + n_p:])
     gpsi2 = dops.zeros(1, ppk.numel)
     seed = None if dact is None else Dual(ops.zeros(E, 4, 4), dact.contiguous())
     dmem2, dpreds2 = f_bwd(dops, DWf, fcache2, sink=GradSink(dops, fpk, gphi2, shared=True), dactions=seed)
@@ -172,9 +180,9 @@ def meta_step(model, data, ridx=None):
                            dlogits=dlog1.view(E, NQ, C), dboxes=dbox1.view(E, NQ, 4))
 
     # the batch's meta-gradients, summed over episodes --------------------------------------------
-    g_theta = ops.colsum(g_det.view(1, E, tpk.numel))
-    g_psi = ops.add(ops.add(gpsi, gpsi2.t), gpsi1)
-    flat = {"theta": g_theta, "psi": g_psi, "phi": gphi2.t}
+    ops.colsum(g_det.view(1, E, n_t), out=G[:, :n_t])
+    ops.copy2d_(G[:, n_t:n_t + n_p], ops.add(ops.add(gpsi, gpsi2.t), gpsi1))
+    flat = {"all": G, "theta": G[:, :n_t], "psi": G[:, n_t:n_t + n_p], "phi": G[:, n_t + n_p:]}
 
     det = {k: det_host[:, i] for i, k in enumerate(("loss_ce", "class_error", "cardinality_error", "loss_bbox",
                                                       "loss_giou"))}

@@ -46,6 +46,7 @@ class _Base(nn.Module):
         self._graphs = {}
         self._bb_key = None
         self.use_cuda_graph = os.environ.get("ITN_CUDA_GRAPH", "1") != "0"
+        self.sync_meta_grads = True
 
     # -- reference surface ------------------------------------------------------------
     def eval(self):
@@ -167,8 +168,14 @@ class _Adaptive(_Base):
         of the detector loss; default = the reference's `random.randint(0, 4)` draw per episode.
         Dropout is not applied (the reference's forward in eval() mode); see meta.py."""
         from . import meta
+        from . import parallel
         predictions, losses, flat = meta.meta_step(self, data, ridx)
-        self.last_meta_grads = flat                       # flat [1,n] buffers: what a trainer all-reduces
+        if self.sync_meta_grads:
+            # one process per GPU, the batch's episodes sharded over ranks: the meta-gradient is a sum
+            # over episodes -> ONE all-reduce(SUM) of the flat buffer (replaces nn.DataParallel,
+            # reference engine/interactron_trainer.py:43-46); no-op in a single process
+            parallel.allreduce_meta_grads(flat["all"])
+        self.last_meta_grads = flat
         meta.accumulate_grads(self, flat)
         return predictions, losses
 

@@ -3,9 +3,15 @@
 Episodes are independent (the reference loops over them serially, models/interactron.py:84), so
 evaluation shards them with NO data-path collective: rank r adapts episodes r, r+W, r+2W, ...
 and the python-side detections are gathered once at the end (outside any timed region).  The only
-collectives are the barrier / max-over-ranks used for timing.  (The meta-training step, not built
-yet, is where the one real exchange — an NCCL all-reduce(SUM) of the meta-gradient — belongs.)
-"""
+collectives there are the barrier / max-over-ranks used for timing.
+
+The meta-training step has the path's one real exchange: the batch's meta-gradient is the SUM over
+episodes (reference models/interactron.py:123,134 call .backward() once per episode), so with the
+episodes of a batch sharded over ranks it is ONE all-reduce(SUM) over the flat fp32 buffer
+[theta | psi | phi] (NCCL over NVLink; `allreduce_meta_grads`).  `interactron.path_storage` - the trie
+of best action paths that labels the policy loss (models/interactron.py:105-118) - is per-process
+state updated by every episode, so the (initial_image_path, actions, reward) triples are exchanged
+and replayed in global episode order on every rank (`exchange_in_order`)."""
 import torch
 import torch.distributed as dist
 
@@ -46,3 +52,29 @@ def max_over_ranks(values, device="cpu"):
     if w > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return t.tolist()
+
+
+def allreduce_meta_grads(flat):
+    """In-place SUM over ranks of the flat meta-gradient buffer (one collective per step)."""
+    _, w = world()
+    if w > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    return flat
+
+
+def exchange_in_order(local_items):
+    """local_items: this rank's per-episode host objects, local order.  Global episode i of a batch
+    lives on rank i % W at local position i // W (shard_episodes).  -> list of (rank, local_pos, item)
+    for ALL episodes of the batch in global order, identical on every rank."""
+    r, w = world()
+    if w == 1:
+        return [(0, j, it) for j, it in enumerate(local_items)]
+    buckets = [None] * w
+    dist.all_gather_object(buckets, list(local_items))
+    out, j = [], 0
+    while any(j < len(b) for b in buckets):
+        for rank, b in enumerate(buckets):
+            if j < len(b):
+                out.append((rank, j, b[j]))
+        j += 1
+    return out

@@ -24,8 +24,12 @@ def _worker(rank, world, port, q):
     local = [(e, {"episode": e, "score": float(e) * 0.5}) for e in mine]
     allres = parallel.gather_detections(local, len(ids))
     tmax = parallel.max_over_ranks([1.0 + rank, 5.0 - rank])
+    # meta-training step exchanges: SUM all-reduce of the flat meta-gradient, ordered path replay
+    flat = torch.full((1, 7), float(rank + 1))
+    parallel.allreduce_meta_grads(flat)
+    order = parallel.exchange_in_order([("ep%d" % e, [rank, e % 4], 0.5 * e) for e in mine])
     dist.barrier()
-    q.put((rank, mine, [r["episode"] for r in allres], tmax))
+    q.put((rank, mine, [r["episode"] for r in allres], tmax, flat.tolist(), order))
     dist.destroy_process_group()
 
 
@@ -42,9 +46,12 @@ def test_episode_sharding_world2():
         assert p.exitcode == 0
     ids = list(range(100, 111))
     assert res[0][1] == ids[0::2] and res[1][1] == ids[1::2]           # disjoint cover, round robin
-    for _, _, gathered, tmax in res:
+    for _, _, gathered, tmax, flat, order in res:
         assert gathered == ids                                          # order restored on every rank
         assert tmax == [2.0, 5.0]                                       # max over ranks
+        assert flat == [[3.0] * 7]                                      # 1 + 2 summed on both ranks
+        assert [it[0] for _, _, it in order] == ["ep%d" % e for e in ids]   # global episode order
+        assert [(r, j) for r, j, _ in order] == [(i % 2, i // 2) for i in range(len(ids))]
 
 
 def test_single_process_fallbacks():
@@ -52,3 +59,6 @@ def test_single_process_fallbacks():
     assert parallel.shard_episodes([1, 2, 3]) == [1, 2, 3]
     assert parallel.gather_detections([(1, "a"), (2, "b")], 2) == ["a", "b"]
     assert parallel.max_over_ranks([3.0]) == [3.0]
+    assert parallel.exchange_in_order(["a", "b"]) == [(0, 0, "a"), (0, 1, "b")]
+    t = torch.ones(1, 3)
+    assert parallel.allreduce_meta_grads(t) is t
