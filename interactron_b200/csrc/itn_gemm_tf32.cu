@@ -75,6 +75,7 @@ struct GemmKParams {
   int act, epi, accumulate, round_out, act_pos;
   int variant;   // epilogue_variant(...)
   int vec;       // 1: 128-bit epilogue path is legal (alignment / N % 4 checked on the host)
+  float rz_eps;  // tf32x3: mean relative loss of one round-toward-zero TMEM accumulate (see splitters)
   int dbg;       // ITN_TRACE builds only: 1 = skip global stores, 2 = skip TMEM read, 4 = skip smem transpose
 };
 
@@ -477,8 +478,25 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (tid == 0) ITN_TRACE_AT(1, gk);
         const float4* raw = reinterpret_cast<const float4*>(smem + s * Cfg::kStageBytes);
         float4* lo = reinterpret_cast<float4*>(smem + s * Cfg::kStageBytes + Cfg::kRawBytes);
+        // Accumulator compensation.  Every tcgen05.mma adds into TMEM with round-toward-zero: an old
+        // partial sum loses rz_eps (~0.6 * 2^-24) of its magnitude per later accumulate, i.e. the
+        // k-block kb of a chain of 12*num_kb MMAs arrives weighted by 1 - rz_eps * (accumulates still
+        // to come).  That weighting is linear in the contribution, so it is undone here, for free,
+        // by folding  x * delta_kb  into the residual tile of A (delta_kb <= 5e-5 sits well inside
+        // the 2^-11 range of x_lo).  Measured (tools/gemm_precision.py): K=2048 random operands
+        // 1.5e-5 -> see profiles/README.md.
+        const float delta = p.rz_eps * (12.0f * static_cast<float>(num_kb - kb) - 5.5f);
+        constexpr int kAVec = Cfg::kABytes / 16;
 #pragma unroll 8
-        for (int i = tid; i < Cfg::kRawBytes / 16; i += 128) lo[i] = tf32_residual(raw[i]);
+        for (int i = tid; i < Cfg::kRawBytes / 16; i += 128) {
+          const float4 x = raw[i];
+          float4 r = tf32_residual(x);
+          if (i < kAVec) {
+            r.x = fmaf(x.x, delta, r.x); r.y = fmaf(x.y, delta, r.y);
+            r.z = fmaf(x.z, delta, r.z); r.w = fmaf(x.w, delta, r.w);
+          }
+          lo[i] = r;
+        }
         fence_proxy_async();
         __syncwarp();
         if (tid == 0) ITN_TRACE_AT(2, gk);
@@ -777,6 +795,9 @@ static void fill_kparams(GemmKParams& p, const itn_gemm_desc_t* d) {
           al(d->aux, d->ldaux, d->aux_sb0, d->aux_sb1) && al(d->C2, d->ldc2, d->c2_sb0, d->c2_sb1);
   if (getenv("ITN_GEMM_NOVEC")) p.vec = 0;
   p.dbg = getenv("ITN_GEMM_DBG") ? atoi(getenv("ITN_GEMM_DBG")) : 0;
+  // mean loss per round-toward-zero accumulate, in units of 2^-24 (ITN_GEMM_RZ_COMP=0 disables)
+  static const float rz = getenv("ITN_GEMM_RZ_COMP") ? (float)atof(getenv("ITN_GEMM_RZ_COMP")) : 0.59f;
+  p.rz_eps = rz * 5.9604645e-8f;
 }
 
 static int validate(const itn_gemm_desc_t* d) {

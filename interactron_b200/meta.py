@@ -60,6 +60,131 @@ def _targets(data, E, S):
     return [{"labels": data["category_ids"][e][f], "boxes": data["boxes"][e][f]} for e in range(E) for f in range(S)]
 
 
+class MetaParts:
+    """The two launch-only halves of the step, separated by the host work (LSAP of the matcher, the
+    path trie): `part_a` = steps 1-3 (+ the 1-frame pass of step 6) up to the detector outputs the
+    criterion needs, `part_b` = steps 4-6 from the criterion's gradients to the flat meta-gradient.
+    Both are pure kernel sequences on static shapes, so each is captured into a CUDA graph
+    (`graph.GraphedCall`) and replayed; `part_b` reads the activations `part_a` left in `self.st`."""
+
+    def __init__(self, model):
+        self.model, self.loop = model, model._get_loop()
+        self.st = None
+
+    def part_a(self, frames, masks, idx):
+        loop = self.loop
+        ops = loop.ops
+        E, S = frames.shape[:2]
+        C = loop.detector.class_embed.out_features
+        NQ, D = detr_t.NQ, detr_t.D
+        tpk = loop.theta_pack
+        f_fwd = fusion.fusion_a_forward if loop.kind == "A" else fusion.fusion_b_forward
+        f_bwd = fusion.fusion_a_backward if loop.kind == "A" else fusion.fusion_b_backward
+        # 1. pre-adapt pass, learned loss, inner gradient
+        src_r, pos, kmask, (h, w) = loop.features(frames.flatten(0, 1), masks.flatten(0, 1))
+        L = h * w
+        src3 = src_r.view(E, S * L, -1)
+        Wd = loop._det_weights(loop.theta, loop.theta_r, loop.theta_t)
+        Wf = loop._fusion_weights()
+        preds = ops.empty(E * S * NQ, D + C + 4)
+        pre, cache = detr_t.detr_t_forward(ops, Wd, src3, pos, kmask, E, S, L, preds=preds)
+        fout, fcache = f_fwd(ops, Wf, pre["memory_r"], preds, E, S, L)
+        dmemory, dpreds = f_bwd(ops, Wf, fcache)
+        g = ops.empty(E, tpk.numel)
+        detr_t.detr_t_backward(ops, Wd, cache, GradSink(ops, tpk, g), dpreds=dpreds, dmemory=dmemory)
+        del cache, fcache, dmemory, dpreds
+        # 2. fast weights + clip mask, W^T twins of theta'
+        theta_p, theta_p_r, cmask = ops.sgd_clip_update(loop.theta, g, loop.lr, loop.clip, want_mask=True)
+        theta_p_t = tpk.transpose_into(ops, theta_p, ops.zeros(E, tpk.numel))
+        Wp = loop._det_weights(theta_p, theta_p_r, theta_p_t)
+        # 3. post-adapt pass on the 5 frames; 6a. on one chosen frame per episode (theta'' == theta')
+        post, pcache = detr_t.detr_t_forward(ops, Wp, src3, pos, kmask, E, S, L)
+        src1 = src_r.index_select(0, idx).view(E, L, -1)
+        pos1 = pos.view(E * S, L, -1).index_select(0, idx).reshape(E * L, -1)
+        km1 = kmask.index_select(0, idx)
+        post1, c1 = detr_t.detr_t_forward(ops, Wp, src1, pos1, km1, E, 1, L)
+        self.st = dict(E=E, S=S, L=L, C=C, src3=src3, pos=pos, kmask=kmask, cmask=cmask, Wp=Wp, pcache=pcache, c1=c1)
+        return {"post_logits": post["logits"].view(E * S, NQ, C), "post_boxes": post["boxes"].view(E * S, NQ, 4),
+                "post1_logits": post1["logits"].view(E, NQ, C), "post1_boxes": post1["boxes"].view(E, NQ, 4),
+                "actions": fout["actions"]}
+
+    def part_b(self, dlog, dbox, dlog1, dbox1, dact=None):
+        loop, st = self.loop, self.st
+        ops = loop.ops
+        E, S, L, C = st["E"], st["S"], st["L"], st["C"]
+        NQ, D = detr_t.NQ, detr_t.D
+        tpk, ppk, fpk = loop.theta_pack, loop.psi_pack, loop.phi_pack
+        n_t, n_p, n_f = tpk.numel, ppk.numel, fpk.numel
+        f_fwd = fusion.fusion_a_forward if loop.kind == "A" else fusion.fusion_b_forward
+        f_bwd = fusion.fusion_a_backward if loop.kind == "A" else fusion.fusion_b_backward
+        Wp, src3, pos, kmask = st["Wp"], st["src3"], st["pos"], st["kmask"]
+        # 4. backward of the post-adapt pass: dL_sup/dtheta' per episode, direct psi gradient
+        g_sup = ops.empty(E, n_t)
+        gpsi = ops.zeros(1, n_p)
+        detr_t.detr_t_backward(ops, Wp, st["pcache"],
+                               MultiSink(GradSink(ops, tpk, g_sup), GradSink(ops, ppk, gpsi, shared=True)),
+                               dlogits=dlog.view(E, S * NQ, C), dboxes=dbox.view(E, S * NQ, 4))
+        # 5. second order: one dual pass of step 1 along v = -lr * mask * dL_sup/dtheta'
+        v = ops.mul_mask_u8(g_sup, st["cmask"], -loop.lr)
+        v_t = tpk.transpose_into(ops, v, ops.zeros(E, n_t))
+        dops = DualOps(ops)
+        DWd = DualWeights((tpk, loop.theta, loop.theta_t, v, v_t), (ppk, loop.psi, loop.psi_t, None, None))
+        DWf = DualWeights((fpk, loop.phi, loop.phi_t, None, None))
+        preds2 = dops.empty(E * S * NQ, D + C + 4)
+        pre2, cache2 = detr_t.detr_t_forward(dops, DWd, src3, pos, kmask, E, S, L, preds=preds2)
+        _, fcache2 = f_fwd(dops, DWf, pre2["memory_r"], preds2, E, S, L)
+        # the step's meta-gradient: ONE flat buffer [theta | psi | phi] (what gets all-reduced)
+        G = ops.zeros(1, n_t + n_p + n_f)
+        gphi2 = Dual(ops.zeros(1, n_f), G[:, n_t + n_p:])
+        gpsi2 = dops.zeros(1, n_p)
+        # the policy loss's first-order gradient rides along as a tangent seed on the action logits
+        seed = None if dact is None else Dual(ops.zeros(E, 4, 4), dact)
+        dmem2, dpreds2 = f_bwd(dops, DWf, fcache2, sink=GradSink(dops, fpk, gphi2, shared=True), dactions=seed)
+        detr_t.detr_t_backward(dops, DWd, cache2, GradSink(dops, ppk, gpsi2, shared=True), dpreds=dpreds2,
+                               dmemory=dmem2)
+        del cache2, fcache2
+        # 6b. detector loss backward (first order): theta gets the gradient wrt theta'' unchanged
+        g_det = ops.empty(E, n_t)
+        gpsi1 = ops.zeros(1, n_p)
+        detr_t.detr_t_backward(ops, Wp, st["c1"],
+                               MultiSink(GradSink(ops, tpk, g_det), GradSink(ops, ppk, gpsi1, shared=True)),
+                               dlogits=dlog1.view(E, NQ, C), dboxes=dbox1.view(E, NQ, 4))
+        ops.colsum(g_det.view(1, E, n_t), out=G[:, :n_t])
+        ops.copy2d_(G[:, n_t:n_t + n_p], ops.add(ops.add(gpsi, gpsi2.t), gpsi1))
+        return {"G": G}
+
+
+def _parts_runner(model, frames, masks, idx):
+    """-> (run_a, run_b): the two halves, CUDA-graph replayed when the model allows it."""
+    loop = model._get_loop()
+    use_graph = model.use_cuda_graph and frames.is_cuda
+    if not use_graph:
+        parts = MetaParts(model)
+        return parts.part_a, (lambda *t: parts.part_b(*t)), None
+    from .graph import GraphedCall
+    bb = loop.detector.backbone
+    bb_key = tuple(t.data_ptr() for t in list(bb.parameters()) + list(bb.buffers()))
+    key = ("meta", tuple(frames.shape), tuple(masks.shape), loop.kind, bb_key)
+    ent = model._graphs.get(key)
+    if ent is None:
+        for k in [k for k in model._graphs if k[0] == "meta"]:
+            del model._graphs[k]                       # one meta geometry at a time: the caches are large
+        ent = model._graphs[key] = {"parts": MetaParts(model), "a": None, "b": None}
+    parts = ent["parts"]
+
+    def run_a(f, m, i):
+        if ent["a"] is None:
+            ent["a"] = GraphedCall(parts.part_a, [f, m, i])
+        return ent["a"](f, m, i, clone=False)
+
+    def run_b(*t):
+        if ent["b"] is None:
+            ent["b"] = GraphedCall(lambda *x: parts.part_b(*x), list(t))
+        return {"G": ent["b"](*t, clone=False)["G"].clone()}     # callers keep views of it in .grad
+
+    return run_a, run_b, ent
+
+
 def meta_step(model, data, ridx=None):
     """-> (predictions, losses, flat_grads): flat_grads["all"] is ONE [1, n_theta+n_psi+n_phi] buffer
     with this rank's summed meta-gradients (not yet added to .grad; "theta"/"psi"/"phi" are its views,
@@ -74,52 +199,35 @@ def meta_step(model, data, ridx=None):
     masks = data["masks"].to(dev, non_blocking=True)
     E, S = frames.shape[:2]
     assert S == 5, "the meta-training step is defined on full 5-frame episodes"
-    lr, clip = loop.lr, loop.clip
     C = loop.detector.class_embed.out_features
-    NQ, D = detr_t.NQ, detr_t.D
+    NQ = detr_t.NQ
     tpk, ppk, fpk = loop.theta_pack, loop.psi_pack, loop.phi_pack
     kind = loop.kind
-    f_fwd = fusion.fusion_a_forward if kind == "A" else fusion.fusion_b_forward
-    f_bwd = fusion.fusion_a_backward if kind == "A" else fusion.fusion_b_backward
+    if ridx is None:
+        ridx = [random.randint(0, 4) for _ in range(E)]                     # reference :129, one draw per task
+    idx = torch.tensor([e * S + int(r) for e, r in enumerate(ridx)]).to(dev)
+    run_a, run_b, _ = _parts_runner(model, frames, masks, idx)
 
-    # 1. pre-adapt pass, learned loss, inner gradient ------------------------------------------
-    src_r, pos, kmask, (h, w) = loop.features(frames.flatten(0, 1), masks.flatten(0, 1))
-    L = h * w
-    src3 = src_r.view(E, S * L, -1)
-    Wd = loop._det_weights(loop.theta, loop.theta_r, loop.theta_t)
-    Wf = loop._fusion_weights()
-    preds = ops.empty(E * S * NQ, D + C + 4)
-    pre, cache = detr_t.detr_t_forward(ops, Wd, src3, pos, kmask, E, S, L, preds=preds)
-    fout, fcache = f_fwd(ops, Wf, pre["memory_r"], preds, E, S, L)
-    dmemory, dpreds = f_bwd(ops, Wf, fcache)
-    g = ops.empty(E, tpk.numel)
-    detr_t.detr_t_backward(ops, Wd, cache, GradSink(ops, tpk, g), dpreds=dpreds, dmemory=dmemory)
-    del cache, fcache, dmemory, dpreds
-
-    # 2. fast weights + clip mask -----------------------------------------------------------------
-    theta_p, theta_p_r, cmask = ops.sgd_clip_update(loop.theta, g, lr, clip, want_mask=True)
-    theta_p_t = tpk.transpose_into(ops, theta_p, ops.zeros(E, tpk.numel))
-    Wp = loop._det_weights(theta_p, theta_p_r, theta_p_t)
-
-    # 3. post-adapt pass on the 5 frames, supervisor loss ---------------------------------------
-    post, pcache = detr_t.detr_t_forward(ops, Wp, src3, pos, kmask, E, S, L)
+    # steps 1-3 (+ 1-frame pass): detector outputs with the fast weights ---------------------------
+    a = run_a(frames, masks, idx)
     targets = _targets(data, E, S)
-    outs = {"pred_logits": post["logits"].view(E * S, NQ, C), "pred_boxes": post["boxes"].view(E * S, NQ, 4)}
+    keys5 = ("loss_ce", "class_error", "cardinality_error", "loss_bbox", "loss_giou")
+    outs = {"pred_logits": a["post_logits"], "pred_boxes": a["post_boxes"]}
     sup_l, dlog, dbox = crit.loss_and_grad(outs, targets, background_c=0.1, groups=E, weights=LOSS_W)
     sup_host = sup_l.cpu()                                                        # [E,5]
-    sup = {k: sup_host[:, i] for i, k in enumerate(("loss_ce", "class_error", "cardinality_error", "loss_bbox",
-                                                      "loss_giou"))}
+    sup = {k: sup_host[:, i] for i, k in enumerate(keys5)}
+    grads_in = [dlog, dbox]
     dact = None
     if kind == "A":
         # lowest-loss policy labels (reference models/interactron.py:105-118)
-        f0 = {"pred_logits": post["logits"].view(E, S, NQ, C)[:, 0].contiguous(),
-              "pred_boxes": post["boxes"].view(E, S, NQ, 4)[:, 0].contiguous()}
+        f0 = {"pred_logits": a["post_logits"].view(E, S, NQ, C)[:, 0].contiguous(),
+              "pred_boxes": a["post_boxes"].view(E, S, NQ, 4)[:, 0].contiguous()}
         t0 = [targets[e * S] for e in range(E)]
         gt = crit.group_losses(f0, t0, background_c=0.1, groups=E).cpu()
         rew = gt[:, 0] + 5 * gt[:, 4] + 2 * gt[:, 3]
         # the trie is process state fed by every episode of the (global) batch: replay all ranks' episodes
         # in global order, keep the labels of our own
-        mine = [(data["initial_image_path"][e], [int(a) for a in data["actions"][e][:4]], float(rew[e]))
+        mine = [(data["initial_image_path"][e], [int(x) for x in data["actions"][e][:4]], float(rew[e]))
                 for e in range(E)]
         rank = parallel.world()[0]
         best = [None] * E
@@ -128,69 +236,31 @@ def meta_step(model, data, ridx=None):
             store.add_path(path, cost)
             if r_ == rank:
                 best[j] = store.get_label(path)
-        best = torch.tensor(best, dtype=torch.long, device=dev)                     # [E,4]
+        best = torch.tensor(best, dtype=torch.long).to(dev)                          # [E,4]
         # 16 logits per episode: CE over the 4 action heads and its gradient
-        logp = F.log_softmax(fout["actions"].view(E, 4, 4), dim=-1)
+        logp = F.log_softmax(a["actions"].view(E, 4, 4), dim=-1)
         loss_path = -logp.gather(-1, best[..., None]).squeeze(-1).mean(-1)            # [E]
-        dact = (logp.exp() - F.one_hot(best, 4).to(logp.dtype)) / 4.0
+        dact = ((logp.exp() - F.one_hot(best, 4).to(logp.dtype)) / 4.0).contiguous()
         sup["loss_path"] = loss_path.cpu()
         sup["policy_reward"] = rew
-
-    # 4. backward of the post-adapt pass: dL_sup/dtheta' per episode, direct psi gradient ----------
-    g_sup = ops.empty(E, tpk.numel)
-    gpsi = ops.zeros(1, ppk.numel)
-    detr_t.detr_t_backward(ops, Wp, pcache, MultiSink(GradSink(ops, tpk, g_sup), GradSink(ops, ppk, gpsi, shared=True)),
-                           dlogits=dlog.view(E, S * NQ, C), dboxes=dbox.view(E, S * NQ, 4))
-    del pcache
-
-    # 5. second order: one dual pass of step 1 along v = -lr * mask * dL_sup/dtheta' ---------------
-    v = ops.mul_mask_u8(g_sup, cmask, -lr)
-    v_t = tpk.transpose_into(ops, v, ops.zeros(E, tpk.numel))
-    dops = DualOps(ops)
-    DWd = DualWeights((tpk, loop.theta, loop.theta_t, v, v_t), (ppk, loop.psi, loop.psi_t, None, None))
-    DWf = DualWeights((fpk, loop.phi, loop.phi_t, None, None))
-    preds2 = dops.empty(E * S * NQ, D + C + 4)
-    pre2, cache2 = detr_t.detr_t_forward(dops, DWd, src3, pos, kmask, E, S, L, preds=preds2)
-    _, fcache2 = f_fwd(dops, DWf, pre2["memory_r"], preds2, E, S, L)
-    # the step's meta-gradient: ONE flat buffer [theta | psi | phi] (what gets all-reduced)
-    n_t, n_p, n_f = tpk.numel, ppk.numel, fpk.numel
-    G = ops.zeros(1, n_t + n_p + n_f)
-    gphi2 = Dual(ops.zeros(1, n_f), G[:, n_t + n_p:])
-    gpsi2 = dops.zeros(1, ppk.numel)
-    seed = None if dact is None else Dual(ops.zeros(E, 4, 4), dact.contiguous())
-    dmem2, dpreds2 = f_bwd(dops, DWf, fcache2, sink=GradSink(dops, fpk, gphi2, shared=True), dactions=seed)
-    detr_t.detr_t_backward(dops, DWd, cache2, GradSink(dops, ppk, gpsi2, shared=True), dpreds=dpreds2, dmemory=dmem2)
-    del cache2, fcache2
-
-    # 6. detector loss on one random frame per episode (first order) ------------------------------
-    if ridx is None:
-        ridx = [random.randint(0, 4) for _ in range(E)]                     # reference :129, one draw per task
-    idx = torch.tensor([e * S + int(r) for e, r in enumerate(ridx)], device=dev)
-    src1 = src_r.index_select(0, idx).view(E, L, -1)
-    pos1 = pos.view(E * S, L, -1).index_select(0, idx).reshape(E * L, -1)
-    km1 = kmask.index_select(0, idx)
-    post1, c1 = detr_t.detr_t_forward(ops, Wp, src1, pos1, km1, E, 1, L)
     t1 = [targets[e * S + int(r)] for e, r in enumerate(ridx)]
-    o1 = {"pred_logits": post1["logits"].view(E, NQ, C), "pred_boxes": post1["boxes"].view(E, NQ, 4)}
+    o1 = {"pred_logits": a["post1_logits"], "pred_boxes": a["post1_boxes"]}
     det_l, dlog1, dbox1 = crit.loss_and_grad(o1, t1, background_c=0.1, groups=E, weights=LOSS_W)
     det_host = det_l.cpu()
-    g_det = ops.empty(E, tpk.numel)
-    gpsi1 = ops.zeros(1, ppk.numel)
-    detr_t.detr_t_backward(ops, Wp, c1, MultiSink(GradSink(ops, tpk, g_det), GradSink(ops, ppk, gpsi1, shared=True)),
-                           dlogits=dlog1.view(E, NQ, C), dboxes=dbox1.view(E, NQ, 4))
+    grads_in += [dlog1, dbox1] + ([dact] if dact is not None else [])
 
-    # the batch's meta-gradients, summed over episodes --------------------------------------------
-    ops.colsum(g_det.view(1, E, n_t), out=G[:, :n_t])
-    ops.copy2d_(G[:, n_t:n_t + n_p], ops.add(ops.add(gpsi, gpsi2.t), gpsi1))
+    # steps 4-6: backward passes + the dual (second-order) pass -> flat meta-gradient -----------------
+    G = run_b(*grads_in)["G"]
+    n_t, n_p = tpk.numel, ppk.numel
     flat = {"all": G, "theta": G[:, :n_t], "psi": G[:, n_t:n_t + n_p], "phi": G[:, n_t + n_p:]}
 
-    det = {k: det_host[:, i] for i, k in enumerate(("loss_ce", "class_error", "cardinality_error", "loss_bbox",
-                                                      "loss_giou"))}
+    det = {k: det_host[:, i] for i, k in enumerate(keys5)}
     order = ("loss_ce", "class_error", "loss_bbox", "loss_giou", "cardinality_error")
     losses = {k.replace("loss", "loss_detector"): det[k].mean().to(dev) for k in order}
     sup_order = order + (("loss_path", "policy_reward") if kind == "A" else ())
     losses.update({k.replace("loss", "loss_supervisor"): sup[k].mean().to(dev) for k in sup_order})
-    predictions = {"pred_logits": post1["logits"].view(E, 1, NQ, C), "pred_boxes": post1["boxes"].view(E, 1, NQ, 4)}
+    predictions = {"pred_logits": a["post1_logits"].view(E, 1, NQ, C).clone(),
+                   "pred_boxes": a["post1_boxes"].view(E, 1, NQ, 4).clone()}
     return predictions, losses, flat
 
 

@@ -246,6 +246,14 @@ class CudaOps:
         if out is None:
             out = self.empty(G, cols)
         assert out.shape == (G, cols) and (cols == 1 or out.stride(1) == 1)
+        # few groups x many rows (the shared sinks of the meta-training step sum over all episodes):
+        # one block per 32 columns would walk all rows serially.  Split the rows over `d` blocks
+        # (d | rows), reduce the d partial sums in a second pass - same fixed order every time.
+        if rows >= 2048 and G * ((cols + 31) // 32) < 296 and x.stride(1) == cols:
+            d = next((k for k in range(min(256, rows // 64), 1, -1) if rows % k == 0), 1)
+            if d > 1:
+                part = self.colsum(x.reshape(G * d, rows // d, cols))
+                return self.colsum(part.view(G, d, cols), out=out)
         _lib.check(self.lib.itn_colsum(_ptr(x), _ptr(out), G, rows, cols, x.stride(1),
                                        out.stride(0) if G > 1 else cols, self._stream()))
         return out

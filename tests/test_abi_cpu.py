@@ -49,7 +49,7 @@ def test_no_cpu_fallback():
     from interactron_b200.synthetic import synthetic_episode
     with pytest.raises(RuntimeError, match="no CPU path"):
         m.predict(synthetic_episode(0))
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError, match="no CPU path"):
         m.forward(synthetic_episode(0))
 
 

@@ -102,5 +102,11 @@ def test_detr_t_forward_backward_matches_reference_autograd(setup):
     print("worst theta-grad rel errs", errs[:8])
     assert worst < 1e-9, errs[:8]
     g_psi_ref = torch.autograd.grad(loss, [named[n] for n in pp.names])
+    top = max(float(gr.norm()) for gr in g_psi_ref)
     for name, gr in zip(pp.names, g_psi_ref):
-        assert rel(pp.view(gpsi, name)[0], gr) < 1e-9, name
+        mine = pp.view(gpsi, name)[0]
+        if float(gr.norm()) < 1e-9 * top:
+            # mathematically zero (decoder layer 0 self-attention sees tgt == 0: q/k rows get only round-off)
+            assert float(mine.norm()) < 1e-9 * top, name
+            continue
+        assert rel(mine, gr) < 1e-9, name

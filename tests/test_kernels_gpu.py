@@ -274,6 +274,11 @@ def test_colsum_add_copy_sigmoid_norm(ops):
     gen = torch.Generator(device="cuda").manual_seed(2)
     x = torch.randn(3, 1805, 256, generator=gen, device="cuda")
     assert rel(ops.colsum(x), x.double().sum(1)) < FP32_TOL
+    for shape in ((1, 7220, 256), (2, 4096, 512), (1, 2053, 64)):      # two-pass path (rows split) + prime rows
+        big = torch.randn(*shape, generator=gen, device="cuda")
+        out = torch.zeros(shape[0], shape[2] + 8, device="cuda")
+        ops.colsum(big, out=out[:, :shape[2]])
+        assert rel(out[:, :shape[2]], big.double().sum(1)) < FP32_TOL and out[:, shape[2]:].abs().sum() == 0
     pos = torch.randn(1805, 256, generator=gen, device="cuda")
     assert rel(ops.add(x, pos), x + pos) < 1e-7
     dst = torch.zeros(250, 1496, device="cuda")

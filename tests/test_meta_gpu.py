@@ -106,5 +106,5 @@ def test_forward_batch_equals_singles():
     model(collate_episodes(eps[1:]), ridx=[4])
     top = max(float(g.norm()) for g in both.values())
     for n, p in model.named_parameters():
-        if p.grad is not None and float(both[n].norm()) > 1e-6 * top:     # skip the mathematically-zero ones
+        if p.grad is not None and float(both[n].norm()) > 1e-5 * top:     # skip the mathematically-zero ones
             assert rel(p.grad, both[n]) < 2e-3, n        # different batch shapes -> different GEMM tilings
