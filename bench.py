@@ -147,7 +147,11 @@ def gemm_roofline(loop, frames, masks, bf16_peak):
         e0.record()
         out = orig(a, b, **kw)
         e1.record()
-        rec.append((2.0 * M * N * K * nb, e0, e1))
+        # algorithmic bytes: every operand once (broadcast operands once per launch), the output once,
+        # plus the streamed epilogue operand (residual / mask / accumulate) when there is one
+        extra = sum(1 for k in ("residual", "aux") if kw.get(k) is not None) + (1 if kw.get("accumulate") else 0)
+        nbytes = 4.0 * (a.numel() + b.numel() + (1 + extra) * M * N * nb)
+        rec.append((2.0 * M * N * K * nb, e0, e1, nbytes))
         return out
 
     ops.matmul = timed
@@ -168,10 +172,23 @@ def gemm_roofline(loop, frames, masks, bf16_peak):
     ms = sum(r[1].elapsed_time(r[2]) for r in rec)
     achieved = flops / (ms * 1e-3) / 1e12
     peak = bf16_peak / 2.0          # kind::tf32 runs at half the bf16 rate
-    return {"bound": "tensor", "kernel": "gemm_tf32_kernel (tcgen05 kind::tf32, tf32x3 mode = 3 MMAs per k-step)",
+    roof = {"bound": "tensor", "kernel": "gemm_tf32_kernel (tcgen05 kind::tf32, tf32x3 mode = 3 MMAs per k-step)",
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+            "mma_issue_frac": 3.0 * achieved / peak,
             "gemm_launches_per_step": len(rec), "algorithmic_gflop_per_step": flops / 1e9,
-            "gemm_ms_per_step_eager": ms, "step_ms_eager": t0.elapsed_time(t1)}, launches
+            "algorithmic_gemm_gb_per_step": sum(r[3] for r in rec) / 1e9,
+            "gemm_ms_per_step_eager": ms, "step_ms_eager": t0.elapsed_time(t1)}
+    # DRAM traffic of the same kernel family over one step, from the committed ncu launch list of
+    # `tools/profile_step.py 32 interactron_random` (dram__bytes_read.sum + dram__bytes_write.sum)
+    tp = os.path.join(ROOT, "profiles", "r01c_traffic_e32_interactron_random.json")
+    if os.path.exists(tp) and frames.shape[0] == 32 and loop.kind == "B":
+        k = json.load(open(tp))["kernels"].get("itn::gemm_tf32_kernel")
+        if k:
+            roof["traffic"] = (k["dram_read_bytes"] + k["dram_write_bytes"]) / k["launches"]
+            roof["traffic_note"] = ("mean DRAM bytes per GEMM launch (ncu, profiles/r01c_traffic_e32_interactron_random.json: "
+                                    f"{(k['dram_read_bytes'] + k['dram_write_bytes']) / 1e9:.1f} GB over {k['launches']} launches of one step); "
+                                    "compare with algorithmic_gemm_gb_per_step")
+    return roof, launches
 
 
 def run_gpu_arm(args):
@@ -371,7 +388,7 @@ def run_meta_arm(args):
             "dtype": "tf32x3", "data": "synthetic",
             "config": {"workload": f"{name}.yaml forward() = BASELINE configs[4] (meta-training step), eval-mode "
                                    "numerics (no dropout), D1", "episodes_per_step_per_gpu": E,
-                       "allreduce_elems": n_flat if world > 1 else 0, "cuda_graph": False,
+                       "allreduce_elems": n_flat if world > 1 else 0, "cuda_graph": bool(model.use_cuda_graph),
                        "l2": "256 MiB buffer written between timed steps"},
             "e2e": {"value": v, "unit": "episodes/s", "h2d_bytes_per_step": batches[0]["frames"].numel() * 4 +
                     batches[0]["masks"].numel() * 8, "d2h_bytes_per_step": 4,

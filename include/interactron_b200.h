@@ -272,6 +272,29 @@ int itn_sigmoid_bwd_jvp(const float* dy, const float* dy_dot, const float* y, co
 int itn_l2norm_jvp(const float* x_dot, const float* nrm, const float* d, float* n_dot, float* d_dot,
                    int groups, int n, void* stream);
 
+/* ---- trainer step over the flat buffers -------------------------------------
+ * Replaces, for the meta-training loop of engine/interactron_trainer.py:106-110,
+ *   torch.nn.utils.clip_grad_norm_(model.parameters(), GRAD_NORM_CLIP)
+ *   detector_optimizer.step(); supervisor_optimizer.step()     (torch.optim.Adam, default betas/eps)
+ *   detector_optimizer.zero_grad(); supervisor_optimizer.zero_grad()
+ * itn_sumsq_partials: partial[i] = sum of squares of a fixed slice of g[0..n); *n_partials (host int)
+ * receives how many were written (<= max_partials, <= 1184).  Fixed summation order.
+ * itn_clip_adam_step: one segment (w, g, m, v of n elements; g may point inside the buffer the
+ * partials were taken over).  total = sqrt(sum(partial)) is the global gradient norm (written to
+ * norm_out if not NULL); g is scaled by min(1, max_norm / (total + 1e-6)) when max_norm > 0 and
+ * partial != NULL; then m, v, w are updated exactly as torch.optim.Adam does at step `step` (1-based)
+ * with learning rate lr (hyper-parameters are doubles, like torch's Python scalars: 1 - beta2 must not be
+ * formed in fp32); zero_grad != 0 clears g afterwards.
+ * An element of g whose bit pattern is ITN_NO_GRAD_BITS (a quiet NaN with a payload arithmetic never
+ * produces) means "no gradient" (torch: .grad is None): it adds nothing to the norm and its w, m, v
+ * are left untouched, as clip_grad_norm_ / Adam skip such parameters.  Genuine NaNs propagate. */
+#define ITN_NO_GRAD_BITS 0x7FC0DEADu
+int itn_sumsq_partials(const float* g, long long n, float* partial, int max_partials, int* n_partials,
+                       void* stream);
+int itn_clip_adam_step(float* w, float* g, float* m, float* v, long long n, const float* partial,
+                       int n_partials, float max_norm, double lr, double beta1, double beta2, double eps,
+                       int step, int zero_grad, float* norm_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -41,13 +41,17 @@ class InnerLoop:
         self.refresh_weights()
 
     # ------------------------------------------------------------------ weights
-    def refresh_weights(self):
+    def refresh_weights(self, repack=True):
         """(Re)pack theta / psi / phi into the persistent flat fp32 buffers (+ TF32-rounded twins
-        in single-pass mode).  In place, so captured CUDA graphs keep reading valid addresses."""
+        in single-pass mode).  In place, so captured CUDA graphs keep reading valid addresses.
+        repack=False: the flat buffers already hold the current weights (the Parameters alias them,
+        trainer.MetaTrainerStep) - only the derived twins are rebuilt."""
         ops = self.ops
         dev = ops.device
 
         def fill(buf, pack, params):
+            if buf is not None and not repack:
+                return buf
             flat = pack.pack(params, device=dev, dtype=getattr(ops, "dtype", torch.float32))
             if buf is None:
                 return flat.unsqueeze(0)

@@ -25,32 +25,55 @@ def lin(ops, x, W, b=None, **kw):
 def attention_fwd(ops, q, k, v, B, Lq, Lk, nh, hd, scale, kmask):
     """softmax(scale * q k^T + mask) v per (batch, head).
     q [B,Lq,nh*hd], k/v [B,Lk,nh*hd] (strided views ok) -> o [B,Lq,nh*hd] (TF32-clean), P."""
-    qh = q.reshape(B, Lq, nh, hd).permute(0, 2, 1, 3)            # [B,nh,Lq,hd]
-    khT = k.reshape(B, Lk, nh, hd).permute(0, 2, 3, 1)           # [B,nh,hd,Lk]
-    vh = v.reshape(B, Lk, nh, hd).permute(0, 2, 1, 3)            # [B,nh,Lk,hd]
     P = ops.empty(B, nh, Lq, pad4(Lk))                           # row stride padded to 16 bytes for TMA
-    p = P[..., :Lk]
-    ops.matmul(qh, khT, out=p, out_pad=True)
-    ops.softmax_(P, Lk, scale, kmask, rows_per_mask=nh * Lq)
     o = ops.empty(B, Lq, nh * hd)
-    ops.matmul(p, vh, out=o.view(B, Lq, nh, hd).permute(0, 2, 1, 3), rnd=True)
+    for b0, b1 in _l2_chunks(ops, B, nh * Lq * pad4(Lk) * 4, 1):
+        qh = q[b0:b1].reshape(b1 - b0, Lq, nh, hd).permute(0, 2, 1, 3)            # [b,nh,Lq,hd]
+        khT = k[b0:b1].reshape(b1 - b0, Lk, nh, hd).permute(0, 2, 3, 1)           # [b,nh,hd,Lk]
+        vh = v[b0:b1].reshape(b1 - b0, Lk, nh, hd).permute(0, 2, 1, 3)            # [b,nh,Lk,hd]
+        Pc = P[b0:b1]
+        p = Pc[..., :Lk]
+        ops.matmul(qh, khT, out=p, out_pad=True)
+        ops.softmax_(Pc, Lk, scale, None if kmask is None else kmask[b0:b1], rows_per_mask=nh * Lq)
+        ops.matmul(p, vh, out=o[b0:b1].view(b1 - b0, Lq, nh, hd).permute(0, 2, 1, 3), rnd=True)
     return o, P
+
+
+def _l2_chunks(ops, B, bytes_per_batch, live):
+    """Batch ranges whose score tensors (`live` of them, `bytes_per_batch` each per batch entry) fit the
+    L2 budget `ops.attn_l2_mb`: the unfused QK^T -> softmax -> PV chain then re-reads its score tile
+    from L2 instead of HBM (same kernels on the same rows: results are bit-identical to one pass).
+    Dual-number passes (Dual tensors do not slice) and small problems take one chunk."""
+    budget = getattr(ops, "attn_l2_mb", 0) * (1 << 20)
+    total = B * bytes_per_batch * live
+    if budget <= 0 or total <= budget:
+        return [(0, B)]
+    step = max(1, int(budget // (bytes_per_batch * live)))
+    n = -(-B // step)
+    step = -(-B // n)                                            # equal-sized chunks
+    return [(b, min(B, b + step)) for b in range(0, B, step)]
 
 
 def attention_bwd(ops, dO, q, k, v, P, B, Lq, Lk, nh, hd, scale, dq, dk, dv):
     """dO [B,Lq,nh*hd] (TF32-clean).  Writes TF32-clean dq/dk/dv into the given [B,L,nh*hd] views."""
-    qh = q.reshape(B, Lq, nh, hd).permute(0, 2, 1, 3)
-    kh = k.reshape(B, Lk, nh, hd).permute(0, 2, 1, 3)
-    vhT = v.reshape(B, Lk, nh, hd).permute(0, 2, 3, 1)
-    dOh = dO.reshape(B, Lq, nh, hd).permute(0, 2, 1, 3)
-    p = P[..., :Lk]
-    dP = ops.empty(B, nh, Lq, pad4(Lk))
-    dp = dP[..., :Lk]
-    ops.matmul(dOh, vhT, out=dp, out_pad=True)                                                    # dP = dO V^T
-    ops.matmul(T(p), dOh, out=dv.view(B, Lk, nh, hd).permute(0, 2, 1, 3), rnd=True)  # dV = P^T dO
-    ops.softmax_bwd_(P, dP, Lk, scale)                                              # dS (in dP)
-    ops.matmul(dp, kh, out=dq.view(B, Lq, nh, hd).permute(0, 2, 1, 3), rnd=True)     # dQ = dS K
-    ops.matmul(T(dp), qh, out=dk.view(B, Lk, nh, hd).permute(0, 2, 1, 3), rnd=True)  # dK = dS^T Q
+    chunks = _l2_chunks(ops, B, nh * Lq * pad4(Lk) * 4, 2)
+    # one chunk: dP for the whole batch; several: ONE chunk-sized dP buffer reused (it stays in L2)
+    dP_all = ops.empty(chunks[0][1] - chunks[0][0], nh, Lq, pad4(Lk))
+    for b0, b1 in chunks:
+        n = b1 - b0
+        qh = q[b0:b1].reshape(n, Lq, nh, hd).permute(0, 2, 1, 3)
+        kh = k[b0:b1].reshape(n, Lk, nh, hd).permute(0, 2, 1, 3)
+        vhT = v[b0:b1].reshape(n, Lk, nh, hd).permute(0, 2, 3, 1)
+        dOh = dO[b0:b1].reshape(n, Lq, nh, hd).permute(0, 2, 1, 3)
+        Pc = P[b0:b1]
+        p = Pc[..., :Lk]
+        dP = dP_all[:n]
+        dp = dP[..., :Lk]
+        ops.matmul(dOh, vhT, out=dp, out_pad=True)                                                    # dP = dO V^T
+        ops.matmul(T(p), dOh, out=dv[b0:b1].view(n, Lk, nh, hd).permute(0, 2, 1, 3), rnd=True)  # dV = P^T dO
+        ops.softmax_bwd_(Pc, dP, Lk, scale)                                              # dS (in dP)
+        ops.matmul(dp, kh, out=dq[b0:b1].view(n, Lq, nh, hd).permute(0, 2, 1, 3), rnd=True)     # dQ = dS K
+        ops.matmul(T(dp), qh, out=dk[b0:b1].view(n, Lk, nh, hd).permute(0, 2, 1, 3), rnd=True)  # dK = dS^T Q
 
 
 # --------------------------------------------------------------------------- gradient sinks

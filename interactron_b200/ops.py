@@ -50,6 +50,8 @@ class CudaOps:
             raise ValueError(f"ITN_GEMM_PRECISION must be one of {sorted(PRECISION)}")
         self.n_tf32 = 0
         self.n_simt = 0
+        # L2 budget (MiB) for the score tensors of one attention chunk (layers._l2_chunks); 0 = one pass
+        self.attn_l2_mb = int(os.environ.get("ITN_ATTN_L2_MB", "0"))
 
     # ------------------------------------------------------------ plumbing
     def _stream(self):
@@ -437,6 +439,25 @@ class CudaOps:
         _lib.check(self.lib.itn_im2col_nhwc(_ptr(x), _ptr(out), N, H, W, Cc, kh, kw, stride, pad, dil, Ho, Wo, ld,
                                             self._stream()))
         return out, Ho, Wo
+
+    # ------------------------------------------------------------ trainer step
+    def sumsq_partials(self, g):
+        """Fixed-order partial sums of squares of the flat gradient buffer -> float32 [n_partials]."""
+        assert g.is_contiguous()
+        part = self.empty(1184)
+        n = C.c_int(0)
+        _lib.check(self.lib.itn_sumsq_partials(_ptr(g), g.numel(), _ptr(part), part.numel(), C.byref(n), self._stream()))
+        return part[:n.value]
+
+    def clip_adam_step_(self, w, g, m, v, partials, max_norm, lr, betas, eps, step, zero_grad=False, norm_out=None):
+        """In place on one flat segment: g *= clip coefficient of the global norm sqrt(sum(partials)),
+        Adam moments and weights updated as torch.optim.Adam does at `step` (1-based)."""
+        for t in (w, g, m, v):
+            assert t.is_contiguous() and t.numel() == w.numel() and t.dtype == torch.float32
+        _lib.check(self.lib.itn_clip_adam_step(
+            _ptr(w), _ptr(g), _ptr(m), _ptr(v), w.numel(), _ptr(partials), 0 if partials is None else partials.numel(),
+            float(max_norm), float(lr), float(betas[0]), float(betas[1]), float(eps), int(step), 1 if zero_grad else 0,
+            _ptr(norm_out), self._stream()))
 
     def maxpool3x3s2_nhwc(self, x):
         assert x.is_contiguous() and x.dim() == 4

@@ -109,6 +109,20 @@ def synthetic_episode(episode_id, frames=5, res=300, with_targets=True):
     return data
 
 
+def masked_episode(episode_id, frames=5, res=300, with_targets=True):
+    """synthetic_episode with padded frames: frame 1 padded on the right quarter, frame 3 on the right
+    quarter and the bottom sixth (mask = 1, pixels zeroed, as DETR's NestedTensor padding does).  The
+    dataset never produces such masks (datasets/sequence_dataset.py:56) but the interface carries them
+    into the key-padding masks and the sine position embedding."""
+    data = synthetic_episode(episode_id, frames, res, with_targets)
+    m = data["masks"]
+    m[0, 1, :, res - res // 4:] = 1
+    m[0, 3, :, res - res // 4:] = 1
+    m[0, 3, res - res // 6:, :] = 1
+    data["frames"] = data["frames"] * (m == 0)[:, :, None].to(data["frames"].dtype)
+    return data
+
+
 def collate_episodes(episodes):
     """Stack batch-1 episodes into one batch-B `data` dict."""
     out = {

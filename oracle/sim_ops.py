@@ -332,6 +332,36 @@ class SimOps:
             return out, out, (step.abs() <= clip).to(torch.uint8)
         return out, out
 
+    # trainer step: torch.nn.utils.clip_grad_norm_ + torch.optim.Adam restated on flat buffers
+    # (reference engine/interactron_trainer.py:106-110; formulas of torch/optim/adam.py _single_tensor_adam)
+    def sumsq_partials(self, g):
+        self.calls += 1
+        return (torch.nan_to_num(g.reshape(-1), nan=0.0) ** 2).sum().reshape(1)      # NaN marks "no gradient"
+
+    def clip_adam_step_(self, w, g, m, v, partials, max_norm, lr, betas, eps, step, zero_grad=False, norm_out=None):
+        self.calls += 1
+        skip = torch.isnan(g)                       # the simulator treats every NaN as the no-gradient marker
+        w0, m0, v0 = w.clone(), m.clone(), v.clone()
+        g.copy_(torch.nan_to_num(g, nan=0.0))
+        if partials is not None:
+            total = partials.sum().sqrt()
+            if norm_out is not None:
+                norm_out.copy_(total)
+            if max_norm > 0:
+                g.mul_(torch.clamp(max_norm / (total + 1e-6), max=1.0))
+        b1, b2 = betas
+        m.lerp_(g, 1 - b1)
+        v.mul_(b2).addcmul_(g, g, value=1 - b2)
+        bc1, bc2 = 1 - b1 ** step, 1 - b2 ** step
+        denom = (v.sqrt() / (bc2 ** 0.5)).add_(eps)
+        w.addcdiv_(m, denom, value=-(lr / bc1))
+        for t, t0 in ((w, w0), (m, m0), (v, v0)):
+            t.copy_(torch.where(skip, t0, t))
+        if zero_grad:
+            g.zero_()
+        else:
+            g.masked_fill_(skip, float("nan"))
+
     def im2col_nhwc(self, x, kh, kw, stride, pad, dil):
         self.calls += 1
         N, H, W, Cc = x.shape

@@ -42,6 +42,20 @@ def test_port_matches_committed_reference_goldens(model_type, kind):
     assert ((gn - g["g_norms"]).abs() / g["g_norms"]).max().item() < 2e-3
 
 
+def test_port_matches_padded_frames_golden():
+    """Non-zero masks: key-padding + mask-dependent position embedding (tools/make_golden_masked.py)."""
+    from interactron_b200.synthetic import masked_episode
+    m = _model("interactron_random")
+    gold = torch.load(os.path.join(GOLD, "interactron_random_predict_masked.pt"))
+    for ep, g in gold.items():
+        tr = {}
+        out = port.predict(m.state_dict(), m.detector.backbone[0].body, masked_episode(ep), "B",
+                           lr=m.config.ADAPTIVE_LR, trace=tr)
+        assert rel(out["pred_logits"], g["pred_logits"]) < 1e-4
+        assert rel(out["pred_boxes"], g["pred_boxes"]) < 1e-4
+        assert rel(tr["learned_loss"], g["learned_loss"]) < 1e-5
+
+
 @pytest.mark.skipif(not rh.reference_available(), reason="reference checkout not present")
 def test_port_matches_live_reference():
     from interactron_b200.synthetic import synthetic_episode

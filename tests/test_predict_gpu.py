@@ -66,6 +66,35 @@ def test_adapt_detect_trace_matches_reference(name, rand_model, full_model):
         assert rel(out["box_features"][0], g["box_features"][0]) < TOL
 
 
+def test_padded_frames_match_reference(rand_model):
+    """Non-zero masks (padded frames): key-padding masks in every encoder / cross attention and the
+    mask-dependent sine position embedding, against the reference golden (tools/make_golden_masked.py)."""
+    from interactron_b200.synthetic import collate_episodes, masked_episode, synthetic_episode
+    gold = torch.load(os.path.join(GOLD, "interactron_random_predict_masked.pt"))
+    loop = rand_model._get_loop()
+    for ep, g in gold.items():
+        d = masked_episode(ep)
+        assert int(d["masks"].sum()) > 0
+        out = loop.adapt_detect(d["frames"].cuda(), d["masks"].cuda(), post_frames=(0,), want_trace=True)
+        t = out["trace"]
+        assert rel(t["pre_logits"][0], g["pre_logits"]) < TOL
+        assert rel(t["pre_boxes"][0], g["pre_boxes"]) < TOL
+        assert rel(out["learned_loss"][0], g["learned_loss"]) < TOL
+        gn = torch.stack([loop.theta_pack.view(t["g"], n)[0].norm() for n in loop.theta_pack.names]).cpu()
+        assert ((gn - g["g_norms"]).abs() / g["g_norms"]).max().item() < 5e-3
+        assert rel(out["pred_logits"][0], g["pred_logits"][0]) < TOL
+        assert rel(out["pred_boxes"][0], g["pred_boxes"][0]) < TOL
+        # the mask must matter (an unmasked run of the same pixels differs), and a padded episode in a
+        # batch with an unpadded one gives the same answer as alone (per-frame masks, ragged batch)
+        d0 = dict(d)
+        d0["masks"] = torch.zeros_like(d["masks"])
+        o0 = rand_model.predict(d0)
+        assert rel(o0["pred_logits"][0], g["pred_logits"][0]) > 10 * TOL
+        both = rand_model.predict(collate_episodes([synthetic_episode(1), d]))
+        assert rel(both["pred_logits"][1], g["pred_logits"][0]) < TOL
+        assert rel(both["pred_boxes"][1], g["pred_boxes"][0]) < TOL
+
+
 def test_predict_public_api_graph_and_eager(rand_model):
     """predict(data) with host tensors: CUDA-graph replay == eager launches, shapes as the reference."""
     from interactron_b200.synthetic import synthetic_episode

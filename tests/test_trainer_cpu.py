@@ -1,0 +1,101 @@
+"""Trainer step on the flat buffers (trainer.MetaTrainerStep) vs the reference's own sequence
+`clip_grad_norm_` + Adam(detector) + Adam(fusion) + zero_grad (engine/interactron_trainer.py:70-71,
+106-110), float64 on the simulator backend: host logic, layout, aliasing, LR schedule."""
+import copy
+import math
+
+import pytest
+import torch
+
+from oracle.sim_ops import SimOps
+
+
+def _reference_iteration(ref, opt_d, opt_s, grads, clip):
+    for (n, p) in ref.named_parameters():
+        p.grad = None if grads[n] is None else grads[n].clone()
+    torch.nn.utils.clip_grad_norm_(ref.parameters(), clip)
+    opt_d.step()
+    opt_s.step()
+    opt_d.zero_grad()
+    opt_s.zero_grad()
+
+
+@pytest.mark.parametrize("model_type", ["interactron_random", "interactron"])
+def test_trainer_step_matches_torch_adam(model_type):
+    import interactron_b200 as ib
+    from interactron_b200 import meta
+    from interactron_b200.trainer import MetaTrainerStep
+    torch.manual_seed(0)
+    model = ib.build_model(ib.default_config(model_type, weights="synthetic").MODEL).eval().double()
+    model._ops = SimOps(torch.float64)
+    ref = copy.deepcopy(model)
+    lr_d, lr_s, clip = 1e-3, 3e-3, 1.0
+    opt_d = torch.optim.Adam(ref.detector.parameters(), lr=lr_d)
+    opt_s = torch.optim.Adam(ref.fusion.parameters(), lr=lr_s)
+    tr = MetaTrainerStep(model, lr_d, lr_s, clip)
+    loop = model._get_loop()
+    sizes = (loop.theta_pack.numel, loop.psi_pack.numel, loop.phi_pack.numel)
+    before = {n: p.detach().clone() for n, p in model.named_parameters()}
+    for it in range(3):
+        G = torch.zeros(1, sum(sizes), dtype=torch.float64)       # padding between tensors stays zero, as in meta.py
+        base = 0
+        for pack in (loop.theta_pack, loop.psi_pack, loop.phi_pack):
+            for nm in pack.names:
+                pack.view(G[:, base:base + pack.numel], nm).normal_(0.0, 10.0 if it == 0 else 1e-4)   # clipped / not
+            base += pack.numel
+        flat = {"all": G, "theta": G[:, :sizes[0]], "psi": G[:, sizes[0]:sizes[0] + sizes[1]], "phi": G[:, sizes[0] + sizes[1]:]}
+        model.last_meta_grads = flat
+        meta.accumulate_grads(model, flat)
+        grads = {n: (None if p.grad is None else p.grad.clone()) for n, p in model.named_parameters()}
+        assert sum(g is None for g in grads.values()) > 50           # frozen backbone + unused fusion heads
+        want_norm = torch.sqrt(sum((g ** 2).sum() for g in grads.values() if g is not None))
+        out = tr.step()
+        assert float(out["grad_norm"]) == pytest.approx(float(want_norm), rel=1e-12)
+        _reference_iteration(ref, opt_d, opt_s, grads, clip)
+        assert all(p.grad is None for p in model.parameters())
+        for (n, p), (_, q) in zip(model.named_parameters(), ref.named_parameters()):
+            assert torch.allclose(p, q, rtol=0, atol=1e-13), (it, n)
+    moved = sum(int(not torch.equal(p, before[n])) for n, p in model.named_parameters())
+    assert moved > 250
+    # the Parameters alias the flat buffers, and the W^T twins follow the update
+    name = "transformer.encoder.layers.0.linear1.weight"
+    w = dict(model.detector.named_parameters())[name]
+    assert w.data_ptr() == loop.theta_pack.view(loop.theta, name).data_ptr()
+    assert torch.equal(loop.theta_pack.view_t(loop.theta_t, name)[0], w.t())
+    assert torch.equal(model.state_dict()["detector." + name], w)
+    # gradients that do not alias the flat buffer (set by hand) take the gather path
+    for p in model.parameters():
+        p.grad = None
+    model.last_meta_grads = None
+    grads = {}
+    for n, p in model.named_parameters():
+        if n.startswith("fusion.loss_decoder") or n.endswith("norm1.weight"):
+            p.grad = torch.randn_like(p)
+        grads[n] = None if p.grad is None else p.grad.clone()
+    tr.step()
+    _reference_iteration(ref, opt_d, opt_s, grads, clip)
+    for (n, p), (_, q) in zip(model.named_parameters(), ref.named_parameters()):
+        assert torch.allclose(p, q, rtol=0, atol=1e-13), n
+
+
+def test_supervisor_lr_schedule():
+    """Warm-up / cosine decay by frames seen, applied to the supervisor LR only (reference :113-124)."""
+    import interactron_b200 as ib
+    from interactron_b200.trainer import MetaTrainerStep
+    model = ib.build_model(ib.default_config("interactron_random", weights="synthetic").MODEL).eval().double()
+    model._ops = SimOps(torch.float64)
+    tr = MetaTrainerStep(model, 1e-5, 1e-4, 1.0, lr_decay=True, warmup_tokens=160, final_tokens=800)
+    tokens, lrs = 0, []
+    for it in range(12):
+        lrs.append(tr.step(n_frames=80)["lr"])
+    want, lr = [], 1e-4
+    for it in range(12):
+        want.append(lr)
+        tokens += 80
+        if tokens < 160:
+            mult = tokens / 160
+        else:
+            mult = max(0.1, 0.5 * (1.0 + math.cos(math.pi * (tokens - 160) / (800 - 160))))
+        lr = 1e-4 * mult
+    assert lrs == pytest.approx(want, rel=1e-12)
+    assert tr.detector_lr == 1e-5
