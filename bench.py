@@ -41,27 +41,38 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.stop_flag = index, [], threading.Event()
+        self.t_mark = None
+
+    def mark(self):
+        """Start of the timed region.  The thread is started a little earlier (during the last warm-up
+        steps, same load) because one nvidia-smi query takes 0.3-1 s on a multi-GPU box."""
+        self.t_mark = time.perf_counter()
 
     def run(self):
         while not self.stop_flag.is_set():
             try:
+                t = time.perf_counter()
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                       "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
                 parts = [x.strip() for x in out.strip().split(",")]
                 if len(parts) >= 6:
-                    self.samples.append(parts)
+                    self.samples.append((t, time.perf_counter(), parts))
             except Exception:
                 pass
             self.stop_flag.wait(0.2)
 
     def summary(self):
-        if not self.samples:
+        timed = [p for (t0, t1, p) in self.samples if self.t_mark is None or t1 >= self.t_mark]
+        window = "timed region"
+        if not timed and self.samples:          # region shorter than one query: the warm-up steps just before it
+            timed, window = [p for (_, _, p) in self.samples], "last warm-up steps + timed region"
+        if not timed:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = sorted(float(s[0]) for s in self.samples)
+        sm = sorted(float(s[0]) for s in timed)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
-                "samples": len(sm)}
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in timed)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(timed[0][1]), "reasons": reasons,
+                "samples": len(sm), "window": window}
 
 
 def make_batch(E, first_id, pin):
@@ -234,11 +245,13 @@ def run_gpu_arm(args):
         torch.cuda.synchronize()
 
     # ---- device-resident throughput (`value`)
-    for i in range(args.warmup):
-        model._graphed("bench", run, *dev_batches[i % 2], clone=False)
     sampler = ClockSampler(local)
+    for i in range(args.warmup):
+        if i == args.warmup - 2:
+            sampler.start()
+        model._graphed("bench", run, *dev_batches[i % 2], clone=False)
     barrier()
-    sampler.start()
+    sampler.mark()
     ev = []
     for i in range(args.steps):
         flush.zero_()
@@ -267,7 +280,10 @@ def run_gpu_arm(args):
     barrier()
     sampler.stop_flag.set()
     e2e_ms = sum(a.elapsed_time(b) for a, b in ev2)
-    h2d = batches[0]["frames"].numel() * 4 + batches[0]["masks"].numel() * 8
+    # predict() ships the frames as they are and, of the int64 padding masks, only the 19x19 pixels per
+    # frame that the nearest-neighbour down-sampling reads (episode.sample_masks_host), as uint8
+    from interactron_b200.episode import sample_masks_host
+    h2d = batches[0]["frames"].numel() * 4 + sample_masks_host(batches[0]["masks"]).numel()
     d2h = lg.numel() * 4 + bx.numel() * 4
 
     t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device="cuda")
@@ -345,12 +361,21 @@ def run_meta_arm(args):
         _, losses = model(batches[i % 2], ridx=[(i + e) % 5 for e in range(E)])
         return float(losses["loss_supervisor_ce"])          # D2H read of the step's result
 
-    for i in range(args.warmup):
-        step(i)
-    sampler = ClockSampler(local)
-    barrier()
-    sampler.start()
+    # launches of one step, counted on an eager (non-graph) pass: graph replays bypass the counter
+    graphs_on = model.use_cuda_graph
+    model.use_cuda_graph = False
     l0 = ops.launch_count()
+    step(0)
+    torch.cuda.synchronize()
+    launches_per_step = ops.launch_count() - l0
+    model.use_cuda_graph = graphs_on
+    sampler = ClockSampler(local)
+    for i in range(args.warmup):
+        if i == args.warmup - 2:
+            sampler.start()
+        step(i)
+    barrier()
+    sampler.mark()
     ev = []
     for i in range(args.steps):
         flush.zero_()
@@ -361,7 +386,7 @@ def run_meta_arm(args):
         ev.append((e0, e1))
     barrier()
     sampler.stop_flag.set()
-    launches = ops.launch_count() - l0
+    launches = launches_per_step * args.steps
     ms = torch.tensor([sum(a.elapsed_time(b) for a, b in ev)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -391,7 +416,7 @@ def run_meta_arm(args):
                        "allreduce_elems": n_flat if world > 1 else 0, "cuda_graph": bool(model.use_cuda_graph),
                        "l2": "256 MiB buffer written between timed steps"},
             "e2e": {"value": v, "unit": "episodes/s", "h2d_bytes_per_step": batches[0]["frames"].numel() * 4 +
-                    batches[0]["masks"].numel() * 8, "d2h_bytes_per_step": 4,
+                    E * 5 * 361, "d2h_bytes_per_step": 4,
                     "api": "model(data) with pinned host frames; grads left on .grad; one loss read back"},
             "gpu_launches": launches, "gpu_launches_per_step": launches // args.steps, "roofline": None,
             "cpu_baseline": cpu, "clocks": sampler.summary()}), flush=True)

@@ -24,6 +24,45 @@ from .params import ParamPack, Weights, detector_packs
 L_TOK = 361      # 19x19 feature map of a 300x300 frame
 
 
+def trunk_hw(H, W):
+    """Feature-map size of the ResNet-50-DC5 trunk (stride 16: stem conv s2, max-pool s2, layer2 s2,
+    layer3 s2, layer4 dilated) for an HxW frame."""
+    def down(n, k, p):
+        return (n + 2 * p - k) // 2 + 1
+    out = []
+    for n in (H, W):
+        n = down(n, 7, 3)       # conv1 7x7 s2 p3
+        n = down(n, 3, 1)       # max-pool 3x3 s2 p1
+        n = down(n, 3, 1)       # layer2 (3x3 s2 p1; the 1x1 s2 shortcut gives the same size)
+        n = down(n, 3, 1)       # layer3
+        out.append(n)
+    return tuple(out)
+
+
+_NEAREST = {}
+
+
+def sample_masks_host(masks):
+    """The padding mask at feature-map resolution, taken on the HOST from a CPU `data["masks"]`
+    ([..., H, W], any dtype; nonzero = padded) -> uint8 [..., h, w].  The reference interpolates the
+    full-resolution mask to the feature map with mode="nearest" on the device
+    (detr_models/backbone.py:77); nearest picks one source pixel per output pixel, so only those
+    h*w pixels have to cross PCIe (300x300 int64 frames: 720 KB -> 361 B each).  The source indices are
+    produced by F.interpolate itself on an index ramp, so the sampling rule is torch's by construction."""
+    H, W = masks.shape[-2:]
+    h, w = trunk_hw(H, W)
+    key = (H, W)
+    if key not in _NEAREST:
+        F = torch.nn.functional
+        iy = F.interpolate(torch.arange(H, dtype=torch.float32)[None, None], size=h)[0, 0].long()
+        ix = F.interpolate(torch.arange(W, dtype=torch.float32)[None, None], size=w)[0, 0].long()
+        _NEAREST[key] = (iy, ix)
+    iy, ix = _NEAREST[key]
+    lead = masks.shape[:-2]
+    m = masks.reshape(-1, H, W).index_select(1, iy).index_select(2, ix)
+    return m.ne(0).to(torch.uint8).reshape(*lead, h, w)
+
+
 class InnerLoop:
     def __init__(self, ops, detector, fusion_mod, kind, lr, clip=0.01):
         assert kind in ("A", "B") and (fusion_mod is not None or kind == "B")
@@ -99,7 +138,10 @@ class InnerLoop:
         N, h, w, C = src.shape
         self.src = src.reshape(N, h * w, C)
         src_r = ops.round_tf32(self.src)
-        m = torch.nn.functional.interpolate(masks[None].float(), size=(h, w)).to(torch.bool)[0]
+        if masks.dtype == torch.uint8 and tuple(masks.shape[-2:]) == (h, w):
+            m = masks.to(torch.bool)               # sampled on the host already (sample_masks_host)
+        else:
+            m = torch.nn.functional.interpolate(masks[None].float(), size=(h, w)).to(torch.bool)[0]
         pos = ops.pos_embed_sine(m).reshape(N * h * w, -1)
         kmask = m.reshape(N, h * w).to(torch.uint8).contiguous()
         return src_r, pos, kmask, (h, w)

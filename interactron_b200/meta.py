@@ -196,7 +196,11 @@ def meta_step(model, data, ridx=None):
     crit = model.criterion
     dev = ops.device
     frames = data["frames"].to(dev, non_blocking=True)
-    masks = data["masks"].to(dev, non_blocking=True)
+    masks = data["masks"]
+    if not masks.is_cuda and dev.type == "cuda":
+        from .episode import sample_masks_host
+        masks = sample_masks_host(masks)              # only the h*w sampled mask pixels cross PCIe
+    masks = masks.to(dev, non_blocking=True)
     E, S = frames.shape[:2]
     assert S == 5, "the meta-training step is defined on full 5-frame episodes"
     C = loop.detector.class_embed.out_features

@@ -102,8 +102,14 @@ class _Base(nn.Module):
 
     @staticmethod
     def _frames_masks(data, device):
+        """Host tensors cross PCIe here: the frames as they are; of a CPU mask only the h*w pixels per
+        frame the nearest-neighbour down-sampling reads (episode.sample_masks_host)."""
+        from .episode import sample_masks_host
         frames = data["frames"].to(device, non_blocking=True)
-        masks = data["masks"].to(device, non_blocking=True)
+        masks = data["masks"]
+        if not masks.is_cuda and torch.device(device).type == "cuda":
+            masks = sample_masks_host(masks)
+        masks = masks.to(device, non_blocking=True)
         return frames, masks
 
 

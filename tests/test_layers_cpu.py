@@ -37,3 +37,24 @@ def test_l2_chunked_attention_is_identical():
     assert (o - ref[0]).abs().max() < 1e-12
     for a, b in zip(g, ref[2:]):
         assert (a - b).abs().max() < 1e-12
+
+
+def test_host_mask_sampling_is_interpolate_nearest():
+    """episode.sample_masks_host == the reference's F.interpolate(mask, size=feature map) (nearest,
+    detr_models/backbone.py:77) on the host, and trunk_hw == the real ResNet-50-DC5 output size."""
+    import torch.nn.functional as F
+    import torchvision
+    from interactron_b200.episode import sample_masks_host, trunk_hw
+    torch.manual_seed(0)
+    for (H, W) in ((300, 300), (224, 320), (301, 299), (512, 640)):
+        h, w = trunk_hw(H, W)
+        m = (torch.rand(2, 5, H, W) < 0.3).long() * 7
+        ref = F.interpolate(m.flatten(0, 1)[None].float(), size=(h, w)).to(torch.bool)[0].reshape(2, 5, h, w)
+        got = sample_masks_host(m)
+        assert got.dtype == torch.uint8 and torch.equal(got.bool(), ref), (H, W)
+    body = torchvision.models.resnet50(replace_stride_with_dilation=[False, False, True])
+    body = torch.nn.Sequential(*list(body.children())[:-2]).eval()
+    for (H, W) in ((300, 300), (224, 320), (301, 299)):
+        with torch.no_grad():
+            o = body(torch.zeros(1, 3, H, W))
+        assert tuple(o.shape[-2:]) == trunk_hw(H, W), (H, W)
