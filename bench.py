@@ -323,6 +323,108 @@ def run_gpu_arm(args):
         dist.destroy_process_group()
 
 
+def run_rollout_arm(args):
+    """BASELINE configs[3]: learned-policy evaluation of `interactron.yaml` - per episode 4 policy steps
+    `get_next_action()` on the 1..4 frames seen so far, then `predict()` on the 5-frame episode (reference
+    engine/interactive_evaluator.py:48-66), batch 1 as in the reference, episodes sharded over the ranks
+    with no collective.  The environment is synthetic: the action does not change which frame comes next.
+    Everything is host-driven (frames arrive from the environment one at a time), so the only figure is
+    the end-to-end one.  Default: the E environments of a step advance in lock-step (`get_next_actions`, one
+    batched policy pass per step); --sequential: one episode at a time, as the reference evaluator does.
+    Not the driver's headline line; run with --workload rollout."""
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import interactron_b200 as ib
+    from interactron_b200.synthetic import synthetic_episode
+    model = ib.build_model(ib.default_config("interactron", weights="synthetic").MODEL).to(f"cuda:{local}").eval()
+    ops = model._get_ops()
+    E = args.episodes
+    from interactron_b200.synthetic import collate_episodes
+    lock = not args.sequential
+    eps = []
+    groups = [list(range(E))] if lock else [[e] for e in range(E)]
+    for grp in groups:
+        d = collate_episodes([synthetic_episode(1000 * rank + e, with_targets=False) for e in grp])
+        d["frames"], d["masks"] = d["frames"].pin_memory(), d["masks"].pin_memory()
+        eps.append(d)
+
+    def view(d, s):
+        o = dict(d)
+        o["frames"], o["masks"] = d["frames"][:, :s], d["masks"][:, :s]
+        return o
+
+    def episode(d):
+        """One rollout of the environments in `d` (all E in lock-step, or one): 4 policy steps + predict."""
+        if lock:
+            acts = [model.get_next_actions(view(d, s)) for s in range(1, 5)]
+        else:
+            acts = [model.get_next_action(view(d, s)) for s in range(1, 5)]
+        out = model.predict(d)
+        return acts, out["pred_logits"].cpu(), out["pred_boxes"].cpu()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    graphs_on = model.use_cuda_graph
+    model.use_cuda_graph = False
+    l0 = ops.launch_count()
+    episode(eps[0])
+    launches_per_episode = ops.launch_count() - l0
+    model.use_cuda_graph = graphs_on
+    sampler = ClockSampler(local)
+    for i in range(args.warmup):
+        if i == args.warmup - 2:
+            sampler.start()
+        for d in eps:
+            episode(d)
+    barrier()
+    sampler.mark()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        for d in eps:
+            episode(d)
+    e1.record()
+    barrier()
+    sampler.stop_flag.set()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms)
+    if rank == 0:
+        v = E * world * args.steps / (ms * 1e-3)
+        h2d = sum(5 * 3 * 300 * 300 * 4 * s // 5 for s in (1, 2, 3, 4, 5))
+        print(json.dumps({
+            "metric": "Interactron episodes/s (learned-policy rollout: 4x get_next_action + predict)", "value": v,
+            "unit": "episodes/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "tf32x3", "data": "synthetic",
+            "config": {"workload": "interactron.yaml learned-policy eval = BASELINE configs[3]; host-driven, synthetic "
+                                   "environment; " + ("E environments advanced in lock-step (get_next_actions)" if lock
+                                                      else "one episode at a time, batch 1 as in the reference"),
+                       "episodes_per_step_per_gpu": E, "cuda_graph": bool(graphs_on),
+                       "ms_per_episode": ms / args.steps / E},
+            "e2e": {"value": v, "unit": "episodes/s", "h2d_bytes_per_step": h2d * E, "d2h_bytes_per_step": E * 50 * 1240 * 4,
+                    "api": "4x model.get_next_action(data[:s]) + model.predict(data), pinned host frames, results read back"},
+            "gpu_launches": launches_per_episode * len(eps) * args.steps,
+            "gpu_launches_per_step": launches_per_episode * len(eps),
+            "roofline": None, "cpu_baseline": None, "clocks": sampler.summary()}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_meta_arm(args):
     """BASELINE configs[4]: the meta-training step `forward(data)` (second-order MAML gradients), the
     batch's episodes sharded over the ranks and the flat meta-gradient all-reduced (SUM) with NCCL.
@@ -431,8 +533,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--episodes", type=int, default=None, help="episodes per step per GPU (default 32; 2 for meta_*)")
     ap.add_argument("--workload", default="interactron_random",
-                    choices=sorted(WORKLOADS) + ["meta_" + w for w in sorted(WORKLOADS)])
+                    choices=sorted(WORKLOADS) + ["meta_" + w for w in sorted(WORKLOADS)] + ["rollout"])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--sequential", action="store_true",
+                    help="rollout workload: one episode at a time (batch 1) instead of E environments in lock-step")
     ap.add_argument("--cpu-episodes", type=int, default=None,
                     help="episodes in the bounded CPU-baseline sample (0 disables)")
     args = ap.parse_args()
@@ -442,8 +546,12 @@ def main():
         args.cpu_episodes = 1 if args.impl == "reference" else 40       # ~10 s of host time
     meta = args.workload.startswith("meta_")
     if args.episodes is None:
-        args.episodes = 2 if meta else 32
-    if meta and args.impl == "b200":
+        args.episodes = 2 if meta else (8 if args.workload == "rollout" else 32)
+    if args.workload == "rollout":
+        if args.impl == "reference":
+            raise SystemExit("--impl reference times the predict() workloads")
+        run_rollout_arm(args)
+    elif meta and args.impl == "b200":
         run_meta_arm(args)
     elif args.impl == "reference":
         if meta:

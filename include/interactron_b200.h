@@ -295,6 +295,19 @@ int itn_clip_adam_step(float* w, float* g, float* m, float* v, long long n, cons
                        int n_partials, float max_norm, double lr, double beta1, double beta2, double eps,
                        int step, int zero_grad, float* norm_out, void* stream);
 
+/* ---- evaluator post-processing ------------------------------------------------
+ * Replaces, per image, engine/random_policy_evaluator.py:65-78 (= engine/interactive_evaluator.py:71-84):
+ *   pred_scores, pred_cats = logits.softmax(-1).max(-1); drop pred_cats == background_class;
+ *   boxes cxcywh -> xyxy (detr_models/util/box_ops.py:8-12); torchvision.ops.nms(boxes, scores, iou_threshold).
+ * logits [images, queries, classes], boxes [images, queries, 4] (cxcywh) ->
+ *   count [images]: detections kept; for k < count[i], in decreasing score order (ties: lower query first):
+ *   keep_idx [images, queries] (query index, -1 beyond count), score, cat (int32), xyxy [images, queries, 4].
+ * queries <= 128.  The keep/suppress decisions are bit-identical to torchvision's CPU nms on the same
+ * xyxy boxes and scores (same operation order, no fused multiply-add). */
+int itn_detect_postprocess(const float* logits, const float* boxes, int images, int queries, int classes,
+                           int background_class, float iou_threshold, int* count, int* keep_idx,
+                           float* score, int* cat, float* xyxy, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -199,17 +199,37 @@ class interactron(_Adaptive):
     def get_next_action(self, data):
         """Policy step (reference models/interactron.py:174-197): detector + fusion A forward on the
         s frames seen so far, argmax of the s-th action head -> python int."""
+        b, s = data["frames"].shape[:2]
+        actions = self._policy_logits(data, 1, b * s)
+        return int(actions[0, s - 1].argmax(dim=-1).item())
+
+    def get_next_actions(self, data):
+        """Extension for driving b environments in lock-step: the policy step of b independent episodes
+        (each with the same number s of frames seen) in one pass -> list of b ints, element i equal to
+        `get_next_action` on episode i alone.  (The reference's method folds a batch into ONE sequence of
+        b*s frames, which only means something for b == 1.)"""
+        b, s = data["frames"].shape[:2]
+        actions = self._policy_logits(data, b, s)
+        return [int(a) for a in actions[:, s - 1].argmax(dim=-1).tolist()]
+
+    def _policy_logits(self, data, E, S):
+        """Action logits [E, 4, 4] of E sequences of S frames each (E * S = all frames in `data`)."""
         from . import fusion
         loop = self._get_loop()
         ops = loop.ops
         frames, masks = self._frames_masks(data, ops.device)
-        b, s = frames.shape[:2]
-        out, _, hw = loop.detect(frames.flatten(0, 1), masks.flatten(0, 1), want_preds=True)
-        L = hw[0] * hw[1]
-        N = b * s
-        fout, _ = fusion.fusion_a_forward(ops, loop._fusion_weights(), out["memory_r"].view(1, N * L, -1),
-                                          out["preds"], 1, N, L, need_cache=False)
-        return int(fout["actions"][0, s - 1].argmax(dim=-1).item())
+
+        def run(f, m):
+            out, _, hw = loop.detect(f.flatten(0, 1), m.flatten(0, 1), want_preds=True)
+            L = hw[0] * hw[1]
+            fout, _ = fusion.fusion_a_forward(ops, loop._fusion_weights(), out["memory_r"].view(E, S * L, -1),
+                                              out["preds"], E, S, L, need_cache=False)
+            return {"actions": fout["actions"]}
+
+        # one CUDA graph per (episodes, frames seen): s = 1..4 in the evaluator's rollout, ~500 launches each
+        if self.use_cuda_graph and frames.is_cuda:
+            return self._graphed(("action", E, S), run, frames, masks, clone=False)["actions"]
+        return run(frames, masks)["actions"]
 
 
 class detr(_Base):

@@ -50,6 +50,8 @@ class CudaOps:
             raise ValueError(f"ITN_GEMM_PRECISION must be one of {sorted(PRECISION)}")
         self.n_tf32 = 0
         self.n_simt = 0
+        self.n_split_k = 0
+        self.split_k = os.environ.get("ITN_SPLIT_K", "1") != "0"
         # L2 budget (MiB) for the score tensors of one attention chunk (layers._l2_chunks); 0 = one pass
         self.attn_l2_mb = int(os.environ.get("ITN_ATTN_L2_MB", "0"))
 
@@ -107,7 +109,7 @@ class CudaOps:
 
     def matmul(self, a, b, *, bias=None, act=None, residual=None, out=None, out_pre=None,
                alpha=1.0, accumulate=False, epi=None, aux=None, rnd=False, act_after_residual=False,
-               out_pad=False):
+               out_pad=False, _nosplit=False):
         """out = epilogue(alpha * a @ b), a [..,M,K], b [..,K,N]; see itn_gemm_desc_t.
         rnd: store `out` rounded to TF32 (set when `out` only feeds further GEMMs).
         out_pad: `out` is a [..., :N] view of rows padded to a multiple of 4 columns and the pad may
@@ -120,6 +122,12 @@ class CudaOps:
             raise ValueError(f"matmul inner dims differ: {tuple(a.shape)} @ {tuple(b.shape)}")
         nb0 = max(a4.shape[0], b4.shape[0])
         nb1 = max(a4.shape[1], b4.shape[1])
+        plain = (bias is None and act is None and residual is None and out_pre is None and epi is None and aux is None
+                 and alpha == 1.0 and not out_pad and not (rnd and self._clean))
+        if plain and not _nosplit and out is not None and self.split_k:
+            S = self._split_k_factor(a4, b4, out, M, N, K, nb0, nb1)
+            if S > 1:
+                return self._matmul_split_k(a4, b4, out, S, accumulate)
         for t in (a4, b4):
             if t.shape[0] not in (1, nb0) or t.shape[1] not in (1, nb1):
                 raise ValueError(f"batch dims not broadcastable: {tuple(a.shape)} @ {tuple(b.shape)}")
@@ -177,6 +185,48 @@ class CudaOps:
             self.n_simt += 1
         del keep_a, keep_b
         return ret
+
+    # split-K: weight-gradient GEMMs at few episodes per step (dW[256,256] = dy^T[256,3610] x[3610,256]) are
+    # 4-32 output tiles with a 57-113 k-block chain each: 3-20 % of the 148 SMs busy for 40-130 us.  The K
+    # range is cut into S equal chunks that run as one more batch dimension of the same kernel (strided
+    # views, nothing is copied), and the S partial products are summed in a fixed order by colsum.
+    # Measured (bench.py --workload meta_*, 2 episodes/step): +5-6 %.  K < 2048 (the per-episode gradients of
+    # a 1-episode predict(), K = 1805) is left alone: there the second launch costs more than it saves (-4 %).
+    def _split_k_factor(self, a4, b4, out, M, N, K, nb0, nb1):
+        if nb0 != 1 or K < 2048 or M < 32 or N < 32:
+            return 1
+        o4 = _as4d(out)
+        if o4.shape[0] != 1 or o4.shape[1] != nb1 or (N > 1 and o4.stride(3) != 1) or (M > 1 and o4.stride(2) != N):
+            return 1
+        tiles = ((M + 127) // 128) * ((N + 127) // 128) * nb1
+        if tiles > 37:
+            return 1
+        # a chunk boundary must keep every operand TMA-legal: 16-byte aligned batch stride when K is the
+        # contiguous dim (MN-major operands step by whole rows and are always fine)
+        need4 = (a4.stride(3) == 1 and a4.stride(2) != 1) or (b4.stride(2) == 1 and b4.stride(3) != 1)
+        best = 1
+        for S in range(2, 65):
+            if K % S or K // S < 64 or tiles * S > 296 or (need4 and (K // S) % 4):
+                continue
+            best = S
+        return best if best >= 4 else 1
+
+    def _matmul_split_k(self, a4, b4, out, S, accumulate):
+        K = a4.shape[3]
+        Kc = K // S
+        nb1 = max(a4.shape[1], b4.shape[1])
+        M, N = a4.shape[2], b4.shape[3]
+        a5 = a4[0].unflatten(-1, (S, Kc)).movedim(-2, 1)         # [nb1|1, S, M, Kc]
+        b5 = b4[0].unflatten(-2, (S, Kc))                        # [nb1|1, S, Kc, N]
+        extra = 1 if accumulate else 0
+        part = self.empty(nb1, S + extra, M, N)
+        self.matmul(a5, b5, out=part[:, :S], _nosplit=True)
+        o3 = _as4d(out)[0]                                       # [nb1, M, N], rows contiguous
+        if accumulate:
+            part[:, S].copy_(o3)
+        self.colsum(part.view(nb1, S + extra, M * N), out=o3.flatten(1))
+        self.n_split_k += 1
+        return out
 
     # ------------------------------------------------------------ row-wise
     def layernorm_fwd(self, x, gamma, beta, eps=1e-5):
@@ -458,6 +508,20 @@ class CudaOps:
             _ptr(w), _ptr(g), _ptr(m), _ptr(v), w.numel(), _ptr(partials), 0 if partials is None else partials.numel(),
             float(max_norm), float(lr), float(betas[0]), float(betas[1]), float(eps), int(step), 1 if zero_grad else 0,
             _ptr(norm_out), self._stream()))
+
+    # ------------------------------------------------------------ evaluator post-processing
+    def detect_postprocess(self, logits, boxes, background, iou_threshold=0.5):
+        """logits [I,Q,C], boxes [I,Q,4] cxcywh -> (count [I] int32, keep_idx [I,Q] int32, score [I,Q],
+        cat [I,Q] int32, xyxy [I,Q,4]): softmax-max, background filter, class-agnostic NMS per image."""
+        assert logits.is_contiguous() and boxes.is_contiguous() and logits.dim() == 3
+        I, Q, Cc = logits.shape
+        i32 = lambda *s: torch.empty(*s, dtype=torch.int32, device=self.device)
+        count, keep, cat = i32(I), i32(I, Q), i32(I, Q)
+        score, xyxy = self.empty(I, Q), self.empty(I, Q, 4)
+        _lib.check(self.lib.itn_detect_postprocess(_ptr(logits), _ptr(boxes), I, Q, Cc, int(background),
+                                                   float(iou_threshold), _ptr(count), _ptr(keep), _ptr(score),
+                                                   _ptr(cat), _ptr(xyxy), self._stream()))
+        return count, keep, score, cat, xyxy
 
     def maxpool3x3s2_nhwc(self, x):
         assert x.is_contiguous() and x.dim() == 4

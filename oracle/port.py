@@ -303,3 +303,74 @@ def set_criterion(logits, boxes, targets, indices, background_c=0.1):
     loss_giou = (1 - giou).sum() / num_boxes                                    # :162-165
     return {"loss_ce": loss_ce, "class_error": class_error, "loss_bbox": loss_bbox, "loss_giou": loss_giou,
             "cardinality_error": cardinality_error}
+
+
+# ------------------------------------------------------------------ evaluator post-processing
+def match_predictions_to_detections(ious):
+    """Restatement of utils/detection_utils.py:401-421 (proposal rounds between predictions and ground
+    truths) on a CPU tensor [p, g] -> (best_ious [g], best_idxs [g])."""
+    p, g = ious.shape
+    dev = ious.device                                                           # the reference allocates on ious.device
+    pref = torch.argsort(ious, dim=1, descending=True)                           # :402
+    ptr = torch.zeros(p, dtype=torch.long, device=dev)
+    free = torch.ones(p, device=dev).bool()
+    tent = -torch.ones(g, dtype=torch.long, device=dev)
+    for _ in range(g):                                                          # :406
+        prop = pref[torch.arange(p, device=dev), ptr]
+        for j in range(g):
+            new = torch.argmax(ious[:, j] * (prop == j))                         # :409
+            if tent[j] != -1 and tent[j] != new:
+                free[tent[j]] = True
+            tent[j] = new
+            free[tent[j]] = False
+        ptr[free] += 1                                                          # :414
+        if torch.count_nonzero(~free) >= min(p, g):
+            break
+    best = torch.zeros(g, device=dev)
+    best[tent != -1] = ious[tent[tent != -1], tent != -1]                         # :419
+    tent[best == 0.0] = -1
+    return best, tent
+
+
+def evaluator_records(pred_logits, pred_boxes, gt_boxes_cxcywh, gt_cats, img, class_ids, match_fn=None,
+                      background=1235):
+    """Restatement of the per-image body of engine/random_policy_evaluator.py:63-146 with torch /
+    torchvision CPU ops: pred_logits [Q,C], pred_boxes [Q,4] cxcywh -> list of TP / FP / FN dicts.
+    match_fn: the reference's own match_predictions_to_detections when it is importable (golden
+    generation), else the restatement above."""
+    import torchvision
+    match_fn = match_fn or match_predictions_to_detections
+    item = lambda t: t.item()
+    pb = _xyxy(pred_boxes)                                                       # :65
+    ps, pc = pred_logits.softmax(dim=-1).max(dim=-1)                             # :66
+    gb, gc = _xyxy(gt_boxes_cxcywh.reshape(-1, 4)), gt_cats
+    keep = pc != background                                                      # :70-73
+    pb, pc, ps = pb[keep], pc[keep], ps[keep]
+    kept = torchvision.ops.nms(pb, ps, iou_threshold=0.5)                        # :75
+    pc, pb, ps = pc[kept], pb[kept], ps[kept]
+    pset, gset = set([int(c) for c in pc]), set([int(c) for c in gc])            # :80-81
+    ponly = set(class_ids).intersection(pset - gset)
+
+    def rec(kind, match, cat, iou, score, box):
+        return {"iou": iou, "category_match": match, "type": kind, "pred_cat": cat, "pred_score": score,
+                "box": [item(c) for c in box], "area": item((box[2] - box[0]) * (box[3] - box[1])), "img": img}
+
+    out = []
+    for cat in gset:                                                            # :84
+        if torch.any(pc == cat):
+            cpb, cps, cgb = pb[pc == cat], ps[pc == cat], gb[gc == cat]
+            ious = torchvision.ops.box_iou(cpb, cgb)
+            best_ious, best_idx = match_fn(ious)
+            for i in range(ious.shape[0]):                                      # :91-114
+                kind = "tp" if torch.any(best_idx == i) else "fp"
+                out.append(rec(kind, True, cat, item(ious[i].max()), item(cps[i]), cpb[i]))
+            for j in range(ious.shape[1]):                                      # :115-127
+                if best_ious[j] == 0.0:
+                    out.append(rec("fn", False, cat, 0.0, 0.0, cgb[j]))
+        else:                                                                   # :128-141
+            for box in gb[gc == cat]:
+                out.append(rec("fn", False, cat, 0.0, 0.0, box))
+    for cat in ponly:                                                           # :142-156
+        for box, sc in zip(pb[pc == cat], ps[pc == cat]):
+            out.append(rec("fp", False, cat, 0.0, item(sc), box))
+    return out

@@ -420,3 +420,40 @@ def test_gemm_trunk_matches_cudnn_fp32():
     b = run_backbone(body, x, tf32=False)
     assert a.shape == b.shape == (3, 19, 19, 2048)
     assert rel(a, b) < 2e-4       # 53 convolutions deep; cuDNN fp32 and tf32x3 each carry ~1e-5 per layer
+
+
+@pytest.mark.parametrize("E,rows,n_out,k_in", [(1, 3610, 256, 256), (1, 3610, 2048, 256), (2, 3610, 256, 512),
+                                               (1, 7220, 512, 512), (1, 4096, 256, 256)])
+def test_gemm_split_k_weight_gradients(ops3, E, rows, n_out, k_in):
+    """Weight-gradient GEMMs with few output tiles and a long K run split-K (K chunks as a batch dim +
+    fixed-order colsum): same result as the one-chain launch and as fp64, into a strided slot of a flat
+    gradient buffer, with and without accumulation; bit-identical across repeats."""
+    gen = torch.Generator(device="cuda").manual_seed(rows + n_out)
+    dy = torch.randn(E, rows, n_out, generator=gen, device="cuda")
+    x = torch.randn(E, rows, k_in, generator=gen, device="cuda")
+    want = dy.double().transpose(-1, -2) @ x.double()
+    flat = torch.zeros(E, n_out * k_in + 8, device="cuda")
+    out = flat[:, :n_out * k_in].view(E, n_out, k_in)
+    n0 = ops3.n_split_k
+    ops3.matmul(dy.transpose(-1, -2), x, out=out)
+    assert ops3.n_split_k == n0 + 1, "split-K path not taken"
+    assert rel(out, want) < X3_TOL and float(flat[:, n_out * k_in:].abs().sum()) == 0.0
+    first = out.clone()
+    ops3.matmul(dy.transpose(-1, -2), x, out=out)
+    assert torch.equal(out, first)
+    ops3.matmul(dy.transpose(-1, -2), x, out=out, accumulate=True)
+    assert rel(out, 2 * want) < X3_TOL
+    ops3.split_k = False
+    try:
+        one = torch.empty_like(out)
+        ops3.matmul(dy.transpose(-1, -2), x, out=one)
+        assert ops3.n_split_k == n0 + 3
+    finally:
+        ops3.split_k = True
+    assert rel(first, one) < 1e-5
+    if rows == 4096:                         # K-contiguous operands split too when the chunks stay 16-byte aligned
+        a = torch.randn(1, n_out, rows, generator=gen, device="cuda")
+        b = torch.randn(1, k_in, rows, generator=gen, device="cuda")
+        o2 = torch.empty(1, n_out, k_in, device="cuda")
+        ops3.matmul(a, b.transpose(-1, -2), out=o2)
+        assert ops3.n_split_k == n0 + 4 and rel(o2, a.double() @ b.double().transpose(-1, -2)) < X3_TOL

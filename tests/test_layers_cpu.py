@@ -58,3 +58,45 @@ def test_host_mask_sampling_is_interpolate_nearest():
         with torch.no_grad():
             o = body(torch.zeros(1, 3, H, W))
         assert tuple(o.shape[-2:]) == trunk_hw(H, W), (H, W)
+
+
+def test_split_k_decomposition_host_logic():
+    """ops.CudaOps split-K: the K range as one more batch dim of strided views + fixed-order sum of the
+    partials == the plain product (host-side view arithmetic; the kernels are replaced by torch here)."""
+    from interactron_b200.ops import CudaOps, _as4d
+
+    class Fake:
+        n_split_k = 0
+
+        def empty(self, *shape):
+            return torch.full(shape, float("nan"), dtype=torch.float64)
+
+        def matmul(self, a, b, out=None, _nosplit=False):
+            assert _nosplit
+            out.copy_(torch.matmul(a, b))
+
+        colsum = SimOps.colsum
+        calls = 0
+
+    torch.manual_seed(1)
+    fake = Fake()
+    for E, rows, n_out, k_in in ((1, 3610, 256, 256), (2, 3610, 256, 512), (1, 1805 * 3, 64, 96)):
+        dy = torch.randn(E, rows, n_out, dtype=torch.float64)
+        x = torch.randn(E, rows, k_in, dtype=torch.float64)
+        a4, b4 = _as4d(dy.transpose(-1, -2)), _as4d(x)                 # dW = dy^T x, both operands MN-major
+        flat = torch.zeros(E, n_out * k_in + 8, dtype=torch.float64)
+        out = flat[:, :n_out * k_in].view(E, n_out, k_in)              # a slot of a flat gradient buffer
+        S = CudaOps._split_k_factor(fake, a4, b4, out, n_out, k_in, rows, 1, E)
+        assert S >= 4 and rows % S == 0, (S, rows)
+        CudaOps._matmul_split_k(fake, a4, b4, out, S, False)
+        want = dy.transpose(-1, -2) @ x
+        assert (out - want).abs().max() < 1e-10 and float(flat[:, n_out * k_in:].abs().sum()) == 0.0
+        CudaOps._matmul_split_k(fake, a4, b4, out, S, True)             # accumulate: out += product
+        assert (out - 2 * want).abs().max() < 1e-10
+    # K-contiguous operands need 16-byte aligned chunk starts; big problems and small K are left alone
+    a4, b4 = _as4d(torch.zeros(1, 256, 3610)), _as4d(torch.zeros(1, 3610, 256))
+    assert CudaOps._split_k_factor(fake, a4, b4, torch.zeros(1, 256, 256), 256, 256, 3610, 1, 1) == 1
+    a4 = _as4d(torch.zeros(1, 256, 4096))
+    assert CudaOps._split_k_factor(fake, a4, _as4d(torch.zeros(1, 4096, 256)), torch.zeros(1, 256, 256), 256, 256, 4096, 1, 1) >= 4
+    big = _as4d(torch.zeros(32, 2048, 1805).transpose(-1, -2).transpose(-1, -2))
+    assert CudaOps._split_k_factor(fake, big, _as4d(torch.zeros(32, 1805, 256)), torch.zeros(32, 2048, 256), 2048, 256, 1805, 1, 32) == 1

@@ -172,6 +172,22 @@ def test_policy_actions_match_reference(full_model):
         assert full_model.get_next_action(d) == acts[s]
 
 
+def test_batched_policy_step_equals_single_episodes(full_model):
+    """get_next_actions (extension: b environments in lock-step) == get_next_action per episode."""
+    from interactron_b200.synthetic import collate_episodes, synthetic_episode
+    eps = [synthetic_episode(e) for e in (0, 5, 6)]
+    for s in (1, 3):
+        def cut(d):
+            o = dict(d)
+            o["frames"], o["masks"] = d["frames"][:, :s], d["masks"][:, :s]
+            return o
+        singles = [full_model.get_next_action(cut(d)) for d in eps]
+        batch = cut(collate_episodes(eps))
+        assert full_model.get_next_actions(batch) == singles
+        one = torch.cat([full_model._policy_logits(cut(d), 1, s).clone() for d in eps])
+        assert rel(full_model._policy_logits(batch, 3, s), one) < 1e-4
+
+
 def test_baselines_match_reference():
     from interactron_b200.synthetic import synthetic_episode
     base = torch.load(os.path.join(GOLD, "baselines_predict.pt"))
