@@ -59,3 +59,37 @@ def test_predict_batches_episodes():
         one = model.predict(e)
         assert rel(both["pred_logits"][i], one["pred_logits"][0]) < 1e-4
         assert rel(both["pred_boxes"][i], one["pred_boxes"][0]) < 1e-4
+
+
+def test_policy_steps_match_reference_and_reuse_features():
+    """get_next_action over a rollout (1..3 frames seen): equal to the reference's action at every step,
+    with the per-frame detector outputs of the previous step reused (host logic of models._policy_logits);
+    the batched get_next_actions gives the same actions per episode."""
+    import interactron_b200 as ib
+    from interactron_b200.synthetic import collate_episodes, synthetic_episode
+    cfg = ib.default_config("interactron", weights="synthetic")
+    model = ib.build_model(cfg.MODEL).eval()
+    model._ops = SimOps()
+    ref = rh.build_reference_model("interactron", model.state_dict())
+    eps = [synthetic_episode(0), synthetic_episode(4)]
+
+    def cut(d, s):
+        o = dict(d)
+        o["frames"], o["masks"] = d["frames"][:, :s], d["masks"][:, :s]
+        o["category_ids"], o["boxes"] = [d["category_ids"][0][:s]], [d["boxes"][0][:s]]
+        return o
+
+    acts = []
+    for d in eps:
+        h0 = model.policy_cache_hits
+        mine = [model.get_next_action(cut(d, s)) for s in (1, 2, 3)]
+        assert model.policy_cache_hits == h0 + 2
+        with torch.no_grad():
+            theirs = [ref.get_next_action(cut(d, s)) for s in (1, 2, 3)]
+        assert mine == theirs
+        acts.append(mine)
+    both = collate_episodes(eps)
+    for s in (1, 2, 3):
+        o = dict(both)
+        o["frames"], o["masks"] = both["frames"][:, :s], both["masks"][:, :s]
+        assert model.get_next_actions(o) == [a[s - 1] for a in acts]

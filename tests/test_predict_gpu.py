@@ -188,6 +188,46 @@ def test_batched_policy_step_equals_single_episodes(full_model):
         assert rel(full_model._policy_logits(batch, 3, s), one) < 1e-4
 
 
+def test_policy_rollout_reuses_per_frame_features(full_model):
+    """The policy steps of a rollout (s = 1..4 frames of the same episodes) run the detector only on the new
+    frame; same action logits as recomputing every frame; a changed prefix or changed weights miss."""
+    from interactron_b200.synthetic import collate_episodes, synthetic_episode
+    m = full_model
+    batch = collate_episodes([synthetic_episode(e) for e in (7, 8)])
+
+    def cut(d, s):
+        o = dict(d)
+        o["frames"], o["masks"] = d["frames"][:, :s], d["masks"][:, :s]
+        return o
+
+    m.policy_cache = False
+    want = [m._policy_logits(cut(batch, s), 2, s).clone() for s in range(1, 5)]
+    m.policy_cache, m._policy_cache = True, None
+    h0 = m.policy_cache_hits
+    got = [m._policy_logits(cut(batch, s), 2, s).clone() for s in range(1, 5)]
+    assert m.policy_cache_hits == h0 + 3
+    for a, b in zip(got, want):
+        assert rel(a, b) < 1e-5
+    # another episode's frames with the same geometry: prefix differs -> full recompute, correct answer
+    other = collate_episodes([synthetic_episode(e) for e in (9, 8)])
+    m._policy_logits(cut(batch, 2), 2, 2)
+    h1 = m.policy_cache_hits
+    o3 = m._policy_logits(cut(other, 3), 2, 3).clone()
+    assert m.policy_cache_hits == h1
+    m.policy_cache = False
+    assert rel(o3, m._policy_logits(cut(other, 3), 2, 3)) < 1e-5
+    m.policy_cache = True
+    # a weight update between two steps invalidates the cache
+    m._policy_logits(cut(batch, 1), 2, 1)
+    with torch.no_grad():
+        m.detector.class_embed.bias.add_(0.01)
+    h2 = m.policy_cache_hits
+    m._policy_logits(cut(batch, 2), 2, 2)
+    assert m.policy_cache_hits == h2
+    with torch.no_grad():
+        m.detector.class_embed.bias.sub_(0.01)
+
+
 def test_baselines_match_reference():
     from interactron_b200.synthetic import synthetic_episode
     base = torch.load(os.path.join(GOLD, "baselines_predict.pt"))
