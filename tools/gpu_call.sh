@@ -1,7 +1,11 @@
 set -x
-python -m pytest tests/test_predict_gpu.py -m gpu -x -q 2>&1 | tail -15 > gpurun_out/s11_pytest.log; tail -15 gpurun_out/s11_pytest.log
-python bench.py --workload rollout --episodes 32 --steps 3 --warmup 3 > gpurun_out/s11_rollout_lock32.json 2> gpurun_out/s11_rollout.err; cut -c1-700 gpurun_out/s11_rollout_lock32.json; tail -3 gpurun_out/s11_rollout.err
-python bench.py --workload rollout --episodes 8 --sequential --steps 3 --warmup 3 > gpurun_out/s11_rollout_seq.json 2> gpurun_out/s11_rollout.err; cut -c1-700 gpurun_out/s11_rollout_seq.json; tail -3 gpurun_out/s11_rollout.err
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_tf32 -s 120 -c 40 -o gpurun_out/s11_prof_gemm python tools/profile_step.py 32 interactron_random 1 > gpurun_out/s11_prof_full.log 2>&1; tail -2 gpurun_out/s11_prof_full.log
-ncu -i gpurun_out/s11_prof_gemm.ncu-rep --page raw --csv --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed,sm__warps_active.avg.pct_of_peak_sustained_active,launch__registers_per_thread,lts__t_sector_hit_rate.pct,dram__throughput.avg.pct_of_peak_sustained_elapsed,sm__throughput.avg.pct_of_peak_sustained_elapsed > gpurun_out/s11_ncu_full_gemm_e32.csv 2>&1; head -5 gpurun_out/s11_ncu_full_gemm_e32.csv | cut -c1-400
-rm -f gpurun_out/s11_prof_gemm.ncu-rep
+for c in 0 1; do
+  echo "== SPLIT_WARPS=8 CORR16=$c"
+  ITN_GEMM_CORR16=$c python tools/gemm_one.py 16480 2048 512 2>&1 | tail -1
+  ITN_GEMM_CORR16=$c python tools/gemm_one.py 57760 512 4608 2>&1 | tail -1
+  ITN_GEMM_CORR16=$c python tools/gemm_one.py 57760 256 256 2>&1 | tail -1
+  ITN_GEMM_CORR16=$c python tools/gemm_one.py 8192 8192 2048 2>&1 | tail -1
+  ITN_GEMM_CORR16=$c python tools/gemm_one.py 1805 256 2048 tf32x3 256 32 2>&1 | tail -1
+  ITN_GEMM_CORR16=$c python bench.py --steps 6 --warmup 3 --cpu-episodes 0 2>&1 | tail -1 | cut -c1-200
+done
+ITN_GEMM_CORR16=1 python -m pytest tests/test_kernels_gpu.py -m gpu -x -q -k "gemm" 2>&1 | tail -3
