@@ -25,11 +25,6 @@
 //     A*B  +  A_lo*B  +  A*B_lo        (the tensor core sees A, B as their truncated hi parts)
 // in TMEM, which restores ~fp32 accuracy (dropped terms are O(2^-20)) at 3 MMAs per k-step
 // and no extra HBM/L2 traffic.
-// Mixed variant (corr16, both operands K-major): the two correction products are 2^-11 of the result, so
-// their operands only need ~9 bits.  The splitters write them as bf16 tiles (A_lo, A, B_lo, B rounded to
-// nearest, 64-byte rows in the SWIZZLE_64B layout) and the issuer runs them as kind::f16 MMAs of K=16:
-// 4 tf32 + 4 bf16 instructions per k-block instead of 12 tf32, and 96 KB instead of 144 KB of operand
-// reads from shared memory (per 128x256x32 block).
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -53,13 +48,6 @@ __device__ long long* g_trace = nullptr;
 #endif
 
 // x - trunc_tf32(x): the part of an fp32 operand the tensor core drops (kind::tf32 truncates).
-// two floats -> packed bf16x2 (round to nearest even), first argument in the low half
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-  uint32_t r;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-  return r;
-}
-
 __device__ __forceinline__ float4 tf32_residual(const float4 v) {
   float4 r;
   r.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
@@ -69,10 +57,6 @@ __device__ __forceinline__ float4 tf32_residual(const float4 v) {
   return r;
 }
 
-#ifndef ITN_SPLIT_WARPS
-#define ITN_SPLIT_WARPS 4
-#endif
-constexpr int kSplitWarps = ITN_SPLIT_WARPS;   // residual splitter warps of the tf32x3 kernels
 constexpr int kBM = 128;
 constexpr int kBK = 32;                    // floats per k-block = 128 B swizzle row
 constexpr int kAtomBytes = 32 * kBK * 4;   // one 32(mn) x 32(k) MN-major box = 4096 B
@@ -92,7 +76,6 @@ struct GemmKParams {
   int variant;   // epilogue_variant(...)
   int vec;       // 1: 128-bit epilogue path is legal (alignment / N % 4 checked on the host)
   float rz_eps;  // tf32x3: mean relative loss of one round-toward-zero TMEM accumulate (see splitters)
-  int corr16;    // tf32x3, K-major operands: correction products A_lo*B + A*B_lo as bf16 MMAs (kind::f16)
   int dbg;       // ITN_TRACE builds only: 1 = skip global stores, 2 = skip TMEM read, 4 = skip smem transpose
 };
 
@@ -329,8 +312,8 @@ struct TileCfg {
   static constexpr int kStages = kMaxStages > 8 ? 8 : kMaxStages;
   static constexpr int kAccCols = BN < 32 ? 32 : BN;
   static constexpr int kTmemCols = 2 * kAccCols;               // two accumulators (double buffer)
-  static constexpr int kThreads = X3 ? 64 + 32 * kSplitWarps + 128 : 192;
-  static constexpr int kEpiWarp0 = X3 ? 2 + kSplitWarps : 2;
+  static constexpr int kThreads = X3 ? 320 : 192;
+  static constexpr int kEpiWarp0 = X3 ? 6 : 2;
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + (3 * kStages + 4) * 8 + 16 + 1024;
   static_assert(kStages >= 2, "need at least a double-buffered operand ring");
   static_assert(kSmemBytes <= 227 * 1024, "exceeds shared memory per CTA");
@@ -369,7 +352,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&split_bar[s], kSplitWarps);   // one arrival per splitter warp
+      mbar_init(&split_bar[s], 4);   // one arrival per splitter warp
       mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -433,7 +416,6 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // --------------------------------------------------------- MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_tf32(kBM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
-      const bool corr16 = p.corr16 != 0;
       int s = 0;
       uint32_t ph = 0;
       int acc = 0;
@@ -462,25 +444,12 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const uint64_t bd = B_MN ? umma_smem_desc(sb + k * 1024, kAtomBytes, 512, kLayoutSW128Base32)
                                      : umma_smem_desc(sb + k * 32, 16, 1024, kLayoutSW128);
             umma_tf32(tacc, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
-            if (X3 && !(corr16 && !A_MN && !B_MN)) {
+            if (X3) {
               // residual tiles live kRawBytes after their raw twins, same layout: the descriptor
               // start address is in 16-byte units
               constexpr uint64_t kLoOff = static_cast<uint64_t>(Cfg::kRawBytes >> 4);
               umma_tf32(tacc, ad + kLoOff, bd, idesc, 1u);   // A_lo * B_hi
               umma_tf32(tacc, ad, bd + kLoOff, idesc, 1u);   // A_hi * B_lo
-            }
-          }
-          if (X3 && !A_MN && !B_MN && corr16) {
-            // bf16 tiles after the raw ones: [A_lo | A | B_lo | B], 64-byte rows, 8-row groups 512 B apart
-            constexpr uint32_t idesc16 = umma_idesc_bf16(kBM, BN);
-            const uint32_t a_lo = sa + Cfg::kRawBytes, a_h = a_lo + Cfg::kABytes / 2;
-            const uint32_t b_lo = a_lo + Cfg::kABytes, b_h = b_lo + Cfg::kBBytes / 2;
-#pragma unroll
-            for (int k = 0; k < kBK / 16; ++k) {
-              umma_bf16(tacc, umma_smem_desc(a_lo + k * 32, 16, 512, kLayoutSW64),
-                        umma_smem_desc(b_h + k * 32, 16, 512, kLayoutSW64), idesc16, 1u);   // A_lo * B
-              umma_bf16(tacc, umma_smem_desc(a_h + k * 32, 16, 512, kLayoutSW64),
-                        umma_smem_desc(b_lo + k * 32, 16, 512, kLayoutSW64), idesc16, 1u);  // A * B_lo
             }
           }
           umma_commit(&empty_bar[s]);  // frees the smem slot once the MMAs have read it
@@ -501,7 +470,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // then also waits for those loads; 224 -> 160 TFLOP/s on 16480x2048x512.)
     int s = 0;
     uint32_t ph = 0;
-    const int tid = threadIdx.x - 64;               // 0 .. 32 * kSplitWarps - 1
+    const int tid = threadIdx.x - 64;               // 0..127
     int gk = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       for (int kb = 0; kb < num_kb; ++kb, ++gk) {
@@ -516,43 +485,17 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // by folding  x * delta_kb  into the residual tile of A (delta_kb <= 5e-5 sits well inside
         // the 2^-11 range of x_lo).  Measured (tools/gemm_precision.py): K=2048 random operands
         // 1.5e-5 -> see profiles/README.md.
+        const float delta = p.rz_eps * (12.0f * static_cast<float>(num_kb - kb) - 5.5f);
         constexpr int kAVec = Cfg::kABytes / 16;
-        if (!p.corr16) {
-          const float delta = p.rz_eps * (12.0f * static_cast<float>(num_kb - kb) - 5.5f);
 #pragma unroll 8
-          for (int i = tid; i < Cfg::kRawBytes / 16; i += 32 * kSplitWarps) {
-            const float4 x = raw[i];
-            float4 r = tf32_residual(x);
-            if (i < kAVec) {
-              r.x = fmaf(x.x, delta, r.x); r.y = fmaf(x.y, delta, r.y);
-              r.z = fmaf(x.z, delta, r.z); r.w = fmaf(x.w, delta, r.w);
-            }
-            lo[i] = r;
+        for (int i = tid; i < Cfg::kRawBytes / 16; i += 128) {
+          const float4 x = raw[i];
+          float4 r = tf32_residual(x);
+          if (i < kAVec) {
+            r.x = fmaf(x.x, delta, r.x); r.y = fmaf(x.y, delta, r.y);
+            r.z = fmaf(x.z, delta, r.z); r.w = fmaf(x.w, delta, r.w);
           }
-        } else {
-          // 8 accumulates per k-block in this mode (4 tf32 + 4 bf16 instructions)
-          const float delta = p.rz_eps * (8.0f * static_cast<float>(num_kb - kb) - 3.5f);
-          uint8_t* lo8 = reinterpret_cast<uint8_t*>(lo);
-#pragma unroll 4
-          for (int i = tid; i < Cfg::kRawBytes / 16; i += 32 * kSplitWarps) {
-            const float4 x = raw[i];
-            float4 r = tf32_residual(x);
-            const bool is_a = i < kAVec;
-            if (is_a) {
-              r.x = fmaf(x.x, delta, r.x); r.y = fmaf(x.y, delta, r.y);
-              r.z = fmaf(x.z, delta, r.z); r.w = fmaf(x.w, delta, r.w);
-            }
-            // raw tile: 128-byte rows, 16-byte chunk index XOR (row % 8)  (TMA SWIZZLE_128B);
-            // bf16 tiles: 64-byte rows, 16-byte chunk index XOR ((row / 2) % 4)  (UMMA SWIZZLE_64B)
-            const int li = is_a ? i : i - kAVec;
-            const int row = li >> 3;
-            const int c = (li & 7) ^ (row & 7);                  // logical chunk: floats 4c .. 4c+3 of the row
-            const uint32_t off = row * 64 + ((((c >> 1) ^ (row >> 1)) & 3) << 4) + ((c & 1) << 3);
-            uint8_t* base = lo8 + (is_a ? 0 : Cfg::kABytes);
-            const uint32_t half = is_a ? Cfg::kABytes / 2 : Cfg::kBBytes / 2;
-            *reinterpret_cast<uint2*>(base + off) = make_uint2(pack_bf16(r.x, r.y), pack_bf16(r.z, r.w));
-            *reinterpret_cast<uint2*>(base + half + off) = make_uint2(pack_bf16(x.x, x.y), pack_bf16(x.z, x.w));
-          }
+          lo[i] = r;
         }
         fence_proxy_async();
         __syncwarp();
@@ -855,9 +798,6 @@ static void fill_kparams(GemmKParams& p, const itn_gemm_desc_t* d) {
   // mean loss per round-toward-zero accumulate, in units of 2^-24 (ITN_GEMM_RZ_COMP=0 disables)
   static const float rz = getenv("ITN_GEMM_RZ_COMP") ? (float)atof(getenv("ITN_GEMM_RZ_COMP")) : 0.59f;
   p.rz_eps = rz * 5.9604645e-8f;
-  // mixed tf32 + bf16-correction mode: only when both operands are K-major (the kernel checks the majors)
-  static const int corr16 = getenv("ITN_GEMM_CORR16") ? atoi(getenv("ITN_GEMM_CORR16")) : 0;
-  p.corr16 = (corr16 && d->A.major == 0 && d->B.major == 0) ? 1 : 0;
 }
 
 static int validate(const itn_gemm_desc_t* d) {

@@ -90,16 +90,6 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// kind::f16 with bf16 operands, fp32 accumulate (the correction terms of the mixed tf32x3 mode).
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
-                                          uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
 // Arrive on `bar` once all previously issued tcgen05.mma of this thread retire.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
@@ -132,7 +122,6 @@ __device__ __forceinline__ void tmem_ld_wait() {
 //                                 tensor core accepts for MN-major 32-bit (tf32) operands)
 constexpr uint32_t kLayoutSW128 = 2;
 constexpr uint32_t kLayoutSW128Base32 = 1;
-constexpr uint32_t kLayoutSW64 = 4;
 __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t lbo_bytes,
                                                    uint32_t sbo_bytes, uint32_t layout_type) {
   uint64_t d = 0;
@@ -151,12 +140,6 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32(int m, int n, int a_mn_ma
                                                        int b_mn_major) {
   return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
          (static_cast<uint32_t>(b_mn_major) << 16) | (static_cast<uint32_t>(n >> 3) << 17) |
-         (static_cast<uint32_t>(m >> 4) << 24);
-}
-
-// kind::f16, bf16 x bf16 -> fp32, K-major operands.  [7,10) a_format=1 (BF16)  [10,13) b_format=1 (BF16)
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
          (static_cast<uint32_t>(m >> 4) << 24);
 }
 
