@@ -122,6 +122,7 @@ __device__ __forceinline__ void tmem_ld_wait() {
 //                                 tensor core accepts for MN-major 32-bit (tf32) operands)
 constexpr uint32_t kLayoutSW128 = 2;
 constexpr uint32_t kLayoutSW128Base32 = 1;
+constexpr uint32_t kLayoutSW64 = 4;
 __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t lbo_bytes,
                                                    uint32_t sbo_bytes, uint32_t layout_type) {
   uint64_t d = 0;
