@@ -91,7 +91,14 @@ typedef struct {
   int c_pad;        /* 1: columns [N, round_up(N,4)) of every C row belong to C and may be overwritten
                        (with zeros): lets N % 4 != 0 outputs such as attention scores use 128-bit stores.
                        Honoured only for bias-free plain epilogues; otherwise ignored. */
+  const float* B_lo; /* optional (may be NULL): B - trunc_tf32(B), element for element at the same offsets and
+                       strides as B.ptr (itn_tf32_residual), for a K-major B in tf32x3 mode.  The residual tile of
+                       B then arrives by TMA instead of being recomputed in shared memory for every k-block:
+                       what static weights are for (+5-10 % on those GEMMs); results are bit-identical. */
 } itn_gemm_desc_t;
+
+/* lo = x - trunc_tf32(x): the part of an fp32 value kind::tf32 drops (see itn_gemm_desc_t::B_lo). */
+int itn_tf32_residual(const float* x, float* lo, long long n, void* stream);
 
 /* tcgen05/TMA path.  Requires 16-byte aligned operand bases and ld/sb* multiples
  * of 4 elements; returns ITN_ERR_UNSUPPORTED otherwise (use itn_gemm_simt). */

@@ -33,6 +33,7 @@ class GemmDesc(C.Structure):
         ("C2", C.c_void_p), ("ldc2", C.c_longlong), ("c2_sb0", C.c_longlong), ("c2_sb1", C.c_longlong),
         ("alpha", C.c_float), ("act", C.c_int), ("epi", C.c_int), ("accumulate", C.c_int),
         ("round_out", C.c_int), ("precision", C.c_int), ("act_pos", C.c_int), ("c_pad", C.c_int),
+        ("B_lo", C.c_void_p),
     ]
 
 
@@ -42,6 +43,7 @@ SIGNATURES = {
     "itn_last_error": (C.c_char_p, []),
     "itn_version": (C.c_char_p, []),
     "itn_launch_count": (_LL, []),
+    "itn_tf32_residual": (_I, [_P, _P, _LL, _P]),
     "itn_gemm_tf32": (_I, [C.POINTER(GemmDesc), _P]),
     "itn_gemm_tf32_supported": (_I, [C.POINTER(GemmDesc)]),
     "itn_gemm_simt": (_I, [C.POINTER(GemmDesc), _P]),

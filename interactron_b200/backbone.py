@@ -124,6 +124,9 @@ class GemmTrunk:
                         down=self._prep(blk.downsample[0], blk.downsample[1]) if blk.downsample is not None else None))
         self.layers = (stem, blocks)
         self.key = key
+        if hasattr(self.ops, "register_presplit"):          # frozen trunk: every conv weight is a static B operand
+            for L in [stem] + [blk[k] for blk in blocks for k in ("a", "b", "c", "down") if blk[k] is not None]:
+                self.ops.register_presplit(L["w"])
 
     def _conv(self, x, L, act="relu", residual=None):
         """x [N,H,W,Cin] channels-last -> [N,Ho,Wo,Cout]; bias (+ residual) + ReLU fused in the GEMM."""

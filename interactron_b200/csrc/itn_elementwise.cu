@@ -230,9 +230,27 @@ pos_embed_sine_kernel(const unsigned char* __restrict__ mask, float* __restrict_
   }
 }
 
+// lo = x - trunc_tf32(x), the same expression the GEMM's splitter warps evaluate in shared memory
+__global__ void __launch_bounds__(256)
+tf32_residual_kernel(const float* __restrict__ x, float* __restrict__ lo, long long n) {
+  pdl_wait();
+  pdl_trigger();
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float v = x[i];
+    lo[i] = v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+  }
+}
+
 }  // namespace itn
 
 using namespace itn;
+
+extern "C" int itn_tf32_residual(const float* x, float* lo, long long n, void* stream) {
+  ITN_REQUIRE(x && lo && n > 0, "tf32_residual: bad arguments");
+  launch(tf32_residual_kernel, grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream), x, lo, n);
+  return check_launch("tf32_residual_kernel");
+}
 
 extern "C" int itn_sgd_clip_update(const float* theta, long long theta_stride, const float* g,
                                    float* theta_out, float* theta_out_r, unsigned char* clip_mask,

@@ -80,6 +80,7 @@ struct GemmKParams {
   int variant;   // epilogue_variant(...)
   int vec;       // 1: 128-bit epilogue path is legal (alignment / N % 4 checked on the host)
   float rz_eps;  // tf32x3: mean relative loss of one round-toward-zero TMEM accumulate (see splitters)
+  int b_presplit;  // tf32x3, K-major B: the residual tile of B is loaded through tmBlo (itn_gemm_desc_t::B_lo)
   int dbg;       // ITN_TRACE builds only: 1 = skip global stores, 2 = skip TMEM read, 4 = skip smem transpose;
                  // any build (ITN_GEMM_DBG, timing experiments): 16 = skip the residual split, 32 = skip the correction MMAs
 };
@@ -329,7 +330,7 @@ struct TileCfg {
 template <int BN, bool A_MN, bool B_MN, bool X3>
 __global__ void __launch_bounds__(TileCfg<BN, X3>::kThreads, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ GemmKParams p) {
+                 const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ GemmKParams p) {
   // p is __grid_constant__: it is read straight from the constant bank even where its address is
   // taken (a by-value copy lands on the local-memory stack and turns every p.ld* into an LDL).
   using Cfg = TileCfg<BN, X3>;
@@ -356,6 +357,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (p.b_presplit) tma_prefetch_desc(&tmBlo);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&split_bar[s], 4);   // one arrival per splitter warp
@@ -396,7 +398,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int kb = 0; kb < num_kb; ++kb, ++gk) {
           mbar_wait(&empty_bar[s], ph ^ 1);
           ITN_TRACE_AT(0, gk);
-          mbar_expect_tx(&full_bar[s], Cfg::kRawBytes);
+          // pre-split B (static weights): its residual tile arrives by TMA, the splitters do A only
+          const bool presplit = X3 && !B_MN && p.b_presplit;
+          mbar_expect_tx(&full_bar[s], Cfg::kRawBytes + (presplit ? Cfg::kBBytes : 0));
           uint8_t* sa = smem + s * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
           const int k0 = kb * kBK;
@@ -409,6 +413,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           if (!B_MN) {
             tma_load_4d(sb, &tmB, &full_bar[s], k0, n0, b_c1, b_c0);
+            if (presplit) tma_load_4d(sb + Cfg::kRawBytes, &tmBlo, &full_bar[s], k0, n0, b_c1, b_c0);
           } else {
 #pragma unroll
             for (int j = 0; j < BN / 32; ++j)
@@ -498,7 +503,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         constexpr int kAVec = Cfg::kABytes / 16;
         if (!(p.dbg & 16))                 // dbg 16 (timing experiments only): no residual pass, garbage lo tiles
 #pragma unroll 8
-        for (int i = tid; i < Cfg::kRawBytes / 16; i += 128) {
+        for (int i = tid; i < (p.b_presplit && !B_MN ? Cfg::kABytes : Cfg::kRawBytes) / 16; i += 128) {
           const float4 x = raw[i];
           float4 r = tf32_residual(x);
           if (i < kAVec) {
@@ -809,6 +814,8 @@ static void fill_kparams(GemmKParams& p, const itn_gemm_desc_t* d) {
   // mean loss per round-toward-zero accumulate, in units of 2^-24 (ITN_GEMM_RZ_COMP=0 disables)
   static const float rz = getenv("ITN_GEMM_RZ_COMP") ? (float)atof(getenv("ITN_GEMM_RZ_COMP")) : 0.59f;
   p.rz_eps = rz * 5.9604645e-8f;
+  p.b_presplit = (d->B_lo != nullptr && d->precision == ITN_PREC_TF32X3 && d->B.major == 0 &&
+                  (reinterpret_cast<uintptr_t>(d->B_lo) & 15) == 0) ? 1 : 0;
 }
 
 static int validate(const itn_gemm_desc_t* d) {
@@ -847,11 +854,19 @@ static int launch_tile(const itn_gemm_desc_t* d, cudaStream_t stream) {
   const long long nt = (long long)p.tiles_m * p.tiles_n * d->nb0 * d->nb1;
   if (nt > 0x7fffffffLL) return set_error(ITN_ERR_ARG, "gemm: too many tiles");
   p.num_tiles = (int)nt;
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmBlo;
   int rc = make_operand_map(&tmA, d->A, d->M, d->K, d->nb0, d->nb1, kBM, &p.a_m0, &p.a_m1);
   if (rc) return rc;
   rc = make_operand_map(&tmB, d->B, d->N, d->K, d->nb0, d->nb1, BN, &p.b_m0, &p.b_m1);
   if (rc) return rc;
+  tmBlo = tmB;
+  if (p.b_presplit) {
+    itn_operand_t blo = d->B;
+    blo.ptr = d->B_lo;
+    int m0 = 0, m1 = 0;
+    rc = make_operand_map(&tmBlo, blo, d->N, d->K, d->nb0, d->nb1, BN, &m0, &m1);
+    if (rc) return rc;
+  }
   auto kern = gemm_tf32_kernel<BN, A_MN, B_MN, X3>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
@@ -863,7 +878,7 @@ static int launch_tile(const itn_gemm_desc_t* d, cudaStream_t stream) {
     attr_set = true;
   }
   const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();   // persistent: <= 1 CTA per SM
-  launch(kern, grid, Cfg::kThreads, Cfg::kSmemBytes, stream, tmA, tmB, p);
+  launch(kern, grid, Cfg::kThreads, Cfg::kSmemBytes, stream, tmA, tmB, tmBlo, p);
   return check_launch("gemm_tf32_kernel");
 }
 

@@ -118,6 +118,12 @@ class InnerLoop:
                 dst = ops.zeros(*src.shape)
                 setattr(self, nm + "_t", dst)
             pack.transpose_into(ops, src, dst)
+        # static weights of the tf32x3 GEMMs: keep their tf32 residuals beside them (ops.register_presplit)
+        if hasattr(ops, "register_presplit"):
+            for nm in ("theta", "psi", "phi", "theta_t", "psi_t", "phi_t"):
+                buf = getattr(self, nm, None)
+                if buf is not None:
+                    ops.register_presplit(buf)
 
     def _det_weights(self, theta, theta_r, theta_t=None):
         return Weights((self.theta_pack, theta, theta_r, theta_t), (self.psi_pack, self.psi, self.psi_r, self.psi_t))

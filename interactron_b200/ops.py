@@ -52,6 +52,10 @@ class CudaOps:
         self.n_simt = 0
         self.n_split_k = 0
         self.split_k = os.environ.get("ITN_SPLIT_K", "1") != "0"
+        # static GEMM weights registered with their tf32 residuals (register_presplit): [(base, end, lo, src)]
+        self._presplit = []
+        self.presplit = os.environ.get("ITN_PRESPLIT", "1") != "0"
+        self.n_presplit = 0
         # L2 budget (MiB) for the score tensors of one attention chunk (layers._l2_chunks); 0 = one pass
         self.attn_l2_mb = int(os.environ.get("ITN_ATTN_L2_MB", "0"))
 
@@ -72,6 +76,41 @@ class CudaOps:
     def _clean(self):
         """True when GEMM operands must be stored TF32-rounded (single-pass mode only)."""
         return self.precision == "tf32"
+
+    # ------------------------------------------------- pre-split weights (itn_gemm_desc_t::B_lo)
+    def register_presplit(self, w):
+        """Keep `lo = w - trunc_tf32(w)` next to a persistent weight buffer `w` (contiguous).  Every tf32x3
+        GEMM whose K-major B operand is a view into `w` then receives the matching view of `lo` as B_lo, so the
+        residual tile of the weights arrives by TMA instead of being recomputed per k-block.  Call again after
+        `w` changed in place (same tensor: the residual is refreshed in place; bit-identical results either
+        way, the kernel evaluates the same expression)."""
+        if not self.presplit or self.precision != "tf32x3":
+            return
+        assert w.is_contiguous() and w.dtype == torch.float32
+        base = w.data_ptr()
+        for ent in self._presplit:
+            if ent[0] == base and ent[3] is w:
+                _lib.check(self.lib.itn_tf32_residual(_ptr(w), _ptr(ent[2]), w.numel(), self._stream()))
+                return
+        lo = torch.empty_like(w)
+        _lib.check(self.lib.itn_tf32_residual(_ptr(w), _ptr(lo), w.numel(), self._stream()))
+        # the entry holds `w` itself: its address range cannot be handed to another tensor while it is listed
+        self._presplit.append((base, base + w.numel() * 4, lo, w))
+        self._presplit.sort(key=lambda e: e[0])
+
+    def _b_lo_ptr(self, ptr):
+        ents = self._presplit
+        lo_i, hi_i = 0, len(ents)
+        while lo_i < hi_i:                       # last entry with base <= ptr
+            mid = (lo_i + hi_i) // 2
+            if ents[mid][0] <= ptr:
+                lo_i = mid + 1
+            else:
+                hi_i = mid
+        if lo_i == 0:
+            return 0
+        base, end, lo, _ = ents[lo_i - 1]
+        return lo.data_ptr() + (ptr - base) if ptr < end else 0
 
     # ---------------------------------------------------------------- GEMM
     @staticmethod
@@ -140,6 +179,11 @@ class CudaOps:
         d.M, d.N, d.K, d.nb0, d.nb1 = M, N, K, nb0, nb1
         d.A, keep_a = self._operand(a4, nb0, nb1, True)
         d.B, keep_b = self._operand(b4, nb0, nb1, False)
+        if self._presplit and d.B.major == 0 and self.precision == "tf32x3" and keep_b is b4:
+            blo = self._b_lo_ptr(b4.data_ptr())
+            if blo:
+                d.B_lo = blo
+                self.n_presplit += 1
 
         def mat(t, what):
             t4 = _as4d(t)

@@ -457,3 +457,43 @@ def test_gemm_split_k_weight_gradients(ops3, E, rows, n_out, k_in):
         o2 = torch.empty(1, n_out, k_in, device="cuda")
         ops3.matmul(a, b.transpose(-1, -2), out=o2)
         assert ops3.n_split_k == n0 + 4 and rel(o2, a.double() @ b.double().transpose(-1, -2)) < X3_TOL
+
+
+def test_gemm_presplit_weights_bit_identical(ops3):
+    """Static weights registered with their tf32 residuals (ops.register_presplit -> itn_gemm_desc_t::B_lo):
+    the residual tile of B arrives by TMA instead of being recomputed in shared memory.  Same expression, so
+    the results must be bit-identical to the plain launch - for whole weights, row slices, per-group stacks,
+    transposed twins, and after an in-place update followed by a re-registration."""
+    from interactron_b200.ops import CudaOps
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    ops = CudaOps()                                   # own registry
+    flat = torch.randn(1, 3 * 256 * 512 + 512 * 256, generator=gen, device="cuda")
+    w = flat[:, :3 * 256 * 512].view(1, 768, 512)             # a packed in_proj-like weight [G=1, 3D, K]
+    wt = flat[:, 3 * 256 * 512:].view(1, 512, 256)            # a transposed twin [G, K, N]
+    x = torch.randn(1, 1805, 512, generator=gen, device="cuda")
+    dy = torch.randn(1, 1805, 256, generator=gen, device="cuda")
+
+    def run():
+        return [ops.matmul(x, w.transpose(-1, -2)),                  # forward: x W^T, W [N, K] read K-major
+                ops.matmul(x, w[:, 256:512].transpose(-1, -2)),      # a row slice (one of q / k / v)
+                ops.matmul(dy, wt.transpose(-1, -2)),                # data gradient through the W^T twin, K-major
+                ops.matmul(x, wt)]                                   # the twin read MN-major: plain path
+
+    plain = [t.clone() for t in run()]
+    assert ops.n_presplit == 0
+    ops.register_presplit(flat)
+    got = run()
+    assert ops.n_presplit == 3          # the last product reads wt MN-major: no pre-split path for it
+    for a, b in zip(got, plain):
+        assert torch.equal(a, b)
+    assert rel(got[0], x.double() @ w.double().transpose(-1, -2)) < X3_TOL
+    # an activation operand outside every registered buffer is left alone
+    n0 = ops.n_presplit
+    ops.matmul(x, torch.randn(1, 512, 64, generator=gen, device="cuda"))
+    assert ops.n_presplit == n0
+    # in-place weight update: stale residuals until re-registered, exact again afterwards
+    flat.mul_(1.37)
+    ops.register_presplit(flat)
+    after = ops.matmul(x, w.transpose(-1, -2))
+    ops2 = CudaOps()
+    assert torch.equal(after, ops2.matmul(x, w.transpose(-1, -2)))
