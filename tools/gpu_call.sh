@@ -1,3 +1,3 @@
 set -x
-python -m pytest tests -m gpu -x -q 2>&1 | tail -12
-python __graft_entry__.py smoke 2>&1 | tail -1
+python bench.py > gpurun_out/s21_bench.json 2> gpurun_out/s21_bench.err; cut -c1-300 gpurun_out/s21_bench.json; tail -2 gpurun_out/s21_bench.err
+python bench.py --impl reference --steps 5 --warmup 3 2>/dev/null | cut -c1-200
