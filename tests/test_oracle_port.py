@@ -42,14 +42,15 @@ def test_port_matches_committed_reference_goldens(model_type, kind):
     assert ((gn - g["g_norms"]).abs() / g["g_norms"]).max().item() < 2e-3
 
 
-def test_port_matches_padded_frames_golden():
+@pytest.mark.parametrize("model_type,kind", [("interactron_random", "B"), ("interactron", "A")])
+def test_port_matches_padded_frames_golden(model_type, kind):
     """Non-zero masks: key-padding + mask-dependent position embedding (tools/make_golden_masked.py)."""
     from interactron_b200.synthetic import masked_episode
-    m = _model("interactron_random")
-    gold = torch.load(os.path.join(GOLD, "interactron_random_predict_masked.pt"))
+    m = _model(model_type)
+    gold = torch.load(os.path.join(GOLD, f"{model_type}_predict_masked.pt"))
     for ep, g in gold.items():
         tr = {}
-        out = port.predict(m.state_dict(), m.detector.backbone[0].body, masked_episode(ep), "B",
+        out = port.predict(m.state_dict(), m.detector.backbone[0].body, masked_episode(ep), kind,
                            lr=m.config.ADAPTIVE_LR, trace=tr)
         assert rel(out["pred_logits"], g["pred_logits"]) < 1e-4
         assert rel(out["pred_boxes"], g["pred_boxes"]) < 1e-4

@@ -66,11 +66,13 @@ def test_adapt_detect_trace_matches_reference(name, rand_model, full_model):
         assert rel(out["box_features"][0], g["box_features"][0]) < TOL
 
 
-def test_padded_frames_match_reference(rand_model):
+@pytest.mark.parametrize("name", ["interactron_random", "interactron"])
+def test_padded_frames_match_reference(name, rand_model, full_model):
     """Non-zero masks (padded frames): key-padding masks in every encoder / cross attention and the
     mask-dependent sine position embedding, against the reference golden (tools/make_golden_masked.py)."""
     from interactron_b200.synthetic import collate_episodes, masked_episode, synthetic_episode
-    gold = torch.load(os.path.join(GOLD, "interactron_random_predict_masked.pt"))
+    rand_model = rand_model if name == "interactron_random" else full_model
+    gold = torch.load(os.path.join(GOLD, f"{name}_predict_masked.pt"))
     loop = rand_model._get_loop()
     for ep, g in gold.items():
         d = masked_episode(ep)

@@ -1,3 +1,2 @@
 set -x
-python bench.py > gpurun_out/s21_bench.json 2> gpurun_out/s21_bench.err; cut -c1-300 gpurun_out/s21_bench.json; tail -2 gpurun_out/s21_bench.err
-python bench.py --impl reference --steps 5 --warmup 3 2>/dev/null | cut -c1-200
+python -m pytest tests/test_predict_gpu.py -m gpu -x -q 2>&1 | tail -8
