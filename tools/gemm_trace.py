@@ -18,12 +18,13 @@ prec = sys.argv[4] if len(sys.argv) > 4 else "tf32x3"
 if len(sys.argv) > 5 and sys.argv[5] != "0":
     os.environ["ITN_GEMM_BN"] = sys.argv[5]
 pad = len(sys.argv) > 6 and sys.argv[6] == "pad"     # rows padded to 4 columns, 128-bit stores (c_pad)
+ld_out = int(sys.argv[7]) if len(sys.argv) > 7 else 0  # explicit row pitch of the output (floats)
 ops = CudaOps()
 ops.precision = prec
 ops.lib.itn_debug_set_trace.argtypes = [C.c_void_p]
 a = torch.randn(M, K, device="cuda")
 w = torch.randn(N, K, device="cuda")
-out = torch.empty(M, (N + 3) // 4 * 4 if pad else N, device="cuda")[:, :N]
+out = torch.empty(M, ld_out if ld_out else ((N + 3) // 4 * 4 if pad else N), device="cuda")[:, :N]
 for _ in range(3):
     ops.matmul(a, w.t(), out=out, out_pad=pad)
 torch.cuda.synchronize()
