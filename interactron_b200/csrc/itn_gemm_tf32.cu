@@ -877,7 +877,16 @@ static int launch_tile(const itn_gemm_desc_t* d, cudaStream_t stream) {
                        cudaGetErrorString(e));
     attr_set = true;
   }
-  const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();   // persistent: <= 1 CTA per SM
+  int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();   // persistent: <= 1 CTA per SM
+  // A CTA walks tiles blockIdx.x, blockIdx.x + grid, ... with n fastest.  When the last n-tile is partial
+  // (N=361 at BN=256: 8 live 32-column chunks, then 4) and grid shares a factor with tiles_n, every CTA sees
+  // the same n positions over and over: half of them only full tiles, half only partial ones, and the
+  // epilogue-bound products (K=32 attention scores) wait for the heavy half.  A grid coprime to tiles_n
+  // rotates the positions (147 CTAs instead of 148: measured 325 -> see profiles/README.md).
+  if (p.tiles_n > 1 && d->N % BN != 0 && grid == sm_count()) {
+    auto gcd = [](int a, int b) { while (b) { const int t = a % b; a = b; b = t; } return a; };
+    while (grid > 1 && gcd(grid, p.tiles_n) != 1) --grid;
+  }
   launch(kern, grid, Cfg::kThreads, Cfg::kSmemBytes, stream, tmA, tmB, tmBlo, p);
   return check_launch("gemm_tf32_kernel");
 }

@@ -1,6 +1,6 @@
 set -x
-python tools/gemm_trace.py 46208 361 32 tf32x3 0 pad 384 2>&1 | head -3
-python tools/gemm_trace.py 46208 361 32 tf32x3 0 pad 2>&1 | head -3
-python tools/gemm_trace.py 46208 384 32 tf32x3 0 pad 2>&1 | head -3
-python tools/gemm_trace.py 16480 2048 512 2>&1 | head -3
-python tools/gemm_trace.py 46208 512 32 2>&1 | head -3
+python tools/gemm_scores.py 0 2>&1 | tail -1
+python tools/gemm_scores.py 0 50 361 32 160 2>&1 | tail -1
+python tools/gemm_scores.py 0 255 1805 64 32 2>&1 | tail -1
+python -m pytest tests/test_kernels_gpu.py tests/test_predict_gpu.py -m gpu -x -q 2>&1 | tail -4
+python bench.py --steps 10 --warmup 3 --cpu-episodes 0 2>/dev/null | tail -1 | cut -c1-250
