@@ -109,6 +109,44 @@ int itn_gemm_tf32_supported(const itn_gemm_desc_t* d);
  * Used for the few unaligned / degenerate shapes (N=1 data-grad) on the path. */
 int itn_gemm_simt(const itn_gemm_desc_t* d, void* stream);
 
+/* ------------------------------------------------------- fused attention --- */
+/* Multi-head attention with the score matrix kept on chip (tcgen05 MMAs with tensor-memory
+ * operands, TMA-streamed K/V blocks, online softmax), tf32x3 arithmetic like itn_gemm_tf32.
+ * Replaces, forward and backward, the q@k^T -> masked softmax -> @v chains of
+ *   models/gpt.py:43-53 (CausalSelfAttention with its all-ones mask = full attention, hd 64),
+ *   models/detr_models/transformer.py:154-155 (encoder self-attention, hd 32),
+ *   models/detr_models/transformer.py:219-226 (decoder self- and cross-attention; also the
+ *   fusion-B layers of models/new_transformer.py:23-25, hd 64),
+ * i.e. F.multi_head_attention_forward after the in-projections and before out_proj, with
+ * key_padding_mask, eval-mode (no dropout), and the autograd nodes of those ops under
+ * models/interactron.py:51-52.  Every tensor is a [B, L, nh*hd] view: element (b, i, h, d) lives at
+ * ptr[b*sb + i*ld + h*hd + d] (heads are column blocks of the projection output; q and k may be
+ * column halves of one [B, L, 2*nh*hd] buffer).  hd is 32 or 64; pointers 16-byte aligned, ld and
+ * sb multiples of 4 elements (otherwise ITN_ERR_UNSUPPORTED; itn_attention_supported tests it).
+ *   forward : o = softmax(scale * q k^T + mask) v ;  lse[b,h,i] = log2(sum_j 2^(scale*log2(e)*q_i.k_j))
+ *             (log-sum-exp in base 2, what the backward needs to recompute the probabilities).
+ *             key_mask (may be NULL): uint8 [B, Lk], 1 = padded key (probability 0).
+ *   backward: dq, dk, dv from q, k, v, o, d_o, lse; delta [B, nh, Lq] is scratch (rowsum(d_o * o)).
+ * No atomics: bit-reproducible.  Two launches for the backward (dQ; dK and dV). */
+typedef struct {
+  int B, nh, hd, Lq, Lk;
+  float scale;
+  const float* q;   long long q_ld, q_sb;
+  const float* k;   long long k_ld, k_sb;
+  const float* v;   long long v_ld, v_sb;
+  const unsigned char* key_mask;
+  float* o;         long long o_ld, o_sb;     /* forward: output; backward: input */
+  float* lse;                                  /* [B, nh, Lq]; forward: output; backward: input */
+  const float* d_o; long long do_ld, do_sb;   /* backward only from here */
+  float* dq;        long long dq_ld, dq_sb;
+  float* dk;        long long dk_ld, dk_sb;
+  float* dv;        long long dv_ld, dv_sb;
+  float* delta;
+} itn_attention_desc_t;
+int itn_attention_supported(const itn_attention_desc_t* d);
+int itn_attention_fwd(const itn_attention_desc_t* d, void* stream);
+int itn_attention_bwd(const itn_attention_desc_t* d, void* stream);
+
 /* ------------------------------------------------------------- row-wise --- */
 /* y = LayerNorm(x) * gamma + beta over the last dim `cols` (eps as given;
  * the reference uses nn.LayerNorm default 1e-5: detr_models/transformer.py:139-140,

@@ -37,6 +37,24 @@ class GemmDesc(C.Structure):
     ]
 
 
+class AttentionDesc(C.Structure):
+    _fields_ = [
+        ("B", C.c_int), ("nh", C.c_int), ("hd", C.c_int), ("Lq", C.c_int), ("Lk", C.c_int),
+        ("scale", C.c_float),
+        ("q", C.c_void_p), ("q_ld", C.c_longlong), ("q_sb", C.c_longlong),
+        ("k", C.c_void_p), ("k_ld", C.c_longlong), ("k_sb", C.c_longlong),
+        ("v", C.c_void_p), ("v_ld", C.c_longlong), ("v_sb", C.c_longlong),
+        ("key_mask", C.c_void_p),
+        ("o", C.c_void_p), ("o_ld", C.c_longlong), ("o_sb", C.c_longlong),
+        ("lse", C.c_void_p),
+        ("d_o", C.c_void_p), ("do_ld", C.c_longlong), ("do_sb", C.c_longlong),
+        ("dq", C.c_void_p), ("dq_ld", C.c_longlong), ("dq_sb", C.c_longlong),
+        ("dk", C.c_void_p), ("dk_ld", C.c_longlong), ("dk_sb", C.c_longlong),
+        ("dv", C.c_void_p), ("dv_ld", C.c_longlong), ("dv_sb", C.c_longlong),
+        ("delta", C.c_void_p),
+    ]
+
+
 # name -> (restype, argtypes); mirrors include/interactron_b200.h one to one.
 _P, _LL, _I, _F = C.c_void_p, C.c_longlong, C.c_int, C.c_float
 SIGNATURES = {
@@ -47,6 +65,9 @@ SIGNATURES = {
     "itn_gemm_tf32": (_I, [C.POINTER(GemmDesc), _P]),
     "itn_gemm_tf32_supported": (_I, [C.POINTER(GemmDesc)]),
     "itn_gemm_simt": (_I, [C.POINTER(GemmDesc), _P]),
+    "itn_attention_supported": (_I, [C.POINTER(AttentionDesc)]),
+    "itn_attention_fwd": (_I, [C.POINTER(AttentionDesc), _P]),
+    "itn_attention_bwd": (_I, [C.POINTER(AttentionDesc), _P]),
     "itn_layernorm_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _LL, _I, _I, _LL, _F, _P]),
     "itn_layernorm_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _LL, _I, _I, _LL, _LL, _P]),
     "itn_softmax_fwd": (_I, [_P, _LL, _I, _LL, _F, _P, _LL, _I, _P]),

@@ -1,0 +1,924 @@
+// Fused multi-head attention on tcgen05 tensor cores (sm_100a), forward and backward, in the same
+// error-compensated tf32x3 arithmetic as itn_gemm_tf32.  The score matrix never leaves the SM:
+//   forward   O = softmax(scale * Q K^T + key mask) V            -> O, LSE (one float per row)
+//   backward  dQ, dK, dV from Q, K, V, O, dO, LSE                 (scores recomputed per tile)
+// See include/interactron_b200.h (itn_attention_fwd / itn_attention_bwd) for the contract and the
+// reference call sites (models/gpt.py:43-53, models/detr_models/transformer.py:154-155,219-226).
+//
+// One CTA owns 128 rows (the 128 TMEM lanes) of one (batch, head) and walks the other sequence in
+// blocks of BLK tokens.  Five warps:
+//   warps 0-3  "row threads": thread t owns row t.  They load their row operand straight from global
+//              memory into TENSOR MEMORY (tcgen05.st; value and tf32 residual), so every MMA of the
+//              kernel takes its A operand from TMEM and shared memory only holds the streamed blocks;
+//              they split the streamed blocks into value + residual in place, run the softmax /
+//              dS arithmetic on the accumulators (tcgen05.ld), write probabilities back to TMEM as
+//              the A operand of the next MMA, and keep the output rows in registers.
+//   warp 4     controller: one lane issues the TMA loads of the streamed blocks (two stages) and all
+//              tcgen05.mma (kind::tf32, 128 x N x 8, A from TMEM, B from shared memory).
+// Hand-offs are mbarriers; several CTAs share an SM (TMEM columns permitting) and overlap each
+// other's phases.  No atomics: results are bit-reproducible.
+//
+//   forward        S = Q K^T (B = K block, K-major)          P V      (B = V block, MN-major)
+//   backward dQ    S, dP = dO V^T (B = V, K-major)           dS K     (B = K block, MN-major)
+//   backward dK/dV S^T = K Q^T, dP^T = V dO^T (B = Q, dO K-major)   P^T dO, dS^T Q (B MN-major)
+// The two backward kernels recompute S (and dP) instead of exchanging partial dQ through atomics.
+//
+// tf32x3: kind::tf32 truncates fp32 operands to 10 mantissa bits.  Every product is issued as
+// A*B + A_lo*B + A*B_lo with x_lo = x - trunc_tf32(x) (3 MMAs per k-step), which restores ~fp32
+// accuracy; accumulation chains are short (<= 3*BLK/8 MMAs) and the per-block results are summed
+// in fp32 registers, so the round-toward-zero accumulate of TMEM needs no compensation here.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <mutex>
+
+#include "itn_common.cuh"
+#include "itn_ptx.cuh"
+
+namespace itn {
+namespace attn {
+
+constexpr int kRows = 128;      // rows per CTA = TMEM lanes
+constexpr int kThreads = 160;   // 4 row warps + controller warp
+constexpr int kStages = 2;
+
+struct RowView {                // element (b, i, h, d) at p[b*sb + i*ld + h*HD + d]
+  float* p;
+  long long ld, sb;
+};
+
+struct Params {
+  RowView q, k, v, o, d_o, dq, dk, dv;
+  float* lse;                   // [B*nh, Lq]  log2-sum-exp2 of the scaled scores
+  float* delta;                 // [B*nh, Lq]  rowsum(dO * O)
+  const unsigned char* kmask;   // [B, Lk], 1 = padded key (may be null)
+  int nh, Lq, Lk, tiles;
+  float scale, scale_log2;
+};
+
+// ------------------------------------------------------------------------------- device helpers
+__device__ __forceinline__ void wait_bar(uint64_t* bar, uint32_t parity) {
+  // a protocol error must not hang the GPU: trap after ~1 s of failed waits
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 24)) __trap();
+  }
+}
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__device__ __forceinline__ float tf32_lo(float x) {
+  return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+}
+__device__ __forceinline__ float4 tf32_lo4(const float4 v) {
+  return make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
+}
+
+__device__ __forceinline__ constexpr uint32_t tmem_cols(uint32_t need) {
+  return need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512;
+}
+
+// 32 consecutive floats of a row (zeros for a row outside the sequence), times `mul`
+__device__ __forceinline__ void load32(uint32_t (&v)[32], const float* src, bool valid, float mul) {
+  if (valid) {
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 x = __ldg(s4 + j);
+      v[4 * j + 0] = __float_as_uint(x.x * mul);
+      v[4 * j + 1] = __float_as_uint(x.y * mul);
+      v[4 * j + 2] = __float_as_uint(x.z * mul);
+      v[4 * j + 3] = __float_as_uint(x.w * mul);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = 0u;
+  }
+}
+
+// this thread's row (HD floats at src) -> TMEM: value at columns t_hi.., tf32 residual at t_lo..
+template <int HD>
+__device__ __forceinline__ void put_row(uint32_t t_hi, uint32_t t_lo, const float* src, bool valid, float mul) {
+#pragma unroll
+  for (int c = 0; c < HD / 32; ++c) {
+    uint32_t v[32];
+    load32(v, src + 32 * c, valid, mul);
+    tmem_st_32x32(t_hi + 32 * c, v);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(tf32_lo(__uint_as_float(v[j])));
+    tmem_st_32x32(t_lo + 32 * c, v);
+  }
+}
+
+template <int HD>
+__device__ __forceinline__ void store_row(float* dst, const float (&acc)[HD], float mul) {
+  float4* d4 = reinterpret_cast<float4*>(dst);
+#pragma unroll
+  for (int j = 0; j < HD / 4; ++j)
+    d4[j] = make_float4(acc[4 * j] * mul, acc[4 * j + 1] * mul, acc[4 * j + 2] * mul, acc[4 * j + 3] * mul);
+}
+
+// acc[0..HD) += the HD accumulator columns at taddr (this thread's TMEM lane)
+template <int HD>
+__device__ __forceinline__ void add_cols(float (&acc)[HD], uint32_t taddr) {
+#pragma unroll
+  for (int c = 0; c < HD / 32; ++c) {
+    uint32_t v[32];
+    tmem_ld_32x32(taddr + 32 * c, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[32 * c + j] += __uint_as_float(v[j]);
+  }
+}
+
+// residual tiles of one stage: lo = x - trunc_tf32(x), element-wise on the raw bytes (layout-agnostic,
+// so the TMA swizzle is preserved), written hi_bytes further
+__device__ __forceinline__ void split_lo(uint8_t* stage, int hi_bytes, int tid) {
+  const float4* raw = reinterpret_cast<const float4*>(stage);
+  float4* lo = reinterpret_cast<float4*>(stage + hi_bytes);
+#pragma unroll 4
+  for (int i = tid; i < hi_bytes / 16; i += kRows) lo[i] = tf32_lo4(raw[i]);
+}
+
+// K-major streamed tile ([rows][HD], HD contiguous) = HD/32 TMA boxes of [rows x 32 floats], SWIZZLE_128B.
+template <int HD>
+__device__ __forceinline__ void tma_tile_k(uint8_t* tile, const CUtensorMap* m, uint64_t* bar, int rows,
+                                           int row0, int h, int b) {
+#pragma unroll
+  for (int c = 0; c < HD / 32; ++c) tma_load_4d(tile + c * rows * 128, m, bar, 32 * c, row0, h, b);
+}
+// descriptor of k-step ks (8 floats of HD) of such a tile used as the B operand [N = rows, K = HD]
+__device__ __forceinline__ uint64_t desc_k(uint32_t tile, int rows, int ks) {
+  return umma_smem_desc(tile + (ks >> 2) * rows * 128 + (ks & 3) * 32, 16, 1024, kLayoutSW128);
+}
+// MN-major streamed tile (the same [rows][HD] block used as B operand [N = HD, K = rows]): 4096-byte
+// atoms of 32 (HD) x 32 (rows), SWIZZLE_128B_ATOM_32B, atom (kb, jm) at (kb * HD/32 + jm) * 4096.
+template <int HD, int BLK>
+__device__ __forceinline__ void tma_tile_mn(uint8_t* tile, const CUtensorMap* m, uint64_t* bar, int row0,
+                                            int h, int b) {
+#pragma unroll
+  for (int kb = 0; kb < BLK / 32; ++kb)
+#pragma unroll
+    for (int jm = 0; jm < HD / 32; ++jm)
+      tma_load_4d(tile + (kb * (HD / 32) + jm) * 4096, m, bar, 32 * jm, row0 + 32 * kb, h, b);
+}
+template <int HD>
+__device__ __forceinline__ uint64_t desc_mn(uint32_t tile, int ks) {
+  return umma_smem_desc(tile + (ks >> 2) * (HD / 32) * 4096 + (ks & 3) * 1024, 4096, 512, kLayoutSW128Base32);
+}
+
+// D[128 x N] (+)= A B with A = (a_hi, a_lo) in TMEM and B = (bd, bd + lo_off) in shared memory
+template <int N, bool B_MN>
+__device__ __forceinline__ void mma_x3(uint32_t td, uint32_t a_hi, uint32_t a_lo, uint64_t bd, uint64_t lo_off,
+                                       bool first) {
+  constexpr uint32_t idesc = umma_idesc_tf32(kRows, N, 0, B_MN ? 1 : 0);
+  umma_tf32_ts(td, a_hi, bd, idesc, first ? 0u : 1u);
+  umma_tf32_ts(td, a_lo, bd, idesc, 1u);
+  umma_tf32_ts(td, a_hi, bd + lo_off, idesc, 1u);
+}
+
+__device__ __forceinline__ void workers_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+#define ITN_ATTN_PROLOGUE(NBARS)                                                                     \
+  extern __shared__ uint8_t smem_raw[];                                                              \
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);                       \
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;                                        \
+  const int bh = blockIdx.x / p.tiles, tile = blockIdx.x % p.tiles;                                  \
+  const int b = bh / p.nh, h = bh % p.nh;
+
+// =============================================================================================
+// forward
+// =============================================================================================
+template <int HD, int BLK>
+struct FwdCfg {
+  static constexpr int kTile = BLK * HD * 4;
+  static constexpr int kHi = 2 * kTile;                  // K (K-major) | V (MN-major)
+  static constexpr int kStage = 2 * kHi;                 // + residual tiles
+  static constexpr uint32_t cXH = 0, cXL = HD, cS = 2 * HD, cPL = 2 * HD + BLK, cO = 2 * HD + 2 * BLK;
+  static constexpr uint32_t kCols = tmem_cols(3 * HD + 2 * BLK);
+  static constexpr int kSmem = kStages * kStage + kStages * BLK * 4 + 16 * 8 + 1024;
+};
+
+template <int HD, int BLK, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                const __grid_constant__ Params p) {
+  using Cfg = FwdCfg<HD, BLK>;
+  ITN_ATTN_PROLOGUE()
+  float* kbias = reinterpret_cast<float*>(smem + kStages * Cfg::kStage);        // [stage][BLK]: 0 or -inf
+  uint64_t* kv_full = reinterpret_cast<uint64_t*>(kbias + kStages * BLK);       // [2] TMA landed
+  uint64_t* split_done = kv_full + 2;                                           // [2] residual tiles written
+  uint64_t* s_ready = kv_full + 4;                                              // S accumulator complete
+  uint64_t* p_ready = kv_full + 5;                                              // P in TMEM (4 warps)
+  uint64_t* o_ready = kv_full + 6;                                              // P V complete
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(kv_full + 8);
+  const int n_blk = (p.Lk + BLK - 1) / BLK;
+
+  if (threadIdx.x == 128) {
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&split_done[s], 1);
+    }
+    mbar_init(s_ready, 1);
+    mbar_init(p_ready, 4);
+    mbar_init(o_ready, 1);
+    fence_mbar_init();
+  }
+  if (warp == 4) tmem_alloc<Cfg::kCols>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = *tmem_ptr;
+  pdl_wait();
+  pdl_trigger();
+
+  if (warp == 4) {
+    if (lane == 0) {
+      // ------------------------------------------------------------------ controller
+      auto issue_tma = [&](int j) {
+        const int s = j & 1;
+        uint8_t* st = smem + s * Cfg::kStage;
+        mbar_expect_tx(&kv_full[s], Cfg::kHi);
+        tma_tile_k<HD>(st, &tmK, &kv_full[s], BLK, j * BLK, h, b);
+        tma_tile_mn<HD, BLK>(st + Cfg::kTile, &tmV, &kv_full[s], j * BLK, h, b);
+      };
+      for (int j = 0; j < kStages && j < n_blk; ++j) issue_tma(j);
+      constexpr uint64_t kLo = static_cast<uint64_t>(Cfg::kHi >> 4);
+      for (int j = 0; j < n_blk; ++j) {
+        const int s = j & 1;
+        wait_bar(&split_done[s], (j >> 1) & 1);
+        tc_fence_after();
+        const uint32_t st = smem_u32(smem + s * Cfg::kStage);
+#pragma unroll
+        for (int ks = 0; ks < HD / 8; ++ks)
+          mma_x3<BLK, false>(tbase + Cfg::cS, tbase + Cfg::cXH + 8 * ks, tbase + Cfg::cXL + 8 * ks,
+                             desc_k(st, BLK, ks), kLo, ks == 0);
+        umma_commit(s_ready);
+        wait_bar(p_ready, j & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < BLK / 8; ++ks)
+          mma_x3<HD, true>(tbase + Cfg::cO, tbase + Cfg::cS + 8 * ks, tbase + Cfg::cPL + 8 * ks,
+                           desc_mn<HD>(st + Cfg::kTile, ks), kLo, ks == 0);
+        umma_commit(o_ready);
+        wait_bar(o_ready, j & 1);        // stage s and the S/P columns are free again
+        if (j + kStages < n_blk) issue_tma(j + kStages);
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------------- row threads
+    const int r = threadIdx.x;
+    const int i = tile * kRows + r;
+    const bool valid = i < p.Lq;
+    const uint32_t tw = tbase + (static_cast<uint32_t>(warp * 32) << 16);
+    // scores come out of the tensor core in log2 units: q is pre-multiplied by scale * log2(e)
+    put_row<HD>(tw + Cfg::cXH, tw + Cfg::cXL, p.q.p + b * p.q.sb + (long long)i * p.q.ld + h * HD, valid,
+                p.scale_log2);
+    tmem_st_wait();
+    auto do_split = [&](int j) {
+      const int s = j & 1;
+      wait_bar(&kv_full[s], (j >> 1) & 1);
+      split_lo(smem + s * Cfg::kStage, Cfg::kHi, r);
+      if (r < BLK) {
+        const int key = j * BLK + r;
+        const bool ok = key < p.Lk && !(p.kmask != nullptr && p.kmask[(long long)b * p.Lk + key] != 0);
+        kbias[s * BLK + r] = ok ? 0.0f : -INFINITY;
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      workers_sync();
+      if (r == 0) mbar_arrive(&split_done[s]);
+    };
+    do_split(0);
+    float m_run = -INFINITY, l_run = 0.0f;
+    float oacc[HD];
+#pragma unroll
+    for (int d = 0; d < HD; ++d) oacc[d] = 0.0f;
+    for (int j = 0; j < n_blk; ++j) {
+      const float* kb = kbias + (j & 1) * BLK;
+      wait_bar(s_ready, j & 1);
+      tc_fence_after();
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < BLK / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tw + Cfg::cS + 32 * c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int t = 0; t < 32; ++t) mx = fmaxf(mx, __uint_as_float(v[t]) + kb[32 * c + t]);
+      }
+      const float m_new = fmaxf(m_run, mx);
+      const float m_use = m_new == -INFINITY ? 0.0f : m_new;     // fully masked so far: keep exp2 finite
+      const float alpha = ex2(m_run - m_use);
+      float rs = 0.0f;
+#pragma unroll
+      for (int c = 0; c < BLK / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tw + Cfg::cS + 32 * c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int t = 0; t < 32; ++t) {
+          const float pv = ex2(__uint_as_float(v[t]) + kb[32 * c + t] - m_use);
+          rs += pv;
+          v[t] = __float_as_uint(pv);
+        }
+        tmem_st_32x32(tw + Cfg::cS + 32 * c, v);                // P over S
+#pragma unroll
+        for (int t = 0; t < 32; ++t) v[t] = __float_as_uint(tf32_lo(__uint_as_float(v[t])));
+        tmem_st_32x32(tw + Cfg::cPL + 32 * c, v);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_ready);
+      l_run = l_run * alpha + rs;
+      m_run = m_new;
+      if (j + 1 < n_blk) do_split(j + 1);                         // overlaps the P V product
+#pragma unroll
+      for (int d = 0; d < HD; ++d) oacc[d] *= alpha;
+      wait_bar(o_ready, j & 1);
+      tc_fence_after();
+      add_cols<HD>(oacc, tw + Cfg::cO);
+    }
+    if (valid) {
+      const float inv = l_run > 0.0f ? 1.0f / l_run : 0.0f;
+      store_row<HD>(p.o.p + b * p.o.sb + (long long)i * p.o.ld + h * HD, oacc, inv);
+      p.lse[(long long)bh * p.Lq + i] = l_run > 0.0f ? m_run + log2f(l_run) : INFINITY;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::kCols>(tbase);
+  }
+}
+
+// =============================================================================================
+// backward, dQ (rows = queries, streamed = key blocks); also writes delta = rowsum(dO * O)
+// =============================================================================================
+template <int HD, int BLK>
+struct DqCfg {
+  static constexpr int kTile = BLK * HD * 4;
+  static constexpr int kHi = 3 * kTile;                  // K (K-major) | V (K-major) | K (MN-major)
+  static constexpr int kStage = 2 * kHi;
+  static constexpr uint32_t cQH = 0, cQL = HD, cDH = 2 * HD, cDL = 3 * HD, cS = 4 * HD, cDP = 4 * HD + BLK,
+                            cDQ = 4 * HD + 2 * BLK;
+  static constexpr uint32_t kCols = tmem_cols(5 * HD + 2 * BLK);
+  static constexpr int kSmem = kStages * kStage + kStages * BLK * 4 + 16 * 8 + 1024;
+};
+
+template <int HD, int BLK, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
+attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmKk, const __grid_constant__ CUtensorMap tmVk,
+                   const __grid_constant__ CUtensorMap tmKm, const __grid_constant__ Params p) {
+  using Cfg = DqCfg<HD, BLK>;
+  ITN_ATTN_PROLOGUE()
+  float* kbias = reinterpret_cast<float*>(smem + kStages * Cfg::kStage);
+  uint64_t* kv_full = reinterpret_cast<uint64_t*>(kbias + kStages * BLK);
+  uint64_t* split_done = kv_full + 2;
+  uint64_t* sdp_ready = kv_full + 4;     // S and dP accumulators complete
+  uint64_t* ds_ready = kv_full + 5;      // dS in TMEM (4 warps)
+  uint64_t* dq_ready = kv_full + 6;      // dS K complete
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(kv_full + 8);
+  const int n_blk = (p.Lk + BLK - 1) / BLK;
+
+  if (threadIdx.x == 128) {
+    tma_prefetch_desc(&tmKk);
+    tma_prefetch_desc(&tmVk);
+    tma_prefetch_desc(&tmKm);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&split_done[s], 1);
+    }
+    mbar_init(sdp_ready, 1);
+    mbar_init(ds_ready, 4);
+    mbar_init(dq_ready, 1);
+    fence_mbar_init();
+  }
+  if (warp == 4) tmem_alloc<Cfg::kCols>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = *tmem_ptr;
+  pdl_wait();
+  pdl_trigger();
+
+  if (warp == 4) {
+    if (lane == 0) {
+      auto issue_tma = [&](int j) {
+        const int s = j & 1;
+        uint8_t* st = smem + s * Cfg::kStage;
+        mbar_expect_tx(&kv_full[s], Cfg::kHi);
+        tma_tile_k<HD>(st, &tmKk, &kv_full[s], BLK, j * BLK, h, b);
+        tma_tile_k<HD>(st + Cfg::kTile, &tmVk, &kv_full[s], BLK, j * BLK, h, b);
+        tma_tile_mn<HD, BLK>(st + 2 * Cfg::kTile, &tmKm, &kv_full[s], j * BLK, h, b);
+      };
+      for (int j = 0; j < kStages && j < n_blk; ++j) issue_tma(j);
+      constexpr uint64_t kLo = static_cast<uint64_t>(Cfg::kHi >> 4);
+      for (int j = 0; j < n_blk; ++j) {
+        const int s = j & 1;
+        wait_bar(&split_done[s], (j >> 1) & 1);
+        tc_fence_after();
+        const uint32_t st = smem_u32(smem + s * Cfg::kStage);
+#pragma unroll
+        for (int ks = 0; ks < HD / 8; ++ks)       // S = Q K^T
+          mma_x3<BLK, false>(tbase + Cfg::cS, tbase + Cfg::cQH + 8 * ks, tbase + Cfg::cQL + 8 * ks,
+                             desc_k(st, BLK, ks), kLo, ks == 0);
+#pragma unroll
+        for (int ks = 0; ks < HD / 8; ++ks)       // dP = dO V^T
+          mma_x3<BLK, false>(tbase + Cfg::cDP, tbase + Cfg::cDH + 8 * ks, tbase + Cfg::cDL + 8 * ks,
+                             desc_k(st + Cfg::kTile, BLK, ks), kLo, ks == 0);
+        umma_commit(sdp_ready);
+        wait_bar(ds_ready, j & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < BLK / 8; ++ks)      // dQ_blk = dS K   (dS value over dP, residual over S)
+          mma_x3<HD, true>(tbase + Cfg::cDQ, tbase + Cfg::cDP + 8 * ks, tbase + Cfg::cS + 8 * ks,
+                           desc_mn<HD>(st + 2 * Cfg::kTile, ks), kLo, ks == 0);
+        umma_commit(dq_ready);
+        wait_bar(dq_ready, j & 1);
+        if (j + kStages < n_blk) issue_tma(j + kStages);
+      }
+    }
+  } else {
+    const int r = threadIdx.x;
+    const int i = tile * kRows + r;
+    const bool valid = i < p.Lq;
+    const uint32_t tw = tbase + (static_cast<uint32_t>(warp * 32) << 16);
+    const float* qrow = p.q.p + b * p.q.sb + (long long)i * p.q.ld + h * HD;
+    const float* dorow = p.d_o.p + b * p.d_o.sb + (long long)i * p.d_o.ld + h * HD;
+    put_row<HD>(tw + Cfg::cQH, tw + Cfg::cQL, qrow, valid, p.scale_log2);
+    put_row<HD>(tw + Cfg::cDH, tw + Cfg::cDL, dorow, valid, 1.0f);
+    float delta = 0.0f, lse2 = INFINITY;
+    if (valid) {
+      const float4* a4 = reinterpret_cast<const float4*>(dorow);
+      const float4* o4 = reinterpret_cast<const float4*>(p.o.p + b * p.o.sb + (long long)i * p.o.ld + h * HD);
+#pragma unroll
+      for (int j = 0; j < HD / 4; ++j) {
+        const float4 x = __ldg(a4 + j), y = __ldg(o4 + j);
+        delta = fmaf(x.x, y.x, delta);
+        delta = fmaf(x.y, y.y, delta);
+        delta = fmaf(x.z, y.z, delta);
+        delta = fmaf(x.w, y.w, delta);
+      }
+      lse2 = p.lse[(long long)bh * p.Lq + i];
+      p.delta[(long long)bh * p.Lq + i] = delta;
+    }
+    tmem_st_wait();
+    auto do_split = [&](int j) {
+      const int s = j & 1;
+      wait_bar(&kv_full[s], (j >> 1) & 1);
+      split_lo(smem + s * Cfg::kStage, Cfg::kHi, r);
+      if (r < BLK) {
+        const int key = j * BLK + r;
+        const bool ok = key < p.Lk && !(p.kmask != nullptr && p.kmask[(long long)b * p.Lk + key] != 0);
+        kbias[s * BLK + r] = ok ? 0.0f : -INFINITY;
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      workers_sync();
+      if (r == 0) mbar_arrive(&split_done[s]);
+    };
+    do_split(0);
+    float dqacc[HD];
+#pragma unroll
+    for (int d = 0; d < HD; ++d) dqacc[d] = 0.0f;
+    for (int j = 0; j < n_blk; ++j) {
+      const float* kb = kbias + (j & 1) * BLK;
+      wait_bar(sdp_ready, j & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < BLK / 32; ++c) {
+        uint32_t sv[32], dp[32];
+        tmem_ld_32x32(tw + Cfg::cS + 32 * c, sv);
+        tmem_ld_32x32(tw + Cfg::cDP + 32 * c, dp);
+        tmem_ld_wait();
+#pragma unroll
+        for (int t = 0; t < 32; ++t) {
+          const float pv = ex2(__uint_as_float(sv[t]) + kb[32 * c + t] - lse2);
+          const float ds = pv * (__uint_as_float(dp[t]) - delta) * p.scale;
+          dp[t] = __float_as_uint(ds);
+          sv[t] = __float_as_uint(tf32_lo(ds));
+        }
+        tmem_st_32x32(tw + Cfg::cDP + 32 * c, dp);
+        tmem_st_32x32(tw + Cfg::cS + 32 * c, sv);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ds_ready);
+      if (j + 1 < n_blk) do_split(j + 1);
+      wait_bar(dq_ready, j & 1);
+      tc_fence_after();
+      add_cols<HD>(dqacc, tw + Cfg::cDQ);
+    }
+    if (valid) store_row<HD>(p.dq.p + b * p.dq.sb + (long long)i * p.dq.ld + h * HD, dqacc, 1.0f);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::kCols>(tbase);
+  }
+}
+
+// =============================================================================================
+// backward, dK / dV (rows = keys, streamed = query blocks)
+// =============================================================================================
+template <int HD, int BLK>
+struct DkvCfg {
+  static constexpr int kTile = BLK * HD * 4;
+  static constexpr int kHi = 4 * kTile;                  // Q (K-major) | dO (K-major) | Q (MN-major) | dO (MN-major)
+  static constexpr int kStage = 2 * kHi;
+  static constexpr uint32_t cKH = 0, cKL = HD, cVH = 2 * HD, cVL = 3 * HD, cST = 4 * HD, cPL = 4 * HD + BLK,
+                            cDPT = 4 * HD + 2 * BLK, cDSL = 4 * HD + 3 * BLK, cDV = 4 * HD + 4 * BLK,
+                            cDK = 5 * HD + 4 * BLK;
+  static constexpr uint32_t kCols = tmem_cols(6 * HD + 4 * BLK);
+  static_assert(6 * HD + 4 * BLK <= 512, "tensor memory has 512 columns");
+  static constexpr int kSmem = kStages * kStage + 2 * kStages * BLK * 4 + 16 * 8 + 1024;
+};
+
+template <int HD, int BLK, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
+attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQk, const __grid_constant__ CUtensorMap tmDOk,
+                    const __grid_constant__ CUtensorMap tmQm, const __grid_constant__ CUtensorMap tmDOm,
+                    const __grid_constant__ Params p) {
+  using Cfg = DkvCfg<HD, BLK>;
+  ITN_ATTN_PROLOGUE()
+  float* lse_s = reinterpret_cast<float*>(smem + kStages * Cfg::kStage);     // [stage][BLK]
+  float* dl_s = lse_s + kStages * BLK;                                       // [stage][BLK]
+  uint64_t* q_full = reinterpret_cast<uint64_t*>(dl_s + kStages * BLK);
+  uint64_t* split_done = q_full + 2;
+  uint64_t* st_ready = q_full + 4;       // S^T and dP^T accumulators complete
+  uint64_t* p_ready = q_full + 5;        // P^T, dS^T in TMEM (4 warps)
+  uint64_t* dkv_ready = q_full + 6;      // P^T dO and dS^T Q complete
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(q_full + 8);
+  const int n_blk = (p.Lq + BLK - 1) / BLK;
+
+  if (threadIdx.x == 128) {
+    tma_prefetch_desc(&tmQk);
+    tma_prefetch_desc(&tmDOk);
+    tma_prefetch_desc(&tmQm);
+    tma_prefetch_desc(&tmDOm);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&q_full[s], 1);
+      mbar_init(&split_done[s], 1);
+    }
+    mbar_init(st_ready, 1);
+    mbar_init(p_ready, 4);
+    mbar_init(dkv_ready, 1);
+    fence_mbar_init();
+  }
+  if (warp == 4) tmem_alloc<Cfg::kCols>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = *tmem_ptr;
+  pdl_wait();
+  pdl_trigger();
+
+  if (warp == 4) {
+    if (lane == 0) {
+      auto issue_tma = [&](int j) {
+        const int s = j & 1;
+        uint8_t* st = smem + s * Cfg::kStage;
+        mbar_expect_tx(&q_full[s], Cfg::kHi);
+        tma_tile_k<HD>(st, &tmQk, &q_full[s], BLK, j * BLK, h, b);
+        tma_tile_k<HD>(st + Cfg::kTile, &tmDOk, &q_full[s], BLK, j * BLK, h, b);
+        tma_tile_mn<HD, BLK>(st + 2 * Cfg::kTile, &tmQm, &q_full[s], j * BLK, h, b);
+        tma_tile_mn<HD, BLK>(st + 3 * Cfg::kTile, &tmDOm, &q_full[s], j * BLK, h, b);
+      };
+      for (int j = 0; j < kStages && j < n_blk; ++j) issue_tma(j);
+      constexpr uint64_t kLo = static_cast<uint64_t>(Cfg::kHi >> 4);
+      for (int j = 0; j < n_blk; ++j) {
+        const int s = j & 1;
+        wait_bar(&split_done[s], (j >> 1) & 1);
+        tc_fence_after();
+        const uint32_t st = smem_u32(smem + s * Cfg::kStage);
+#pragma unroll
+        for (int ks = 0; ks < HD / 8; ++ks)       // S^T = K Q^T
+          mma_x3<BLK, false>(tbase + Cfg::cST, tbase + Cfg::cKH + 8 * ks, tbase + Cfg::cKL + 8 * ks,
+                             desc_k(st, BLK, ks), kLo, ks == 0);
+#pragma unroll
+        for (int ks = 0; ks < HD / 8; ++ks)       // dP^T = V dO^T
+          mma_x3<BLK, false>(tbase + Cfg::cDPT, tbase + Cfg::cVH + 8 * ks, tbase + Cfg::cVL + 8 * ks,
+                             desc_k(st + Cfg::kTile, BLK, ks), kLo, ks == 0);
+        umma_commit(st_ready);
+        wait_bar(p_ready, j & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < BLK / 8; ++ks)      // dV_blk = P^T dO
+          mma_x3<HD, true>(tbase + Cfg::cDV, tbase + Cfg::cST + 8 * ks, tbase + Cfg::cPL + 8 * ks,
+                           desc_mn<HD>(st + 3 * Cfg::kTile, ks), kLo, ks == 0);
+#pragma unroll
+        for (int ks = 0; ks < BLK / 8; ++ks)      // dK_blk = dS^T Q
+          mma_x3<HD, true>(tbase + Cfg::cDK, tbase + Cfg::cDPT + 8 * ks, tbase + Cfg::cDSL + 8 * ks,
+                           desc_mn<HD>(st + 2 * Cfg::kTile, ks), kLo, ks == 0);
+        umma_commit(dkv_ready);
+        wait_bar(dkv_ready, j & 1);
+        if (j + kStages < n_blk) issue_tma(j + kStages);
+      }
+    }
+  } else {
+    const int r = threadIdx.x;
+    const int key = tile * kRows + r;
+    const bool inside = key < p.Lk;
+    const bool kvalid = inside && !(p.kmask != nullptr && p.kmask[(long long)b * p.Lk + key] != 0);
+    const uint32_t tw = tbase + (static_cast<uint32_t>(warp * 32) << 16);
+    put_row<HD>(tw + Cfg::cKH, tw + Cfg::cKL, p.k.p + b * p.k.sb + (long long)key * p.k.ld + h * HD, inside,
+                p.scale_log2);
+    put_row<HD>(tw + Cfg::cVH, tw + Cfg::cVL, p.v.p + b * p.v.sb + (long long)key * p.v.ld + h * HD, inside, 1.0f);
+    tmem_st_wait();
+    auto do_split = [&](int j) {
+      const int s = j & 1;
+      wait_bar(&q_full[s], (j >> 1) & 1);
+      split_lo(smem + s * Cfg::kStage, Cfg::kHi, r);
+      if (r < BLK) {
+        const int qi = j * BLK + r;
+        const bool ok = qi < p.Lq;
+        lse_s[s * BLK + r] = ok ? p.lse[(long long)bh * p.Lq + qi] : INFINITY;
+        dl_s[s * BLK + r] = ok ? p.delta[(long long)bh * p.Lq + qi] : 0.0f;
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      workers_sync();
+      if (r == 0) mbar_arrive(&split_done[s]);
+    };
+    do_split(0);
+    float dvacc[HD], dkacc[HD];
+#pragma unroll
+    for (int d = 0; d < HD; ++d) dvacc[d] = dkacc[d] = 0.0f;
+    for (int j = 0; j < n_blk; ++j) {
+      const float* ls = lse_s + (j & 1) * BLK;
+      const float* dl = dl_s + (j & 1) * BLK;
+      wait_bar(st_ready, j & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < BLK / 32; ++c) {
+        uint32_t sv[32], dp[32];
+        tmem_ld_32x32(tw + Cfg::cST + 32 * c, sv);
+        tmem_ld_32x32(tw + Cfg::cDPT + 32 * c, dp);
+        tmem_ld_wait();
+#pragma unroll
+        for (int t = 0; t < 32; ++t) {
+          const float pv = kvalid ? ex2(__uint_as_float(sv[t]) - ls[32 * c + t]) : 0.0f;
+          const float ds = pv * (__uint_as_float(dp[t]) - dl[32 * c + t]) * p.scale;
+          sv[t] = __float_as_uint(pv);
+          dp[t] = __float_as_uint(ds);
+        }
+        tmem_st_32x32(tw + Cfg::cST + 32 * c, sv);              // P^T over S^T
+        tmem_st_32x32(tw + Cfg::cDPT + 32 * c, dp);             // dS^T over dP^T
+#pragma unroll
+        for (int t = 0; t < 32; ++t) {
+          sv[t] = __float_as_uint(tf32_lo(__uint_as_float(sv[t])));
+          dp[t] = __float_as_uint(tf32_lo(__uint_as_float(dp[t])));
+        }
+        tmem_st_32x32(tw + Cfg::cPL + 32 * c, sv);
+        tmem_st_32x32(tw + Cfg::cDSL + 32 * c, dp);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_ready);
+      if (j + 1 < n_blk) do_split(j + 1);
+      wait_bar(dkv_ready, j & 1);
+      tc_fence_after();
+      add_cols<HD>(dvacc, tw + Cfg::cDV);
+      add_cols<HD>(dkacc, tw + Cfg::cDK);
+    }
+    if (inside) {
+      store_row<HD>(p.dv.p + b * p.dv.sb + (long long)key * p.dv.ld + h * HD, dvacc, 1.0f);
+      store_row<HD>(p.dk.p + b * p.dk.sb + (long long)key * p.dk.ld + h * HD, dkacc, 1.0f);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::kCols>(tbase);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host
+using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                              const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                              CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeFn encode_fn() {
+  static EncodeFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeFn>(f);
+  });
+  return fn;
+}
+
+// [B, L, nh, hd] view (hd contiguous, row stride ld, batch stride sb, head stride hd) as a 4-D map
+// {hd, L, nh, B}.  K-major use: boxes of 32 floats x box_rows rows (SWIZZLE_128B); MN-major use:
+// 32 x 32 atoms (SWIZZLE_128B_ATOM_32B).  Rows beyond L are zero-filled.
+static int make_map(CUtensorMap* tm, const float* ptr, long long ld, long long sb, int L, int nh, int hd, int B,
+                    int box_rows, bool mn) {
+  EncodeFn enc = encode_fn();
+  if (!enc) return set_error(ITN_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t gdim[4] = {(cuuint64_t)hd, (cuuint64_t)L, (cuuint64_t)nh, (cuuint64_t)B};
+  const cuuint64_t bstride = B > 1 ? (cuuint64_t)sb * 4 : (cuuint64_t)ld * 4 * (cuuint64_t)L;
+  cuuint64_t gstr[3] = {(cuuint64_t)ld * 4, (cuuint64_t)hd * 4, bstride};
+  cuuint32_t box[4] = {32u, mn ? 32u : (cuuint32_t)box_rows, 1u, 1u};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(ptr), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   mn ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(ITN_ERR_CUDA, "attention: cuTensorMapEncodeTiled failed (%d): dims %llu %llu %llu %llu "
+                     "strides %llu %llu %llu", (int)r, gdim[0], gdim[1], gdim[2], gdim[3], gstr[0], gstr[1], gstr[2]);
+  return ITN_OK;
+}
+
+static bool view_ok(const float* ptr, long long ld, long long sb, int B) {
+  return ptr != nullptr && (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && ld > 0 && (ld & 3) == 0 &&
+         (B <= 1 || (sb > 0 && (sb & 3) == 0));
+}
+
+static int validate(const itn_attention_desc_t* d, bool bwd) {
+  ITN_REQUIRE(d != nullptr, "attention: null descriptor");
+  ITN_REQUIRE(d->B > 0 && d->nh > 0 && d->Lq > 0 && d->Lk > 0, "attention: B, nh, Lq, Lk must be positive");
+  if (d->hd != 32 && d->hd != 64)
+    return set_error(ITN_ERR_UNSUPPORTED, "attention: head dim %d (32 and 64 are built)", d->hd);
+  ITN_REQUIRE((long long)d->B * d->nh * ((d->Lq > d->Lk ? d->Lq : d->Lk) / kRows + 1) < 0x7fffffffLL,
+              "attention: grid too large");
+  ITN_REQUIRE(d->lse != nullptr, "attention: lse is required");
+  const bool ok = view_ok(d->q, d->q_ld, d->q_sb, d->B) && view_ok(d->k, d->k_ld, d->k_sb, d->B) &&
+                  view_ok(d->v, d->v_ld, d->v_sb, d->B) && view_ok(d->o, d->o_ld, d->o_sb, d->B);
+  if (!ok)
+    return set_error(ITN_ERR_UNSUPPORTED, "attention: q/k/v/o must be 16-byte aligned with row/batch strides "
+                     "multiples of 4 elements");
+  if (bwd) {
+    ITN_REQUIRE(d->delta != nullptr, "attention_bwd: delta scratch is required");
+    const bool okb = view_ok(d->d_o, d->do_ld, d->do_sb, d->B) && view_ok(d->dq, d->dq_ld, d->dq_sb, d->B) &&
+                     view_ok(d->dk, d->dk_ld, d->dk_sb, d->B) && view_ok(d->dv, d->dv_ld, d->dv_sb, d->B);
+    if (!okb)
+      return set_error(ITN_ERR_UNSUPPORTED, "attention_bwd: dO/dq/dk/dv must be 16-byte aligned with row/batch "
+                       "strides multiples of 4 elements");
+  }
+  return ITN_OK;
+}
+
+static Params make_params(const itn_attention_desc_t* d, int rows) {
+  Params p;
+  auto rv = [](const float* ptr, long long ld, long long sb) {
+    RowView v;
+    v.p = const_cast<float*>(ptr);
+    v.ld = ld;
+    v.sb = sb;
+    return v;
+  };
+  p.q = rv(d->q, d->q_ld, d->q_sb);
+  p.k = rv(d->k, d->k_ld, d->k_sb);
+  p.v = rv(d->v, d->v_ld, d->v_sb);
+  p.o = rv(d->o, d->o_ld, d->o_sb);
+  p.d_o = rv(d->d_o, d->do_ld, d->do_sb);
+  p.dq = rv(d->dq, d->dq_ld, d->dq_sb);
+  p.dk = rv(d->dk, d->dk_ld, d->dk_sb);
+  p.dv = rv(d->dv, d->dv_ld, d->dv_sb);
+  p.lse = d->lse;
+  p.delta = d->delta;
+  p.kmask = d->key_mask;
+  p.nh = d->nh;
+  p.Lq = d->Lq;
+  p.Lk = d->Lk;
+  p.tiles = (rows + kRows - 1) / kRows;
+  p.scale = d->scale;
+  p.scale_log2 = d->scale * 1.4426950408889634f;
+  return p;
+}
+
+template <class K>
+static int set_smem(K kern, int bytes, bool* done) {
+  if (*done) return ITN_OK;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess)
+    return set_error(ITN_ERR_CUDA, "attention: cudaFuncSetAttribute(%d B): %s", bytes, cudaGetErrorString(e));
+  *done = true;
+  return ITN_OK;
+}
+
+template <int HD, int BLK, int MINB>
+static int launch_fwd(const itn_attention_desc_t* d, cudaStream_t s) {
+  using Cfg = FwdCfg<HD, BLK>;
+  Params p = make_params(d, d->Lq);
+  CUtensorMap tmK, tmV;
+  int rc = make_map(&tmK, d->k, d->k_ld, d->k_sb, d->Lk, d->nh, HD, d->B, BLK, false);
+  if (rc) return rc;
+  rc = make_map(&tmV, d->v, d->v_ld, d->v_sb, d->Lk, d->nh, HD, d->B, BLK, true);
+  if (rc) return rc;
+  auto kern = attn_fwd_kernel<HD, BLK, MINB>;
+  static bool attr = false;
+  rc = set_smem(kern, Cfg::kSmem, &attr);
+  if (rc) return rc;
+  launch(kern, d->B * d->nh * p.tiles, kThreads, Cfg::kSmem, s, tmK, tmV, p);
+  return check_launch("attn_fwd_kernel");
+}
+
+template <int HD, int BLK, int MINB>
+static int launch_dq(const itn_attention_desc_t* d, cudaStream_t s) {
+  using Cfg = DqCfg<HD, BLK>;
+  Params p = make_params(d, d->Lq);
+  CUtensorMap tmKk, tmVk, tmKm;
+  int rc = make_map(&tmKk, d->k, d->k_ld, d->k_sb, d->Lk, d->nh, HD, d->B, BLK, false);
+  if (rc) return rc;
+  rc = make_map(&tmVk, d->v, d->v_ld, d->v_sb, d->Lk, d->nh, HD, d->B, BLK, false);
+  if (rc) return rc;
+  rc = make_map(&tmKm, d->k, d->k_ld, d->k_sb, d->Lk, d->nh, HD, d->B, BLK, true);
+  if (rc) return rc;
+  auto kern = attn_bwd_dq_kernel<HD, BLK, MINB>;
+  static bool attr = false;
+  rc = set_smem(kern, Cfg::kSmem, &attr);
+  if (rc) return rc;
+  launch(kern, d->B * d->nh * p.tiles, kThreads, Cfg::kSmem, s, tmKk, tmVk, tmKm, p);
+  return check_launch("attn_bwd_dq_kernel");
+}
+
+template <int HD, int BLK, int MINB>
+static int launch_dkv(const itn_attention_desc_t* d, cudaStream_t s) {
+  using Cfg = DkvCfg<HD, BLK>;
+  Params p = make_params(d, d->Lk);
+  CUtensorMap tmQk, tmDOk, tmQm, tmDOm;
+  int rc = make_map(&tmQk, d->q, d->q_ld, d->q_sb, d->Lq, d->nh, HD, d->B, BLK, false);
+  if (rc) return rc;
+  rc = make_map(&tmDOk, d->d_o, d->do_ld, d->do_sb, d->Lq, d->nh, HD, d->B, BLK, false);
+  if (rc) return rc;
+  rc = make_map(&tmQm, d->q, d->q_ld, d->q_sb, d->Lq, d->nh, HD, d->B, BLK, true);
+  if (rc) return rc;
+  rc = make_map(&tmDOm, d->d_o, d->do_ld, d->do_sb, d->Lq, d->nh, HD, d->B, BLK, true);
+  if (rc) return rc;
+  auto kern = attn_bwd_dkv_kernel<HD, BLK, MINB>;
+  static bool attr = false;
+  rc = set_smem(kern, Cfg::kSmem, &attr);
+  if (rc) return rc;
+  launch(kern, d->B * d->nh * p.tiles, kThreads, Cfg::kSmem, s, tmQk, tmDOk, tmQm, tmDOm, p);
+  return check_launch("attn_bwd_dkv_kernel");
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+}  // namespace attn
+}  // namespace itn
+
+extern "C" int itn_attention_supported(const itn_attention_desc_t* d) {
+  using namespace itn::attn;
+  if (!d || d->B <= 0 || d->nh <= 0 || d->Lq <= 0 || d->Lk <= 0 || (d->hd != 32 && d->hd != 64)) return 0;
+  return view_ok(d->q, d->q_ld, d->q_sb, d->B) && view_ok(d->k, d->k_ld, d->k_sb, d->B) &&
+         view_ok(d->v, d->v_ld, d->v_sb, d->B) && view_ok(d->o, d->o_ld, d->o_sb, d->B);
+}
+
+extern "C" int itn_attention_fwd(const itn_attention_desc_t* d, void* stream) {
+  using namespace itn::attn;
+  int rc = validate(d, false);
+  if (rc) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // ITN_ATTN_FWD_BLK: streamed block width (tuning); defaults keep two CTAs per SM (<= 256 TMEM columns)
+  const int blk = env_int("ITN_ATTN_FWD_BLK", 0);
+  if (d->hd == 32) {
+    if (blk == 32) return launch_fwd<32, 32, 2>(d, s);
+    if (blk == 128) return launch_fwd<32, 128, 1>(d, s);
+    return launch_fwd<32, 64, 2>(d, s);
+  }
+  if (blk == 64) return launch_fwd<64, 64, 1>(d, s);
+  return launch_fwd<64, 32, 2>(d, s);
+}
+
+extern "C" int itn_attention_bwd(const itn_attention_desc_t* d, void* stream) {
+  using namespace itn::attn;
+  int rc = validate(d, true);
+  if (rc) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int bq = env_int("ITN_ATTN_DQ_BLK", 0), bkv = env_int("ITN_ATTN_DKV_BLK", 0);
+  // dQ first: it also writes delta = rowsum(dO * O), which the dK/dV kernel reads
+  if (d->hd == 32) {
+    if (bq == 64) rc = launch_dq<32, 64, 1>(d, s);
+    else if (bq == 128) rc = launch_dq<32, 128, 1>(d, s);
+    else rc = launch_dq<32, 32, 2>(d, s);
+    if (rc) return rc;
+    if (bkv == 32) return launch_dkv<32, 32, 1>(d, s);
+    return launch_dkv<32, 64, 1>(d, s);
+  }
+  if (bq == 32) rc = launch_dq<64, 32, 1>(d, s);
+  else rc = launch_dq<64, 64, 1>(d, s);
+  if (rc) return rc;
+  return launch_dkv<64, 32, 1>(d, s);
+}

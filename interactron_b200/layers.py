@@ -24,7 +24,28 @@ def lin(ops, x, W, b=None, **kw):
 # --------------------------------------------------------------------------- attention core
 def attention_fwd(ops, q, k, v, B, Lq, Lk, nh, hd, scale, kmask):
     """softmax(scale * q k^T + mask) v per (batch, head).
-    q [B,Lq,nh*hd], k/v [B,Lk,nh*hd] (strided views ok) -> o [B,Lq,nh*hd] (TF32-clean), P."""
+    q [B,Lq,nh*hd], k/v [B,Lk,nh*hd] (strided views ok) -> o [B,Lq,nh*hd], ctx (what attention_bwd needs).
+    On the B200 backend this is ONE fused tcgen05 kernel (itn_attention_fwd: the score matrix stays in
+    tensor memory, ctx = (o, log-sum-exp)); backends without it (the float64 CPU simulation, the
+    dual-number pass of the meta-training step) run the unfused chain and keep the probabilities."""
+    fused = getattr(ops, "attention_supported", None)
+    if fused is not None and fused(q, k, v, nh):
+        o, lse = ops.attention_fwd(q, k, v, nh, scale, kmask)
+        return o, FusedCtx(o, lse, kmask)
+    return _attention_fwd_unfused(ops, q, k, v, B, Lq, Lk, nh, hd, scale, kmask)
+
+
+class FusedCtx:
+    """Saved state of a fused attention forward: output and base-2 log-sum-exp per row."""
+
+    __slots__ = ("o", "lse", "kmask")
+
+    def __init__(self, o, lse, kmask):
+        self.o, self.lse, self.kmask = o, lse, kmask
+
+
+def _attention_fwd_unfused(ops, q, k, v, B, Lq, Lk, nh, hd, scale, kmask):
+    """QK^T GEMM -> softmax -> PV GEMM with the probabilities P [B,nh,Lq,pad4(Lk)] materialised."""
     P = ops.empty(B, nh, Lq, pad4(Lk))                           # row stride padded to 16 bytes for TMA
     o = ops.empty(B, Lq, nh * hd)
     for b0, b1 in _l2_chunks(ops, B, nh * Lq * pad4(Lk) * 4, 1):
@@ -55,7 +76,11 @@ def _l2_chunks(ops, B, bytes_per_batch, live):
 
 
 def attention_bwd(ops, dO, q, k, v, P, B, Lq, Lk, nh, hd, scale, dq, dk, dv):
-    """dO [B,Lq,nh*hd] (TF32-clean).  Writes TF32-clean dq/dk/dv into the given [B,L,nh*hd] views."""
+    """dO [B,Lq,nh*hd] (TF32-clean).  Writes TF32-clean dq/dk/dv into the given [B,L,nh*hd] views.
+    P is the ctx attention_fwd returned: FusedCtx (scores recomputed on chip) or the probabilities."""
+    if isinstance(P, FusedCtx):
+        ops.attention_bwd(dO, q, k, v, P.o, P.lse, nh, scale, P.kmask, dq, dk, dv)
+        return
     chunks = _l2_chunks(ops, B, nh * Lq * pad4(Lk) * 4, 2)
     # one chunk: dP for the whole batch; several: ONE chunk-sized dP buffer reused (it stays in L2)
     dP_all = ops.empty(chunks[0][1] - chunks[0][0], nh, Lq, pad4(Lk))

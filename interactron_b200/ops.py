@@ -58,6 +58,10 @@ class CudaOps:
         self.n_presplit = 0
         # L2 budget (MiB) for the score tensors of one attention chunk (layers._l2_chunks); 0 = one pass
         self.attn_l2_mb = int(os.environ.get("ITN_ATTN_L2_MB", "0"))
+        # fused tcgen05 attention (itn_attention_fwd/bwd); ITN_FUSED_ATTN=0 keeps the unfused
+        # QK^T -> softmax -> PV chain through HBM (cross-check / dual-number path)
+        self.fused_attention = os.environ.get("ITN_FUSED_ATTN", "1") != "0"
+        self.n_attn = 0
 
     # ------------------------------------------------------------ plumbing
     def _stream(self):
@@ -229,6 +233,70 @@ class CudaOps:
             self.n_simt += 1
         del keep_a, keep_b
         return ret
+
+    # ------------------------------------------------------------ fused attention
+    @staticmethod
+    def _heads_view(d, prefix, t, nh, hd):
+        """[B, L, nh*hd] view with unit inner stride -> (ptr, row stride, batch stride) fields of the descriptor."""
+        if t.dim() != 3 or t.shape[2] != nh * hd or t.stride(2) != 1:
+            raise ValueError(f"attention operand must be [B, L, {nh * hd}] with unit inner stride, got "
+                             f"{tuple(t.shape)} strides {t.stride()}")
+        setattr(d, prefix, t.data_ptr())
+        setattr(d, prefix + "_ld" if prefix != "d_o" else "do_ld", t.stride(1))
+        setattr(d, prefix + "_sb" if prefix != "d_o" else "do_sb", t.stride(0) if t.shape[0] > 1 else 0)
+
+    def _attention_desc(self, q, k, v, o, lse, nh, scale, kmask):
+        B, Lq, D = q.shape
+        Lk = k.shape[1]
+        hd = D // nh
+        d = _lib.AttentionDesc()
+        d.B, d.nh, d.hd, d.Lq, d.Lk, d.scale = B, nh, hd, Lq, Lk, float(scale)
+        for name, t in (("q", q), ("k", k), ("v", v), ("o", o)):
+            self._heads_view(d, name, t, nh, hd)
+        if k.shape != v.shape or k.shape[0] != B or o.shape != q.shape:
+            raise ValueError("attention: shape mismatch between q/k/v/o")
+        if kmask is not None:
+            assert kmask.dtype == torch.uint8 and kmask.is_contiguous() and tuple(kmask.shape) == (B, Lk)
+            d.key_mask = kmask.data_ptr()
+        assert lse.is_contiguous() and lse.numel() == B * nh * Lq
+        d.lse = lse.data_ptr()
+        return d
+
+    def attention_supported(self, q, k, v, nh):
+        """True when the fused tcgen05 attention kernels take these views (hd 32/64, 16-byte aligned rows)."""
+        if self.force_simt or not self.fused_attention or self._clean:
+            return False
+        hd = q.shape[-1] // nh
+        if hd not in (32, 64):
+            return False
+        for t in (q, k, v):
+            if t.dim() != 3 or t.stride(2) != 1 or t.data_ptr() % 16 or t.stride(1) % 4 or \
+                    (t.shape[0] > 1 and t.stride(0) % 4):
+                return False
+        return True
+
+    def attention_fwd(self, q, k, v, nh, scale, kmask=None):
+        """o = softmax(scale q k^T + key mask) v per (batch, head), scores kept on chip.
+        q [B,Lq,nh*hd], k/v [B,Lk,nh*hd] (strided views ok) -> (o [B,Lq,nh*hd], lse [B,nh,Lq] base-2 log-sum-exp)."""
+        B, Lq, D = q.shape
+        o = self.empty(B, Lq, D)
+        lse = self.empty(B, nh, Lq)
+        d = self._attention_desc(q, k, v, o, lse, nh, scale, kmask)
+        _lib.check(self.lib.itn_attention_fwd(C.byref(d), self._stream()))
+        self.n_attn += 1
+        return o, lse
+
+    def attention_bwd(self, dO, q, k, v, o, lse, nh, scale, kmask, dq, dk, dv):
+        """Writes dq/dk/dv (views like q/k/v) given dO [B,Lq,nh*hd]; scores are recomputed from lse."""
+        B, Lq, D = q.shape
+        d = self._attention_desc(q, k, v, o, lse, nh, scale, kmask)
+        hd = D // nh
+        for name, t in (("d_o", dO), ("dq", dq), ("dk", dk), ("dv", dv)):
+            self._heads_view(d, name, t, nh, hd)
+        delta = self.empty(B, nh, Lq)
+        d.delta = delta.data_ptr()
+        _lib.check(self.lib.itn_attention_bwd(C.byref(d), self._stream()))
+        self.n_attn += 2
 
     # split-K: weight-gradient GEMMs at few episodes per step (dW[256,256] = dy^T[256,3610] x[3610,256]) are
     # 4-32 output tiles with a 57-113 k-block chain each: 3-20 % of the 148 SMs busy for 40-130 us.  The K
