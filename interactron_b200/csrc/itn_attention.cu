@@ -54,6 +54,8 @@ struct Params {
   const unsigned char* kmask;   // [B, Lk], 1 = padded key (may be null)
   int nh, Lq, Lk, tiles;
   float scale, scale_log2;
+  int dbg;                      // timing experiments (ITN_ATTN_DBG): 1 = K-major descriptors for the MN-major products (wrong results),
+                                // 2 = no row arithmetic, 4 = no second-phase MMAs, 8 = no first-phase MMAs, 16 = no residual split
 };
 
 // ------------------------------------------------------------------------------- device helpers
@@ -255,6 +257,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__
         wait_bar(&split_done[s], (j >> 1) & 1);
         tc_fence_after();
         const uint32_t st = smem_u32(smem + s * Cfg::kStage);
+        if (!(p.dbg & 8))
 #pragma unroll
         for (int ks = 0; ks < HD / 8; ++ks)
           mma_x3<BLK, false>(tbase + Cfg::cS, tbase + Cfg::cXH + 8 * ks, tbase + Cfg::cXL + 8 * ks,
@@ -262,10 +265,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__
         umma_commit(s_ready);
         wait_bar(p_ready, j & 1);
         tc_fence_after();
+        if (!(p.dbg & 4))
 #pragma unroll
         for (int ks = 0; ks < BLK / 8; ++ks)
-          mma_x3<HD, true>(tbase + Cfg::cO, tbase + Cfg::cS + 8 * ks, tbase + Cfg::cPL + 8 * ks,
-                           desc_mn<HD>(st + Cfg::kTile, ks), kLo, ks == 0);
+          { if (p.dbg & 1) mma_x3<HD, false>(tbase + Cfg::cO, tbase + Cfg::cS + 8 * ks, tbase + Cfg::cPL + 8 * ks, desc_k(st + Cfg::kTile, HD, ks), kLo, ks == 0);
+          else mma_x3<HD, true>(tbase + Cfg::cO, tbase + Cfg::cS + 8 * ks, tbase + Cfg::cPL + 8 * ks, desc_mn<HD>(st + Cfg::kTile, ks), kLo, ks == 0); }
         umma_commit(o_ready);
         wait_bar(o_ready, j & 1);        // stage s and the S/P columns are free again
         if (j + kStages < n_blk) issue_tma(j + kStages);
@@ -284,7 +288,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__
     auto do_split = [&](int j) {
       const int s = j & 1;
       wait_bar(&kv_full[s], (j >> 1) & 1);
-      split_lo(smem + s * Cfg::kStage, Cfg::kHi, r);
+      if (!(p.dbg & 16)) split_lo(smem + s * Cfg::kStage, Cfg::kHi, r);
       if (r < BLK) {
         const int key = j * BLK + r;
         const bool ok = key < p.Lk && !(p.kmask != nullptr && p.kmask[(long long)b * p.Lk + key] != 0);
@@ -305,6 +309,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__
       wait_bar(s_ready, j & 1);
       tc_fence_after();
       float mx = -INFINITY;
+      if (!(p.dbg & 2))
 #pragma unroll
       for (int c = 0; c < BLK / 32; ++c) {
         uint32_t v[32];
@@ -317,6 +322,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__
       const float m_use = m_new == -INFINITY ? 0.0f : m_new;     // fully masked so far: keep exp2 finite
       const float alpha = ex2(m_run - m_use);
       float rs = 0.0f;
+      if (!(p.dbg & 2))
 #pragma unroll
       for (int c = 0; c < BLK / 32; ++c) {
         uint32_t v[32];
@@ -427,10 +433,12 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmKk, const __grid_consta
         wait_bar(&split_done[s], (j >> 1) & 1);
         tc_fence_after();
         const uint32_t st = smem_u32(smem + s * Cfg::kStage);
+        if (!(p.dbg & 8))
 #pragma unroll
         for (int ks = 0; ks < HD / 8; ++ks)       // S = Q K^T
           mma_x3<BLK, false>(tbase + Cfg::cS, tbase + Cfg::cQH + 8 * ks, tbase + Cfg::cQL + 8 * ks,
                              desc_k(st, BLK, ks), kLo, ks == 0);
+        if (!(p.dbg & 8))
 #pragma unroll
         for (int ks = 0; ks < HD / 8; ++ks)       // dP = dO V^T
           mma_x3<BLK, false>(tbase + Cfg::cDP, tbase + Cfg::cDH + 8 * ks, tbase + Cfg::cDL + 8 * ks,
@@ -438,10 +446,11 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmKk, const __grid_consta
         umma_commit(sdp_ready);
         wait_bar(ds_ready, j & 1);
         tc_fence_after();
+        if (!(p.dbg & 4))
 #pragma unroll
         for (int ks = 0; ks < BLK / 8; ++ks)      // dQ_blk = dS K   (dS value over dP, residual over S)
-          mma_x3<HD, true>(tbase + Cfg::cDQ, tbase + Cfg::cDP + 8 * ks, tbase + Cfg::cS + 8 * ks,
-                           desc_mn<HD>(st + 2 * Cfg::kTile, ks), kLo, ks == 0);
+          { if (p.dbg & 1) mma_x3<HD, false>(tbase + Cfg::cDQ, tbase + Cfg::cDP + 8 * ks, tbase + Cfg::cS + 8 * ks, desc_k(st + 2 * Cfg::kTile, HD, ks), kLo, ks == 0);
+          else mma_x3<HD, true>(tbase + Cfg::cDQ, tbase + Cfg::cDP + 8 * ks, tbase + Cfg::cS + 8 * ks, desc_mn<HD>(st + 2 * Cfg::kTile, ks), kLo, ks == 0); }
         umma_commit(dq_ready);
         wait_bar(dq_ready, j & 1);
         if (j + kStages < n_blk) issue_tma(j + kStages);
@@ -475,7 +484,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmKk, const __grid_consta
     auto do_split = [&](int j) {
       const int s = j & 1;
       wait_bar(&kv_full[s], (j >> 1) & 1);
-      split_lo(smem + s * Cfg::kStage, Cfg::kHi, r);
+      if (!(p.dbg & 16)) split_lo(smem + s * Cfg::kStage, Cfg::kHi, r);
       if (r < BLK) {
         const int key = j * BLK + r;
         const bool ok = key < p.Lk && !(p.kmask != nullptr && p.kmask[(long long)b * p.Lk + key] != 0);
@@ -494,6 +503,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmKk, const __grid_consta
       const float* kb = kbias + (j & 1) * BLK;
       wait_bar(sdp_ready, j & 1);
       tc_fence_after();
+      if (!(p.dbg & 2))
 #pragma unroll
       for (int c = 0; c < BLK / 32; ++c) {
         uint32_t sv[32], dp[32];
@@ -602,10 +612,12 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQk, const __grid_const
         wait_bar(&split_done[s], (j >> 1) & 1);
         tc_fence_after();
         const uint32_t st = smem_u32(smem + s * Cfg::kStage);
+        if (!(p.dbg & 8))
 #pragma unroll
         for (int ks = 0; ks < HD / 8; ++ks)       // S^T = K Q^T
           mma_x3<BLK, false>(tbase + Cfg::cST, tbase + Cfg::cKH + 8 * ks, tbase + Cfg::cKL + 8 * ks,
                              desc_k(st, BLK, ks), kLo, ks == 0);
+        if (!(p.dbg & 8))
 #pragma unroll
         for (int ks = 0; ks < HD / 8; ++ks)       // dP^T = V dO^T
           mma_x3<BLK, false>(tbase + Cfg::cDPT, tbase + Cfg::cVH + 8 * ks, tbase + Cfg::cVL + 8 * ks,
@@ -613,14 +625,16 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQk, const __grid_const
         umma_commit(st_ready);
         wait_bar(p_ready, j & 1);
         tc_fence_after();
+        if (!(p.dbg & 4)) {
 #pragma unroll
         for (int ks = 0; ks < BLK / 8; ++ks)      // dV_blk = P^T dO
-          mma_x3<HD, true>(tbase + Cfg::cDV, tbase + Cfg::cST + 8 * ks, tbase + Cfg::cPL + 8 * ks,
-                           desc_mn<HD>(st + 3 * Cfg::kTile, ks), kLo, ks == 0);
+          { if (p.dbg & 1) mma_x3<HD, false>(tbase + Cfg::cDV, tbase + Cfg::cST + 8 * ks, tbase + Cfg::cPL + 8 * ks, desc_k(st + 3 * Cfg::kTile, HD, ks), kLo, ks == 0);
+          else mma_x3<HD, true>(tbase + Cfg::cDV, tbase + Cfg::cST + 8 * ks, tbase + Cfg::cPL + 8 * ks, desc_mn<HD>(st + 3 * Cfg::kTile, ks), kLo, ks == 0); }
 #pragma unroll
         for (int ks = 0; ks < BLK / 8; ++ks)      // dK_blk = dS^T Q
-          mma_x3<HD, true>(tbase + Cfg::cDK, tbase + Cfg::cDPT + 8 * ks, tbase + Cfg::cDSL + 8 * ks,
-                           desc_mn<HD>(st + 2 * Cfg::kTile, ks), kLo, ks == 0);
+          { if (p.dbg & 1) mma_x3<HD, false>(tbase + Cfg::cDK, tbase + Cfg::cDPT + 8 * ks, tbase + Cfg::cDSL + 8 * ks, desc_k(st + 2 * Cfg::kTile, HD, ks), kLo, ks == 0);
+          else mma_x3<HD, true>(tbase + Cfg::cDK, tbase + Cfg::cDPT + 8 * ks, tbase + Cfg::cDSL + 8 * ks, desc_mn<HD>(st + 2 * Cfg::kTile, ks), kLo, ks == 0); }
+        }
         umma_commit(dkv_ready);
         wait_bar(dkv_ready, j & 1);
         if (j + kStages < n_blk) issue_tma(j + kStages);
@@ -639,7 +653,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQk, const __grid_const
     auto do_split = [&](int j) {
       const int s = j & 1;
       wait_bar(&q_full[s], (j >> 1) & 1);
-      split_lo(smem + s * Cfg::kStage, Cfg::kHi, r);
+      if (!(p.dbg & 16)) split_lo(smem + s * Cfg::kStage, Cfg::kHi, r);
       if (r < BLK) {
         const int qi = j * BLK + r;
         const bool ok = qi < p.Lq;
@@ -660,6 +674,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQk, const __grid_const
       const float* dl = dl_s + (j & 1) * BLK;
       wait_bar(st_ready, j & 1);
       tc_fence_after();
+      if (!(p.dbg & 2))
 #pragma unroll
       for (int c = 0; c < BLK / 32; ++c) {
         uint32_t sv[32], dp[32];
@@ -701,6 +716,382 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQk, const __grid_const
   tc_fence_before();
   __syncthreads();
   if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::kCols>(tbase);
+  }
+}
+
+// =============================================================================================
+// Software-pipelined variant (all three passes), 8 warps:
+//   warps 0-3  row threads (arithmetic only)      warp 4  TMA producer (NS stages ahead)
+//   warp 5     TMEM owner + MMA issuer             warps 6-7  residual splitters (+ key-bias / LSE vectors)
+// The first-phase accumulators (S, dP, ...) are DOUBLE-BUFFERED in tensor memory: the issuer puts the
+// products of block j+1 on the tensor pipe before the row threads have finished block j, and the
+// second-phase results (P V, dS K, ...) are read back one block late (double-buffered as well), so
+// neither side waits for the other in steady state.  tcgen05.mma of one thread execute in issue order,
+// which is what makes S(j+2) overwriting the probabilities of block j safe: the product that reads
+// them was issued first.
+//   MODE 0 forward           rows = queries   streamed: K (K-major), V (MN-major)
+//   MODE 1 backward dQ       rows = queries   streamed: K, V (K-major), K (MN-major)
+//   MODE 2 backward dK/dV    rows = keys      streamed: Q, dO (K-major), Q, dO (MN-major)
+// =============================================================================================
+enum { M_FWD = 0, M_DQ = 1, M_DKV = 2 };
+constexpr int kPipeThreads = 256;
+
+template <int MODE, int HD, int BLK>
+struct PipeCfg {
+  static constexpr int kNK = MODE == M_FWD ? 1 : 2;        // K-major streamed tiles
+  static constexpr int kNM = MODE == M_DKV ? 2 : 1;        // MN-major streamed tiles
+  static constexpr int kNX = MODE == M_FWD ? 1 : 2;        // row operands resident in TMEM (value + residual)
+  static constexpr int kNO = MODE == M_DKV ? 2 : 1;        // outputs
+  static constexpr int kSetCols = (MODE == M_DKV ? 4 : 2) * BLK;   // one first-phase buffer set
+  static constexpr int kTile = BLK * HD * 4;
+  static constexpr int kHi = (kNK + kNM) * kTile;
+  static constexpr int kStage = 2 * kHi;
+  static constexpr int kMaxNS = (227 * 1024 - 4096) / kStage;
+  static constexpr int kNS = kMaxNS > 4 ? 4 : kMaxNS;
+  static_assert(kNS >= 2, "need at least two stages");
+  static constexpr uint32_t cX = 0;                        // operand x: value at cX + 2*HD*x, residual HD further
+  static constexpr uint32_t cSet = 2 * HD * kNX;           // buffer set i at cSet + i*kSetCols
+  static constexpr uint32_t cOut = cSet + 2 * kSetCols;    // output buffer i at cOut + i*kNO*HD
+  static constexpr uint32_t kNeed = cOut + 2 * kNO * HD;
+  static_assert(kNeed <= 512, "tensor memory has 512 columns");
+  static constexpr uint32_t kCols = tmem_cols(kNeed);
+  static constexpr int kVecBytes = kNS * BLK * 4 * 2;      // two float vectors per stage
+  static constexpr int kBars = 3 * kNS + 9;
+  static constexpr int kSmem = kNS * kStage + kVecBytes + kBars * 8 + 16 + 1024;
+  static_assert(kSmem <= 227 * 1024, "exceeds shared memory per CTA");
+};
+
+template <int MODE, int HD, int BLK, int MINB>
+__global__ void __launch_bounds__(kPipeThreads, MINB)
+attn_pipe_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
+                 const __grid_constant__ CUtensorMap tm2, const __grid_constant__ CUtensorMap tm3,
+                 const __grid_constant__ Params p) {
+  using Cfg = PipeCfg<MODE, HD, BLK>;
+  constexpr int NS = Cfg::kNS;
+  ITN_ATTN_PROLOGUE()
+  float* vec0 = reinterpret_cast<float*>(smem + NS * Cfg::kStage);   // [NS][BLK]  key bias (fwd, dQ) / LSE (dK,dV)
+  float* vec1 = vec0 + NS * BLK;                                     // [NS][BLK]  delta (dK,dV)
+  uint64_t* full = reinterpret_cast<uint64_t*>(vec1 + NS * BLK);     // [NS] TMA landed
+  uint64_t* split = full + NS;                                       // [NS] residual tiles + vectors written (2 warps)
+  uint64_t* free_ = split + NS;                                      // [NS] second-phase MMAs of the block retired
+  uint64_t* p1_ready = free_ + NS;                                   // [2] first-phase accumulators complete
+  uint64_t* a2_ready = p1_ready + 2;                                 // [2] second-phase A operands in TMEM (4 warps)
+  uint64_t* out_ready = a2_ready + 2;                                // [2] second-phase products complete
+  uint64_t* out_free = out_ready + 2;                                // [2] row threads have read them (4 warps)
+  uint64_t* x_ready = out_free + 2;                                  // row operands in TMEM (4 warps)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(x_ready + 1);
+  const int n_blk = ((MODE == M_DKV ? p.Lq : p.Lk) + BLK - 1) / BLK;
+
+  if (threadIdx.x == 128) {
+    tma_prefetch_desc(&tm0);
+    tma_prefetch_desc(&tm1);
+    if (MODE != M_FWD) tma_prefetch_desc(&tm2);
+    if (MODE == M_DKV) tma_prefetch_desc(&tm3);
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&split[s], 2);
+      mbar_init(&free_[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&p1_ready[i], 1);
+      mbar_init(&a2_ready[i], 4);
+      mbar_init(&out_ready[i], 1);
+      mbar_init(&out_free[i], 4);
+    }
+    mbar_init(x_ready, 4);
+    fence_mbar_init();
+  }
+  if (warp == 5) tmem_alloc<Cfg::kCols>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = *tmem_ptr;
+  pdl_wait();
+  pdl_trigger();
+
+  if (warp == 4) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      for (int j = 0; j < n_blk; ++j) {
+        const int s = j % NS, k = j / NS;
+        if (k > 0) wait_bar(&free_[s], (k - 1) & 1);
+        uint8_t* st = smem + s * Cfg::kStage;
+        mbar_expect_tx(&full[s], Cfg::kHi);
+        tma_tile_k<HD>(st, &tm0, &full[s], BLK, j * BLK, h, b);
+        if (MODE == M_FWD) {
+          tma_tile_mn<HD, BLK>(st + Cfg::kTile, &tm1, &full[s], j * BLK, h, b);
+        } else {
+          tma_tile_k<HD>(st + Cfg::kTile, &tm1, &full[s], BLK, j * BLK, h, b);
+          tma_tile_mn<HD, BLK>(st + 2 * Cfg::kTile, &tm2, &full[s], j * BLK, h, b);
+          if (MODE == M_DKV) tma_tile_mn<HD, BLK>(st + 3 * Cfg::kTile, &tm3, &full[s], j * BLK, h, b);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint64_t kLo = static_cast<uint64_t>(Cfg::kHi >> 4);
+      auto phase2 = [&](int i) {
+        const int set = i & 1;
+        wait_bar(&a2_ready[set], (i >> 1) & 1);
+        if (i >= 2) wait_bar(&out_free[set], ((i >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t st = smem_u32(smem + (i % NS) * Cfg::kStage);
+        const uint32_t ts = tbase + Cfg::cSet + set * Cfg::kSetCols;
+        const uint32_t to = tbase + Cfg::cOut + set * Cfg::kNO * HD;
+        if (!(p.dbg & 4)) {
+          if (MODE == M_FWD) {
+#pragma unroll
+            for (int ks = 0; ks < BLK / 8; ++ks)      // O_blk = P V
+              mma_x3<HD, true>(to, ts + 8 * ks, ts + BLK + 8 * ks, desc_mn<HD>(st + Cfg::kTile, ks), kLo, ks == 0);
+          } else if (MODE == M_DQ) {
+#pragma unroll
+            for (int ks = 0; ks < BLK / 8; ++ks)      // dQ_blk = dS K   (dS value over dP, residual over S)
+              mma_x3<HD, true>(to, ts + BLK + 8 * ks, ts + 8 * ks, desc_mn<HD>(st + 2 * Cfg::kTile, ks), kLo, ks == 0);
+          } else {
+#pragma unroll
+            for (int ks = 0; ks < BLK / 8; ++ks)      // dV_blk = P^T dO
+              mma_x3<HD, true>(to, ts + 8 * ks, ts + BLK + 8 * ks, desc_mn<HD>(st + 3 * Cfg::kTile, ks), kLo, ks == 0);
+#pragma unroll
+            for (int ks = 0; ks < BLK / 8; ++ks)      // dK_blk = dS^T Q
+              mma_x3<HD, true>(to + HD, ts + 2 * BLK + 8 * ks, ts + 3 * BLK + 8 * ks,
+                               desc_mn<HD>(st + 2 * Cfg::kTile, ks), kLo, ks == 0);
+          }
+        }
+        umma_commit(&out_ready[set]);
+        umma_commit(&free_[i % NS]);
+      };
+      wait_bar(x_ready, 0);
+      for (int j = 0; j < n_blk; ++j) {
+        const int s = j % NS;
+        wait_bar(&split[s], (j / NS) & 1);
+        tc_fence_after();
+        const uint32_t st = smem_u32(smem + s * Cfg::kStage);
+        const uint32_t ts = tbase + Cfg::cSet + (j & 1) * Cfg::kSetCols;
+        const uint32_t x0 = tbase + Cfg::cX, x1 = tbase + Cfg::cX + 2 * HD;
+        if (!(p.dbg & 8)) {
+#pragma unroll
+          for (int ks = 0; ks < HD / 8; ++ks)         // S = Q K^T   |   S^T = K Q^T
+            mma_x3<BLK, false>(ts, x0 + 8 * ks, x0 + HD + 8 * ks, desc_k(st, BLK, ks), kLo, ks == 0);
+          if (MODE != M_FWD) {
+            const uint32_t td = ts + (MODE == M_DQ ? BLK : 2 * BLK);
+#pragma unroll
+            for (int ks = 0; ks < HD / 8; ++ks)       // dP = dO V^T  |  dP^T = V dO^T
+              mma_x3<BLK, false>(td, x1 + 8 * ks, x1 + HD + 8 * ks, desc_k(st + Cfg::kTile, BLK, ks), kLo, ks == 0);
+          }
+        }
+        umma_commit(&p1_ready[j & 1]);
+        if (j >= 1) phase2(j - 1);
+      }
+      phase2(n_blk - 1);
+    }
+  } else if (warp >= 6) {
+    // ------------------------------------------------------------------ residual splitters
+    const int tid = threadIdx.x - 192;      // 0..63
+    for (int j = 0; j < n_blk; ++j) {
+      const int s = j % NS;
+      wait_bar(&full[s], (j / NS) & 1);
+      if (!(p.dbg & 16)) {
+        const float4* raw = reinterpret_cast<const float4*>(smem + s * Cfg::kStage);
+        float4* lo = reinterpret_cast<float4*>(smem + s * Cfg::kStage + Cfg::kHi);
+#pragma unroll 4
+        for (int i = tid; i < Cfg::kHi / 16; i += 64) lo[i] = tf32_lo4(raw[i]);
+      }
+      for (int t = tid; t < BLK; t += 64) {
+        const int idx = j * BLK + t;
+        if (MODE == M_DKV) {
+          const bool ok = idx < p.Lq;
+          vec0[s * BLK + t] = ok ? p.lse[(long long)bh * p.Lq + idx] : INFINITY;
+          vec1[s * BLK + t] = ok ? p.delta[(long long)bh * p.Lq + idx] : 0.0f;
+        } else {
+          const bool ok = idx < p.Lk && !(p.kmask != nullptr && p.kmask[(long long)b * p.Lk + idx] != 0);
+          vec0[s * BLK + t] = ok ? 0.0f : -INFINITY;
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&split[s]);
+    }
+  } else {
+    // ------------------------------------------------------------------ row threads
+    const int r = threadIdx.x;
+    const int i = tile * kRows + r;
+    const uint32_t tw = tbase + (static_cast<uint32_t>(warp * 32) << 16);
+    const uint32_t x0 = tw + Cfg::cX, x1 = tw + Cfg::cX + 2 * HD;
+    bool valid;
+    float lse2 = INFINITY, delta = 0.0f;
+    if (MODE == M_DKV) {
+      const bool inside = i < p.Lk;
+      valid = inside && !(p.kmask != nullptr && p.kmask[(long long)b * p.Lk + i] != 0);
+      put_row<HD>(x0, x0 + HD, p.k.p + b * p.k.sb + (long long)i * p.k.ld + h * HD, inside, p.scale_log2);
+      put_row<HD>(x1, x1 + HD, p.v.p + b * p.v.sb + (long long)i * p.v.ld + h * HD, inside, 1.0f);
+    } else {
+      valid = i < p.Lq;
+      put_row<HD>(x0, x0 + HD, p.q.p + b * p.q.sb + (long long)i * p.q.ld + h * HD, valid, p.scale_log2);
+      if (MODE == M_DQ) {
+        const float* dorow = p.d_o.p + b * p.d_o.sb + (long long)i * p.d_o.ld + h * HD;
+        put_row<HD>(x1, x1 + HD, dorow, valid, 1.0f);
+        if (valid) {
+          const float4* a4 = reinterpret_cast<const float4*>(dorow);
+          const float4* o4 = reinterpret_cast<const float4*>(p.o.p + b * p.o.sb + (long long)i * p.o.ld + h * HD);
+#pragma unroll
+          for (int t = 0; t < HD / 4; ++t) {
+            const float4 x = __ldg(a4 + t), y = __ldg(o4 + t);
+            delta = fmaf(x.x, y.x, delta);
+            delta = fmaf(x.y, y.y, delta);
+            delta = fmaf(x.z, y.z, delta);
+            delta = fmaf(x.w, y.w, delta);
+          }
+          lse2 = p.lse[(long long)bh * p.Lq + i];
+          p.delta[(long long)bh * p.Lq + i] = delta;
+        }
+      }
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(x_ready);
+
+    float acc0[HD];
+    float acc1[MODE == M_DKV ? HD : 1];
+#pragma unroll
+    for (int d = 0; d < HD; ++d) acc0[d] = 0.0f;
+    if (MODE == M_DKV) {
+#pragma unroll
+      for (int d = 0; d < (MODE == M_DKV ? HD : 1); ++d) acc1[d] = 0.0f;
+    }
+    float m_run = -INFINITY, l_run = 0.0f, alpha_pend = 1.0f;
+
+    auto consume = [&](int blk) {            // read back the second-phase products of block `blk`
+      const int set = blk & 1;
+      wait_bar(&out_ready[set], (blk >> 1) & 1);
+      tc_fence_after();
+      const uint32_t to = tw + Cfg::cOut + set * Cfg::kNO * HD;
+      if (MODE == M_FWD) {
+#pragma unroll
+        for (int d = 0; d < HD; ++d) acc0[d] *= alpha_pend;
+      }
+      add_cols<HD>(acc0, to);
+      if (MODE == M_DKV) add_cols<(MODE == M_DKV ? HD : 1)>(acc1, to + HD);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&out_free[set]);
+    };
+
+    for (int j = 0; j < n_blk; ++j) {
+      const int s = j % NS;
+      const float* v0 = vec0 + s * BLK;
+      const float* v1 = vec1 + s * BLK;
+      wait_bar(&split[s], (j / NS) & 1);        // vectors of this stage visible (long complete)
+      wait_bar(&p1_ready[j & 1], (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t ts = tw + Cfg::cSet + (j & 1) * Cfg::kSetCols;
+      float alpha = 1.0f;
+      if (MODE == M_FWD) {
+        float mx = -INFINITY;
+        if (!(p.dbg & 2))
+#pragma unroll
+        for (int c = 0; c < BLK / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(ts + 32 * c, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int t = 0; t < 32; ++t) mx = fmaxf(mx, __uint_as_float(v[t]) + v0[32 * c + t]);
+        }
+        const float m_new = fmaxf(m_run, mx);
+        const float m_use = m_new == -INFINITY ? 0.0f : m_new;     // fully masked so far: keep exp2 finite
+        alpha = ex2(m_run - m_use);
+        float rs = 0.0f;
+        if (!(p.dbg & 2))
+#pragma unroll
+        for (int c = 0; c < BLK / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(ts + 32 * c, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int t = 0; t < 32; ++t) {
+            const float pv = ex2(__uint_as_float(v[t]) + v0[32 * c + t] - m_use);
+            rs += pv;
+            v[t] = __float_as_uint(pv);
+          }
+          tmem_st_32x32(ts + 32 * c, v);                          // P over S
+#pragma unroll
+          for (int t = 0; t < 32; ++t) v[t] = __float_as_uint(tf32_lo(__uint_as_float(v[t])));
+          tmem_st_32x32(ts + BLK + 32 * c, v);
+        }
+        l_run = l_run * alpha + rs;
+        m_run = m_new;
+      } else if (MODE == M_DQ) {
+        if (!(p.dbg & 2))
+#pragma unroll
+        for (int c = 0; c < BLK / 32; ++c) {
+          uint32_t sv[32], dp[32];
+          tmem_ld_32x32(ts + 32 * c, sv);
+          tmem_ld_32x32(ts + BLK + 32 * c, dp);
+          tmem_ld_wait();
+#pragma unroll
+          for (int t = 0; t < 32; ++t) {
+            const float pv = ex2(__uint_as_float(sv[t]) + v0[32 * c + t] - lse2);
+            const float ds = pv * (__uint_as_float(dp[t]) - delta) * p.scale;
+            dp[t] = __float_as_uint(ds);
+            sv[t] = __float_as_uint(tf32_lo(ds));
+          }
+          tmem_st_32x32(ts + BLK + 32 * c, dp);
+          tmem_st_32x32(ts + 32 * c, sv);
+        }
+      } else {
+        if (!(p.dbg & 2))
+#pragma unroll
+        for (int c = 0; c < BLK / 32; ++c) {
+          uint32_t sv[32], dp[32];
+          tmem_ld_32x32(ts + 32 * c, sv);
+          tmem_ld_32x32(ts + 2 * BLK + 32 * c, dp);
+          tmem_ld_wait();
+#pragma unroll
+          for (int t = 0; t < 32; ++t) {
+            const float pv = valid ? ex2(__uint_as_float(sv[t]) - v0[32 * c + t]) : 0.0f;
+            const float ds = pv * (__uint_as_float(dp[t]) - v1[32 * c + t]) * p.scale;
+            sv[t] = __float_as_uint(pv);
+            dp[t] = __float_as_uint(ds);
+          }
+          tmem_st_32x32(ts + 32 * c, sv);                         // P^T over S^T
+          tmem_st_32x32(ts + 2 * BLK + 32 * c, dp);               // dS^T over dP^T
+#pragma unroll
+          for (int t = 0; t < 32; ++t) {
+            sv[t] = __float_as_uint(tf32_lo(__uint_as_float(sv[t])));
+            dp[t] = __float_as_uint(tf32_lo(__uint_as_float(dp[t])));
+          }
+          tmem_st_32x32(ts + BLK + 32 * c, sv);
+          tmem_st_32x32(ts + 3 * BLK + 32 * c, dp);
+        }
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&a2_ready[j & 1]);
+      if (j >= 1) consume(j - 1);
+      alpha_pend = alpha;
+    }
+    consume(n_blk - 1);
+
+    if (MODE == M_FWD) {
+      if (valid) {
+        const float inv = l_run > 0.0f ? 1.0f / l_run : 0.0f;
+        store_row<HD>(p.o.p + b * p.o.sb + (long long)i * p.o.ld + h * HD, acc0, inv);
+        p.lse[(long long)bh * p.Lq + i] = l_run > 0.0f ? m_run + log2f(l_run) : INFINITY;
+      }
+    } else if (MODE == M_DQ) {
+      if (valid) store_row<HD>(p.dq.p + b * p.dq.sb + (long long)i * p.dq.ld + h * HD, acc0, 1.0f);
+    } else if (i < p.Lk) {
+      store_row<HD>(p.dv.p + b * p.dv.sb + (long long)i * p.dv.ld + h * HD, acc0, 1.0f);
+      store_row<(MODE == M_DKV ? HD : 1)>(p.dk.p + b * p.dk.sb + (long long)i * p.dk.ld + h * HD, acc1, 1.0f);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
     tc_fence_after();
     tmem_dealloc<Cfg::kCols>(tbase);
   }
@@ -801,6 +1192,7 @@ static Params make_params(const itn_attention_desc_t* d, int rows) {
   p.tiles = (rows + kRows - 1) / kRows;
   p.scale = d->scale;
   p.scale_log2 = d->scale * 1.4426950408889634f;
+  p.dbg = getenv("ITN_ATTN_DBG") ? atoi(getenv("ITN_ATTN_DBG")) : 0;
   return p;
 }
 
@@ -871,6 +1263,37 @@ static int launch_dkv(const itn_attention_desc_t* d, cudaStream_t s) {
   return check_launch("attn_bwd_dkv_kernel");
 }
 
+template <int MODE, int HD, int BLK, int MINB = 1>
+static int launch_pipe(const itn_attention_desc_t* d, cudaStream_t s) {
+  using Cfg = PipeCfg<MODE, HD, BLK>;
+  Params p = make_params(d, MODE == M_DKV ? d->Lk : d->Lq);
+  CUtensorMap tm[4];
+  int rc;
+  if (MODE == M_DKV) {
+    rc = make_map(&tm[0], d->q, d->q_ld, d->q_sb, d->Lq, d->nh, HD, d->B, BLK, false);
+    if (!rc) rc = make_map(&tm[1], d->d_o, d->do_ld, d->do_sb, d->Lq, d->nh, HD, d->B, BLK, false);
+    if (!rc) rc = make_map(&tm[2], d->q, d->q_ld, d->q_sb, d->Lq, d->nh, HD, d->B, BLK, true);
+    if (!rc) rc = make_map(&tm[3], d->d_o, d->do_ld, d->do_sb, d->Lq, d->nh, HD, d->B, BLK, true);
+  } else if (MODE == M_DQ) {
+    rc = make_map(&tm[0], d->k, d->k_ld, d->k_sb, d->Lk, d->nh, HD, d->B, BLK, false);
+    if (!rc) rc = make_map(&tm[1], d->v, d->v_ld, d->v_sb, d->Lk, d->nh, HD, d->B, BLK, false);
+    if (!rc) rc = make_map(&tm[2], d->k, d->k_ld, d->k_sb, d->Lk, d->nh, HD, d->B, BLK, true);
+    tm[3] = tm[0];
+  } else {
+    rc = make_map(&tm[0], d->k, d->k_ld, d->k_sb, d->Lk, d->nh, HD, d->B, BLK, false);
+    if (!rc) rc = make_map(&tm[1], d->v, d->v_ld, d->v_sb, d->Lk, d->nh, HD, d->B, BLK, true);
+    tm[2] = tm[0];
+    tm[3] = tm[0];
+  }
+  if (rc) return rc;
+  auto kern = attn_pipe_kernel<MODE, HD, BLK, MINB>;
+  static bool attr = false;
+  rc = set_smem(kern, Cfg::kSmem, &attr);
+  if (rc) return rc;
+  launch(kern, d->B * d->nh * p.tiles, kPipeThreads, Cfg::kSmem, s, tm[0], tm[1], tm[2], tm[3], p);
+  return check_launch("attn_pipe_kernel");
+}
+
 static int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return v ? atoi(v) : dflt;
@@ -886,13 +1309,25 @@ extern "C" int itn_attention_supported(const itn_attention_desc_t* d) {
          view_ok(d->v, d->v_ld, d->v_sb, d->B) && view_ok(d->o, d->o_ld, d->o_sb, d->B);
 }
 
+// Which kernel runs a pass: measured on B200 (tools/attn_sweep.py, profiles/README.md).  "seq": the
+// sequential-phase kernels (two CTAs per SM overlap each other); "pipe": the software-pipelined kernel.
+// ITN_ATTN_FWD / ITN_ATTN_DQ / ITN_ATTN_DKV = seq | pipe and ITN_ATTN_*_BLK override for experiments.
+static bool want_pipe(const char* name, bool dflt) {
+  const char* v = getenv(name);
+  if (!v) return dflt;
+  return v[0] == 'p';
+}
+
 extern "C" int itn_attention_fwd(const itn_attention_desc_t* d, void* stream) {
   using namespace itn::attn;
   int rc = validate(d, false);
   if (rc) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  // ITN_ATTN_FWD_BLK: streamed block width (tuning); defaults keep two CTAs per SM (<= 256 TMEM columns)
   const int blk = env_int("ITN_ATTN_FWD_BLK", 0);
+  if (want_pipe("ITN_ATTN_FWD", d->hd == 64)) {
+    if (d->hd == 32) return blk == 32 ? launch_pipe<M_FWD, 32, 32, 2>(d, s) : launch_pipe<M_FWD, 32, 64>(d, s);
+    return blk == 32 ? launch_pipe<M_FWD, 64, 32>(d, s) : launch_pipe<M_FWD, 64, 64>(d, s);
+  }
   if (d->hd == 32) {
     if (blk == 32) return launch_fwd<32, 32, 2>(d, s);
     if (blk == 128) return launch_fwd<32, 128, 1>(d, s);
@@ -908,17 +1343,27 @@ extern "C" int itn_attention_bwd(const itn_attention_desc_t* d, void* stream) {
   if (rc) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int bq = env_int("ITN_ATTN_DQ_BLK", 0), bkv = env_int("ITN_ATTN_DKV_BLK", 0);
+  const int only = env_int("ITN_ATTN_BWD_ONLY", 0);   // timing experiments: 1 = dQ kernel only, 2 = dK/dV kernel only
   // dQ first: it also writes delta = rowsum(dO * O), which the dK/dV kernel reads
-  if (d->hd == 32) {
-    if (bq == 64) rc = launch_dq<32, 64, 1>(d, s);
-    else if (bq == 128) rc = launch_dq<32, 128, 1>(d, s);
-    else rc = launch_dq<32, 32, 2>(d, s);
+  if (only != 2) {
+    if (want_pipe("ITN_ATTN_DQ", false)) {
+      if (d->hd == 32) rc = bq == 32 ? launch_pipe<M_DQ, 32, 32>(d, s) : launch_pipe<M_DQ, 32, 64>(d, s);
+      else rc = launch_pipe<M_DQ, 64, 32>(d, s);
+    } else if (d->hd == 32) {
+      if (bq == 64) rc = launch_dq<32, 64, 1>(d, s);
+      else if (bq == 128) rc = launch_dq<32, 128, 1>(d, s);
+      else rc = launch_dq<32, 32, 2>(d, s);
+    } else {
+      if (bq == 32) rc = launch_dq<64, 32, 1>(d, s);
+      else rc = launch_dq<64, 64, 1>(d, s);
+    }
     if (rc) return rc;
+  }
+  if (only == 1) return ITN_OK;
+  if (d->hd == 32) {
+    if (want_pipe("ITN_ATTN_DKV", true)) return launch_pipe<M_DKV, 32, 32>(d, s);
     if (bkv == 32) return launch_dkv<32, 32, 1>(d, s);
     return launch_dkv<32, 64, 1>(d, s);
   }
-  if (bq == 32) rc = launch_dq<64, 32, 1>(d, s);
-  else rc = launch_dq<64, 64, 1>(d, s);
-  if (rc) return rc;
   return launch_dkv<64, 32, 1>(d, s);
 }
