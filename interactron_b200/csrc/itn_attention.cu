@@ -241,39 +241,46 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__
   pdl_trigger();
 
   if (warp == 4) {
-    if (lane == 0) {
-      // ------------------------------------------------------------------ controller
-      auto issue_tma = [&](int j) {
-        const int s = j & 1;
-        uint8_t* st = smem + s * Cfg::kStage;
-        mbar_expect_tx(&kv_full[s], Cfg::kHi);
-        tma_tile_k<HD>(st, &tmK, &kv_full[s], BLK, j * BLK, h, b);
-        tma_tile_mn<HD, BLK>(st + Cfg::kTile, &tmV, &kv_full[s], j * BLK, h, b);
-      };
+    // ------------------------------------------------------------------ controller (converged warp, elect.sync)
+    auto issue_tma = [&](int j) {
+      const int s = j & 1;
+      uint8_t* st = smem + s * Cfg::kStage;
+      mbar_expect_tx(&kv_full[s], Cfg::kHi);
+      tma_tile_k<HD>(st, &tmK, &kv_full[s], BLK, j * BLK, h, b);
+      tma_tile_mn<HD, BLK>(st + Cfg::kTile, &tmV, &kv_full[s], j * BLK, h, b);
+    };
+    if (elect_one())
       for (int j = 0; j < kStages && j < n_blk; ++j) issue_tma(j);
-      constexpr uint64_t kLo = static_cast<uint64_t>(Cfg::kHi >> 4);
-      for (int j = 0; j < n_blk; ++j) {
-        const int s = j & 1;
-        wait_bar(&split_done[s], (j >> 1) & 1);
-        tc_fence_after();
-        const uint32_t st = smem_u32(smem + s * Cfg::kStage);
+    __syncwarp();
+    constexpr uint64_t kLo = static_cast<uint64_t>(Cfg::kHi >> 4);
+    for (int j = 0; j < n_blk; ++j) {
+      const int s = j & 1;
+      wait_bar(&split_done[s], (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t st = smem_u32(smem + s * Cfg::kStage);
+      if (elect_one()) {
         if (!(p.dbg & 8))
 #pragma unroll
         for (int ks = 0; ks < HD / 8; ++ks)
           mma_x3<BLK, false>(tbase + Cfg::cS, tbase + Cfg::cXH + 8 * ks, tbase + Cfg::cXL + 8 * ks,
                              desc_k(st, BLK, ks), kLo, ks == 0);
         umma_commit(s_ready);
-        wait_bar(p_ready, j & 1);
-        tc_fence_after();
+      }
+      __syncwarp();
+      wait_bar(p_ready, j & 1);
+      tc_fence_after();
+      if (elect_one()) {
         if (!(p.dbg & 4))
 #pragma unroll
         for (int ks = 0; ks < BLK / 8; ++ks)
-          { if (p.dbg & 1) mma_x3<HD, false>(tbase + Cfg::cO, tbase + Cfg::cS + 8 * ks, tbase + Cfg::cPL + 8 * ks, desc_k(st + Cfg::kTile, HD, ks), kLo, ks == 0);
-          else mma_x3<HD, true>(tbase + Cfg::cO, tbase + Cfg::cS + 8 * ks, tbase + Cfg::cPL + 8 * ks, desc_mn<HD>(st + Cfg::kTile, ks), kLo, ks == 0); }
+          mma_x3<HD, true>(tbase + Cfg::cO, tbase + Cfg::cS + 8 * ks, tbase + Cfg::cPL + 8 * ks,
+                           desc_mn<HD>(st + Cfg::kTile, ks), kLo, ks == 0);
         umma_commit(o_ready);
-        wait_bar(o_ready, j & 1);        // stage s and the S/P columns are free again
-        if (j + kStages < n_blk) issue_tma(j + kStages);
       }
+      __syncwarp();
+      wait_bar(o_ready, j & 1);        // stage s and the S/P columns are free again
+      if (j + kStages < n_blk && elect_one()) issue_tma(j + kStages);
+      __syncwarp();
     }
   } else {
     // ---------------------------------------------------------------------- row threads
@@ -417,44 +424,51 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmKk, const __grid_consta
   pdl_trigger();
 
   if (warp == 4) {
-    if (lane == 0) {
-      auto issue_tma = [&](int j) {
-        const int s = j & 1;
-        uint8_t* st = smem + s * Cfg::kStage;
-        mbar_expect_tx(&kv_full[s], Cfg::kHi);
-        tma_tile_k<HD>(st, &tmKk, &kv_full[s], BLK, j * BLK, h, b);
-        tma_tile_k<HD>(st + Cfg::kTile, &tmVk, &kv_full[s], BLK, j * BLK, h, b);
-        tma_tile_mn<HD, BLK>(st + 2 * Cfg::kTile, &tmKm, &kv_full[s], j * BLK, h, b);
-      };
+    auto issue_tma = [&](int j) {
+      const int s = j & 1;
+      uint8_t* st = smem + s * Cfg::kStage;
+      mbar_expect_tx(&kv_full[s], Cfg::kHi);
+      tma_tile_k<HD>(st, &tmKk, &kv_full[s], BLK, j * BLK, h, b);
+      tma_tile_k<HD>(st + Cfg::kTile, &tmVk, &kv_full[s], BLK, j * BLK, h, b);
+      tma_tile_mn<HD, BLK>(st + 2 * Cfg::kTile, &tmKm, &kv_full[s], j * BLK, h, b);
+    };
+    if (elect_one())
       for (int j = 0; j < kStages && j < n_blk; ++j) issue_tma(j);
-      constexpr uint64_t kLo = static_cast<uint64_t>(Cfg::kHi >> 4);
-      for (int j = 0; j < n_blk; ++j) {
-        const int s = j & 1;
-        wait_bar(&split_done[s], (j >> 1) & 1);
-        tc_fence_after();
-        const uint32_t st = smem_u32(smem + s * Cfg::kStage);
-        if (!(p.dbg & 8))
+    __syncwarp();
+    constexpr uint64_t kLo = static_cast<uint64_t>(Cfg::kHi >> 4);
+    for (int j = 0; j < n_blk; ++j) {
+      const int s = j & 1;
+      wait_bar(&split_done[s], (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t st = smem_u32(smem + s * Cfg::kStage);
+      if (elect_one()) {
+        if (!(p.dbg & 8)) {
 #pragma unroll
-        for (int ks = 0; ks < HD / 8; ++ks)       // S = Q K^T
-          mma_x3<BLK, false>(tbase + Cfg::cS, tbase + Cfg::cQH + 8 * ks, tbase + Cfg::cQL + 8 * ks,
-                             desc_k(st, BLK, ks), kLo, ks == 0);
-        if (!(p.dbg & 8))
+          for (int ks = 0; ks < HD / 8; ++ks)       // S = Q K^T
+            mma_x3<BLK, false>(tbase + Cfg::cS, tbase + Cfg::cQH + 8 * ks, tbase + Cfg::cQL + 8 * ks,
+                               desc_k(st, BLK, ks), kLo, ks == 0);
 #pragma unroll
-        for (int ks = 0; ks < HD / 8; ++ks)       // dP = dO V^T
-          mma_x3<BLK, false>(tbase + Cfg::cDP, tbase + Cfg::cDH + 8 * ks, tbase + Cfg::cDL + 8 * ks,
-                             desc_k(st + Cfg::kTile, BLK, ks), kLo, ks == 0);
+          for (int ks = 0; ks < HD / 8; ++ks)       // dP = dO V^T
+            mma_x3<BLK, false>(tbase + Cfg::cDP, tbase + Cfg::cDH + 8 * ks, tbase + Cfg::cDL + 8 * ks,
+                               desc_k(st + Cfg::kTile, BLK, ks), kLo, ks == 0);
+        }
         umma_commit(sdp_ready);
-        wait_bar(ds_ready, j & 1);
-        tc_fence_after();
+      }
+      __syncwarp();
+      wait_bar(ds_ready, j & 1);
+      tc_fence_after();
+      if (elect_one()) {
         if (!(p.dbg & 4))
 #pragma unroll
         for (int ks = 0; ks < BLK / 8; ++ks)      // dQ_blk = dS K   (dS value over dP, residual over S)
-          { if (p.dbg & 1) mma_x3<HD, false>(tbase + Cfg::cDQ, tbase + Cfg::cDP + 8 * ks, tbase + Cfg::cS + 8 * ks, desc_k(st + 2 * Cfg::kTile, HD, ks), kLo, ks == 0);
-          else mma_x3<HD, true>(tbase + Cfg::cDQ, tbase + Cfg::cDP + 8 * ks, tbase + Cfg::cS + 8 * ks, desc_mn<HD>(st + 2 * Cfg::kTile, ks), kLo, ks == 0); }
+          mma_x3<HD, true>(tbase + Cfg::cDQ, tbase + Cfg::cDP + 8 * ks, tbase + Cfg::cS + 8 * ks,
+                           desc_mn<HD>(st + 2 * Cfg::kTile, ks), kLo, ks == 0);
         umma_commit(dq_ready);
-        wait_bar(dq_ready, j & 1);
-        if (j + kStages < n_blk) issue_tma(j + kStages);
       }
+      __syncwarp();
+      wait_bar(dq_ready, j & 1);
+      if (j + kStages < n_blk && elect_one()) issue_tma(j + kStages);
+      __syncwarp();
     }
   } else {
     const int r = threadIdx.x;
@@ -595,50 +609,57 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQk, const __grid_const
   pdl_trigger();
 
   if (warp == 4) {
-    if (lane == 0) {
-      auto issue_tma = [&](int j) {
-        const int s = j & 1;
-        uint8_t* st = smem + s * Cfg::kStage;
-        mbar_expect_tx(&q_full[s], Cfg::kHi);
-        tma_tile_k<HD>(st, &tmQk, &q_full[s], BLK, j * BLK, h, b);
-        tma_tile_k<HD>(st + Cfg::kTile, &tmDOk, &q_full[s], BLK, j * BLK, h, b);
-        tma_tile_mn<HD, BLK>(st + 2 * Cfg::kTile, &tmQm, &q_full[s], j * BLK, h, b);
-        tma_tile_mn<HD, BLK>(st + 3 * Cfg::kTile, &tmDOm, &q_full[s], j * BLK, h, b);
-      };
+    auto issue_tma = [&](int j) {
+      const int s = j & 1;
+      uint8_t* st = smem + s * Cfg::kStage;
+      mbar_expect_tx(&q_full[s], Cfg::kHi);
+      tma_tile_k<HD>(st, &tmQk, &q_full[s], BLK, j * BLK, h, b);
+      tma_tile_k<HD>(st + Cfg::kTile, &tmDOk, &q_full[s], BLK, j * BLK, h, b);
+      tma_tile_mn<HD, BLK>(st + 2 * Cfg::kTile, &tmQm, &q_full[s], j * BLK, h, b);
+      tma_tile_mn<HD, BLK>(st + 3 * Cfg::kTile, &tmDOm, &q_full[s], j * BLK, h, b);
+    };
+    if (elect_one())
       for (int j = 0; j < kStages && j < n_blk; ++j) issue_tma(j);
-      constexpr uint64_t kLo = static_cast<uint64_t>(Cfg::kHi >> 4);
-      for (int j = 0; j < n_blk; ++j) {
-        const int s = j & 1;
-        wait_bar(&split_done[s], (j >> 1) & 1);
-        tc_fence_after();
-        const uint32_t st = smem_u32(smem + s * Cfg::kStage);
-        if (!(p.dbg & 8))
+    __syncwarp();
+    constexpr uint64_t kLo = static_cast<uint64_t>(Cfg::kHi >> 4);
+    for (int j = 0; j < n_blk; ++j) {
+      const int s = j & 1;
+      wait_bar(&split_done[s], (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t st = smem_u32(smem + s * Cfg::kStage);
+      if (elect_one()) {
+        if (!(p.dbg & 8)) {
 #pragma unroll
-        for (int ks = 0; ks < HD / 8; ++ks)       // S^T = K Q^T
-          mma_x3<BLK, false>(tbase + Cfg::cST, tbase + Cfg::cKH + 8 * ks, tbase + Cfg::cKL + 8 * ks,
-                             desc_k(st, BLK, ks), kLo, ks == 0);
-        if (!(p.dbg & 8))
+          for (int ks = 0; ks < HD / 8; ++ks)       // S^T = K Q^T
+            mma_x3<BLK, false>(tbase + Cfg::cST, tbase + Cfg::cKH + 8 * ks, tbase + Cfg::cKL + 8 * ks,
+                               desc_k(st, BLK, ks), kLo, ks == 0);
 #pragma unroll
-        for (int ks = 0; ks < HD / 8; ++ks)       // dP^T = V dO^T
-          mma_x3<BLK, false>(tbase + Cfg::cDPT, tbase + Cfg::cVH + 8 * ks, tbase + Cfg::cVL + 8 * ks,
-                             desc_k(st + Cfg::kTile, BLK, ks), kLo, ks == 0);
+          for (int ks = 0; ks < HD / 8; ++ks)       // dP^T = V dO^T
+            mma_x3<BLK, false>(tbase + Cfg::cDPT, tbase + Cfg::cVH + 8 * ks, tbase + Cfg::cVL + 8 * ks,
+                               desc_k(st + Cfg::kTile, BLK, ks), kLo, ks == 0);
+        }
         umma_commit(st_ready);
-        wait_bar(p_ready, j & 1);
-        tc_fence_after();
+      }
+      __syncwarp();
+      wait_bar(p_ready, j & 1);
+      tc_fence_after();
+      if (elect_one()) {
         if (!(p.dbg & 4)) {
 #pragma unroll
-        for (int ks = 0; ks < BLK / 8; ++ks)      // dV_blk = P^T dO
-          { if (p.dbg & 1) mma_x3<HD, false>(tbase + Cfg::cDV, tbase + Cfg::cST + 8 * ks, tbase + Cfg::cPL + 8 * ks, desc_k(st + 3 * Cfg::kTile, HD, ks), kLo, ks == 0);
-          else mma_x3<HD, true>(tbase + Cfg::cDV, tbase + Cfg::cST + 8 * ks, tbase + Cfg::cPL + 8 * ks, desc_mn<HD>(st + 3 * Cfg::kTile, ks), kLo, ks == 0); }
+          for (int ks = 0; ks < BLK / 8; ++ks)      // dV_blk = P^T dO
+            mma_x3<HD, true>(tbase + Cfg::cDV, tbase + Cfg::cST + 8 * ks, tbase + Cfg::cPL + 8 * ks,
+                             desc_mn<HD>(st + 3 * Cfg::kTile, ks), kLo, ks == 0);
 #pragma unroll
-        for (int ks = 0; ks < BLK / 8; ++ks)      // dK_blk = dS^T Q
-          { if (p.dbg & 1) mma_x3<HD, false>(tbase + Cfg::cDK, tbase + Cfg::cDPT + 8 * ks, tbase + Cfg::cDSL + 8 * ks, desc_k(st + 2 * Cfg::kTile, HD, ks), kLo, ks == 0);
-          else mma_x3<HD, true>(tbase + Cfg::cDK, tbase + Cfg::cDPT + 8 * ks, tbase + Cfg::cDSL + 8 * ks, desc_mn<HD>(st + 2 * Cfg::kTile, ks), kLo, ks == 0); }
+          for (int ks = 0; ks < BLK / 8; ++ks)      // dK_blk = dS^T Q
+            mma_x3<HD, true>(tbase + Cfg::cDK, tbase + Cfg::cDPT + 8 * ks, tbase + Cfg::cDSL + 8 * ks,
+                             desc_mn<HD>(st + 2 * Cfg::kTile, ks), kLo, ks == 0);
         }
         umma_commit(dkv_ready);
-        wait_bar(dkv_ready, j & 1);
-        if (j + kStages < n_blk) issue_tma(j + kStages);
       }
+      __syncwarp();
+      wait_bar(dkv_ready, j & 1);
+      if (j + kStages < n_blk && elect_one()) issue_tma(j + kStages);
+      __syncwarp();
     }
   } else {
     const int r = threadIdx.x;
@@ -812,11 +833,11 @@ attn_pipe_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
   pdl_trigger();
 
   if (warp == 4) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      for (int j = 0; j < n_blk; ++j) {
-        const int s = j % NS, k = j / NS;
-        if (k > 0) wait_bar(&free_[s], (k - 1) & 1);
+    // ------------------------------------------------------------------ TMA producer (converged warp)
+    for (int j = 0; j < n_blk; ++j) {
+      const int s = j % NS, k = j / NS;
+      if (k > 0) wait_bar(&free_[s], (k - 1) & 1);
+      if (elect_one()) {
         uint8_t* st = smem + s * Cfg::kStage;
         mbar_expect_tx(&full[s], Cfg::kHi);
         tma_tile_k<HD>(st, &tm0, &full[s], BLK, j * BLK, h, b);
@@ -828,19 +849,20 @@ attn_pipe_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
           if (MODE == M_DKV) tma_tile_mn<HD, BLK>(st + 3 * Cfg::kTile, &tm3, &full[s], j * BLK, h, b);
         }
       }
+      __syncwarp();
     }
   } else if (warp == 5) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint64_t kLo = static_cast<uint64_t>(Cfg::kHi >> 4);
-      auto phase2 = [&](int i) {
-        const int set = i & 1;
-        wait_bar(&a2_ready[set], (i >> 1) & 1);
-        if (i >= 2) wait_bar(&out_free[set], ((i >> 1) & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t st = smem_u32(smem + (i % NS) * Cfg::kStage);
-        const uint32_t ts = tbase + Cfg::cSet + set * Cfg::kSetCols;
-        const uint32_t to = tbase + Cfg::cOut + set * Cfg::kNO * HD;
+    // ------------------------------------------------------------------ MMA issuer (converged warp, elect.sync)
+    constexpr uint64_t kLo = static_cast<uint64_t>(Cfg::kHi >> 4);
+    auto phase2 = [&](int i) {
+      const int set = i & 1;
+      wait_bar(&a2_ready[set], (i >> 1) & 1);
+      if (i >= 2) wait_bar(&out_free[set], ((i >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t st = smem_u32(smem + (i % NS) * Cfg::kStage);
+      const uint32_t ts = tbase + Cfg::cSet + set * Cfg::kSetCols;
+      const uint32_t to = tbase + Cfg::cOut + set * Cfg::kNO * HD;
+      if (elect_one()) {
         if (!(p.dbg & 4)) {
           if (MODE == M_FWD) {
 #pragma unroll
@@ -862,15 +884,18 @@ attn_pipe_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
         }
         umma_commit(&out_ready[set]);
         umma_commit(&free_[i % NS]);
-      };
-      wait_bar(x_ready, 0);
-      for (int j = 0; j < n_blk; ++j) {
-        const int s = j % NS;
-        wait_bar(&split[s], (j / NS) & 1);
-        tc_fence_after();
-        const uint32_t st = smem_u32(smem + s * Cfg::kStage);
-        const uint32_t ts = tbase + Cfg::cSet + (j & 1) * Cfg::kSetCols;
-        const uint32_t x0 = tbase + Cfg::cX, x1 = tbase + Cfg::cX + 2 * HD;
+      }
+      __syncwarp();
+    };
+    wait_bar(x_ready, 0);
+    for (int j = 0; j < n_blk; ++j) {
+      const int s = j % NS;
+      wait_bar(&split[s], (j / NS) & 1);
+      tc_fence_after();
+      const uint32_t st = smem_u32(smem + s * Cfg::kStage);
+      const uint32_t ts = tbase + Cfg::cSet + (j & 1) * Cfg::kSetCols;
+      const uint32_t x0 = tbase + Cfg::cX, x1 = tbase + Cfg::cX + 2 * HD;
+      if (elect_one()) {
         if (!(p.dbg & 8)) {
 #pragma unroll
           for (int ks = 0; ks < HD / 8; ++ks)         // S = Q K^T   |   S^T = K Q^T
@@ -883,10 +908,11 @@ attn_pipe_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
           }
         }
         umma_commit(&p1_ready[j & 1]);
-        if (j >= 1) phase2(j - 1);
       }
-      phase2(n_blk - 1);
+      __syncwarp();
+      if (j >= 1) phase2(j - 1);
     }
+    phase2(n_blk - 1);
   } else if (warp >= 6) {
     // ------------------------------------------------------------------ residual splitters
     const int tid = threadIdx.x - 192;      // 0..63
@@ -1366,4 +1392,71 @@ extern "C" int itn_attention_bwd(const itn_attention_desc_t* d, void* stream) {
     return launch_dkv<32, 64, 1>(d, s);
   }
   return launch_dkv<64, 32, 1>(d, s);
+}
+
+// ---- tensor-pipe micro-benchmark (tools/mma_bench.py): cycles per tcgen05.mma kind::tf32 128 x N x 8 for the
+// operand sources / layouts the attention kernels use.  One warp per CTA; lane 0 issues `iters` MMAs into one
+// accumulator, commits and waits; out[blockIdx.x] = elapsed cycles.  Operand contents are whatever shared /
+// tensor memory holds (timing only).
+namespace itn {
+namespace attn {
+template <int N>
+__global__ void __launch_bounds__(32, 1) mma_bench_kernel(int a_tmem, int b_mn, int iters, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 96 * 1024);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar + 1);
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  tmem_alloc<512>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = *tmem_ptr;
+  for (int i = threadIdx.x; i < 96 * 1024 / 4; i += 32) reinterpret_cast<float*>(smem)[i] = 1.0f + i * 1e-6f;
+  fence_proxy_async();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t sa = smem_u32(smem), sb = smem_u32(smem + 32 * 1024);
+    const uint32_t idesc = umma_idesc_tf32(kRows, N, 0, b_mn ? 1 : 0);
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+      const int ks = i & 3;
+      const uint64_t bd = b_mn ? umma_smem_desc(sb + ks * 1024, 4096, 512, kLayoutSW128Base32)
+                               : umma_smem_desc(sb + ks * 32, 16, 1024, kLayoutSW128);
+      if (a_tmem) umma_tf32_ts(tbase, tbase + 256 + 8 * ks, bd, idesc, i > 0 ? 1u : 0u);
+      else umma_tf32(tbase, umma_smem_desc(sa + ks * 32, 16, 1024, kLayoutSW128), bd, idesc, i > 0 ? 1u : 0u);
+    }
+    const long long t1 = clock64();
+    umma_commit(bar);
+    wait_bar(bar, 0);
+    const long long t2 = clock64();
+    out[2 * blockIdx.x] = t2 - t0;
+    out[2 * blockIdx.x + 1] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  tmem_dealloc<512>(tbase);
+}
+}  // namespace attn
+}  // namespace itn
+
+extern "C" int itn_debug_mma_bench(int n, int a_tmem, int b_mn, int iters, int grid, long long* out, void* stream) {
+  using namespace itn::attn;
+  const int smem = 96 * 1024 + 64 + 1024;
+  void (*kern)(int, int, int, long long*) = nullptr;
+  switch (n) {
+    case 32: kern = mma_bench_kernel<32>; break;
+    case 64: kern = mma_bench_kernel<64>; break;
+    case 128: kern = mma_bench_kernel<128>; break;
+    case 256: kern = mma_bench_kernel<256>; break;
+    default: return itn::set_error(ITN_ERR_ARG, "mma_bench: N must be 32, 64, 128 or 256");
+  }
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return itn::set_error(ITN_ERR_CUDA, "mma_bench: %s", cudaGetErrorString(e));
+  itn::launch(kern, grid, 32, smem, static_cast<cudaStream_t>(stream), a_tmem, b_mn, iters, out);
+  return itn::check_launch("mma_bench_kernel");
 }

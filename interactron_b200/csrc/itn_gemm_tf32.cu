@@ -381,8 +381,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   pdl_trigger();
 
   if (warp == 0) {
-    // ------------------------------------------------------- TMA producer
-    if (lane == 0) {
+    // ------------------------------------------------------- TMA producer (converged warp, elect.sync)
+    {
       int s = 0;
       uint32_t ph = 0;
       int gk = 0;   // running k-block counter (trace index)
@@ -397,35 +397,38 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int b_c0 = b0 * p.b_m0, b_c1 = b1 * p.b_m1;
         for (int kb = 0; kb < num_kb; ++kb, ++gk) {
           mbar_wait(&empty_bar[s], ph ^ 1);
-          ITN_TRACE_AT(0, gk);
-          // pre-split B (static weights): its residual tile arrives by TMA, the splitters do A only
-          const bool presplit = X3 && !B_MN && p.b_presplit;
-          mbar_expect_tx(&full_bar[s], Cfg::kRawBytes + (presplit ? Cfg::kBBytes : 0));
-          uint8_t* sa = smem + s * Cfg::kStageBytes;
-          uint8_t* sb = sa + Cfg::kABytes;
-          const int k0 = kb * kBK;
-          if (!A_MN) {
-            tma_load_4d(sa, &tmA, &full_bar[s], k0, m0, a_c1, a_c0);
-          } else {
+          if (elect_one()) {
+            ITN_TRACE_AT(0, gk);
+            // pre-split B (static weights): its residual tile arrives by TMA, the splitters do A only
+            const bool presplit = X3 && !B_MN && p.b_presplit;
+            mbar_expect_tx(&full_bar[s], Cfg::kRawBytes + (presplit ? Cfg::kBBytes : 0));
+            uint8_t* sa = smem + s * Cfg::kStageBytes;
+            uint8_t* sb = sa + Cfg::kABytes;
+            const int k0 = kb * kBK;
+            if (!A_MN) {
+              tma_load_4d(sa, &tmA, &full_bar[s], k0, m0, a_c1, a_c0);
+            } else {
 #pragma unroll
-            for (int j = 0; j < kBM / 32; ++j)
-              tma_load_4d(sa + j * kAtomBytes, &tmA, &full_bar[s], m0 + 32 * j, k0, a_c1, a_c0);
-          }
-          if (!B_MN) {
-            tma_load_4d(sb, &tmB, &full_bar[s], k0, n0, b_c1, b_c0);
-            if (presplit) tma_load_4d(sb + Cfg::kRawBytes, &tmBlo, &full_bar[s], k0, n0, b_c1, b_c0);
-          } else {
+              for (int j = 0; j < kBM / 32; ++j)
+                tma_load_4d(sa + j * kAtomBytes, &tmA, &full_bar[s], m0 + 32 * j, k0, a_c1, a_c0);
+            }
+            if (!B_MN) {
+              tma_load_4d(sb, &tmB, &full_bar[s], k0, n0, b_c1, b_c0);
+              if (presplit) tma_load_4d(sb + Cfg::kRawBytes, &tmBlo, &full_bar[s], k0, n0, b_c1, b_c0);
+            } else {
 #pragma unroll
-            for (int j = 0; j < BN / 32; ++j)
-              tma_load_4d(sb + j * kAtomBytes, &tmB, &full_bar[s], n0 + 32 * j, k0, b_c1, b_c0);
+              for (int j = 0; j < BN / 32; ++j)
+                tma_load_4d(sb + j * kAtomBytes, &tmB, &full_bar[s], n0 + 32 * j, k0, b_c1, b_c0);
+            }
           }
+          __syncwarp();
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // --------------------------------------------------------- MMA issuer
-    if (lane == 0) {
+    // --------------------------------------------------------- MMA issuer (converged warp, elect.sync)
+    {
       constexpr uint32_t idesc = umma_idesc_tf32(kBM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       int s = 0;
       uint32_t ph = 0;
@@ -434,42 +437,45 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int gk = 0, gt = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++gt) {
         mbar_wait(&tempty_bar[acc], acc_ph ^ 1);     // epilogue has drained this accumulator
-        ITN_TRACE_AT(7, gt);
+        if (lane == 0) ITN_TRACE_AT(7, gt);
         tc_fence_after();
         const uint32_t tacc = tmem_base + acc * Cfg::kAccCols;
         for (int kb = 0; kb < num_kb; ++kb, ++gk) {
           mbar_wait(X3 ? &split_bar[s] : &full_bar[s], ph);
-          ITN_TRACE_AT(3, gk);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + s * Cfg::kStageBytes);
-          const uint32_t sb = sa + Cfg::kABytes;
+          if (elect_one()) {
+            ITN_TRACE_AT(3, gk);
+            const uint32_t sa = smem_u32(smem + s * Cfg::kStageBytes);
+            const uint32_t sb = sa + Cfg::kABytes;
 #pragma unroll
-          for (int k = 0; k < kBK / 8; ++k) {
-            // K-major (SWIZZLE_128B): rows of 32 floats, 8-row groups 1024 B apart (SBO); the
-            //   k-th MMA starts 8 floats = 32 B further along the swizzled row.
-            // MN-major (SWIZZLE_128B_BASE32B): k-rows of 32 mn-floats, 4-row swizzle atoms 512 B
-            //   apart (SBO), 32-wide mn blocks one TMA box = 4096 B apart (LBO); the k-th MMA
-            //   starts 8 k-rows = 1024 B further.
-            constexpr uint32_t kKLayout = kBK == 32 ? kLayoutSW128 : kLayoutSW64;   // K-major: rows of kBK floats
-            constexpr uint32_t kKSbo = 8 * kBK * 4;                                 // 8-row groups
-            const uint64_t ad = A_MN ? umma_smem_desc(sa + k * 1024, kAtomBytes, 512, kLayoutSW128Base32)
-                                     : umma_smem_desc(sa + k * 32, 16, kKSbo, kKLayout);
-            const uint64_t bd = B_MN ? umma_smem_desc(sb + k * 1024, kAtomBytes, 512, kLayoutSW128Base32)
-                                     : umma_smem_desc(sb + k * 32, 16, kKSbo, kKLayout);
-            umma_tf32(tacc, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
-            if (X3 && !(p.dbg & 32)) {     // dbg 32 (timing experiments only): main product alone
-              // residual tiles live kRawBytes after their raw twins, same layout: the descriptor
-              // start address is in 16-byte units
-              constexpr uint64_t kLoOff = static_cast<uint64_t>(Cfg::kRawBytes >> 4);
-              umma_tf32(tacc, ad + kLoOff, bd, idesc, 1u);   // A_lo * B_hi
-              umma_tf32(tacc, ad, bd + kLoOff, idesc, 1u);   // A_hi * B_lo
+            for (int k = 0; k < kBK / 8; ++k) {
+              // K-major (SWIZZLE_128B): rows of 32 floats, 8-row groups 1024 B apart (SBO); the
+              //   k-th MMA starts 8 floats = 32 B further along the swizzled row.
+              // MN-major (SWIZZLE_128B_BASE32B): k-rows of 32 mn-floats, 4-row swizzle atoms 512 B
+              //   apart (SBO), 32-wide mn blocks one TMA box = 4096 B apart (LBO); the k-th MMA
+              //   starts 8 k-rows = 1024 B further.
+              constexpr uint32_t kKLayout = kBK == 32 ? kLayoutSW128 : kLayoutSW64;   // K-major: rows of kBK floats
+              constexpr uint32_t kKSbo = 8 * kBK * 4;                                 // 8-row groups
+              const uint64_t ad = A_MN ? umma_smem_desc(sa + k * 1024, kAtomBytes, 512, kLayoutSW128Base32)
+                                       : umma_smem_desc(sa + k * 32, 16, kKSbo, kKLayout);
+              const uint64_t bd = B_MN ? umma_smem_desc(sb + k * 1024, kAtomBytes, 512, kLayoutSW128Base32)
+                                       : umma_smem_desc(sb + k * 32, 16, kKSbo, kKLayout);
+              umma_tf32(tacc, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+              if (X3 && !(p.dbg & 32)) {     // dbg 32 (timing experiments only): main product alone
+                // residual tiles live kRawBytes after their raw twins, same layout: the descriptor
+                // start address is in 16-byte units
+                constexpr uint64_t kLoOff = static_cast<uint64_t>(Cfg::kRawBytes >> 4);
+                umma_tf32(tacc, ad + kLoOff, bd, idesc, 1u);   // A_lo * B_hi
+                umma_tf32(tacc, ad, bd + kLoOff, idesc, 1u);   // A_hi * B_lo
+              }
             }
+            umma_commit(&empty_bar[s]);  // frees the smem slot once the MMAs have read it
+            ITN_TRACE_AT(4, gk);
+            if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);  // accumulator complete
           }
-          umma_commit(&empty_bar[s]);  // frees the smem slot once the MMAs have read it
-          ITN_TRACE_AT(4, gk);
+          __syncwarp();
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
-        umma_commit(&tfull_bar[acc]);  // accumulator complete
         acc ^= 1;
         if (acc == 0) acc_ph ^= 1;
       }

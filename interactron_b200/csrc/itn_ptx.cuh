@@ -45,6 +45,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// One lane of a CONVERGED warp (elect.sync).  The single-lane roles (TMA producer, MMA issuer) keep their
+// whole warp in the loop and issue under this predicate: inside `if (lane == 0)` the compiler has to wrap
+// every tcgen05.mma in an ELECT / BRA.U.ANY loop over the active lanes (measured ~96 cycles per instruction,
+// tools/mma_bench.py, so every product narrower than 128 x 256 x 8 is issue-bound), under elect.sync it emits
+// straight uniform-datapath code (UTCHMMA back to back).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // --------------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

@@ -1,23 +1,22 @@
 """Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list.
 usage: python tools/launch_summary.py launches.csv [--gemm] [--step LAST|ALL]"""
 import collections
-import csv
+import os
 import re
 import sys
 
-
-def load(path):
-    with open(path) as f:
-        lines = [l for l in f if not l.startswith("==")]
-    return list(csv.DictReader(lines))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from _ncu_csv import last_step, load_launches  # noqa: E402
 
 
 def main():
     path = sys.argv[1]
-    rows = load(path)
+    launches = load_launches(path)
     if "--all" not in sys.argv:
-        rows = rows[len(rows) // 2:]        # second of the two profiled steps
-    dur = lambda r: float(r["Metric Value"].replace(",", ""))
+        launches = last_step(launches)      # the last profiled step, cut at profile_step.py's marker launches
+    rows = [{"Kernel Name": d["name"], "Grid Size": d["grid"], "t": d.get("gpu__time_duration.sum", 0.0)}
+            for d in launches]
+    dur = lambda r: r["t"]
     tot = sum(dur(r) for r in rows)
     print(f"{len(rows)} launches, {tot/1e6:.3f} ms (serialised, cold cache: compare shares)")
     agg = collections.defaultdict(lambda: [0, 0.0])

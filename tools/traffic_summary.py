@@ -1,31 +1,26 @@
 """DRAM traffic per kernel family from an ncu launch list taken with
     ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv ...
-of `tools/profile_step.py E workload 2` (second step is summarised).
+of `tools/profile_step.py E workload 2`; the LAST step is summarised, cut at the marker launches
+profile_step.py emits (tools/_ncu_csv.py) and checked to contain exactly one sgd_clip_update.
 usage: python tools/traffic_summary.py launches.csv [out.json]"""
 import collections
-import csv
 import json
+import os
 import re
 import sys
 
-UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1.0, "us": 1e3, "ms": 1e6, "usecond": 1e3,
-        "nsecond": 1.0, "msecond": 1e6}
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from _ncu_csv import last_step, load_launches  # noqa: E402
 
 
 def main():
     path = sys.argv[1]
-    with open(path) as f:
-        rows = list(csv.DictReader([l for l in f if not l.startswith("==")]))
-    per = collections.OrderedDict()          # launch id -> {metric: value}
-    for r in rows:
-        d = per.setdefault(r["ID"], {"name": r["Kernel Name"]})
-        d[r["Metric Name"]] = float(r["Metric Value"].replace(",", "")) * UNIT.get(r["Metric Unit"], 1.0)
-    launches = list(per.values())
-    launches = launches[len(launches) // 2:]          # second of the two profiled steps
+    launches = last_step(load_launches(path))
     fam = collections.defaultdict(lambda: [0, 0.0, 0.0, 0.0])
     for d in launches:
         k = re.sub(r"^void ", "", re.sub(r"\(.*", "", d["name"]))
-        k = "itn::gemm_tf32_kernel" if "gemm_tf32_kernel" in k else k[:60]
+        k = "itn::gemm_tf32_kernel" if "gemm_tf32_kernel" in k else k
+        k = re.sub(r"attn_(\w+)_kernel<.*", r"attn_\1_kernel", k)[:60]
         v = fam[k]
         v[0] += 1
         v[1] += d.get("gpu__time_duration.sum", 0.0)
