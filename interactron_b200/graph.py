@@ -7,6 +7,8 @@ kernels, the few torch gather/zero-fill ops — is captured once into a CUDA gra
 Weights are read from persistent flat buffers (episode.InnerLoop.refresh_weights updates them in
 place), so optimizer steps between calls do not invalidate a captured graph.
 """
+import gc
+
 import torch
 
 
@@ -15,6 +17,9 @@ class GraphedCall:
 
     def __init__(self, fn, example_inputs, warmup=2):
         self.fn = fn
+        # a CUDAGraph that is garbage-collected WHILE another stream capture is in progress fails the capture
+        # ("operation not permitted when stream is capturing (function reset)"): collect dead graphs first
+        gc.collect()
         self.static_in = [torch.empty_like(t) for t in example_inputs]
         for s, t in zip(self.static_in, example_inputs):
             s.copy_(t)

@@ -108,7 +108,9 @@ class MetaParts:
                 "post1_logits": post1["logits"].view(E, NQ, C), "post1_boxes": post1["boxes"].view(E, NQ, 4),
                 "actions": fout["actions"]}
 
-    def part_b(self, dlog, dbox, dlog1, dbox1, dact=None):
+    def part_b1(self, dlog, dbox, dact=None):
+        """Steps 4-5.  Leaves the flat meta-gradient buffer G = [theta | psi | phi] in self.st with its phi
+        segment FINAL (the second-order gradients of the fusion network) -> {"Gphi": that segment}."""
         loop, st = self.loop, self.st
         ops = loop.ops
         E, S, L, C = st["E"], st["S"], st["L"], st["C"]
@@ -143,33 +145,52 @@ class MetaParts:
         detr_t.detr_t_backward(dops, DWd, cache2, GradSink(dops, ppk, gpsi2, shared=True), dpreds=dpreds2,
                                dmemory=dmem2)
         del cache2, fcache2
-        # 6b. detector loss backward (first order): theta gets the gradient wrt theta'' unchanged
+        st["G"], st["gpsi"], st["gpsi2"] = G, gpsi, gpsi2.t
+        return {"Gphi": G[:, n_t + n_p:]}
+
+    def part_b2(self, dlog1, dbox1):
+        """Step 6b: detector loss backward (first order): theta gets the gradient wrt theta'' unchanged.
+        Completes the theta and psi segments of G -> {"Gtp": [theta | psi] segment}."""
+        loop, st = self.loop, self.st
+        ops = loop.ops
+        E, C = st["E"], st["C"]
+        NQ = detr_t.NQ
+        tpk, ppk = loop.theta_pack, loop.psi_pack
+        n_t, n_p = tpk.numel, ppk.numel
+        G = st["G"]
         g_det = ops.empty(E, n_t)
         gpsi1 = ops.zeros(1, n_p)
-        detr_t.detr_t_backward(ops, Wp, st["c1"],
+        detr_t.detr_t_backward(ops, st["Wp"], st["c1"],
                                MultiSink(GradSink(ops, tpk, g_det), GradSink(ops, ppk, gpsi1, shared=True)),
                                dlogits=dlog1.view(E, NQ, C), dboxes=dbox1.view(E, NQ, 4))
         ops.colsum(g_det.view(1, E, n_t), out=G[:, :n_t])
-        ops.copy2d_(G[:, n_t:n_t + n_p], ops.add(ops.add(gpsi, gpsi2.t), gpsi1))
-        return {"G": G}
+        ops.copy2d_(G[:, n_t:n_t + n_p], ops.add(ops.add(st["gpsi"], st["gpsi2"]), gpsi1))
+        return {"Gtp": G[:, :n_t + n_p]}
+
+    def part_b(self, dlog, dbox, dlog1, dbox1, dact=None):
+        self.part_b1(dlog, dbox, dact)
+        self.part_b2(dlog1, dbox1)
+        return {"G": self.st["G"]}
 
 
 def _parts_runner(model, frames, masks, idx):
-    """-> (run_a, run_b): the two halves, CUDA-graph replayed when the model allows it."""
+    """-> (run_a, run_b1, run_b2): the launch-only pieces, CUDA-graph replayed when the model allows it."""
     loop = model._get_loop()
     use_graph = model.use_cuda_graph and frames.is_cuda
     if not use_graph:
         parts = MetaParts(model)
-        return parts.part_a, (lambda *t: parts.part_b(*t)), None
+        return parts.part_a, parts.part_b1, parts.part_b2
     from .graph import GraphedCall
     bb = loop.detector.backbone
-    bb_key = tuple(t.data_ptr() for t in list(bb.parameters()) + list(bb.buffers()))
-    key = ("meta", tuple(frames.shape), tuple(masks.shape), loop.kind, bb_key)
+    bb_key = tuple((t.data_ptr(), t._version) for t in list(bb.parameters()) + list(bb.buffers()))
+    # everything the capture bakes in as a kernel scalar or a branch is part of the key
+    key = ("meta", tuple(frames.shape), tuple(masks.shape), loop.kind, bb_key, float(loop.lr), float(loop.clip),
+           loop.ops.precision, loop.backbone_impl, bool(loop.ops.fused_attention))
     ent = model._graphs.get(key)
     if ent is None:
         for k in [k for k in model._graphs if k[0] == "meta"]:
             del model._graphs[k]                       # one meta geometry at a time: the caches are large
-        ent = model._graphs[key] = {"parts": MetaParts(model), "a": None, "b": None}
+        ent = model._graphs[key] = {"parts": MetaParts(model), "a": None, "b1": None, "b2": None}
     parts = ent["parts"]
 
     def run_a(f, m, i):
@@ -177,18 +198,25 @@ def _parts_runner(model, frames, masks, idx):
             ent["a"] = GraphedCall(parts.part_a, [f, m, i])
         return ent["a"](f, m, i, clone=False)
 
-    def run_b(*t):
-        if ent["b"] is None:
-            ent["b"] = GraphedCall(lambda *x: parts.part_b(*x), list(t))
-        return {"G": ent["b"](*t, clone=False)["G"].clone()}     # callers keep views of it in .grad
+    def run_b1(*t):
+        if ent["b1"] is None:
+            ent["b1"] = GraphedCall(lambda *x: parts.part_b1(*x), list(t))
+        return ent["b1"](*t, clone=False)
 
-    return run_a, run_b, ent
+    def run_b2(*t):
+        if ent["b2"] is None:
+            ent["b2"] = GraphedCall(lambda *x: parts.part_b2(*x), list(t))
+        return ent["b2"](*t, clone=False)
+
+    return run_a, run_b1, run_b2
 
 
-def meta_step(model, data, ridx=None):
+def meta_step(model, data, ridx=None, sync=False):
     """-> (predictions, losses, flat_grads): flat_grads["all"] is ONE [1, n_theta+n_psi+n_phi] buffer
-    with this rank's summed meta-gradients (not yet added to .grad; "theta"/"psi"/"phi" are its views,
-    laid out by the loop's packs)."""
+    with the summed meta-gradients (not yet added to .grad; "theta"/"psi"/"phi" are its views, laid out by
+    the loop's packs).  sync: all-reduce (SUM) it over the ranks in two buckets - phi, final after the
+    dual pass, on a side stream while the 1-frame detector backward runs; then theta | psi (parallel.
+    BucketedAllReduce); flat_grads["allreduce"] holds the CUDA events that time the collective."""
     loop = model._get_loop()
     ops = loop.ops
     if ops._clean:
@@ -210,7 +238,7 @@ def meta_step(model, data, ridx=None):
     if ridx is None:
         ridx = [random.randint(0, 4) for _ in range(E)]                     # reference :129, one draw per task
     idx = torch.tensor([e * S + int(r) for e, r in enumerate(ridx)]).to(dev)
-    run_a, run_b, _ = _parts_runner(model, frames, masks, idx)
+    run_a, run_b1, run_b2 = _parts_runner(model, frames, masks, idx)
 
     # steps 1-3 (+ 1-frame pass): detector outputs with the fast weights ---------------------------
     a = run_a(frames, masks, idx)
@@ -220,7 +248,6 @@ def meta_step(model, data, ridx=None):
     sup_l, dlog, dbox = crit.loss_and_grad(outs, targets, background_c=0.1, groups=E, weights=LOSS_W)
     sup_host = sup_l.cpu()                                                        # [E,5]
     sup = {k: sup_host[:, i] for i, k in enumerate(keys5)}
-    grads_in = [dlog, dbox]
     dact = None
     if kind == "A":
         # lowest-loss policy labels (reference models/interactron.py:105-118)
@@ -251,12 +278,21 @@ def meta_step(model, data, ridx=None):
     o1 = {"pred_logits": a["post1_logits"], "pred_boxes": a["post1_boxes"]}
     det_l, dlog1, dbox1 = crit.loss_and_grad(o1, t1, background_c=0.1, groups=E, weights=LOSS_W)
     det_host = det_l.cpu()
-    grads_in += [dlog1, dbox1] + ([dact] if dact is not None else [])
 
     # steps 4-6: backward passes + the dual (second-order) pass -> flat meta-gradient -----------------
-    G = run_b(*grads_in)["G"]
-    n_t, n_p = tpk.numel, ppk.numel
+    n_t, n_p, n_f = tpk.numel, ppk.numel, fpk.numel
+    G = ops.empty(1, n_t + n_p + n_f)              # callers keep views of it in .grad: a fresh buffer per step
+    red = parallel.BucketedAllReduce() if sync else None
+    gphi = run_b1(*([dlog, dbox] + ([dact] if dact is not None else [])))["Gphi"]
+    G[:, n_t + n_p:].copy_(gphi)
+    if red is not None:
+        red.launch_async(G[:, n_t + n_p:])           # overlaps the detector pass below
+    gtp = run_b2(dlog1, dbox1)["Gtp"]
+    G[:, :n_t + n_p].copy_(gtp)
     flat = {"all": G, "theta": G[:, :n_t], "psi": G[:, n_t:n_t + n_p], "phi": G[:, n_t + n_p:]}
+    if red is not None:
+        red.finish(G[:, :n_t + n_p])
+        flat["allreduce"] = red
 
     det = {k: det_host[:, i] for i, k in enumerate(keys5)}
     order = ("loss_ce", "class_error", "loss_bbox", "loss_giou", "cardinality_error")

@@ -155,8 +155,10 @@ class _Adaptive(_Base):
 
     def _check_backbone_moved(self):
         bb = self._detector().backbone
-        bb_key = tuple(t.data_ptr() for t in list(bb.parameters()) + list(bb.buffers()))
-        if bb_key != self._bb_key:          # backbone tensors moved: captured conv launches are stale
+        # (data_ptr, _version): an in-place change of the frozen trunk (load_state_dict of another checkpoint)
+        # re-folds BN into NEW weight tensors (backbone.refresh) the captured launches do not point to
+        bb_key = tuple((t.data_ptr(), t._version) for t in list(bb.parameters()) + list(bb.buffers()))
+        if bb_key != self._bb_key:          # backbone tensors moved or changed: captured conv launches are stale
             self._graphs.clear()
             self._bb_key = bb_key
 
@@ -164,8 +166,10 @@ class _Adaptive(_Base):
         """Replay (capturing on first use) the CUDA graph of `fn` for this input geometry."""
         from .graph import GraphedCall
         self._check_backbone_moved()
+        # everything a capture bakes in as a kernel scalar or a branch is part of the key
         key = (tag, tuple(frames.shape), tuple(masks.shape), self._loop.ops.precision, self._loop.backbone_tf32,
-               self._loop.backbone_impl)
+               self._loop.backbone_impl, float(self._loop.lr), float(self._loop.clip),
+               bool(self._loop.ops.fused_attention))
         g = self._graphs.get(key)
         if g is None:
             g = self._graphs[key] = GraphedCall(fn, [frames, masks])
@@ -180,13 +184,11 @@ class _Adaptive(_Base):
         of the detector loss; default = the reference's `random.randint(0, 4)` draw per episode.
         Dropout is not applied (the reference's forward in eval() mode); see meta.py."""
         from . import meta
-        from . import parallel
-        predictions, losses, flat = meta.meta_step(self, data, ridx)
-        if self.sync_meta_grads:
-            # one process per GPU, the batch's episodes sharded over ranks: the meta-gradient is a sum
-            # over episodes -> ONE all-reduce(SUM) of the flat buffer (replaces nn.DataParallel,
-            # reference engine/interactron_trainer.py:43-46); no-op in a single process
-            parallel.allreduce_meta_grads(flat["all"])
+        # one process per GPU, the batch's episodes sharded over ranks: the meta-gradient is a sum over
+        # episodes -> all-reduce(SUM) of the flat buffer [theta | psi | phi] (replaces nn.DataParallel,
+        # reference engine/interactron_trainer.py:43-46), in two buckets so that the fusion part overlaps
+        # the detector pass (meta.meta_step); no-op in a single process
+        predictions, losses, flat = meta.meta_step(self, data, ridx, sync=self.sync_meta_grads)
         self.last_meta_grads = flat
         meta.accumulate_grads(self, flat)
         return predictions, losses
@@ -274,7 +276,8 @@ class interactron(_Adaptive):
         """CUDA-graph replay of fn(a, b) keyed by tag and input geometry (policy rollout pieces)."""
         from .graph import GraphedCall
         self._check_backbone_moved()
-        key = (tag, tuple(a.shape), tuple(b.shape), a.dtype, b.dtype, self._loop.ops.precision)
+        key = (tag, tuple(a.shape), tuple(b.shape), a.dtype, b.dtype, self._loop.ops.precision,
+               bool(self._loop.ops.fused_attention))
         g = self._graphs.get(key)
         if g is None:
             g = self._graphs[key] = GraphedCall(fn, [a, b])

@@ -62,6 +62,69 @@ def allreduce_meta_grads(flat):
     return flat
 
 
+class BucketedAllReduce:
+    """The meta-gradient exchange of one step in two buckets (reference semantics: gradients are summed over
+    the tasks of the batch, models/interactron.py:121-134; engine/interactron_trainer.py:106-111 then clips
+    and steps on the sum).  `launch_async(first)`: all-reduce(SUM) of the bucket that is final early, on a
+    side stream that waits for the producer stream - the caller keeps launching compute.  `finish(second)`:
+    all-reduce of the rest on the caller's stream, then join the side stream.  CUDA events bracket both
+    collectives: `ms()` -> (first bucket, second bucket + join = the exposed part).  No-op without a
+    process group (events still recorded, ~0 ms)."""
+
+    _side = {}
+
+    def __init__(self):
+        self.ev = None
+
+    @classmethod
+    def _stream(cls, device):
+        key = (device.type, device.index)
+        if key not in cls._side:
+            cls._side[key] = torch.cuda.Stream(device=device)
+        return cls._side[key]
+
+    def launch_async(self, buf):
+        _, w = world()
+        if not buf.is_cuda:                               # gloo / CPU tests: plain blocking collective
+            if w > 1:
+                dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+            return
+        main = torch.cuda.current_stream(buf.device)
+        side = self._stream(buf.device)
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        ready = torch.cuda.Event()
+        ready.record(main)
+        side.wait_event(ready)
+        with torch.cuda.stream(side):
+            e[0].record(side)
+            if w > 1:
+                dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+            e[1].record(side)
+        buf.record_stream(side)
+        self.ev = e
+
+    def finish(self, buf):
+        _, w = world()
+        if not buf.is_cuda:
+            if w > 1:
+                dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+            return
+        main = torch.cuda.current_stream(buf.device)
+        e = self.ev
+        e[2].record(main)
+        if w > 1:
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+        main.wait_event(e[1])
+        e[3].record(main)
+
+    def ms(self):
+        """(first bucket on the side stream, exposed: second bucket + join) in ms; synchronises."""
+        if self.ev is None:
+            return 0.0, 0.0
+        self.ev[3].synchronize()
+        return self.ev[0].elapsed_time(self.ev[1]), self.ev[2].elapsed_time(self.ev[3])
+
+
 def exchange_in_order(local_items):
     """local_items: this rank's per-episode host objects, local order.  Global episode i of a batch
     lives on rank i % W at local position i // W (shard_episodes).  -> list of (rank, local_pos, item)

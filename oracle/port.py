@@ -31,7 +31,7 @@ def sine_position(mask, feats=128, temperature=10000.0):
     x = nm.cumsum(2, dtype=torch.float32)
     y = y / (y[:, -1:, :] + 1e-6) * (2 * math.pi)
     x = x / (x[:, :, -1:] + 1e-6) * (2 * math.pi)
-    dim_t = torch.arange(feats, dtype=torch.float32)
+    dim_t = torch.arange(feats, dtype=torch.float32, device=mask.device)
     dim_t = temperature ** (2 * (dim_t // 2) / feats)
     px, py = x[..., None] / dim_t, y[..., None] / dim_t
     px = torch.stack((px[..., 0::2].sin(), px[..., 1::2].cos()), dim=4).flatten(3)
@@ -55,7 +55,7 @@ def mha(P, pre, q_in, k_in, v_in, nh, key_padding_mask=None):
     v = v.reshape(Lk, N * nh, hd).transpose(0, 1)
     s = torch.bmm(q, k.transpose(1, 2))
     if key_padding_mask is not None:
-        add = torch.zeros(N, Lk).masked_fill(key_padding_mask, float("-inf"))
+        add = torch.zeros(N, Lk, device=s.device).masked_fill(key_padding_mask, float("-inf"))
         s = s + add[:, None, None, :].expand(N, nh, 1, Lk).reshape(N * nh, 1, Lk)
     a = torch.softmax(s, dim=-1)
     o = torch.bmm(a, v).transpose(0, 1).reshape(Lq, N, Dm)
