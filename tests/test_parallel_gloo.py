@@ -28,8 +28,13 @@ def _worker(rank, world, port, q):
     flat = torch.full((1, 7), float(rank + 1))
     parallel.allreduce_meta_grads(flat)
     order = parallel.exchange_in_order([("ep%d" % e, [rank, e % 4], 0.5 * e) for e in mine])
+    # the two-bucket exchange forward() uses: [theta | psi | phi] with phi reduced first
+    G = torch.arange(10, dtype=torch.float32).view(1, 10) * (rank + 1)
+    red = parallel.BucketedAllReduce()
+    red.launch_async(G[:, 6:])
+    red.finish(G[:, :6])
     dist.barrier()
-    q.put((rank, mine, [r["episode"] for r in allres], tmax, flat.tolist(), order))
+    q.put((rank, mine, [r["episode"] for r in allres], tmax, flat.tolist(), order, G.tolist(), red.ms()))
     dist.destroy_process_group()
 
 
@@ -46,7 +51,9 @@ def test_episode_sharding_world2():
         assert p.exitcode == 0
     ids = list(range(100, 111))
     assert res[0][1] == ids[0::2] and res[1][1] == ids[1::2]           # disjoint cover, round robin
-    for _, _, gathered, tmax, flat, order in res:
+    for _, _, gathered, tmax, flat, order, G, ar_ms in res:
+        assert G == [[3.0 * i for i in range(10)]]                      # both buckets summed over the ranks
+        assert tuple(ar_ms) == (0.0, 0.0)                               # CPU tensors: no CUDA events
         assert gathered == ids                                          # order restored on every rank
         assert tmax == [2.0, 5.0]                                       # max over ranks
         assert flat == [[3.0] * 7]                                      # 1 + 2 summed on both ranks
@@ -62,3 +69,7 @@ def test_single_process_fallbacks():
     assert parallel.exchange_in_order(["a", "b"]) == [(0, 0, "a"), (0, 1, "b")]
     t = torch.ones(1, 3)
     assert parallel.allreduce_meta_grads(t) is t
+    red = parallel.BucketedAllReduce()
+    red.launch_async(t[:, 2:])
+    red.finish(t[:, :2])
+    assert t.tolist() == [[1.0, 1.0, 1.0]] and red.ms() == (0.0, 0.0)
