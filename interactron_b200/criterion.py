@@ -31,8 +31,11 @@ def _ops_for(t):
 _OPS = {}
 
 
-def _pack_targets(targets, device, dtype=torch.float32):
-    """list of {"labels": [T_f], "boxes": [T_f,4]} -> concatenated labels/boxes + int32 offsets."""
+def _pack_targets(targets, device, dtype=torch.float32, num_logits=None):
+    """list of {"labels": [T_f], "boxes": [T_f,4]} -> concatenated labels/boxes + int32 offsets.
+    num_logits: width of the logits rows the labels index (matcher cost / criterion kernels read
+    logits[label]): a label outside [0, num_logits) raises IndexError here, as torch's gather / cross_entropy
+    does in the reference (models/detr_models/matcher.py:61, detr.py:126), instead of an out-of-bounds read."""
     sizes = [int(t["labels"].numel()) for t in targets]
     off = [0]
     for n in sizes:
@@ -40,6 +43,11 @@ def _pack_targets(targets, device, dtype=torch.float32):
     if off[-1]:
         labels = torch.cat([t["labels"].reshape(-1) for t in targets]).to(device=device, dtype=torch.int64)
         boxes = torch.cat([t["boxes"].reshape(-1, 4) for t in targets]).to(device=device, dtype=dtype)
+        if num_logits is not None:
+            lo, hi = int(labels.min()), int(labels.max())          # one min/max over all labels of the call
+            if lo < 0 or hi >= num_logits:
+                raise IndexError(f"target label out of range: labels span [{lo}, {hi}] but the logits have "
+                                 f"{num_logits} classes")
     else:
         labels = torch.zeros(0, dtype=torch.int64, device=device)
         boxes = torch.zeros(0, 4, dtype=dtype, device=device)
@@ -61,7 +69,7 @@ class HungarianMatcher(nn.Module):
         boxes = outputs["pred_boxes"].detach().to(dt).contiguous()
         Fn, Q = logits.shape[:2]
         ops = self._ops_override or _ops_for(logits)
-        labels, tboxes, off_t, sizes, off = _pack_targets(targets, logits.device, logits.dtype)
+        labels, tboxes, off_t, sizes, off = _pack_targets(targets, logits.device, logits.dtype, logits.shape[-1])
         if off[-1] == 0:
             e = torch.zeros(0, dtype=torch.int64)
             return [(e, e) for _ in range(Fn)]
@@ -105,7 +113,7 @@ class SetCriterion(nn.Module):
         if len(targets) != Fn or len(indices) != Fn or Fn % groups:
             raise ValueError("targets / indices must have one entry per frame")
         ops = self._ops_override or _ops_for(logits)
-        labels, tboxes, off_t, sizes, off = _pack_targets(targets, logits.device, logits.dtype)
+        labels, tboxes, off_t, sizes, off = _pack_targets(targets, logits.device, logits.dtype, logits.shape[-1])
         rows, tg, moff = [], [], [0]
         per_group = Fn // groups
         for f, (i, j) in enumerate(indices):

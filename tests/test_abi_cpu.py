@@ -96,3 +96,19 @@ def test_state_dict_layout_matches_reference():
         a, b = m.state_dict(), ref.state_dict()
         assert list(a.keys()) == list(b.keys())
         assert all(a[k].shape == b[k].shape for k in a)
+
+
+def test_target_labels_are_range_checked():
+    """A label outside [0, classes) must raise (torch's gather / cross_entropy do in the reference) instead of
+    becoming an out-of-bounds read in the matcher-cost / criterion kernels."""
+    import pytest
+    import torch
+    from interactron_b200.criterion import _pack_targets
+    ok = [{"labels": torch.tensor([1, 1235]), "boxes": torch.rand(2, 4)}, {"labels": torch.zeros(0, dtype=torch.long),
+                                                                          "boxes": torch.zeros(0, 4)}]
+    labels, boxes, off, sizes, offs = _pack_targets(ok, torch.device("cpu"), num_logits=1236)
+    assert labels.tolist() == [1, 1235] and offs == [0, 2, 2]
+    for bad in (1236, -1):
+        with pytest.raises(IndexError):
+            _pack_targets([{"labels": torch.tensor([3, bad]), "boxes": torch.rand(2, 4)}], torch.device("cpu"),
+                          num_logits=1236)

@@ -107,3 +107,21 @@ def test_port_matcher_cost_reproduces_reference_assignments():
             tb = torch.cat([torch.rand(n, 2, generator=gen) * 0.6 + 0.2, torch.rand(n, 2, generator=gen) * 0.3 + 0.05], 1)
             i, j = linear_sum_assignment(port.hungarian_cost(logits[f], boxes[f], labels, tb).numpy())
             assert torch.equal(torch.as_tensor(i), ref_idx[f][0]) and torch.equal(torch.as_tensor(j), ref_idx[f][1])
+
+
+def test_d1_gap_against_the_unmodified_reference_is_what_the_fixture_says():
+    """The travelling oracle is D1 (frozen backbone).  Against the reference run WITHOUT D1 (199 fast weights,
+    tools/make_golden_unfrozen.py) it differs by the gap the fixture recorded from the reference's own D1 run:
+    the number every "matches the reference" statement of this repo has to be read with."""
+    import interactron_b200 as ib
+    from interactron_b200.synthetic import synthetic_episode
+    from oracle import port
+    gold = torch.load(os.path.join(GOLD, "interactron_random_predict_unfrozen.pt"))
+    assert gold["n_theta"] == 199 and gold["n_theta_backbone"] == 42
+    model = ib.build_model(ib.default_config("interactron_random", weights="synthetic").MODEL).eval()
+    out = port.predict(model.state_dict(), model.detector.backbone[0].body, synthetic_episode(gold["episode"]), "B",
+                       lr=model.config.ADAPTIVE_LR)
+    rel = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm())
+    gl, gb = rel(out["pred_logits"], gold["pred_logits"]), rel(out["pred_boxes"], gold["pred_boxes"])
+    assert gl > 0.05 and gb > 0.01                                       # far outside the 1e-3 bar: D1 is not the reference
+    assert abs(gl - gold["d1_gap_logits"]) < 2e-3 and abs(gb - gold["d1_gap_boxes"]) < 2e-3

@@ -266,3 +266,19 @@ def test_matcher_assignments_bit_exact():
             c = cost[50 * off[f]:50 * off[f + 1]].view(50, n)
             i, j = linear_sum_assignment(c.numpy())
             assert torch.equal(torch.as_tensor(i), ref_idx[f][0]) and torch.equal(torch.as_tensor(j), ref_idx[f][1])
+
+
+@pytest.mark.xfail(strict=True, reason="decision D1: this repo freezes the backbone (157 fast weights); the UNMODIFIED "
+                                       "reference also adapts ResNet layer2-4 (199 tensors, reference "
+                                       "models/detr_models/backbone.py:61-63) - SURVEY.md section 8f-3, not built")
+def test_unmodified_reference_without_d1(rand_model):
+    """Yardstick of the D1 gap: predict() against the reference run WITHOUT freezing the backbone
+    (tools/make_golden_unfrozen.py).  On the synthetic weights D1 itself moves the logits by 13 % and the boxes
+    by 3 % (stored in the fixture), far outside the 1e-3 bar - every parity statement of this repo is D1 mode."""
+    from interactron_b200.synthetic import synthetic_episode
+    gold = torch.load(os.path.join(GOLD, "interactron_random_predict_unfrozen.pt"))
+    assert gold["n_theta"] == 199 and gold["n_theta_backbone"] == 42
+    out = rand_model.predict({k: (v.cuda() if torch.is_tensor(v) else v)
+                              for k, v in synthetic_episode(gold["episode"]).items()})
+    assert rel(out["pred_logits"], gold["pred_logits"]) < TOL
+    assert rel(out["pred_boxes"], gold["pred_boxes"]) < TOL
