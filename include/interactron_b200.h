@@ -340,6 +340,12 @@ int itn_clip_adam_step(float* w, float* g, float* m, float* v, long long n, cons
                        int n_partials, float max_norm, double lr, double beta1, double beta2, double eps,
                        int step, int zero_grad, float* norm_out, void* stream);
 
+/* Windowed checkpoint average (engine/interactron_trainer.py:48-57: `saved[k] = w * v` on the first record,
+ * `saved[k] += w * v` afterwards, w = 1/SAVE_WINDOW over the last SAVE_WINDOW epochs) on a flat weight buffer:
+ * acc = (first ? 0 : acc) + w * x, element-wise in torch's operation order (product rounded, then the sum:
+ * bit-identical to the reference's two torch ops).  One launch per flat buffer per recorded epoch. */
+int itn_ckpt_accumulate(const float* x, float* acc, long long n, float w, int first, void* stream);
+
 /* ---- evaluator post-processing ------------------------------------------------
  * Replaces, per image, engine/random_policy_evaluator.py:65-78 (= engine/interactive_evaluator.py:71-84):
  *   pred_scores, pred_cats = logits.softmax(-1).max(-1); drop pred_cats == background_class;

@@ -96,6 +96,7 @@ SIGNATURES = {
     "itn_l2norm_jvp": (_I, [_P, _P, _P, _P, _P, _I, _I, _P]),
     "itn_sumsq_partials": (_I, [_P, _LL, _P, _I, C.POINTER(C.c_int), _P]),
     "itn_clip_adam_step": (_I, [_P, _P, _P, _P, _LL, _P, _I, _F, C.c_double, C.c_double, C.c_double, C.c_double, _I, _I, _P, _P]),
+    "itn_ckpt_accumulate": (_I, [_P, _P, _LL, _F, _I, _P]),
     "itn_detect_postprocess": (_I, [_P, _P, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P]),
     "itn_criterion": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _F, _F, _F, _P, _P, _P, _P, _P]),
 }

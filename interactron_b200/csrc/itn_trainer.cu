@@ -121,6 +121,32 @@ clip_adam_kernel(float* __restrict__ w, float* __restrict__ g, float* __restrict
   }
 }
 
+
+// acc = (first ? 0 : acc) + w * x, in torch's operation order (product rounded, then the sum rounded: no FMA
+// contraction), float4 grid-stride.  The windowed checkpoint average of the trainer.
+__global__ void __launch_bounds__(256) ckpt_accumulate_kernel(const float* __restrict__ x, float* __restrict__ acc,
+                                                              long long n, float w, int first) {
+  pdl_wait();
+  pdl_trigger();
+  const long long n4 = n >> 2;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    float4 a = first ? make_float4(0.f, 0.f, 0.f, 0.f) : reinterpret_cast<float4*>(acc)[i];
+    if (first) {
+      a = make_float4(__fmul_rn(w, v.x), __fmul_rn(w, v.y), __fmul_rn(w, v.z), __fmul_rn(w, v.w));
+    } else {
+      a.x = __fadd_rn(a.x, __fmul_rn(w, v.x));
+      a.y = __fadd_rn(a.y, __fmul_rn(w, v.y));
+      a.z = __fadd_rn(a.z, __fmul_rn(w, v.z));
+      a.w = __fadd_rn(a.w, __fmul_rn(w, v.w));
+    }
+    reinterpret_cast<float4*>(acc)[i] = a;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (long long i = n4 << 2; i < n; ++i) acc[i] = first ? __fmul_rn(w, x[i]) : __fadd_rn(acc[i], __fmul_rn(w, x[i]));
+}
+
 }  // namespace itn
 
 using namespace itn;
@@ -162,4 +188,14 @@ extern "C" int itn_clip_adam_step(float* w, float* g, float* m, float* v, long l
   launch(clip_adam_kernel, dim3((unsigned)blocks), 256, 0, static_cast<cudaStream_t>(stream), w, g, m, v, n,
          partial, n_partials, norm_out, a);
   return check_launch("clip_adam_kernel");
+}
+
+extern "C" int itn_ckpt_accumulate(const float* x, float* acc, long long n, float w, int first, void* stream) {
+  ITN_REQUIRE(x && acc && n > 0, "ckpt_accumulate: bad arguments");
+  ITN_REQUIRE((((uintptr_t)x | (uintptr_t)acc) & 15) == 0, "ckpt_accumulate: pointers must be 16-byte aligned");
+  long long blocks = ((n >> 2) + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  itn::launch(itn::ckpt_accumulate_kernel, (int)blocks, 256, 0, static_cast<cudaStream_t>(stream), x, acc, n, w, first);
+  return itn::check_launch("ckpt_accumulate_kernel");
 }

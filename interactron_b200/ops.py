@@ -621,6 +621,13 @@ class CudaOps:
             float(max_norm), float(lr), float(betas[0]), float(betas[1]), float(eps), int(step), 1 if zero_grad else 0,
             _ptr(norm_out), self._stream()))
 
+    def ckpt_accumulate_(self, acc, x, w, first):
+        """acc = (first ? 0 : acc) + w * x on flat buffers, in torch's operation order (trainer.CheckpointAverager)."""
+        assert acc.is_contiguous() and x.is_contiguous() and acc.numel() == x.numel() and acc.dtype == torch.float32
+        _lib.check(self.lib.itn_ckpt_accumulate(_ptr(x), _ptr(acc), x.numel(), float(w), 1 if first else 0,
+                                                self._stream()))
+        return acc
+
     # ------------------------------------------------------------ evaluator post-processing (SURVEY 8f-2)
     def detect_postprocess(self, logits, boxes, background, iou_threshold=0.5):
         """logits [I,Q,C], boxes [I,Q,4] cxcywh -> (count [I] int32, keep_idx [I,Q] int32, score [I,Q],

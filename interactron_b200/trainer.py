@@ -174,3 +174,83 @@ class MetaTrainerStep:
                 mult = max(0.1, 0.5 * (1.0 + math.cos(math.pi * progress)))
             self.supervisor_lr = self.base_supervisor_lr * mult
         return {"grad_norm": self.norm[0], "lr": used_lr}
+
+
+class CheckpointAverager:
+    """The reference trainer's windowed checkpoint average (engine/interactron_trainer.py:48-65,161-163): over the
+    last SAVE_WINDOW epochs `record_checkpoint(w = 1/SAVE_WINDOW)` accumulates `w * state_dict()`, and
+    `save_checkpoint()` writes `{"model": accumulated}` (or the plain state_dict if nothing was recorded).
+
+    Here the trainable weights live in three flat buffers (theta | psi | phi; the Parameters alias them after
+    `MetaTrainerStep`), so one record is ONE `itn_ckpt_accumulate` launch per buffer into three shadow buffers
+    instead of ~330 multiply / add pairs; everything else in the state_dict (the frozen backbone, FrozenBatchNorm
+    statistics, GPT mask buffers, `criterion.empty_weight`, ...) is constant during training and is accumulated
+    with the same two torch ops the reference uses.  `state_dict()` emits the reference's key layout and order;
+    values are bit-identical to the reference's arithmetic on the same snapshots (tests/test_trainer_*.py)."""
+
+    def __init__(self, model):
+        self.model = model
+        self.loop = model._get_loop()
+        self.n = 0
+        self._acc = None          # shadow flat buffers
+        self._rest = None         # state_dict entries that are not views of the flat buffers
+
+    def _segments(self):
+        lp = self.loop
+        return ((lp.theta_pack, lp.theta_params, lp.theta), (lp.psi_pack, lp.psi_params, lp.psi),
+                (lp.phi_pack, lp.phi_params, lp.phi))
+
+    def _flat_slots(self):
+        """{id(parameter): (segment index, pack, name)} for the parameters that live in the flat buffers."""
+        model = self.model
+        if model._loop_key != model._weights_key():
+            self.loop.refresh_weights()                          # parameters changed outside the fused trainer step
+            model._loop_key = model._weights_key()
+        out = {}
+        for i, (pack, params, _) in enumerate(self._segments()):
+            for name, p in zip(pack.names, params):
+                out[id(p)] = (i, pack, name)
+        return out
+
+    def record_checkpoint(self, w=1.0):
+        ops = self.loop.ops
+        slots = self._flat_slots()
+        first = self._acc is None
+        if first:
+            self._acc = [ops.zeros(*flat.shape) for _, _, flat in self._segments()]
+            self._rest = {}
+        for acc, (_, _, flat) in zip(self._acc, self._segments()):
+            ops.ckpt_accumulate_(acc.view(-1), flat.view(-1), w, first)
+        by_id = {id(p): p for p in self.model.parameters()}
+        for k, v in self.model.state_dict().items():
+            if self._key_slot(k, slots, by_id) is not None:
+                continue
+            self._rest[k] = w * v if first else self._rest[k] + w * v
+        self.n += 1
+
+    def _key_slot(self, key, slots, by_id):
+        """state_dict key -> flat slot of the Parameter behind it (None for buffers / frozen parameters)."""
+        if not hasattr(self, "_param_of_key"):
+            self._param_of_key = dict(self.model.named_parameters())
+        p = self._param_of_key.get(key)
+        return None if p is None else slots.get(id(p))
+
+    def state_dict(self):
+        """Averaged weights with the model's state_dict keys and order (plain state_dict if nothing recorded)."""
+        sd = self.model.state_dict()
+        if self._acc is None:
+            return sd
+        slots = self._flat_slots()
+        by_id = {id(p): p for p in self.model.parameters()}
+        out = type(sd)()
+        for k, v in sd.items():
+            slot = self._key_slot(k, slots, by_id)
+            if slot is None:
+                out[k] = self._rest[k]
+            else:
+                i, pack, name = slot
+                out[k] = pack.view(self._acc[i], name)[0].reshape(v.shape)
+        return out
+
+    def save_checkpoint(self, path):
+        torch.save({"model": {k: v.detach().cpu() for k, v in self.state_dict().items()}}, path)

@@ -113,6 +113,12 @@ class SimOps:
         dp.reshape(-1, ld)[:, :cols] = scale * pv * (dv - (pv * dv).sum(-1, keepdim=True))
         return dp
 
+    def ckpt_accumulate_(self, acc, x, w, first):
+        self.calls += 1
+        wx = torch.as_tensor(w, dtype=x.dtype) * x
+        acc.copy_(wx if first else acc + wx)
+        return acc
+
     def colsum(self, x, out=None):
         self.calls += 1
         if x.dim() == 2:

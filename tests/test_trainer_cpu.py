@@ -99,3 +99,47 @@ def test_supervisor_lr_schedule():
         lr = 1e-4 * mult
     assert lrs == pytest.approx(want, rel=1e-12)
     assert tr.detector_lr == 1e-5
+
+
+def _reference_record(saved, sd, w):
+    """engine/interactron_trainer.py:48-57 verbatim semantics."""
+    if saved is None:
+        return {k: w * v for k, v in sd.items()}
+    for k, v in sd.items():
+        saved[k] += w * v
+    return saved
+
+
+@pytest.mark.parametrize("model_type", ["interactron_random", "interactron"])
+def test_windowed_checkpoint_average(model_type):
+    """trainer.CheckpointAverager on the flat buffers == the reference's record_checkpoint / save_checkpoint
+    dict arithmetic over the last SAVE_WINDOW epochs (reference key layout and order)."""
+    import interactron_b200 as ib
+    from interactron_b200 import meta
+    from interactron_b200.trainer import CheckpointAverager, MetaTrainerStep
+    torch.manual_seed(1)
+    model = ib.build_model(ib.default_config(model_type, weights="synthetic").MODEL).eval().double()
+    model._ops = SimOps(torch.float64)
+    tr = MetaTrainerStep(model, 1e-3, 3e-3, 1.0)
+    avg = CheckpointAverager(model)
+    assert list(avg.state_dict().keys()) == list(model.state_dict().keys())     # nothing recorded: plain state_dict
+    loop = model._get_loop()
+    sizes = (loop.theta_pack.numel, loop.psi_pack.numel, loop.phi_pack.numel)
+    window, saved = 3, None
+    for epoch in range(window):
+        G = torch.randn(1, sum(sizes), dtype=torch.float64)
+        flat = {"all": G, "theta": G[:, :sizes[0]], "psi": G[:, sizes[0]:sizes[0] + sizes[1]], "phi": G[:, sizes[0] + sizes[1]:]}
+        model.last_meta_grads = flat
+        meta.accumulate_grads(model, flat)
+        tr.step()                                                                # weights move between the records
+        saved = _reference_record(saved, {k: v.clone() for k, v in model.state_dict().items()}, 1.0 / window)
+        avg.record_checkpoint(1.0 / window)
+    out = avg.state_dict()
+    assert list(out.keys()) == list(saved.keys()) == list(model.state_dict().keys())
+    n_flat = 0
+    for k in saved:
+        assert out[k].shape == saved[k].shape, k
+        assert torch.allclose(out[k].double(), saved[k].double(), rtol=0, atol=1e-14), k
+        n_flat += int(out[k].data_ptr() != saved[k].data_ptr())
+    moved = [k for k in saved if not torch.equal(saved[k], model.state_dict()[k].to(saved[k].dtype))]
+    assert len(moved) > 250                                                       # it is an average, not the last snapshot

@@ -91,3 +91,40 @@ def test_trainer_iteration_matches_torch(model_type):
     out2 = fresh.predict(probe)
     for k in ("pred_logits", "pred_boxes"):
         assert rel(out1[k], out2[k]) < 2e-4, k
+
+
+def test_checkpoint_accumulate_bit_exact_and_windowed_average():
+    """itn_ckpt_accumulate == torch's `saved = w * v` / `saved += w * v` bit for bit (no FMA contraction), and the
+    averager's state_dict equals the reference arithmetic (engine/interactron_trainer.py:48-57) on real snapshots."""
+    import interactron_b200 as ib
+    from interactron_b200.ops import CudaOps
+    from interactron_b200.trainer import CheckpointAverager
+    ops = CudaOps()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x1 = torch.randn(1_000_003, device="cuda", generator=g)
+    x2 = torch.randn(1_000_003, device="cuda", generator=g)
+    acc = torch.full_like(x1, float("nan"))
+    w = 1.0 / 3.0
+    ops.ckpt_accumulate_(acc, x1, w, True)
+    want = torch.tensor(w, dtype=torch.float32, device="cuda") * x1
+    assert torch.equal(acc, want)
+    ops.ckpt_accumulate_(acc, x2, w, False)
+    want += torch.tensor(w, dtype=torch.float32, device="cuda") * x2
+    assert torch.equal(acc, want)
+
+    model = ib.build_model(ib.default_config("interactron_random", weights="synthetic").MODEL).cuda().eval()
+    avg = CheckpointAverager(model)
+    saved, window = None, 2
+    for epoch in range(window):
+        with torch.no_grad():
+            for p in model.parameters():
+                if p.requires_grad:
+                    p.add_(0.01 * (epoch + 1))
+        sd = {k: v.clone() for k, v in model.state_dict().items()}
+        saved = {k: (1.0 / window) * v for k, v in sd.items()} if saved is None else \
+            {k: saved[k] + (1.0 / window) * v for k, v in sd.items()}
+        avg.record_checkpoint(1.0 / window)
+    out = avg.state_dict()
+    assert list(out.keys()) == list(saved.keys())
+    for k in saved:
+        assert torch.equal(out[k], saved[k]), k
