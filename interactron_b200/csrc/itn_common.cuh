@@ -76,6 +76,24 @@ __device__ __forceinline__ float rn_tf32(float x) {
   return __uint_as_float(r);
 }
 
+// The residual operand of the tf32x3 products: x - trunc_tf32(x) (exact in fp32, 13 significant bits), rounded to
+// nearest TF32 so that the tensor core's own truncation of it is exact.  ITN_LO_RN=0 (experiments) leaves the
+// rounding to the tensor core (truncation: a one-sided 2^-21 |x| error per operand).
+#ifndef ITN_LO_RN
+#define ITN_LO_RN 1
+#endif
+__device__ __forceinline__ float tf32_lo_rn(float lo) {
+#if ITN_LO_RN
+  return rn_tf32(lo);
+#else
+  return lo;
+#endif
+}
+__device__ __forceinline__ float tf32_lo_exact(float x) {
+  return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+}
+__device__ __forceinline__ float tf32_lo(float x) { return tf32_lo_rn(tf32_lo_exact(x)); }
+
 __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }

@@ -238,7 +238,7 @@ tf32_residual_kernel(const float* __restrict__ x, float* __restrict__ lo, long l
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const float v = x[i];
-    lo[i] = v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+    lo[i] = tf32_lo(v);
   }
 }
 

@@ -47,14 +47,11 @@ __device__ long long* g_trace = nullptr;
 #define ITN_TRACE_AT(slot, idx) do { } while (0)
 #endif
 
-// x - trunc_tf32(x): the part of an fp32 operand the tensor core drops (kind::tf32 truncates).
+// x - trunc_tf32(x): the part of an fp32 operand the tensor core drops (kind::tf32 truncates), itself rounded
+// to nearest TF32 (tf32_lo, itn_common.cuh): the tensor core would otherwise truncate the 13-bit residual to
+// 11 bits, a one-sided error of up to 2^-21 |x| that does not average out over K.
 __device__ __forceinline__ float4 tf32_residual(const float4 v) {
-  float4 r;
-  r.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-  r.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-  r.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-  r.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-  return r;
+  return make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
 }
 
 constexpr int kBM = 128;
@@ -511,10 +508,12 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll 8
         for (int i = tid; i < (p.b_presplit && !B_MN ? Cfg::kABytes : Cfg::kRawBytes) / 16; i += 128) {
           const float4 x = raw[i];
-          float4 r = tf32_residual(x);
-          if (i < kAVec) {
-            r.x = fmaf(x.x, delta, r.x); r.y = fmaf(x.y, delta, r.y);
-            r.z = fmaf(x.z, delta, r.z); r.w = fmaf(x.w, delta, r.w);
+          float4 r;
+          if (i < kAVec) {       // A: residual + accumulator compensation, rounded to TF32 once
+            r.x = tf32_lo_rn(fmaf(x.x, delta, tf32_lo_exact(x.x))); r.y = tf32_lo_rn(fmaf(x.y, delta, tf32_lo_exact(x.y)));
+            r.z = tf32_lo_rn(fmaf(x.z, delta, tf32_lo_exact(x.z))); r.w = tf32_lo_rn(fmaf(x.w, delta, tf32_lo_exact(x.w)));
+          } else {
+            r = tf32_residual(x);
           }
           lo[i] = r;
         }
