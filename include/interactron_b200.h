@@ -127,6 +127,7 @@ int itn_gemm_simt(const itn_gemm_desc_t* d, void* stream);
  *             (log-sum-exp in base 2, what the backward needs to recompute the probabilities).
  *             key_mask (may be NULL): uint8 [B, Lk], 1 = padded key (probability 0).
  *   backward: dq, dk, dv from q, k, v, o, d_o, lse; delta [B, nh, Lq] is scratch (rowsum(d_o * o)).
+ *             With dropout the SAME (p, seed, site) as the forward must be given.
  * No atomics: bit-reproducible.  Two launches for the backward (dQ; dK and dV). */
 typedef struct {
   int B, nh, hd, Lq, Lk;
@@ -142,6 +143,12 @@ typedef struct {
   float* dk;        long long dk_ld, dk_sb;
   float* dv;        long long dv_ld, dv_sb;
   float* delta;
+  /* train()-mode dropout of the attention probabilities (nn.MultiheadAttention(dropout=0.1), gpt.py:51): element
+   * (b, h, i, j) is kept iff the Philox word of (seed, site, row (b*nh+h)*Lq+i, column j) >= p*2^32 and scaled
+   * by 1/(1-p); see itn_dropout.  drop_p == 0: off.  drop_seed is a DEVICE pointer (graph-replay safe). */
+  float drop_p;
+  const unsigned long long* drop_seed;
+  unsigned int drop_site;
 } itn_attention_desc_t;
 int itn_attention_supported(const itn_attention_desc_t* d);
 int itn_attention_fwd(const itn_attention_desc_t* d, void* stream);
@@ -213,6 +220,19 @@ int itn_sigmoid_bwd(const float* dy, const float* y, float* dx, long long n,
  * dx_g = x_g / ||x_g||  (torch.norm + its backward seed, models/interactron.py:50). */
 int itn_l2norm_fwd_bwd(const float* x, float* loss, float* dx, int groups, int n,
                        void* stream);
+
+/* train()-mode dropout (the reference trainers call model.train(): engine/interactron_trainer.py:73; nn.Dropout
+ * p=0.1 at models/detr_models/transformer.py:156-159,221-230 and models/gpt.py:56,72,195):
+ *   out[r, c] = (residual ? residual[r, c] : 0) + x[r, c] * keep(r, c) / (1 - p)
+ * keep(r, c) is a pure function of (seed, site, row0 + r, c): Philox4x32 (7 rounds) with counter
+ * {row_lo, row_hi, c / 4, site} and key = *seed yields the keep-words of 4 consecutive columns, element kept iff
+ * word[c % 4] >= p * 2^32 (csrc/itn_philox.cuh; oracle/philox.py restates it).  The backward pass, the
+ * dual-number pass and the fused attention kernels regenerate the mask from the same (seed, site) instead of
+ * storing it.  seed is a DEVICE pointer so that captured CUDA graphs draw fresh masks on every replay.
+ * Row strides in elements; in place (out == x) allowed. */
+int itn_dropout(const float* x, long long ldx, const float* residual, long long ldr, float* out, long long ldo,
+                long long rows, int cols, long long row0, float p, const unsigned long long* seed,
+                unsigned int site, void* stream);
 
 /* Fused fast-weight step (utils/meta_utils.py:135-142 sgd_step):
  *   theta_out = theta - clip(lr * g, -clip, +clip)

@@ -52,6 +52,7 @@ class AttentionDesc(C.Structure):
         ("dk", C.c_void_p), ("dk_ld", C.c_longlong), ("dk_sb", C.c_longlong),
         ("dv", C.c_void_p), ("dv_ld", C.c_longlong), ("dv_sb", C.c_longlong),
         ("delta", C.c_void_p),
+        ("drop_p", C.c_float), ("drop_seed", C.c_void_p), ("drop_site", C.c_uint),
     ]
 
 
@@ -96,6 +97,7 @@ SIGNATURES = {
     "itn_l2norm_jvp": (_I, [_P, _P, _P, _P, _P, _I, _I, _P]),
     "itn_sumsq_partials": (_I, [_P, _LL, _P, _I, C.POINTER(C.c_int), _P]),
     "itn_clip_adam_step": (_I, [_P, _P, _P, _P, _LL, _P, _I, _F, C.c_double, C.c_double, C.c_double, C.c_double, _I, _I, _P, _P]),
+    "itn_dropout": (_I, [_P, _LL, _P, _LL, _P, _LL, _LL, _I, _LL, _F, _P, C.c_uint, _P]),
     "itn_ckpt_accumulate": (_I, [_P, _P, _LL, _F, _I, _P]),
     "itn_detect_postprocess": (_I, [_P, _P, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P]),
     "itn_criterion": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _F, _F, _F, _P, _P, _P, _P, _P]),

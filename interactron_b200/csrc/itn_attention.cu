@@ -33,6 +33,7 @@
 #include <mutex>
 
 #include "itn_common.cuh"
+#include "itn_philox.cuh"
 #include "itn_ptx.cuh"
 
 namespace itn {
@@ -54,6 +55,7 @@ struct Params {
   const unsigned char* kmask;   // [B, Lk], 1 = padded key (may be null)
   int nh, Lq, Lk, tiles;
   float scale, scale_log2;
+  DropParams drop;              // train()-mode dropout on the attention probabilities (seed == null: off)
   int dbg;                      // timing experiments (ITN_ATTN_DBG): 1 = K-major descriptors for the MN-major products (wrong results),
                                 // 2 = no row arithmetic, 4 = no second-phase MMAs, 8 = no first-phase MMAs, 16 = no residual split
 };
@@ -687,6 +689,9 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQk, const __grid_const
     float dvacc[HD], dkacc[HD];
 #pragma unroll
     for (int d = 0; d < HD; ++d) dvacc[d] = dkacc[d] = 0.0f;
+    const bool drop = p.drop.seed != nullptr;
+    const unsigned long long dseed = drop ? *p.drop.seed : 0ull;
+    const unsigned long long qrow0 = (unsigned long long)bh * p.Lq;
     for (int j = 0; j < n_blk; ++j) {
       const float* ls = lse_s + (j & 1) * BLK;
       const float* dl = dl_s + (j & 1) * BLK;
@@ -702,8 +707,15 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQk, const __grid_const
 #pragma unroll
         for (int t = 0; t < 32; ++t) {
           const float pv = kvalid ? ex2(__uint_as_float(sv[t]) - ls[32 * c + t]) : 0.0f;
-          const float ds = pv * (__uint_as_float(dp[t]) - dl[32 * c + t]) * p.scale;
-          sv[t] = __float_as_uint(pv);
+          float dpv = __uint_as_float(dp[t]), pd = pv;
+          if (drop) {         // rows are keys here: the mask word of (query row, this key) is word key % 4
+            const uint4 w4 = dropout_words(dseed, p.drop.site, qrow0 + (unsigned)(j * BLK + 32 * c + t), (unsigned)key >> 2);
+            const float kf = word_of(w4, key & 3) >= p.drop.thr ? p.drop.inv_keep : 0.0f;
+            pd = pv * kf;
+            dpv *= kf;
+          }
+          const float ds = pv * (dpv - dl[32 * c + t]) * p.scale;
+          sv[t] = __float_as_uint(pd);
           dp[t] = __float_as_uint(ds);
         }
         tmem_st_32x32(tw + Cfg::cST + 32 * c, sv);              // P^T over S^T
@@ -986,6 +998,10 @@ attn_pipe_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
       for (int d = 0; d < (MODE == M_DKV ? HD : 1); ++d) acc1[d] = 0.0f;
     }
     float m_run = -INFINITY, l_run = 0.0f, alpha_pend = 1.0f;
+    // train()-mode dropout of the probabilities: keep(seed, site, query row, key) regenerated per element
+    const bool drop = p.drop.seed != nullptr;
+    const unsigned long long dseed = drop ? *p.drop.seed : 0ull;
+    const unsigned long long qrow0 = (unsigned long long)bh * p.Lq;     // + query index = mask row
 
     auto consume = [&](int blk) {            // read back the second-phase products of block `blk`
       const int set = blk & 1;
@@ -1033,10 +1049,15 @@ attn_pipe_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
           uint32_t v[32];
           tmem_ld_32x32(ts + 32 * c, v);
           tmem_ld_wait();
+          uint4 w4 = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
           for (int t = 0; t < 32; ++t) {
-            const float pv = ex2(__uint_as_float(v[t]) + v0[32 * c + t] - m_use);
-            rs += pv;
+            float pv = ex2(__uint_as_float(v[t]) + v0[32 * c + t] - m_use);
+            rs += pv;                                               // the row sum is taken before the dropout
+            if (drop) {
+              if ((t & 3) == 0) w4 = dropout_words(dseed, p.drop.site, qrow0 + i, (unsigned)(j * BLK + 32 * c + t) >> 2);
+              pv = word_of(w4, t & 3) >= p.drop.thr ? pv * p.drop.inv_keep : 0.0f;
+            }
             v[t] = __float_as_uint(pv);
           }
           tmem_st_32x32(ts + 32 * c, v);                          // P over S
@@ -1054,10 +1075,16 @@ attn_pipe_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
           tmem_ld_32x32(ts + 32 * c, sv);
           tmem_ld_32x32(ts + BLK + 32 * c, dp);
           tmem_ld_wait();
+          uint4 w4 = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
           for (int t = 0; t < 32; ++t) {
             const float pv = ex2(__uint_as_float(sv[t]) + v0[32 * c + t] - lse2);
-            const float ds = pv * (__uint_as_float(dp[t]) - delta) * p.scale;
+            float dpv = __uint_as_float(dp[t]);
+            if (drop) {       // d(dropped P) -> dP: same mask, same 1/(1-p)
+              if ((t & 3) == 0) w4 = dropout_words(dseed, p.drop.site, qrow0 + i, (unsigned)(j * BLK + 32 * c + t) >> 2);
+              dpv = word_of(w4, t & 3) >= p.drop.thr ? dpv * p.drop.inv_keep : 0.0f;
+            }
+            const float ds = pv * (dpv - delta) * p.scale;
             dp[t] = __float_as_uint(ds);
             sv[t] = __float_as_uint(tf32_lo(ds));
           }
@@ -1075,8 +1102,15 @@ attn_pipe_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
 #pragma unroll
           for (int t = 0; t < 32; ++t) {
             const float pv = valid ? ex2(__uint_as_float(sv[t]) - v0[32 * c + t]) : 0.0f;
-            const float ds = pv * (__uint_as_float(dp[t]) - v1[32 * c + t]) * p.scale;
-            sv[t] = __float_as_uint(pv);
+            float dpv = __uint_as_float(dp[t]), pd = pv;
+            if (drop) {       // rows are keys here: the mask word of (query row, this key) is word key % 4
+              const uint4 w4 = dropout_words(dseed, p.drop.site, qrow0 + (unsigned)(j * BLK + 32 * c + t), (unsigned)i >> 2);
+              const float kf = word_of(w4, i & 3) >= p.drop.thr ? p.drop.inv_keep : 0.0f;
+              pd = pv * kf;
+              dpv *= kf;
+            }
+            const float ds = pv * (dpv - v1[32 * c + t]) * p.scale;
+            sv[t] = __float_as_uint(pd);
             dp[t] = __float_as_uint(ds);
           }
           tmem_st_32x32(ts + 32 * c, sv);                         // P^T over S^T
@@ -1216,6 +1250,10 @@ static Params make_params(const itn_attention_desc_t* d, int rows) {
   p.scale = d->scale;
   p.scale_log2 = d->scale * 1.4426950408889634f;
   p.dbg = getenv("ITN_ATTN_DBG") ? atoi(getenv("ITN_ATTN_DBG")) : 0;
+  p.drop.seed = d->drop_p > 0.f ? d->drop_seed : nullptr;
+  p.drop.site = d->drop_site;
+  p.drop.thr = (unsigned int)((double)d->drop_p * 4294967296.0);
+  p.drop.inv_keep = d->drop_p > 0.f ? 1.0f / (1.0f - d->drop_p) : 1.0f;
   return p;
 }
 
@@ -1347,7 +1385,9 @@ extern "C" int itn_attention_fwd(const itn_attention_desc_t* d, void* stream) {
   if (rc) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int blk = env_int("ITN_ATTN_FWD_BLK", 0);
-  if (want_pipe("ITN_ATTN_FWD", d->hd == 64)) {
+  const bool dropping = d->drop_p > 0.f;      // dropout lives in the pipelined kernels (and the hd-64 dK/dV kernel)
+  if (dropping) ITN_REQUIRE(d->drop_seed != nullptr && d->drop_p < 1.f, "attention: dropout needs a seed and p < 1");
+  if (dropping || want_pipe("ITN_ATTN_FWD", d->hd == 64)) {
     if (d->hd == 32) return blk == 32 ? launch_pipe<M_FWD, 32, 32, 2>(d, s) : launch_pipe<M_FWD, 32, 64>(d, s);
     return blk == 32 ? launch_pipe<M_FWD, 64, 32>(d, s) : launch_pipe<M_FWD, 64, 64>(d, s);
   }
@@ -1369,7 +1409,9 @@ extern "C" int itn_attention_bwd(const itn_attention_desc_t* d, void* stream) {
   const int only = env_int("ITN_ATTN_BWD_ONLY", 0);   // timing experiments: 1 = dQ kernel only, 2 = dK/dV kernel only
   // dQ first: it also writes delta = rowsum(dO * O), which the dK/dV kernel reads
   if (only != 2) {
-    if (want_pipe("ITN_ATTN_DQ", false)) {
+    const bool dropping = d->drop_p > 0.f;
+    if (dropping) ITN_REQUIRE(d->drop_seed != nullptr && d->drop_p < 1.f, "attention: dropout needs a seed and p < 1");
+    if (dropping || want_pipe("ITN_ATTN_DQ", false)) {
       if (d->hd == 32) rc = bq == 32 ? launch_pipe<M_DQ, 32, 32>(d, s) : launch_pipe<M_DQ, 32, 64>(d, s);
       else rc = launch_pipe<M_DQ, 64, 32>(d, s);
     } else if (d->hd == 32) {
@@ -1384,7 +1426,7 @@ extern "C" int itn_attention_bwd(const itn_attention_desc_t* d, void* stream) {
   }
   if (only == 1) return ITN_OK;
   if (d->hd == 32) {
-    if (want_pipe("ITN_ATTN_DKV", true)) return launch_pipe<M_DKV, 32, 32>(d, s);
+    if (d->drop_p > 0.f || want_pipe("ITN_ATTN_DKV", true)) return launch_pipe<M_DKV, 32, 32>(d, s);
     if (bkv == 32) return launch_dkv<32, 32, 1>(d, s);
     return launch_dkv<32, 64, 1>(d, s);
   }

@@ -2,6 +2,7 @@
 // sigmoid fwd/bwd, learned-loss L2 norm, DETR sine position embedding.
 // 128-bit accesses, grid-stride loops sized in multiples of the SM count.
 #include "itn_common.cuh"
+#include "itn_philox.cuh"
 
 namespace itn {
 
@@ -242,6 +243,46 @@ tf32_residual_kernel(const float* __restrict__ x, float* __restrict__ lo, long l
   }
 }
 
+// out[r, c] = (residual ? residual[r, c] : 0) + x[r, c] * keep(seed, site, row0 + r, c) / (1 - p); one thread per
+// 4 consecutive columns (one Philox call).  In place (out == x) is fine.
+__global__ void __launch_bounds__(256)
+dropout_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ residual, long long ldr,
+               float* __restrict__ out, long long ldo, long long rows, int cols, long long row0, DropParams d) {
+  pdl_wait();
+  pdl_trigger();
+  const int groups = (cols + 3) >> 2;
+  const long long total = rows * groups;
+  const unsigned long long seed = *d.seed;
+  const bool vec = ((cols | ldx | ldo | ldr) & 3) == 0 &&
+                   ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) |
+                     reinterpret_cast<uintptr_t>(residual)) & 15) == 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / groups;
+    const int g = (int)(i - r * groups);
+    const uint4 w = dropout_words(seed, d.site, (unsigned long long)(row0 + r), (unsigned int)g);
+    const float k0 = w.x >= d.thr ? d.inv_keep : 0.f, k1 = w.y >= d.thr ? d.inv_keep : 0.f;
+    const float k2 = w.z >= d.thr ? d.inv_keep : 0.f, k3 = w.w >= d.thr ? d.inv_keep : 0.f;
+    const float* xp = x + r * ldx + 4 * g;
+    float* op = out + r * ldo + 4 * g;
+    const float* rp = residual ? residual + r * ldr + 4 * g : nullptr;
+    if (vec) {
+      const float4 v = *reinterpret_cast<const float4*>(xp);
+      float4 y = make_float4(v.x * k0, v.y * k1, v.z * k2, v.w * k3);
+      if (rp) {
+        const float4 q = *reinterpret_cast<const float4*>(rp);
+        y = make_float4(q.x + y.x, q.y + y.y, q.z + y.z, q.w + y.w);
+      }
+      *reinterpret_cast<float4*>(op) = y;
+    } else {
+      const float k[4] = {k0, k1, k2, k3};
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (4 * g + j < cols) op[j] = (rp ? rp[j] : 0.f) + xp[j] * k[j];
+    }
+  }
+}
+
 }  // namespace itn
 
 using namespace itn;
@@ -335,4 +376,20 @@ extern "C" int itn_pos_embed_sine(const unsigned char* mask, float* pos, int fra
   ITN_REQUIRE(smem <= 48 * 1024, "pos_embed_sine: feature map %dx%d too large", h, w);
   launch(pos_embed_sine_kernel, frames, 256, smem, static_cast<cudaStream_t>(stream), mask, pos, h, w, feats);
   return check_launch("pos_embed_sine_kernel");
+}
+
+extern "C" int itn_dropout(const float* x, long long ldx, const float* residual, long long ldr, float* out,
+                           long long ldo, long long rows, int cols, long long row0, float p,
+                           const unsigned long long* seed, unsigned int site, void* stream) {
+  ITN_REQUIRE(x && out && seed && rows > 0 && cols > 0, "dropout: bad arguments");
+  ITN_REQUIRE(p >= 0.f && p < 1.f, "dropout: p must be in [0, 1)");
+  itn::DropParams d;
+  d.seed = seed;
+  d.site = site;
+  d.thr = (unsigned int)((double)p * 4294967296.0);
+  d.inv_keep = 1.0f / (1.0f - p);
+  const long long total = rows * ((cols + 3) / 4);
+  launch(dropout_kernel, grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream), x, ldx, residual, ldr, out,
+         ldo, rows, cols, row0, d);
+  return check_launch("dropout_kernel");
 }

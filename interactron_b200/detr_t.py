@@ -17,7 +17,7 @@ the `_r` twins of LayerNorm outputs); residual streams and gradients accumulate 
 import math
 
 from .layers import (DecDims, GradSink, MultiSink, NullSink, T, attention_bwd, attention_fwd,  # noqa: F401
-                     decoder_layer_bwd, decoder_layer_fwd, lin, mlp_bwd, mlp_fwd)
+                     decoder_layer_bwd, decoder_layer_fwd, lin, mlp_bwd, mlp_fwd, _drop_res, _next)
 
 D, H, HD, FFN, NQ = 256, 8, 32, 2048, 50
 N_ENC, N_DEC = 6, 6
@@ -25,13 +25,15 @@ SCALE = 1.0 / math.sqrt(HD)
 
 
 # --------------------------------------------------------------------------- forward
-def detr_t_forward(ops, W, src_r, pos, kmask, E, Fe, L, preds=None, need_cache=True):
+def detr_t_forward(ops, W, src_r, pos, kmask, E, Fe, L, preds=None, need_cache=True, drop=None):
     """
     src_r : [E, Fe*L, 2048] TF32-clean backbone features, token-major
     pos   : [E*Fe*L, 256] sine position embedding (full fp32)
     kmask : uint8 [E*Fe, L] (1 = padded key) or None
     preds : optional [E*Fe*50, 1496] buffer that receives cat(box_features, logits, boxes)
             TF32-clean, i.e. the prediction tokens fusion embeds (reference models/transformer.py:50)
+    drop  : layers.DropCtx in train() mode (dropout p=0.1 after every attention softmax, sub-layer output and FFN
+            activation, reference transformer.py:154-159,219-230), None in eval()
     Returns (out, cache): out has logits [E,Fe*50,C], boxes [E,Fe*50,4], hs, memory (+ `_r` twins).
     """
     R, Q, B = Fe * L, Fe * NQ, E * Fe
@@ -48,19 +50,30 @@ def detr_t_forward(ops, W, src_r, pos, kmask, E, Fe, L, preds=None, need_cache=T
         qk = lin(ops, qk_in, ipw[:, :2 * D], ipb[:, :2 * D], rnd=True)               # [1,E*R,512]
         v = lin(ops, x_r.view(1, E * R, D), ipw[:, 2 * D:], ipb[:, 2 * D:], rnd=True)
         qk3, v3 = qk.view(B, L, 2 * D), v.view(B, L, D)
-        o, P = attention_fwd(ops, qk3[..., :D], qk3[..., D:], v3, B, L, L, H, HD, SCALE, kmask)
-        a = lin(ops, o.view(E, R, D), W.w(pre + "self_attn.out_proj.weight"),
-                W.p(pre + "self_attn.out_proj.bias"), residual=x)
+        # train(): keys in module order (transformer.py:154-159): attention probabilities, dropout1, FFN dropout, dropout2
+        ka, kd1 = _next(drop, "attn"), _next(drop)
+        o, P = attention_fwd(ops, qk3[..., :D], qk3[..., D:], v3, B, L, L, H, HD, SCALE, kmask, drop=ka)
+        if drop is None:
+            a = lin(ops, o.view(E, R, D), W.w(pre + "self_attn.out_proj.weight"),
+                    W.p(pre + "self_attn.out_proj.bias"), residual=x)
+        else:
+            a = _drop_res(ops, lin(ops, o.view(E, R, D), W.w(pre + "self_attn.out_proj.weight"),
+                                   W.p(pre + "self_attn.out_proj.bias")), kd1, x)
         x1, x1_r, m1, r1 = ops.layernorm_fwd(a.view(E * R, D), W.p(pre + "norm1.weight"),
                                              W.p(pre + "norm1.bias"))
         h = lin(ops, x1_r.view(E, R, D), W.w(pre + "linear1.weight"), W.p(pre + "linear1.bias"),
                 act="relu", rnd=True)
-        f = lin(ops, h, W.w(pre + "linear2.weight"), W.p(pre + "linear2.bias"), residual=x1.view(E, R, D))
+        kf, kd2 = _next(drop), _next(drop)
+        if drop is None:
+            f = lin(ops, h, W.w(pre + "linear2.weight"), W.p(pre + "linear2.bias"), residual=x1.view(E, R, D))
+        else:
+            h = ops.dropout(h, kf, out=h)
+            f = _drop_res(ops, lin(ops, h, W.w(pre + "linear2.weight"), W.p(pre + "linear2.bias")), kd2, x1.view(E, R, D))
         x2, x2_r, m2, r2 = ops.layernorm_fwd(f.view(E * R, D), W.p(pre + "norm2.weight"),
                                              W.p(pre + "norm2.bias"))
         if need_cache:
             enc.append(dict(x_r=x_r, qk_in=qk_in, qk3=qk3, v3=v3, P=P, o=o, a=a, m1=m1, r1=r1,
-                            x1_r=x1_r, h=h, f=f, m2=m2, r2=r2))
+                            x1_r=x1_r, h=h, f=f, m2=m2, r2=r2, drop=None if drop is None else (kd1, kf, kd2)))
         x, x_r = x2.view(E, R, D), x2_r.view(E, R, D)
     memory, memory_r = x, x_r
     mem_pos_r = ops.add(memory.view(E * R, D), pos, rnd=True).view(1, E * R, D)
@@ -72,7 +85,7 @@ def detr_t_forward(ops, W, src_r, pos, kmask, E, Fe, L, preds=None, need_cache=T
     dec = []
     for j in range(N_DEC):
         tgt, tgt_r, dc = decoder_layer_fwd(ops, W, f"transformer.decoder.layers.{j}.", dm, tgt, tgt_r, qpos,
-                                           mem_pos_r, memory_r.view(1, E * R, D), kmask, need_cache)
+                                           mem_pos_r, memory_r.view(1, E * R, D), kmask, need_cache, drop=drop)
         dec.append(dc)
 
     # only hs[-1] is used (reference detr.py:69), so decoder.norm runs once
@@ -151,15 +164,28 @@ def detr_t_backward(ops, W, cache, sink, dpreds=None, dmemory=None, dlogits=None
         df, df_r = ops.layernorm_bwd(dx, s["f"].view(E * R, D), s["m2"], s["r2"], W.p(pre + "norm2.weight"),
                                      **sink.norm(pre + "norm2"))
         df3, df3_r = df.view(E, R, D), df_r.view(E, R, D)
-        sink.linear(pre + "linear2", df3_r, s["h"], df3)
-        dh = ops.matmul(df3_r, W.bwd(pre + "linear2.weight"), epi="relu_mask", aux=s["h"], rnd=True)
+        dk_ = s.get("drop")
+        kd1, kf, kd2 = dk_ if dk_ is not None else (None,) * 3
+        if dk_ is not None:                   # gradient of the dropped branch; the residual path keeps df3
+            dfm = ops.dropout(df3, kd2)
+            dfm_r = dfm
+        else:
+            dfm, dfm_r = df3, df3_r
+        sink.linear(pre + "linear2", dfm_r, s["h"], dfm)
+        dh = ops.matmul(dfm_r, W.bwd(pre + "linear2.weight"), epi="relu_mask", aux=s["h"], rnd=True)
+        if dk_ is not None:
+            dh = ops.dropout(dh, kf, out=dh)  # h is stored dropped: relu_mask kept (h > 0) & keep, this adds 1/(1-p)
         sink.linear(pre + "linear1", dh, s["x1_r"].view(E, R, D))
         dx1 = ops.matmul(dh, W.bwd(pre + "linear1.weight"), residual=df3)
         da, da_r = ops.layernorm_bwd(dx1.view(E * R, D), s["a"].view(E * R, D), s["m1"], s["r1"],
                                      W.p(pre + "norm1.weight"), **sink.norm(pre + "norm1"))
         da3, da3_r = da.view(E, R, D), da_r.view(E, R, D)
-        sink.linear(pre + "self_attn.out_proj", da3_r, s["o"].view(E, R, D), da3)
-        dO = ops.matmul(da3_r, W.bwd(pre + "self_attn.out_proj.weight"), rnd=True)
+        dam, dam_r = da3, da3_r
+        if dk_ is not None:
+            dam = ops.dropout(da3, kd1)
+            dam_r = dam
+        sink.linear(pre + "self_attn.out_proj", dam_r, s["o"].view(E, R, D), dam)
+        dO = ops.matmul(dam_r, W.bwd(pre + "self_attn.out_proj.weight"), rnd=True)
         dqk, dv = ops.empty(B, L, 2 * D), ops.empty(B, L, D)
         attention_bwd(ops, dO.view(B, L, D), s["qk3"][..., :D], s["qk3"][..., D:], s["v3"], s["P"],
                       B, L, L, H, HD, SCALE, dqk[..., :D], dqk[..., D:], dv)

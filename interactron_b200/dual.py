@@ -274,6 +274,20 @@ class DualOps:
             yt = None
         return Dual(y, yt)
 
+    def dropout(self, x, key, residual=None, out=None):
+        """Dropout is linear in x: the same mask on the value and on the tangent."""
+        o = self.o
+        yp = o.dropout(_p(x), key, residual=_p(residual), out=_p(out))
+        xt, rt = _t(x), _t(residual)
+        ot = _t(out) if out is not None else None
+        if xt is None and rt is None:
+            return Dual(yp, ot) if out is not None else Dual(yp, None)
+        if xt is None:
+            yt = rt if ot is None else ot.copy_(rt)
+        else:
+            yt = o.dropout(xt, key, residual=rt, out=ot)
+        return Dual(yp, yt)
+
     def copy2d_(self, dst, src, rnd=False):
         o = self.o
         o.copy2d_(dst.p, _p(src), rnd=rnd)

@@ -77,6 +77,11 @@ class InnerLoop:
         self.theta = self.psi = self.phi = None
         self.theta_t = self.psi_t = self.phi_t = None
         self._idx_cache = {}
+        # train()-mode dropout (layers.DropCtx): DETR's 0.1 is hard-coded in the reference
+        # (models/detr_models/transformer.py:278, new_transformer.py:23); fusion A reads its three from the YAML
+        self.drop_p = 0.1
+        self.fusion_drop = (0.1, 0.1, 0.1)          # residual, attention, embedding
+        self.drop_seed = None                        # device int64[1], rewritten by the model before every train() step
         self.refresh_weights()
 
     # ------------------------------------------------------------------ weights
@@ -166,10 +171,27 @@ class InnerLoop:
         out["preds"] = preds
         return out, src_r, hw
 
+    # dropout contexts of one step: every forward pass draws from its own range of sites
+    PASS_SITES = {"pre": 0, "fusion": 2048, "post": 4096, "post1": 6144}
+
+    def drop_ctx(self, which, train):
+        """layers.DropCtx of pass `which` ("pre", "fusion", "post", "post1") in train() mode, None in eval()."""
+        if not train:
+            return None
+        from .layers import DropCtx
+        if self.drop_seed is None:
+            raise RuntimeError("train()-mode pass without a dropout seed: call it through the model")
+        if which == "fusion":
+            r, a, e = self.fusion_drop
+            return DropCtx(r, self.drop_seed, self.PASS_SITES[which], p_attn=a, p_embd=e)
+        return DropCtx(self.drop_p, self.drop_seed, self.PASS_SITES[which])
+
     # ------------------------------------------------------------------ the hot path
-    def adapt_detect(self, frames, masks, post_frames=(0,), want_trace=False):
+    def adapt_detect(self, frames, masks, post_frames=(0,), want_trace=False, train=False):
         """frames [E,S,3,H,W], masks [E,S,H,W] on the device -> dict with post-adapt
-        pred_logits [E,P,50,C], pred_boxes [E,P,50,4] (P = len(post_frames)) and features."""
+        pred_logits [E,P,50,C], pred_boxes [E,P,50,4] (P = len(post_frames)) and features.
+        train: the reference's train() mode - dropout in the pre-adapt pass, the fusion network and the
+        post-adapt pass (models/interactron.py:31-59 run under model.train())."""
         ops = self.ops
         E, S = frames.shape[:2]
         src_r, pos, kmask, (h, w) = self.features(frames.flatten(0, 1), masks.flatten(0, 1))
@@ -178,13 +200,16 @@ class InnerLoop:
         # -- pre-adapt pass (shared theta) and learned loss
         Wd = self._det_weights(self.theta, self.theta_r, self.theta_t)
         preds = ops.empty(E * S * detr_t.NQ, detr_t.D + C + 4)
-        pre, cache = detr_t.detr_t_forward(ops, Wd, src_r.view(E, S * L, -1), pos, kmask, E, S, L, preds=preds)
+        pre, cache = detr_t.detr_t_forward(ops, Wd, src_r.view(E, S * L, -1), pos, kmask, E, S, L, preds=preds,
+                                           drop=self.drop_ctx("pre", train))
         Wf = self._fusion_weights()
         if self.kind == "A":
-            fout, fcache = fusion.fusion_a_forward(ops, Wf, pre["memory_r"], preds, E, S, L)
+            fout, fcache = fusion.fusion_a_forward(ops, Wf, pre["memory_r"], preds, E, S, L,
+                                                   drop=self.drop_ctx("fusion", train))
             dmemory, dpreds = fusion.fusion_a_backward(ops, Wf, fcache)
         else:
-            fout, fcache = fusion.fusion_b_forward(ops, Wf, pre["memory_r"], preds, E, S, L)
+            fout, fcache = fusion.fusion_b_forward(ops, Wf, pre["memory_r"], preds, E, S, L,
+                                                   drop=self.drop_ctx("fusion", train))
             dmemory, dpreds = fusion.fusion_b_backward(ops, Wf, fcache)
         # -- inner gradient g_e = d learned_loss_e / d theta
         g = ops.empty(E, self.theta_pack.numel)
@@ -207,7 +232,8 @@ class InnerLoop:
             pos_p = pos.view(E * S, L, -1).index_select(0, idx).reshape(E * P * L, -1)
             km_p = kmask.index_select(0, idx)
         Wp = self._det_weights(theta_p, theta_p_r)
-        post, _ = detr_t.detr_t_forward(ops, Wp, src_p, pos_p, km_p, E, P, L, need_cache=False)
+        post, _ = detr_t.detr_t_forward(ops, Wp, src_p, pos_p, km_p, E, P, L, need_cache=False,
+                                        drop=self.drop_ctx("post", train))
         out = {
             "pred_logits": post["logits"].view(E, P, detr_t.NQ, C),
             "pred_boxes": post["boxes"].view(E, P, detr_t.NQ, 4),

@@ -14,7 +14,7 @@ needed on the inner loop (the fusion parameters phi are not adapted): `backward`
 d memory and d preds for detr_t.detr_t_backward.
 """
 from .layers import (DecDims, NullSink, T, attention_bwd, attention_fwd, decoder_layer_bwd,  # noqa: F401
-                     decoder_layer_fwd, lin, mlp_bwd, mlp_fwd)
+                     decoder_layer_fwd, lin, mlp_bwd, mlp_fwd, _drop_res, _next)
 
 DF, NH, NP, NA = 512, 8, 50, 5          # width, heads, predictions per frame, action tokens
 N_LAYERS = 4
@@ -30,7 +30,7 @@ def _learned_loss(ops, W, y_r, E, S, need_cache):
 
 
 # ------------------------------------------------------------------------------------- fusion B
-def fusion_b_forward(ops, W, memory_r, preds, E, S, L, need_cache=True):
+def fusion_b_forward(ops, W, memory_r, preds, E, S, L, need_cache=True, drop=None):
     """-> dict(loss_vec [E,S*50], learned_loss [E], actions [E,4,4]), cache."""
     assert S == 5, "fusion B is only defined for full 5-frame episodes"
     R, Qp, Q = S * L, S * NP, S * NP + NA
@@ -50,7 +50,7 @@ def fusion_b_forward(ops, W, memory_r, preds, E, S, L, need_cache=True):
     x, x_r = tgt, tgt_r
     for j in range(N_LAYERS):
         x, x_r, c = decoder_layer_fwd(ops, W, f"transformer.layers.{j}.", dm, x, x_r, qpos, mem_pos_r, mem_r,
-                                      None, need_cache)
+                                      None, need_cache, drop=drop)
         caches.append(c)
     y, y_r, my, ry = ops.layernorm_fwd(x.view(E * Q, DF), W.p("transformer.norm.weight"),
                                        W.p("transformer.norm.bias"))
@@ -102,7 +102,7 @@ def fusion_b_backward(ops, W, cache, sink=None, dactions=None):
 
 
 # ------------------------------------------------------------------------------------- fusion A
-def fusion_a_forward(ops, W, memory_r, preds, E, S, L, need_cache=True, want_aux_heads=False):
+def fusion_a_forward(ops, W, memory_r, preds, E, S, L, need_cache=True, want_aux_heads=False, drop=None):
     """-> dict(loss_vec [E,S*50], learned_loss [E], actions [E,4,4] (+ pred_boxes/pred_logits)), cache.
     Works for S in 1..5 (the policy rollout feeds 1-4 frames, reference models/interactron.py:174-197)."""
     R, Qp = S * L, S * NP
@@ -117,6 +117,9 @@ def fusion_a_forward(ops, W, memory_r, preds, E, S, L, need_cache=True, want_aux
     ops.copy2d_(seq.view(E, Tn * DF)[:, (R + Qp) * DF:], at.reshape(1, NA * DF).expand(E, NA * DF))
     spe = W.p("model.seq_pos_embed").reshape(1, -1, DF)[:, :Tn].reshape(1, Tn * DF)
     x = ops.add(seq.view(E, Tn * DF), spe.contiguous()).view(1, E * Tn, DF)             # residual stream fp32
+    k_embd = _next(drop, "embd")                                       # train(): x = drop(seq + pos) (gpt.py:195)
+    if drop is not None:
+        x = ops.dropout(x, k_embd, out=x)
     caches = []
     for i in range(N_LAYERS):
         pre = f"model.blocks.{i}."
@@ -127,16 +130,25 @@ def fusion_a_forward(ops, W, memory_r, preds, E, S, L, need_cache=True, want_aux
         v = lin(ops, h_r, W.w(pre + "attn.value.weight"), W.p(pre + "attn.value.bias"), rnd=True)
         q, k, v = q.view(E, Tn, DF), k.view(E, Tn, DF), v.view(E, Tn, DF)
         # the reference's attention mask is all ones (models/gpt.py:35-36): full attention
-        o, P = attention_fwd(ops, q, k, v, E, Tn, Tn, NH, HD, 1.0 / (HD ** 0.5), None)
-        x1 = lin(ops, o.view(1, E * Tn, DF), W.w(pre + "attn.proj.weight"), W.p(pre + "attn.proj.bias"), residual=x)
+        ka, kr = _next(drop, "attn"), _next(drop)                      # attn_drop (gpt.py:51), resid_drop (gpt.py:56)
+        o, P = attention_fwd(ops, q, k, v, E, Tn, Tn, NH, HD, 1.0 / (HD ** 0.5), None, drop=ka)
+        if drop is None:
+            x1 = lin(ops, o.view(1, E * Tn, DF), W.w(pre + "attn.proj.weight"), W.p(pre + "attn.proj.bias"), residual=x)
+        else:
+            x1 = _drop_res(ops, lin(ops, o.view(1, E * Tn, DF), W.w(pre + "attn.proj.weight"),
+                                    W.p(pre + "attn.proj.bias")), kr, x)
         h2, h2_r, m2, r2 = ops.layernorm_fwd(x1.view(E * Tn, DF), W.p(pre + "ln2.weight"), W.p(pre + "ln2.bias"))
         upre = ops.empty(1, E * Tn, 4 * DF)
         u = lin(ops, h2_r.view(1, E * Tn, DF), W.w(pre + "mlp.0.weight"), W.p(pre + "mlp.0.bias"), act="gelu",
                 out_pre=upre, rnd=True)
-        x2 = lin(ops, u, W.w(pre + "mlp.2.weight"), W.p(pre + "mlp.2.bias"), residual=x1)
+        km = _next(drop)                                       # the Dropout closing the MLP (gpt.py:72)
+        if drop is None:
+            x2 = lin(ops, u, W.w(pre + "mlp.2.weight"), W.p(pre + "mlp.2.bias"), residual=x1)
+        else:
+            x2 = _drop_res(ops, lin(ops, u, W.w(pre + "mlp.2.weight"), W.p(pre + "mlp.2.bias")), km, x1)
         if need_cache:
             caches.append(dict(x=x, m1=m1, r1=r1, q=q, k=k, v=v, P=P, x1=x1, m2=m2, r2=r2, upre=upre,
-                               h_r=h_r, o=o, h2_r=h2_r, u=u))
+                               h_r=h_r, o=o, h2_r=h2_r, u=u, drop=None if drop is None else (kr, km)))
         x = x2
     yf, yf_r, mf, rf = ops.layernorm_fwd(x.view(E * Tn, DF), W.p("model.ln_f.weight"), W.p("model.ln_f.bias"))
     yf_r = yf_r.view(E, Tn, DF)
@@ -158,7 +170,7 @@ def fusion_a_forward(ops, W, memory_r, preds, E, S, L, need_cache=True, want_aux
     cache = None
     if need_cache:
         cache = dict(layers=caches, x_last=x, mf=mf, rf=rf, yp_in=yp_in, yp_r=yp_r, dlv=dlv, lhid=lhid,
-                     E=E, S=S, L=L, ya_in=ya_in, ya_r=ya_r, ahid=ahid, memory_r=memory_r, preds=preds)
+                     E=E, S=S, L=L, ya_in=ya_in, ya_r=ya_r, ahid=ahid, memory_r=memory_r, preds=preds, k_embd=k_embd)
     return out, cache
 
 
@@ -188,6 +200,9 @@ def fusion_a_backward(ops, W, cache, sink=None, dactions=None):
         pre = f"model.blocks.{i}."
         s = cache["layers"][i]
         dx_r = ops.round_tf32(dx).view(1, E * Tn, DF)
+        dk_ = s.get("drop")
+        if dk_ is not None:                   # gradient of the dropped MLP branch; the residual path keeps dx
+            dx_r = ops.dropout(dx.view(1, E * Tn, DF), dk_[1])
         sink.linear(pre + "mlp.2", dx_r, s["u"])
         du = ops.matmul(dx_r, W.bwd(pre + "mlp.2.weight"), epi="gelu_grad", aux=s["upre"], rnd=True)
         sink.linear(pre + "mlp.0", du, s["h2_r"].view(1, E * Tn, DF))
@@ -196,6 +211,8 @@ def fusion_a_backward(ops, W, cache, sink=None, dactions=None):
                                        W.p(pre + "ln2.weight"), **sink.norm(pre + "ln2"))
         dx1 = ops.add(dx1, dx)                                                          # + residual path
         dx1_r = ops.round_tf32(dx1).view(1, E * Tn, DF)
+        if dk_ is not None:
+            dx1_r = ops.dropout(dx1.view(1, E * Tn, DF), dk_[0])
         sink.linear(pre + "attn.proj", dx1_r, s["o"].view(1, E * Tn, DF))
         dO = ops.matmul(dx1_r, W.bwd(pre + "attn.proj.weight"), rnd=True)
         dq, dk, dv = ops.empty(E, Tn, DF), ops.empty(E, Tn, DF), ops.empty(E, Tn, DF)
@@ -209,6 +226,8 @@ def fusion_a_backward(ops, W, cache, sink=None, dactions=None):
         dxa, _ = ops.layernorm_bwd(dh.view(E * Tn, DF), s["x"].view(E * Tn, DF), s["m1"], s["r1"],
                                    W.p(pre + "ln1.weight"), **sink.norm(pre + "ln1"))
         dx = ops.add(dxa, dx1)
+    if cache.get("k_embd") is not None:       # through x = drop(seq + pos)
+        dx = ops.dropout(dx.view(1, E * Tn, DF), cache["k_embd"]).view(E * Tn, DF)
     dseq = dx.view(E, Tn * DF)
     if sink.wants("model.seq_pos_embed"):
         assert Tn * DF == W.p("model.seq_pos_embed").numel(), "phi gradients need the full 5-frame sequence"

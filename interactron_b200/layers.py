@@ -21,8 +21,38 @@ def lin(ops, x, W, b=None, **kw):
     return ops.matmul(x, T(W), bias=b, **kw)
 
 
+# --------------------------------------------------------------------------- train()-mode dropout
+class DropCtx:
+    """Dropout state of ONE forward pass in train() mode (the reference trainers call model.train():
+    engine/interactron_trainer.py:73): probability, the device seed tensor (int64[1], rewritten by the host before
+    every step so that replayed CUDA graphs draw fresh masks) and the running site counter.  `next()` is called
+    once per dropout module in the reference's forward order (models/detr_models/transformer.py:154-159,219-230;
+    models/gpt.py:51,56,72,195); the key it returns is kept in the layer cache so that the backward pass and the
+    dual-number pass regenerate the same mask (csrc/itn_philox.cuh)."""
+
+    def __init__(self, p, seed, first_site=0, p_attn=None, p_embd=None):
+        self.p, self.seed, self.site = float(p), seed, int(first_site)
+        self.p_kind = {"attn": float(p if p_attn is None else p_attn), "embd": float(p if p_embd is None else p_embd)}
+
+    def next(self, kind=None):
+        """kind: None (sub-layer / FFN dropout), "attn" (attention probabilities), "embd" (GPT embedding dropout):
+        fusion A has one probability per kind (ATTENTION_PDROP / RESIDUAL_PDROP / EMBEDDING_PDROP)."""
+        key = (self.p_kind.get(kind, self.p), self.seed, self.site)
+        self.site += 1
+        return key
+
+
+def _next(drop, kind=None):
+    return None if drop is None else drop.next(kind)
+
+
+def _drop_res(ops, y, key, residual):
+    """residual + dropout(y): what `x + self.dropoutN(y)` computes in train() mode."""
+    return ops.dropout(y, key, residual=residual)
+
+
 # --------------------------------------------------------------------------- attention core
-def attention_fwd(ops, q, k, v, B, Lq, Lk, nh, hd, scale, kmask):
+def attention_fwd(ops, q, k, v, B, Lq, Lk, nh, hd, scale, kmask, drop=None):
     """softmax(scale * q k^T + mask) v per (batch, head).
     q [B,Lq,nh*hd], k/v [B,Lk,nh*hd] (strided views ok) -> o [B,Lq,nh*hd], ctx (what attention_bwd needs).
     On the B200 backend this is ONE fused tcgen05 kernel (itn_attention_fwd: the score matrix stays in
@@ -30,24 +60,44 @@ def attention_fwd(ops, q, k, v, B, Lq, Lk, nh, hd, scale, kmask):
     dual-number pass of the meta-training step) run the unfused chain and keep the probabilities."""
     fused = getattr(ops, "attention_supported", None)
     if fused is not None and fused(q, k, v, nh):
-        o, lse = ops.attention_fwd(q, k, v, nh, scale, kmask)
-        return o, FusedCtx(o, lse, kmask)
-    return _attention_fwd_unfused(ops, q, k, v, B, Lq, Lk, nh, hd, scale, kmask)
+        o, lse = ops.attention_fwd(q, k, v, nh, scale, kmask, drop=drop)
+        return o, FusedCtx(o, lse, kmask, drop)
+    return _attention_fwd_unfused(ops, q, k, v, B, Lq, Lk, nh, hd, scale, kmask, drop)
 
 
 class FusedCtx:
     """Saved state of a fused attention forward: output and base-2 log-sum-exp per row."""
 
-    __slots__ = ("o", "lse", "kmask")
+    __slots__ = ("o", "lse", "kmask", "drop")
 
-    def __init__(self, o, lse, kmask):
-        self.o, self.lse, self.kmask = o, lse, kmask
+    def __init__(self, o, lse, kmask, drop=None):
+        self.o, self.lse, self.kmask, self.drop = o, lse, kmask, drop
 
 
-def _attention_fwd_unfused(ops, q, k, v, B, Lq, Lk, nh, hd, scale, kmask):
+class UnfusedCtx:
+    """Saved state of an unfused attention forward in train() mode: probabilities before and after dropout."""
+
+    __slots__ = ("P", "Pd", "drop")
+
+    def __init__(self, P, Pd, drop):
+        self.P, self.Pd, self.drop = P, Pd, drop
+
+
+def _attention_fwd_unfused(ops, q, k, v, B, Lq, Lk, nh, hd, scale, kmask, drop=None):
     """QK^T GEMM -> softmax -> PV GEMM with the probabilities P [B,nh,Lq,pad4(Lk)] materialised."""
     P = ops.empty(B, nh, Lq, pad4(Lk))                           # row stride padded to 16 bytes for TMA
     o = ops.empty(B, Lq, nh * hd)
+    if drop is not None:
+        # attention-probability dropout (nn.MultiheadAttention(dropout=0.1), gpt.py:51): mask row = (b*nh+h)*Lq+i
+        qh = q.reshape(B, Lq, nh, hd).permute(0, 2, 1, 3)
+        khT = k.reshape(B, Lk, nh, hd).permute(0, 2, 3, 1)
+        vh = v.reshape(B, Lk, nh, hd).permute(0, 2, 1, 3)
+        ops.matmul(qh, khT, out=P[..., :Lk], out_pad=True)
+        ops.softmax_(P, Lk, scale, kmask, rows_per_mask=nh * Lq)
+        Pd = ops.zeros(B, nh, Lq, pad4(Lk))
+        ops.dropout(P.view(B * nh * Lq, pad4(Lk))[:, :Lk], drop, out=Pd.view(B * nh * Lq, pad4(Lk))[:, :Lk])
+        ops.matmul(Pd[..., :Lk], vh, out=o.view(B, Lq, nh, hd).permute(0, 2, 1, 3), rnd=True)
+        return o, UnfusedCtx(P, Pd, drop)
     for b0, b1 in _l2_chunks(ops, B, nh * Lq * pad4(Lk) * 4, 1):
         qh = q[b0:b1].reshape(b1 - b0, Lq, nh, hd).permute(0, 2, 1, 3)            # [b,nh,Lq,hd]
         khT = k[b0:b1].reshape(b1 - b0, Lk, nh, hd).permute(0, 2, 3, 1)           # [b,nh,hd,Lk]
@@ -79,7 +129,22 @@ def attention_bwd(ops, dO, q, k, v, P, B, Lq, Lk, nh, hd, scale, dq, dk, dv):
     """dO [B,Lq,nh*hd] (TF32-clean).  Writes TF32-clean dq/dk/dv into the given [B,L,nh*hd] views.
     P is the ctx attention_fwd returned: FusedCtx (scores recomputed on chip) or the probabilities."""
     if isinstance(P, FusedCtx):
-        ops.attention_bwd(dO, q, k, v, P.o, P.lse, nh, scale, P.kmask, dq, dk, dv)
+        ops.attention_bwd(dO, q, k, v, P.o, P.lse, nh, scale, P.kmask, dq, dk, dv, drop=P.drop)
+        return
+    if isinstance(P, UnfusedCtx):
+        ctx, ld = P, pad4(Lk)
+        qh = q.reshape(B, Lq, nh, hd).permute(0, 2, 1, 3)
+        kh = k.reshape(B, Lk, nh, hd).permute(0, 2, 1, 3)
+        vhT = v.reshape(B, Lk, nh, hd).permute(0, 2, 3, 1)
+        dOh = dO.reshape(B, Lq, nh, hd).permute(0, 2, 1, 3)
+        dP = ops.zeros(B, nh, Lq, ld)
+        dp = dP[..., :Lk]
+        ops.matmul(dOh, vhT, out=dp, out_pad=True)                                              # d(dropped P)
+        ops.matmul(T(ctx.Pd[..., :Lk]), dOh, out=dv.view(B, Lk, nh, hd).permute(0, 2, 1, 3), rnd=True)
+        ops.dropout(dP.view(B * nh * Lq, ld)[:, :Lk], ctx.drop, out=dP.view(B * nh * Lq, ld)[:, :Lk])    # -> dP
+        ops.softmax_bwd_(ctx.P, dP, Lk, scale)
+        ops.matmul(dp, kh, out=dq.view(B, Lq, nh, hd).permute(0, 2, 1, 3), rnd=True)
+        ops.matmul(T(dp), qh, out=dk.view(B, Lk, nh, hd).permute(0, 2, 1, 3), rnd=True)
         return
     chunks = _l2_chunks(ops, B, nh * Lq * pad4(Lk) * 4, 2)
     # one chunk: dP for the whole batch; several: ONE chunk-sized dP buffer reused (it stays in L2)
@@ -230,7 +295,7 @@ class DecDims:
         self.R = B * Lk // E           # memory rows per episode
 
 
-def decoder_layer_fwd(ops, W, pre, dm, tgt, tgt_r, qpos, mem_pos_r, memory_r, kmask, need_cache=True):
+def decoder_layer_fwd(ops, W, pre, dm, tgt, tgt_r, qpos, mem_pos_r, memory_r, kmask, need_cache=True, drop=None):
     """DETR post-norm decoder layer (reference detr_models/transformer.py:211-232).
     tgt/tgt_r [E,Q,D]; qpos [Gw,Lq,D] added to the queries of every batch; mem_pos_r / memory_r
     [1,E*R,D] TF32-clean keys-input (memory+pos) and values-input (memory).  -> t3, t3_r, cache."""
@@ -242,27 +307,47 @@ def decoder_layer_fwd(ops, W, pre, dm, tgt, tgt_r, qpos, mem_pos_r, memory_r, km
     qk = lin(ops, qk_in, sw[:, :2 * D], sb[:, :2 * D], rnd=True)
     v = lin(ops, tgt_r.view(1, E * Q, D), sw[:, 2 * D:], sb[:, 2 * D:], rnd=True)
     qk3, v3 = qk.view(B, Lq, 2 * D), v.view(B, Lq, D)
-    o, P = attention_fwd(ops, qk3[..., :D], qk3[..., D:], v3, B, Lq, Lq, nh, hd, dm.scale, None)
-    a1 = lin(ops, o.view(E, Q, D), W.w(pre + "self_attn.out_proj.weight"),
-             W.p(pre + "self_attn.out_proj.bias"), residual=tgt)
+    # train(): dropout keys in the reference's module order (transformer.py:219-230): self-attention
+    # probabilities, dropout1, cross-attention probabilities, dropout2, FFN dropout, dropout3
+    ka1 = _next(drop, "attn")
+    o, P = attention_fwd(ops, qk3[..., :D], qk3[..., D:], v3, B, Lq, Lq, nh, hd, dm.scale, None, drop=ka1)
+    kd1 = _next(drop)
+    if drop is None:
+        a1 = lin(ops, o.view(E, Q, D), W.w(pre + "self_attn.out_proj.weight"),
+                 W.p(pre + "self_attn.out_proj.bias"), residual=tgt)
+    else:
+        a1 = _drop_res(ops, lin(ops, o.view(E, Q, D), W.w(pre + "self_attn.out_proj.weight"),
+                                W.p(pre + "self_attn.out_proj.bias")), kd1, tgt)
     t1, t1_r, m1, r1 = ops.layernorm_fwd(a1.view(E * Q, D), W.p(pre + "norm1.weight"), W.p(pre + "norm1.bias"))
     # cross attention into the Lk memory tokens of the batch
     q_in = ops.add(t1.view(E, Q, D), qpos, rnd=True).view(1, E * Q, D)
     qc = lin(ops, q_in, cw[:, :D], cb[:, :D], rnd=True).view(B, Lq, D)
     kc = lin(ops, mem_pos_r, cw[:, D:2 * D], cb[:, D:2 * D], rnd=True).view(B, Lk, D)
     vc = lin(ops, memory_r, cw[:, 2 * D:], cb[:, 2 * D:], rnd=True).view(B, Lk, D)
-    o2, P2 = attention_fwd(ops, qc, kc, vc, B, Lq, Lk, nh, hd, dm.scale, kmask)
-    a2 = lin(ops, o2.view(E, Q, D), W.w(pre + "multihead_attn.out_proj.weight"),
-             W.p(pre + "multihead_attn.out_proj.bias"), residual=t1.view(E, Q, D))
+    ka2 = _next(drop, "attn")
+    o2, P2 = attention_fwd(ops, qc, kc, vc, B, Lq, Lk, nh, hd, dm.scale, kmask, drop=ka2)
+    kd2 = _next(drop)
+    if drop is None:
+        a2 = lin(ops, o2.view(E, Q, D), W.w(pre + "multihead_attn.out_proj.weight"),
+                 W.p(pre + "multihead_attn.out_proj.bias"), residual=t1.view(E, Q, D))
+    else:
+        a2 = _drop_res(ops, lin(ops, o2.view(E, Q, D), W.w(pre + "multihead_attn.out_proj.weight"),
+                                W.p(pre + "multihead_attn.out_proj.bias")), kd2, t1.view(E, Q, D))
     t2, t2_r, m2, r2 = ops.layernorm_fwd(a2.view(E * Q, D), W.p(pre + "norm2.weight"), W.p(pre + "norm2.bias"))
     h = lin(ops, t2_r.view(E, Q, D), W.w(pre + "linear1.weight"), W.p(pre + "linear1.bias"), act="relu", rnd=True)
-    f = lin(ops, h, W.w(pre + "linear2.weight"), W.p(pre + "linear2.bias"), residual=t2.view(E, Q, D))
+    kf, kd3 = _next(drop), _next(drop)
+    if drop is None:
+        f = lin(ops, h, W.w(pre + "linear2.weight"), W.p(pre + "linear2.bias"), residual=t2.view(E, Q, D))
+    else:
+        h = ops.dropout(h, kf, out=h)
+        f = _drop_res(ops, lin(ops, h, W.w(pre + "linear2.weight"), W.p(pre + "linear2.bias")), kd3, t2.view(E, Q, D))
     t3, t3_r, m3, r3 = ops.layernorm_fwd(f.view(E * Q, D), W.p(pre + "norm3.weight"), W.p(pre + "norm3.bias"))
     cache = None
     if need_cache:
         cache = dict(qk3=qk3, v3=v3, P=P, o=o, a1=a1, m1=m1, r1=r1, qc=qc, kc=kc, vc=vc, P2=P2, o2=o2,
                      a2=a2, m2=m2, r2=r2, t2_r=t2_r, h=h, f=f, m3=m3, r3=r3,
-                     qk_in=qk_in, tgt_r=tgt_r, q_in=q_in, mem_pos_r=mem_pos_r, memory_r=memory_r)
+                     qk_in=qk_in, tgt_r=tgt_r, q_in=q_in, mem_pos_r=mem_pos_r, memory_r=memory_r,
+                     drop=None if drop is None else (kd1, kd2, kf, kd3))
     return t3.view(E, Q, D), t3_r.view(E, Q, D), cache
 
 
@@ -279,14 +364,27 @@ def decoder_layer_bwd(ops, W, pre, dm, s, dt, sink, dqpos, dmp, dmem):
     df, df_r = ops.layernorm_bwd(dt, s["f"].view(E * Q, D), s["m3"], s["r3"], W.p(pre + "norm3.weight"),
                                  **nk("norm3"))
     df3, df3_r = df.view(E, Q, D), df_r.view(E, Q, D)
-    dh = ops.matmul(df3_r, W.bwd(pre + "linear2.weight"), epi="relu_mask", aux=s["h"], rnd=True)
-    sink.linear(pre + "linear2", df3_r, s["h"], df3)
+    dk_ = s.get("drop")
+    kd1, kd2, kf, kd3 = dk_ if dk_ is not None else (None,) * 4
+    if dk_ is not None:                       # gradient of the dropped branch; the residual path keeps df3
+        dfm = ops.dropout(df3, kd3)
+        dfm_r = dfm
+    else:
+        dfm, dfm_r = df3, df3_r
+    dh = ops.matmul(dfm_r, W.bwd(pre + "linear2.weight"), epi="relu_mask", aux=s["h"], rnd=True)
+    if dk_ is not None:
+        dh = ops.dropout(dh, kf, out=dh)      # h is stored dropped: relu_mask kept (h > 0) & keep, this adds 1/(1-p)
+    sink.linear(pre + "linear2", dfm_r, s["h"], dfm)
     sink.linear(pre + "linear1", dh, s["t2_r"].view(E, Q, D))
     dt2 = ops.matmul(dh, W.bwd(pre + "linear1.weight"), residual=df3)
     da2, da2_r = ops.layernorm_bwd(dt2.view(E * Q, D), s["a2"].view(E * Q, D), s["m2"], s["r2"],
                                    W.p(pre + "norm2.weight"), **nk("norm2"))
     da2_3r = da2_r.view(E, Q, D)
-    sink.linear(pre + "multihead_attn.out_proj", da2_3r, s["o2"].view(E, Q, D), da2.view(E, Q, D))
+    da2m = da2.view(E, Q, D)
+    if dk_ is not None:
+        da2m = ops.dropout(da2m, kd2)
+        da2_3r = da2m
+    sink.linear(pre + "multihead_attn.out_proj", da2_3r, s["o2"].view(E, Q, D), da2m)
     dO2 = ops.matmul(da2_3r, W.bwd(pre + "multihead_attn.out_proj.weight"), rnd=True)
     dqc, dkc, dvc = ops.empty(B, Lq, D), ops.empty(B, Lk, D), ops.empty(B, Lk, D)
     attention_bwd(ops, dO2.view(B, Lq, D), s["qc"], s["kc"], s["vc"], s["P2"], B, Lq, Lk, nh, hd, dm.scale,
@@ -304,7 +402,11 @@ def decoder_layer_bwd(ops, W, pre, dm, s, dt, sink, dqpos, dmp, dmem):
     da1, da1_r = ops.layernorm_bwd(dt1.view(E * Q, D), s["a1"].view(E * Q, D), s["m1"], s["r1"],
                                    W.p(pre + "norm1.weight"), **nk("norm1"))
     da1_3r = da1_r.view(E, Q, D)
-    sink.linear(pre + "self_attn.out_proj", da1_3r, s["o"].view(E, Q, D), da1.view(E, Q, D))
+    da1m = da1.view(E, Q, D)
+    if dk_ is not None:
+        da1m = ops.dropout(da1m, kd1)
+        da1_3r = da1m
+    sink.linear(pre + "self_attn.out_proj", da1_3r, s["o"].view(E, Q, D), da1m)
     dO = ops.matmul(da1_3r, W.bwd(pre + "self_attn.out_proj.weight"), rnd=True)
     dqk, dv = ops.empty(B, Lq, 2 * D), ops.empty(B, Lq, D)
     attention_bwd(ops, dO.view(B, Lq, D), s["qk3"][..., :D], s["qk3"][..., D:], s["v3"], s["P"],

@@ -18,8 +18,11 @@ Here, for all E episodes of the batch at once (every arithmetic step in the sm_1
      (interactron_b200/dual.py): the tangents of the phi / psi gradients are the second-order
      meta-gradients, and the policy loss's first-order gradient rides along as a tangent seed
   6. 1-frame post-adapt forward/backward for the detector loss (theta'' == theta' numerically)
-The reference's train()-mode dropout (p=0.1) is NOT applied: the step is the reference's
-`forward()` in eval() mode, which is also the mode every parity statement is made in.
+In train() mode (both reference trainers call model.train()) every forward pass applies dropout with
+counter-based masks (layers.DropCtx, csrc/itn_philox.cuh): the pre-adapt pass and the fusion network draw
+their masks once and the backward of step 1 AND the dual pass of step 5 regenerate exactly those; the
+post-adapt passes of steps 3 and 6 draw their own.  PyTorch's generator cannot be reproduced, so train()-mode
+parity with the reference is statistical (tools/dropout_stats.py); eval() mode is the exact-parity mode.
 """
 import random
 
@@ -67,8 +70,9 @@ class MetaParts:
     Both are pure kernel sequences on static shapes, so each is captured into a CUDA graph
     (`graph.GraphedCall`) and replayed; `part_b` reads the activations `part_a` left in `self.st`."""
 
-    def __init__(self, model):
+    def __init__(self, model, train=False):
         self.model, self.loop = model, model._get_loop()
+        self.train = bool(train)
         self.st = None
 
     def part_a(self, frames, masks, idx):
@@ -87,8 +91,10 @@ class MetaParts:
         Wd = loop._det_weights(loop.theta, loop.theta_r, loop.theta_t)
         Wf = loop._fusion_weights()
         preds = ops.empty(E * S * NQ, D + C + 4)
-        pre, cache = detr_t.detr_t_forward(ops, Wd, src3, pos, kmask, E, S, L, preds=preds)
-        fout, fcache = f_fwd(ops, Wf, pre["memory_r"], preds, E, S, L)
+        tr = self.train
+        pre, cache = detr_t.detr_t_forward(ops, Wd, src3, pos, kmask, E, S, L, preds=preds,
+                                           drop=loop.drop_ctx("pre", tr))
+        fout, fcache = f_fwd(ops, Wf, pre["memory_r"], preds, E, S, L, drop=loop.drop_ctx("fusion", tr))
         dmemory, dpreds = f_bwd(ops, Wf, fcache)
         g = ops.empty(E, tpk.numel)
         detr_t.detr_t_backward(ops, Wd, cache, GradSink(ops, tpk, g), dpreds=dpreds, dmemory=dmemory)
@@ -98,11 +104,11 @@ class MetaParts:
         theta_p_t = tpk.transpose_into(ops, theta_p, ops.zeros(E, tpk.numel))
         Wp = loop._det_weights(theta_p, theta_p_r, theta_p_t)
         # 3. post-adapt pass on the 5 frames; 6a. on one chosen frame per episode (theta'' == theta')
-        post, pcache = detr_t.detr_t_forward(ops, Wp, src3, pos, kmask, E, S, L)
+        post, pcache = detr_t.detr_t_forward(ops, Wp, src3, pos, kmask, E, S, L, drop=loop.drop_ctx("post", tr))
         src1 = src_r.index_select(0, idx).view(E, L, -1)
         pos1 = pos.view(E * S, L, -1).index_select(0, idx).reshape(E * L, -1)
         km1 = kmask.index_select(0, idx)
-        post1, c1 = detr_t.detr_t_forward(ops, Wp, src1, pos1, km1, E, 1, L)
+        post1, c1 = detr_t.detr_t_forward(ops, Wp, src1, pos1, km1, E, 1, L, drop=loop.drop_ctx("post1", tr))
         self.st = dict(E=E, S=S, L=L, C=C, src3=src3, pos=pos, kmask=kmask, cmask=cmask, Wp=Wp, pcache=pcache, c1=c1)
         return {"post_logits": post["logits"].view(E * S, NQ, C), "post_boxes": post["boxes"].view(E * S, NQ, 4),
                 "post1_logits": post1["logits"].view(E, NQ, C), "post1_boxes": post1["boxes"].view(E, NQ, 4),
@@ -133,8 +139,10 @@ class MetaParts:
         DWd = DualWeights((tpk, loop.theta, loop.theta_t, v, v_t), (ppk, loop.psi, loop.psi_t, None, None))
         DWf = DualWeights((fpk, loop.phi, loop.phi_t, None, None))
         preds2 = dops.empty(E * S * NQ, D + C + 4)
-        pre2, cache2 = detr_t.detr_t_forward(dops, DWd, src3, pos, kmask, E, S, L, preds=preds2)
-        _, fcache2 = f_fwd(dops, DWf, pre2["memory_r"], preds2, E, S, L)
+        # the dual pass re-runs step 1 on dual numbers: same sites, same seed -> the same dropout masks
+        pre2, cache2 = detr_t.detr_t_forward(dops, DWd, src3, pos, kmask, E, S, L, preds=preds2,
+                                             drop=loop.drop_ctx("pre", self.train))
+        _, fcache2 = f_fwd(dops, DWf, pre2["memory_r"], preds2, E, S, L, drop=loop.drop_ctx("fusion", self.train))
         # the step's meta-gradient: ONE flat buffer [theta | psi | phi] (what gets all-reduced)
         G = ops.zeros(1, n_t + n_p + n_f)
         gphi2 = Dual(ops.zeros(1, n_f), G[:, n_t + n_p:])
@@ -177,20 +185,21 @@ def _parts_runner(model, frames, masks, idx):
     """-> (run_a, run_b1, run_b2): the launch-only pieces, CUDA-graph replayed when the model allows it."""
     loop = model._get_loop()
     use_graph = model.use_cuda_graph and frames.is_cuda
+    train = model.mode == "train"
     if not use_graph:
-        parts = MetaParts(model)
+        parts = MetaParts(model, train)
         return parts.part_a, parts.part_b1, parts.part_b2
     from .graph import GraphedCall
     bb = loop.detector.backbone
     bb_key = tuple((t.data_ptr(), t._version) for t in list(bb.parameters()) + list(bb.buffers()))
     # everything the capture bakes in as a kernel scalar or a branch is part of the key
     key = ("meta", tuple(frames.shape), tuple(masks.shape), loop.kind, bb_key, float(loop.lr), float(loop.clip),
-           loop.ops.precision, loop.backbone_impl, bool(loop.ops.fused_attention))
+           loop.ops.precision, loop.backbone_impl, bool(loop.ops.fused_attention), train)
     ent = model._graphs.get(key)
     if ent is None:
         for k in [k for k in model._graphs if k[0] == "meta"]:
             del model._graphs[k]                       # one meta geometry at a time: the caches are large
-        ent = model._graphs[key] = {"parts": MetaParts(model), "a": None, "b1": None, "b2": None}
+        ent = model._graphs[key] = {"parts": MetaParts(model, train), "a": None, "b1": None, "b2": None}
     parts = ent["parts"]
 
     def run_a(f, m, i):
@@ -231,6 +240,8 @@ def meta_step(model, data, ridx=None, sync=False):
     masks = masks.to(dev, non_blocking=True)
     E, S = frames.shape[:2]
     assert S == 5, "the meta-training step is defined on full 5-frame episodes"
+    if model.mode == "train":
+        model._new_dropout_seed(loop)
     C = loop.detector.class_embed.out_features
     NQ = detr_t.NQ
     tpk, ppk, fpk = loop.theta_pack, loop.psi_pack, loop.phi_pack

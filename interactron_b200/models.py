@@ -50,6 +50,7 @@ class _Base(nn.Module):
         self.policy_cache_hits = 0
         self.use_cuda_graph = os.environ.get("ITN_CUDA_GRAPH", "1") != "0"
         self.sync_meta_grads = True
+        self._drop_gen = None               # host generator of the per-step dropout seeds (train() mode)
 
     # -- reference surface ------------------------------------------------------------
     def eval(self):
@@ -97,6 +98,22 @@ class _Base(nn.Module):
         self._loop_key = key
         return self._loop
 
+    def _new_dropout_seed(self, loop):
+        """train() mode: draw this step's seed on the host and write it into the loop's device seed buffer (the
+        kernels read it through a pointer, so replayed CUDA graphs see the new value).  The stream of seeds
+        follows torch's global seed (`torch.manual_seed`, as reference train.py:15-18 sets it)."""
+        if self._drop_gen is None:
+            self._drop_gen = torch.Generator(device="cpu")
+            self._drop_gen.manual_seed(torch.initial_seed() & 0x7FFFFFFFFFFFFFFF)
+        seed = torch.randint(0, 2 ** 62, (1,), generator=self._drop_gen, dtype=torch.int64)
+        if loop.drop_seed is None:
+            loop.drop_seed = torch.zeros(1, dtype=torch.int64, device=loop.ops.device)
+        loop.drop_seed.copy_(seed, non_blocking=True)
+        cfg = getattr(self, "config", None)
+        if cfg is not None and hasattr(cfg, "RESIDUAL_PDROP"):
+            loop.fusion_drop = (float(cfg.RESIDUAL_PDROP), float(cfg.ATTENTION_PDROP), float(cfg.EMBEDDING_PDROP))
+        return int(seed)
+
     def _detector(self):
         return self.detector
 
@@ -139,19 +156,20 @@ class _Adaptive(_Base):
         """Adapt on the episode(s) and detect on frame 0 with the adapted weights.
         Returns {k: [b,1,...]} for pred_logits, pred_boxes, image_features,
         embedded_memory_features, box_features — the reference's dict for b == 1."""
-        if self.mode == "train":
-            raise NotImplementedError("train()-mode dropout inside predict() is not implemented; call eval()")
         loop = self._get_loop()
+        train = self.mode == "train"         # the reference applies dropout here too when left in train() mode
+        if train:
+            self._new_dropout_seed(loop)
         frames, masks = self._frames_masks(data, loop.ops.device)
         keys = ("pred_logits", "pred_boxes", "image_features", "embedded_memory_features", "box_features")
 
         def run(f, m):
-            out = loop.adapt_detect(f, m, post_frames=(0,))
+            out = loop.adapt_detect(f, m, post_frames=(0,), train=train)
             return {k: out[k] for k in keys}
 
         if not (self.use_cuda_graph and frames.is_cuda):
             return run(frames, masks)
-        return self._graphed("predict", run, frames, masks)
+        return self._graphed("predict_train" if train else "predict", run, frames, masks)
 
     def _check_backbone_moved(self):
         bb = self._detector().backbone
@@ -182,7 +200,8 @@ class _Adaptive(_Base):
         supervisor gradients on fusion + in_proj_*, first-order detector gradients on the fast
         weights).  `train` is ignored, as in the reference.  `ridx` (extension): the per-episode frame
         of the detector loss; default = the reference's `random.randint(0, 4)` draw per episode.
-        Dropout is not applied (the reference's forward in eval() mode); see meta.py."""
+        In train() mode (what both reference trainers run, engine/interactron_trainer.py:73) dropout is applied
+        in every pass with counter-based masks (layers.DropCtx); in eval() mode there is none; see meta.py."""
         from . import meta
         # one process per GPU, the batch's episodes sharded over ranks: the meta-gradient is a sum over
         # episodes -> all-reduce(SUM) of the flat buffer [theta | psi | phi] (replaces nn.DataParallel,

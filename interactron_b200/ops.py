@@ -245,7 +245,7 @@ class CudaOps:
         setattr(d, prefix + "_ld" if prefix != "d_o" else "do_ld", t.stride(1))
         setattr(d, prefix + "_sb" if prefix != "d_o" else "do_sb", t.stride(0) if t.shape[0] > 1 else 0)
 
-    def _attention_desc(self, q, k, v, o, lse, nh, scale, kmask):
+    def _attention_desc(self, q, k, v, o, lse, nh, scale, kmask, drop=None):
         B, Lq, D = q.shape
         Lk = k.shape[1]
         hd = D // nh
@@ -260,6 +260,10 @@ class CudaOps:
             d.key_mask = kmask.data_ptr()
         assert lse.is_contiguous() and lse.numel() == B * nh * Lq
         d.lse = lse.data_ptr()
+        if drop is not None:                         # (p, device seed tensor, site): train()-mode dropout of the probabilities
+            p_, seed, site = drop
+            assert seed.is_cuda and seed.dtype == torch.int64 and seed.numel() == 1
+            d.drop_p, d.drop_seed, d.drop_site = float(p_), seed.data_ptr(), int(site)
         return d
 
     def attention_supported(self, q, k, v, nh):
@@ -275,21 +279,22 @@ class CudaOps:
                 return False
         return True
 
-    def attention_fwd(self, q, k, v, nh, scale, kmask=None):
+    def attention_fwd(self, q, k, v, nh, scale, kmask=None, drop=None):
         """o = softmax(scale q k^T + key mask) v per (batch, head), scores kept on chip.
         q [B,Lq,nh*hd], k/v [B,Lk,nh*hd] (strided views ok) -> (o [B,Lq,nh*hd], lse [B,nh,Lq] base-2 log-sum-exp)."""
         B, Lq, D = q.shape
         o = self.empty(B, Lq, D)
         lse = self.empty(B, nh, Lq)
-        d = self._attention_desc(q, k, v, o, lse, nh, scale, kmask)
+        d = self._attention_desc(q, k, v, o, lse, nh, scale, kmask, drop)
         _lib.check(self.lib.itn_attention_fwd(C.byref(d), self._stream()))
         self.n_attn += 1
         return o, lse
 
-    def attention_bwd(self, dO, q, k, v, o, lse, nh, scale, kmask, dq, dk, dv):
-        """Writes dq/dk/dv (views like q/k/v) given dO [B,Lq,nh*hd]; scores are recomputed from lse."""
+    def attention_bwd(self, dO, q, k, v, o, lse, nh, scale, kmask, dq, dk, dv, drop=None):
+        """Writes dq/dk/dv (views like q/k/v) given dO [B,Lq,nh*hd]; scores are recomputed from lse
+        (and the dropout mask from `drop`, which must be the forward's)."""
         B, Lq, D = q.shape
-        d = self._attention_desc(q, k, v, o, lse, nh, scale, kmask)
+        d = self._attention_desc(q, k, v, o, lse, nh, scale, kmask, drop)
         hd = D // nh
         for name, t in (("d_o", dO), ("dq", dq), ("dk", dk), ("dv", dv)):
             self._heads_view(d, name, t, nh, hd)
@@ -440,6 +445,32 @@ class CudaOps:
         assert n % b_elems == 0
         _lib.check(self.lib.itn_add(_ptr(a), _ptr(b), _ptr(out), n, b_elems, a_group, b_gs,
                                     1 if (rnd and self._clean) else 0, self._stream()))
+        return out
+
+    def dropout(self, x, key, residual=None, out=None):
+        """out = (residual +) x * keep / (1 - p) with the counter-based mask of itn_dropout; key = (p, device seed
+        tensor int64[1], site).  x: contiguous [..., cols] or a 2-D view with unit inner stride (rows = mask rows).
+        out may be x (in place); default: a new tensor."""
+        p_, seed, site = key
+        assert not self._clean, "train()-mode dropout runs in the tf32x3 (fp32-accurate) mode only"
+        assert seed.is_cuda and seed.dtype == torch.int64 and seed.numel() == 1
+        if x.dim() == 2 and not x.is_contiguous():
+            assert x.stride(1) == 1
+            x2 = x
+        else:
+            assert x.is_contiguous()
+            x2 = x.view(-1, x.shape[-1])
+        rows, cols = x2.shape
+        if out is None:
+            out = self.empty(*x.shape)
+        o2 = out if (out.dim() == 2 and not out.is_contiguous()) else out.view(-1, out.shape[-1])
+        assert tuple(o2.shape) == (rows, cols) and o2.stride(1) == 1
+        r2 = None
+        if residual is not None:
+            assert residual.is_contiguous() and residual.numel() == rows * cols
+            r2 = residual.view(rows, cols)
+        _lib.check(self.lib.itn_dropout(_ptr(x2), x2.stride(0), _ptr(r2), cols if r2 is not None else 0, _ptr(o2),
+                                        o2.stride(0), rows, cols, 0, float(p_), _ptr(seed), int(site), self._stream()))
         return out
 
     def copy2d_(self, dst, src, rnd=False):

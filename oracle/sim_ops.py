@@ -113,6 +113,22 @@ class SimOps:
         dp.reshape(-1, ld)[:, :cols] = scale * pv * (dv - (pv * dv).sum(-1, keepdim=True))
         return dp
 
+    def dropout(self, x, key, residual=None, out=None):
+        """Same mask function as itn_dropout (oracle/philox.py); key = (p, seed int tensor[1], site)."""
+        from . import philox
+        self.calls += 1
+        p_, seed, site = key
+        x2 = x if x.dim() == 2 else x.reshape(-1, x.shape[-1])
+        rows, cols = x2.shape
+        keep = torch.from_numpy(philox.keep_mask(int(seed.item()) & 0xFFFFFFFFFFFFFFFF, int(site), rows, cols, float(p_)))
+        y = x2 * keep.to(x.dtype) * (1.0 / (1.0 - float(p_)))
+        if residual is not None:
+            y = residual.reshape(rows, cols) + y
+        if out is None:
+            return y.reshape(x.shape).contiguous()
+        out.copy_(y.reshape(out.shape) if out.numel() == y.numel() and out.is_contiguous() else y)
+        return out
+
     def ckpt_accumulate_(self, acc, x, w, first):
         self.calls += 1
         wx = torch.as_tensor(w, dtype=x.dtype) * x
