@@ -203,10 +203,10 @@ def gemm_roofline(loop, frames, masks, bf16_peak):
         conv_src[out[0].data_ptr()] = x.numel()
         return out
 
-    def att_fwd(q, k, v, nh, scale, kmask=None):
+    def att_fwd(q, k, v, nh, scale, kmask=None, **kw):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        out = orig_fwd(q, k, v, nh, scale, kmask)
+        out = orig_fwd(q, k, v, nh, scale, kmask, **kw)
         e1.record()
         B, Lq, D = q.shape
         att.append((4.0 * B * Lq * k.shape[1] * D, e0, e1, 4.0 * (2 * q.numel() + 2 * k.numel())))
@@ -553,7 +553,7 @@ def run_rollout_arm(args):
         dist.destroy_process_group()
 
 
-def measure_meta(name, E, steps, warmup, cpu_episodes, rank, local, world):
+def measure_meta(name, E, steps, warmup, cpu_episodes, rank, local, world, train=True):
     """BASELINE configs[4]: the meta-training step `forward(data)` (second-order MAML gradients), the batch's
     episodes sharded over the ranks and the flat meta-gradient [theta | psi | phi] all-reduced (SUM) with NCCL in
     two buckets (the fusion part overlaps the detector pass).  The collective's time is reported separately
@@ -561,7 +561,8 @@ def measure_meta(name, E, steps, warmup, cpu_episodes, rank, local, world):
     import torch
     import interactron_b200 as ib
     from interactron_b200.synthetic import collate_episodes, synthetic_episode
-    model = ib.build_model(ib.default_config(name, weights="synthetic").MODEL).to(f"cuda:{local}").eval()
+    model = ib.build_model(ib.default_config(name, weights="synthetic").MODEL).to(f"cuda:{local}")
+    model.train(train)            # the reference trainers run train() mode: dropout p=0.1 in every pass
     ops = model._get_ops()
     batches = []
     for i in range(2):
@@ -627,8 +628,9 @@ def measure_meta(name, E, steps, warmup, cpu_episodes, rank, local, world):
         "unit": "episodes/s", "n_gpus": world, "steps": steps, "warmup": warmup,
         "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "tf32x3", "data": "synthetic",
-        "config": {"workload": f"{name}.yaml forward() = BASELINE configs[4] (meta-training step), eval-mode "
-                               "numerics (no dropout), D1", "episodes_per_step_per_gpu": E,
+        "config": {"workload": f"{name}.yaml forward() = BASELINE configs[4] (meta-training step), " +
+                               ("train() mode (dropout p=0.1 in every pass, as the reference trainer)" if train
+                                else "eval() mode (no dropout)") + ", D1", "episodes_per_step_per_gpu": E,
                    "global_batch": E * world, "cuda_graph": bool(model.use_cuda_graph),
                    "l2": "256 MiB buffer written between timed steps"},
         "allreduce": {"collective": "ncclAllReduce(SUM, fp32) over NVLink, 2 buckets: phi on a side stream under the "
@@ -653,7 +655,7 @@ def run_meta_arm(args):
     import torch.distributed as dist
     rank, local, world = _dist_setup()
     out = measure_meta(args.workload[len("meta_"):], args.episodes, args.steps, args.warmup, args.cpu_episodes,
-                       rank, local, world)
+                       rank, local, world, train=not args.eval_mode)
     if rank == 0:
         print(json.dumps(out), flush=True)
     if world > 1:
@@ -748,6 +750,8 @@ def main():
                     help="episodes in the bounded CPU-baseline sample (0 disables)")
     ap.add_argument("--eager-episodes", type=int, default=20,
                     help="episodes of the eager-PyTorch-on-GPU baseline (oracle/port.py on cuda, TF32 off; N = 1 only; 0 disables)")
+    ap.add_argument("--eval-mode", action="store_true",
+                    help="meta_* workloads: run forward() in eval() mode (no dropout) instead of the trainers' train() mode")
     ap.add_argument("--no-extras", dest="extras", action="store_false",
                     help="skip the `extras` object (the other BASELINE configs: baselines, interactron predict, rollout, meta step)")
     args = ap.parse_args()

@@ -76,15 +76,18 @@ __device__ __forceinline__ float rn_tf32(float x) {
   return __uint_as_float(r);
 }
 
-// The residual operand of the tf32x3 products: x - trunc_tf32(x) (exact in fp32, 13 significant bits), rounded to
-// nearest TF32 so that the tensor core's own truncation of it is exact.  ITN_LO_RN=0 (experiments) leaves the
-// rounding to the tensor core (truncation: a one-sided 2^-21 |x| error per operand).
+// The residual operand of the tf32x3 products: x - trunc_tf32(x) (exact in fp32, 13 significant bits).  tf32_lo
+// (the fused attention kernels) rounds it to nearest TF32 so that the tensor core's own truncation of it is exact
+// (attention outputs 2e-6 -> 1.1e-6 vs fp64); the GEMM splitter keeps tf32_lo_exact (see itn_gemm_tf32.cu).
+// ITN_LO_RN=0 (experiments) leaves the rounding to the tensor core everywhere.
 #ifndef ITN_LO_RN
 #define ITN_LO_RN 1
 #endif
 __device__ __forceinline__ float tf32_lo_rn(float lo) {
 #if ITN_LO_RN
-  return rn_tf32(lo);
+  // round-half-away to 10 mantissa bits with two full-rate integer ops (cvt.rna.tf32.f32 gives the same bits but
+  // issues at 1/8 rate: it cost the tf32x3 main loop 35 % when the splitter warps used it)
+  return __uint_as_float((__float_as_uint(lo) + 0x1000u) & 0xFFFFE000u);
 #else
   return lo;
 #endif

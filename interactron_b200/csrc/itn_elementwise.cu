@@ -239,7 +239,7 @@ tf32_residual_kernel(const float* __restrict__ x, float* __restrict__ lo, long l
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const float v = x[i];
-    lo[i] = tf32_lo(v);
+    lo[i] = tf32_lo_exact(v);      // must equal the in-kernel split of itn_gemm_tf32 bit for bit
   }
 }
 

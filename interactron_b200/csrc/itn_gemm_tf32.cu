@@ -47,11 +47,13 @@ __device__ long long* g_trace = nullptr;
 #define ITN_TRACE_AT(slot, idx) do { } while (0)
 #endif
 
-// x - trunc_tf32(x): the part of an fp32 operand the tensor core drops (kind::tf32 truncates), itself rounded
-// to nearest TF32 (tf32_lo, itn_common.cuh): the tensor core would otherwise truncate the 13-bit residual to
-// 11 bits, a one-sided error of up to 2^-21 |x| that does not average out over K.
+// x - trunc_tf32(x): the part of an fp32 operand the tensor core drops (kind::tf32 truncates).  Exact in fp32
+// (13 significant bits); the tensor core truncates it to 11.  Rounding it to nearest TF32 here (as the attention
+// kernels do, tf32_lo) was measured: small-K products 6.3e-7 -> 4.7e-7 vs fp64, but the splitter warps are the
+// critical path of the tf32x3 main loop and the two extra integer ops per element cost 16480x2048x512
+// 221 -> 186 TFLOP/s and the step 8 % (cvt.rna: 163 TFLOP/s).  Not worth it: left exact.
 __device__ __forceinline__ float4 tf32_residual(const float4 v) {
-  return make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
+  return make_float4(tf32_lo_exact(v.x), tf32_lo_exact(v.y), tf32_lo_exact(v.z), tf32_lo_exact(v.w));
 }
 
 constexpr int kBM = 128;
@@ -508,12 +510,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll 8
         for (int i = tid; i < (p.b_presplit && !B_MN ? Cfg::kABytes : Cfg::kRawBytes) / 16; i += 128) {
           const float4 x = raw[i];
-          float4 r;
-          if (i < kAVec) {       // A: residual + accumulator compensation, rounded to TF32 once
-            r.x = tf32_lo_rn(fmaf(x.x, delta, tf32_lo_exact(x.x))); r.y = tf32_lo_rn(fmaf(x.y, delta, tf32_lo_exact(x.y)));
-            r.z = tf32_lo_rn(fmaf(x.z, delta, tf32_lo_exact(x.z))); r.w = tf32_lo_rn(fmaf(x.w, delta, tf32_lo_exact(x.w)));
-          } else {
-            r = tf32_residual(x);
+          float4 r = tf32_residual(x);
+          if (i < kAVec) {
+            r.x = fmaf(x.x, delta, r.x); r.y = fmaf(x.y, delta, r.y);
+            r.z = fmaf(x.z, delta, r.z); r.w = fmaf(x.w, delta, r.w);
           }
           lo[i] = r;
         }

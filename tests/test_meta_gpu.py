@@ -6,9 +6,11 @@ Predictions and losses: 1e-3 relative (the north star's bar).  Meta-gradients: t
 reference run in fp32 AND in fp64.  These gradients are ill-conditioned (a second derivative through
 12 post-norm layers): the fp32 reference itself sits 2e-4 (`interactron_random`) / 2e-3
 (`interactron`) away from its own fp64 run in relative L2 over all parameters.  The tf32x3 tensor-core
-GEMMs carry ~1e-5 per product instead of fp32's ~1e-6, measured on B200 (tools/meta_parity.py,
-profiles/README.md): 1.3e-3 / 1.1e-2.  Bounds, against the fp64 reference:
-  per group (theta, psi, phi):   max(3e-3, 8 x fp32-reference gap)
+GEMMs carry 0.5-3e-6 per product against torch fp32's 0.3-1.2e-6 (long-K chains accumulate in TMEM with
+round-toward-zero), measured on B200 (tools/meta_parity.py, profiles/README.md): 1.5e-3 / 2.1e-3 over all
+parameters (round 1: 9.4e-4 / 3.8e-3; the same step on the fp32 FMA GEMM, ITN_FORCE_SIMT=1: 1.2e-4, so the
+derivation and every non-GEMM kernel are exact to fp32).  Bounds, against the fp64 reference:
+  per group (theta, psi, phi):   max(2.5e-3, 3 x fp32-reference gap)      (round 1: max(3e-3, 8 x gap))
   per tensor (strided sample):   max(3e-2, 10 x fp32-reference gap); exact zeros stay (near) zero."""
 import os
 
@@ -71,7 +73,7 @@ def _check_round(model, data, gold, r):
     for key, a in groups.items():
         mine_e, ref_e = (a[0] / a[2]) ** 0.5, (a[1] / a[2]) ** 0.5
         print(f"group {key}: ours vs fp64 {mine_e:.3e}, fp32 reference vs fp64 {ref_e:.3e}")
-        assert mine_e < max(3e-3, 8 * ref_e), (key, mine_e, ref_e)
+        assert mine_e < max(2.5e-3, 3 * ref_e), (key, mine_e, ref_e)
     assert per[0][0] < 1.0, per[:5]
 
 
