@@ -91,6 +91,14 @@ typedef struct {
   int c_pad;        /* 1: columns [N, round_up(N,4)) of every C row belong to C and may be overwritten
                        (with zeros): lets N % 4 != 0 outputs such as attention scores use 128-bit stores.
                        Honoured only for bias-free plain epilogues; otherwise ignored. */
+  /* Implicit-GEMM convolution (conv_kh > 0): A.ptr is a channels-last activation [conv_n, conv_h, conv_w, conv_c]
+   * and the A tile of k-block (ky, kx, c0..c0+31) is gathered by the TMA unit itself (im2col tensor map: pixel
+   * traversal with stride, filter offset ky*dil / kx*dil, zero fill in the padding) - no im2col matrix in HBM.
+   * M = conv_n*Ho*Wo, K = conv_kh*conv_kw*conv_c with the (ky, kx, c) column order of itn_im2col_nhwc, conv_c a
+   * multiple of 32.  A.major / A.ld / A.sb* are ignored; nb0 = nb1 = 1.  Replaces itn_im2col_nhwc + GEMM for the
+   * 3x3 and strided 1x1 convolutions of the frozen trunk (models/detr_models/backbone.py:57-92). */
+  int conv_kh, conv_kw, conv_stride, conv_pad, conv_dil;
+  int conv_n, conv_h, conv_w, conv_c, conv_ho, conv_wo;
   const float* B_lo; /* optional (may be NULL): B - trunc_tf32(B), element for element at the same offsets and
                        strides as B.ptr (itn_tf32_residual), for a K-major B in tf32x3 mode.  The residual tile of
                        B then arrives by TMA instead of being recomputed in shared memory for every k-block:

@@ -33,6 +33,9 @@ class GemmDesc(C.Structure):
         ("C2", C.c_void_p), ("ldc2", C.c_longlong), ("c2_sb0", C.c_longlong), ("c2_sb1", C.c_longlong),
         ("alpha", C.c_float), ("act", C.c_int), ("epi", C.c_int), ("accumulate", C.c_int),
         ("round_out", C.c_int), ("precision", C.c_int), ("act_pos", C.c_int), ("c_pad", C.c_int),
+        ("conv_kh", C.c_int), ("conv_kw", C.c_int), ("conv_stride", C.c_int), ("conv_pad", C.c_int), ("conv_dil", C.c_int),
+        ("conv_n", C.c_int), ("conv_h", C.c_int), ("conv_w", C.c_int), ("conv_c", C.c_int), ("conv_ho", C.c_int),
+        ("conv_wo", C.c_int),
         ("B_lo", C.c_void_p),
     ]
 

@@ -134,6 +134,12 @@ class GemmTrunk:
         N, H, W, Cin = x.shape
         if L["kh"] == 1 and L["stride"] == 1:
             a, Ho, Wo = x.view(N * H * W, Cin), H, W
+        elif Cin % 32 == 0 and getattr(ops, "implicit_conv", False) and not ops._clean and not ops.force_simt:
+            # 3x3 / strided convolutions: the TMA unit gathers the patches (im2col tensor map), nothing is materialised
+            res = residual.reshape(-1, L["cout"]) if residual is not None else None
+            y, Ho, Wo = ops.conv_gemm(x, L["w"], L["kh"], L["kw"], L["stride"], L["pad"], L["dil"], bias=L["b"],
+                                      act=act, residual=res, act_after_residual=res is not None)
+            return y.view(N, Ho, Wo, L["cout"])
         else:
             a, Ho, Wo = ops.im2col_nhwc(x, L["kh"], L["kw"], L["stride"], L["pad"], L["dil"])
         res = residual.view(N * Ho * Wo, L["cout"]) if residual is not None else None

@@ -79,6 +79,8 @@ struct GemmKParams {
   int variant;   // epilogue_variant(...)
   int vec;       // 1: 128-bit epilogue path is legal (alignment / N % 4 checked on the host)
   float rz_eps;  // tf32x3: mean relative loss of one round-toward-zero TMEM accumulate (see splitters)
+  // implicit-GEMM convolution (conv_kw > 0): A tiles come through an im2col tensor map
+  int conv_kw, conv_c, conv_stride, conv_pad, conv_dil, conv_wo, conv_howo;
   int b_presplit;  // tf32x3, K-major B: the residual tile of B is loaded through tmBlo (itn_gemm_desc_t::B_lo)
   int dbg;       // ITN_TRACE builds only: 1 = skip global stores, 2 = skip TMEM read, 4 = skip smem transpose;
                  // any build (ITN_GEMM_DBG, timing experiments): 16 = skip the residual split, 32 = skip the correction MMAs
@@ -404,7 +406,16 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             uint8_t* sa = smem + s * Cfg::kStageBytes;
             uint8_t* sb = sa + Cfg::kABytes;
             const int k0 = kb * kBK;
-            if (!A_MN) {
+            if (!A_MN && p.conv_kw > 0) {
+              // k-block -> filter tap (ky, kx) and first channel; tile row m0 -> output pixel (n, py, px)
+              const int tap = k0 / p.conv_c, c0 = k0 - tap * p.conv_c;
+              const int ky = tap / p.conv_kw, kx = tap - ky * p.conv_kw;
+              const int n = m0 / p.conv_howo, rem = m0 - n * p.conv_howo;
+              const int py = rem / p.conv_wo, px = rem - py * p.conv_wo;
+              tma_load_im2col_4d(sa, &tmA, &full_bar[s], c0, px * p.conv_stride - p.conv_pad,
+                                 py * p.conv_stride - p.conv_pad, n, (unsigned short)(kx * p.conv_dil),
+                                 (unsigned short)(ky * p.conv_dil));
+            } else if (!A_MN) {
               tma_load_4d(sa, &tmA, &full_bar[s], k0, m0, a_c1, a_c0);
             } else {
 #pragma unroll
@@ -788,8 +799,50 @@ static int make_operand_map(CUtensorMap* tm, const itn_operand_t& o, int rows, i
   return ITN_OK;
 }
 
+using EncodeIm2colFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeIm2colFn get_encode_im2col_fn() {
+  static EncodeIm2colFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &f, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeIm2colFn>(f);
+  });
+  return fn;
+}
+
+// Channels-last activation [n, h, w, c] as an im2col tensor map {c, w, h, n}: boxes of 32 channels x 128 output
+// pixels; bounding-box corners -pad and pad - (k-1)*dil (forward convolution), traversal stride = conv stride.
+static int make_im2col_map(CUtensorMap* tm, const itn_gemm_desc_t* d) {
+  EncodeIm2colFn enc = get_encode_im2col_fn();
+  if (!enc) return set_error(ITN_ERR_CUDA, "cuTensorMapEncodeIm2col entry point not available");
+  cuuint64_t gdim[4] = {(cuuint64_t)d->conv_c, (cuuint64_t)d->conv_w, (cuuint64_t)d->conv_h, (cuuint64_t)d->conv_n};
+  cuuint64_t gstr[3] = {(cuuint64_t)d->conv_c * 4, (cuuint64_t)d->conv_w * d->conv_c * 4,
+                        (cuuint64_t)d->conv_h * d->conv_w * d->conv_c * 4};
+  int lower[2] = {-d->conv_pad, -d->conv_pad};
+  int upper[2] = {d->conv_pad - (d->conv_kw - 1) * d->conv_dil, d->conv_pad - (d->conv_kh - 1) * d->conv_dil};
+  cuuint32_t estr[4] = {1, (cuuint32_t)d->conv_stride, (cuuint32_t)d->conv_stride, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(d->A.ptr), gdim, gstr, lower, upper,
+                   (cuuint32_t)kBK, (cuuint32_t)kBM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(ITN_ERR_CUDA, "cuTensorMapEncodeIm2col failed (%d): [%d,%d,%d,%d] k %dx%d stride %d pad %d dil %d",
+                     (int)r, d->conv_n, d->conv_h, d->conv_w, d->conv_c, d->conv_kh, d->conv_kw, d->conv_stride,
+                     d->conv_pad, d->conv_dil);
+  return ITN_OK;
+}
+
 static void fill_kparams(GemmKParams& p, const itn_gemm_desc_t* d) {
   p.M = d->M; p.N = d->N; p.K = d->K;
+  p.conv_kw = d->conv_kh > 0 ? d->conv_kw : 0;
+  p.conv_c = d->conv_c; p.conv_stride = d->conv_stride; p.conv_pad = d->conv_pad; p.conv_dil = d->conv_dil;
+  p.conv_wo = d->conv_wo; p.conv_howo = d->conv_ho * d->conv_wo;
   p.nb1 = d->nb1 < 1 ? 1 : d->nb1;
   p.tiles_m = p.tiles_n = p.num_tiles = 0;
   p.a_m0 = p.a_m1 = p.b_m0 = p.b_m1 = 0;
@@ -835,6 +888,18 @@ static int validate(const itn_gemm_desc_t* d) {
   ITN_REQUIRE(d->B.major == 0 || d->B.major == 1, "gemm: bad B.major");
   ITN_REQUIRE(d->precision == ITN_PREC_TF32X3 || d->precision == ITN_PREC_TF32,
               "gemm: bad precision %d", d->precision);
+  if (d->conv_kh > 0) {
+    ITN_REQUIRE(kBK == 32, "gemm: implicit convolution needs 32-float k-blocks");
+    ITN_REQUIRE(d->conv_kw > 0 && d->conv_stride > 0 && d->conv_dil > 0 && d->conv_pad >= 0, "gemm: bad convolution geometry");
+    ITN_REQUIRE(d->conv_c > 0 && d->conv_c % 32 == 0, "gemm: implicit convolution needs channels %% 32 == 0 (got %d)", d->conv_c);
+    ITN_REQUIRE(d->nb0 == 1 && d->nb1 == 1, "gemm: implicit convolution is not batched");
+    ITN_REQUIRE((long long)d->conv_n * d->conv_ho * d->conv_wo == d->M && d->conv_kh * d->conv_kw * d->conv_c == d->K,
+                "gemm: implicit convolution M/K do not match the geometry");
+    ITN_REQUIRE(d->conv_ho == (d->conv_h + 2 * d->conv_pad - d->conv_dil * (d->conv_kh - 1) - 1) / d->conv_stride + 1 &&
+                d->conv_wo == (d->conv_w + 2 * d->conv_pad - d->conv_dil * (d->conv_kw - 1) - 1) / d->conv_stride + 1,
+                "gemm: implicit convolution output size does not match the geometry");
+    ITN_REQUIRE((reinterpret_cast<uintptr_t>(d->A.ptr) & 15) == 0, "gemm: activation must be 16-byte aligned");
+  }
   return ITN_OK;
 }
 
@@ -860,7 +925,8 @@ static int launch_tile(const itn_gemm_desc_t* d, cudaStream_t stream) {
   if (nt > 0x7fffffffLL) return set_error(ITN_ERR_ARG, "gemm: too many tiles");
   p.num_tiles = (int)nt;
   CUtensorMap tmA, tmB, tmBlo;
-  int rc = make_operand_map(&tmA, d->A, d->M, d->K, d->nb0, d->nb1, kBM, &p.a_m0, &p.a_m1);
+  int rc = d->conv_kh > 0 ? make_im2col_map(&tmA, d)
+                          : make_operand_map(&tmA, d->A, d->M, d->K, d->nb0, d->nb1, kBM, &p.a_m0, &p.a_m1);
   if (rc) return rc;
   rc = make_operand_map(&tmB, d->B, d->N, d->K, d->nb0, d->nb1, BN, &p.b_m0, &p.b_m1);
   if (rc) return rc;
@@ -939,7 +1005,9 @@ extern "C" int itn_debug_set_trace(long long* buf) {
 
 extern "C" int itn_gemm_tf32_supported(const itn_gemm_desc_t* d) {
   if (!d || d->M <= 0 || d->N <= 0 || d->K <= 0) return 0;
-  return itn::operand_tma_ok(d->A, d->nb0, d->nb1) && itn::operand_tma_ok(d->B, d->nb0, d->nb1);
+  const bool a_ok = d->conv_kh > 0 ? (d->conv_c % 32 == 0 && (reinterpret_cast<uintptr_t>(d->A.ptr) & 15) == 0)
+                                   : itn::operand_tma_ok(d->A, d->nb0, d->nb1);
+  return a_ok && itn::operand_tma_ok(d->B, d->nb0, d->nb1);
 }
 
 extern "C" int itn_gemm_tf32(const itn_gemm_desc_t* d, void* stream) {

@@ -75,6 +75,19 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// im2col-mode load of a [pixels x channels] tile: (c, w, h, n) = first channel and the base pixel (input
+// coordinates of the filter window's corner for the first output pixel), (off_w, off_h) = filter tap offset.
+// The unit walks `pixelsPerColumn` output pixels (W, then H, then N) with the traversal stride of the map.
+__device__ __forceinline__ void tma_load_im2col_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c,
+                                                   int w, int h, int n, unsigned short off_w, unsigned short off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h),
+      "r"(n), "h"(off_w), "h"(off_h)
+      : "memory");
+}
+
 // ----------------------------------------------------------------- tcgen05
 template <uint32_t kCols>
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result) {

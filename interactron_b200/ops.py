@@ -61,6 +61,8 @@ class CudaOps:
         # fused tcgen05 attention (itn_attention_fwd/bwd); ITN_FUSED_ATTN=0 keeps the unfused
         # QK^T -> softmax -> PV chain through HBM (cross-check / dual-number path)
         self.fused_attention = os.environ.get("ITN_FUSED_ATTN", "1") != "0"
+        # convolutions as implicit GEMMs (TMA im2col tensor maps); ITN_IMPLICIT_CONV=0: explicit itn_im2col_nhwc + GEMM
+        self.implicit_conv = os.environ.get("ITN_IMPLICIT_CONV", "1") != "0"
         self.n_attn = 0
 
     # ------------------------------------------------------------ plumbing
@@ -302,6 +304,43 @@ class CudaOps:
         d.delta = delta.data_ptr()
         _lib.check(self.lib.itn_attention_bwd(C.byref(d), self._stream()))
         self.n_attn += 2
+
+    # ------------------------------------------------------------ implicit-GEMM convolution
+    def conv_gemm(self, x, w, kh, kw, stride, pad, dil, bias=None, act=None, residual=None, act_after_residual=False):
+        """Convolution of channels-last x [N,H,W,C] with w [Cout, kh*kw*C] (columns in (ky, kx, c) order) as ONE
+        tcgen05 GEMM whose A tiles the TMA unit gathers in im2col mode (no patch matrix in HBM) -> [N*Ho*Wo, Cout].
+        C % 32 == 0; bias / activation / residual fused as in `matmul`."""
+        assert x.is_contiguous() and x.dim() == 4 and w.dim() == 2 and w.stride(1) == 1
+        N, H, W_, Cc = x.shape
+        Ho = (H + 2 * pad - dil * (kh - 1) - 1) // stride + 1
+        Wo = (W_ + 2 * pad - dil * (kw - 1) - 1) // stride + 1
+        M, K, Nn = N * Ho * Wo, kh * kw * Cc, w.shape[0]
+        assert Cc % 32 == 0 and w.shape[1] >= K
+        out = self.empty(M, Nn)
+        d = _lib.GemmDesc()
+        d.M, d.N, d.K, d.nb0, d.nb1 = M, Nn, K, 1, 1
+        d.A.ptr, d.A.major, d.A.ld = x.data_ptr(), 0, K
+        d.B, keep_b = self._operand(_as4d(w.t()), 1, 1, False)
+        if self._presplit and d.B.major == 0 and self.precision == "tf32x3":
+            blo = self._b_lo_ptr(w.data_ptr())
+            if blo:
+                d.B_lo = blo
+                self.n_presplit += 1
+        d.C, d.ldc = out.data_ptr(), Nn
+        if bias is not None:
+            assert bias.is_contiguous() and bias.numel() == Nn
+            d.bias = bias.data_ptr()
+        if residual is not None:
+            assert residual.is_contiguous() and residual.numel() == M * Nn
+            d.residual, d.ldr = residual.data_ptr(), Nn
+        d.alpha, d.act, d.precision = 1.0, ACT[act], PRECISION[self.precision]
+        d.act_pos = 1 if act_after_residual else 0
+        d.conv_kh, d.conv_kw, d.conv_stride, d.conv_pad, d.conv_dil = kh, kw, stride, pad, dil
+        d.conv_n, d.conv_h, d.conv_w, d.conv_c, d.conv_ho, d.conv_wo = N, H, W_, Cc, Ho, Wo
+        _lib.check(self.lib.itn_gemm_tf32(C.byref(d), self._stream()))
+        self.n_tf32 += 1
+        del keep_b
+        return out, Ho, Wo
 
     # split-K: weight-gradient GEMMs at few episodes per step (dW[256,256] = dy^T[256,3610] x[3610,256]) are
     # 4-32 output tiles with a 57-113 k-block chain each: 3-20 % of the 148 SMs busy for 40-130 us.  The K
