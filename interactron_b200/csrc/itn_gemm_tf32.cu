@@ -56,6 +56,9 @@ __device__ __forceinline__ float4 tf32_residual(const float4 v) {
   return make_float4(tf32_lo_exact(v.x), tf32_lo_exact(v.y), tf32_lo_exact(v.z), tf32_lo_exact(v.w));
 }
 
+#ifndef ITN_GEMM_PAIR_DEFAULT
+#define ITN_GEMM_PAIR_DEFAULT 1
+#endif
 constexpr int kBM = 128;
 #ifndef ITN_BK
 #define ITN_BK 32
@@ -307,10 +310,14 @@ __device__ __forceinline__ void epilogue_generic(const GemmKParams& p, const Epi
     epilogue_store(p, e, row_base + r, col, st[r * 33 + lane], bias_v);
 }
 
-template <int BN, bool X3>
+// PAIR: the CTA-pair (cta_group::2) variant - 256 x BN tiles computed by two CTAs of a cluster, each holding its
+// 128 rows of A and HALF of the B tile (BN/2 rows): per CTA the shared-memory traffic of the B operand halves
+// (TMA writes and MMA reads), which is what bounds the tf32x3 main loop, and a third stage fits.
+template <int BN, bool X3, bool PAIR = false>
 struct TileCfg {
   static constexpr int kABytes = kBM * kBK * 4;
-  static constexpr int kBBytes = BN * kBK * 4;
+  static constexpr int kBRows = PAIR ? BN / 2 : BN;            // B rows held by this CTA
+  static constexpr int kBBytes = kBRows * kBK * 4;
   static constexpr int kRawBytes = kABytes + kBBytes;          // what TMA delivers per stage
   static constexpr int kStageBytes = X3 ? 2 * kRawBytes : kRawBytes;   // + residual (lo) tiles
   static constexpr int kStagingBytes = 4 * 32 * 36 * 4;        // per-warp transpose buffers (pitch 36)
@@ -326,15 +333,30 @@ struct TileCfg {
   static_assert(kStages >= 2, "need at least a double-buffered operand ring");
   static_assert(kSmemBytes <= 227 * 1024, "exceeds shared memory per CTA");
   static_assert(kSmemBytes > 114 * 1024, "one CTA per SM is assumed (TMEM is allocated in full)");
+  static_assert(!PAIR || (X3 && BN == 256 && kBK == 32), "the CTA-pair variant is built for tf32x3 128x256x32 tiles");
 };
 
-template <int BN, bool A_MN, bool B_MN, bool X3>
-__global__ void __launch_bounds__(TileCfg<BN, X3>::kThreads, 1)
+// a protocol error in the pair kernel must not hang the GPU: trap after ~1 s of failed waits
+__device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 25)) __trap();
+  }
+}
+
+template <int BN, bool A_MN, bool B_MN, bool X3, bool PAIR = false>
+__global__ void __launch_bounds__(TileCfg<BN, X3, PAIR>::kThreads, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ GemmKParams p) {
   // p is __grid_constant__: it is read straight from the constant bank even where its address is
   // taken (a by-value copy lands on the local-memory stack and turns every p.ld* into an LDL).
-  using Cfg = TileCfg<BN, X3>;
+  using Cfg = TileCfg<BN, X3, PAIR>;
+  static_assert(!PAIR || (!A_MN && !B_MN), "the CTA-pair variant takes K-major operands");
+  // PAIR: CTA `rank` of the pair owns m-tile 2*pair_m + rank of the pair's tile and B rows [rank*BN/2, +BN/2);
+  // the leader (rank 0) issues the MMAs for both, every barrier the issuer waits on collects both CTAs
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const int cta_id = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;       // tile-walk index
+  const int cta_n = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   constexpr int STAGES = Cfg::kStages;
 
   extern __shared__ uint8_t smem_raw[];
@@ -361,18 +383,22 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (p.b_presplit) tma_prefetch_desc(&tmBlo);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&split_bar[s], 4);   // one arrival per splitter warp
+      mbar_init(&split_bar[s], PAIR ? 8 : 4);   // one arrival per splitter warp (of both CTAs: the leader issues)
       mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 4);  // one arrival per epilogue warp
+      mbar_init(&tempty_bar[a], PAIR ? 8 : 4);  // one arrival per epilogue warp (of both CTAs)
     }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_ptr_smem);
+  if (warp == 1) {
+    if (PAIR) tmem_alloc_pair<Cfg::kTmemCols>(tmem_ptr_smem);
+    else tmem_alloc<Cfg::kTmemCols>(tmem_ptr_smem);
+  }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();      // the peer's barriers are initialised before anyone signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   // Everything above touches only this CTA's shared memory / TMEM and overlaps the tail of the
@@ -387,17 +413,17 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int s = 0;
       uint32_t ph = 0;
       int gk = 0;   // running k-block counter (trace index)
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int tile = cta_id; tile < p.num_tiles; tile += cta_n) {
         const int nb = tile % p.tiles_n;
         const int t2 = tile / p.tiles_n;
-        const int mb = t2 % p.tiles_m;
+        const int mb = PAIR ? 2 * (t2 % p.tiles_m) + (int)rank : t2 % p.tiles_m;     // PAIR: tiles_m counts pairs
         const int z = t2 / p.tiles_m;
         const int b0 = z / p.nb1, b1 = z % p.nb1;
-        const int m0 = mb * kBM, n0 = nb * BN;
+        const int m0 = mb * kBM, n0 = nb * BN + (PAIR ? (int)rank * (BN / 2) : 0);
         const int a_c0 = b0 * p.a_m0, a_c1 = b1 * p.a_m1;
         const int b_c0 = b0 * p.b_m0, b_c1 = b1 * p.b_m1;
         for (int kb = 0; kb < num_kb; ++kb, ++gk) {
-          mbar_wait(&empty_bar[s], ph ^ 1);
+          if (PAIR) mbar_wait_wd(&empty_bar[s], ph ^ 1); else mbar_wait(&empty_bar[s], ph ^ 1);
           if (elect_one()) {
             ITN_TRACE_AT(0, gk);
             // pre-split B (static weights): its residual tile arrives by TMA, the splitters do A only
@@ -438,20 +464,20 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == 1) {
     // --------------------------------------------------------- MMA issuer (converged warp, elect.sync)
-    {
-      constexpr uint32_t idesc = umma_idesc_tf32(kBM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    if (!PAIR || rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_tf32(PAIR ? 2 * kBM : kBM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       int s = 0;
       uint32_t ph = 0;
       int acc = 0;
       uint32_t acc_ph = 0;
       int gk = 0, gt = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++gt) {
-        mbar_wait(&tempty_bar[acc], acc_ph ^ 1);     // epilogue has drained this accumulator
+      for (int tile = cta_id; tile < p.num_tiles; tile += cta_n, ++gt) {
+        if (PAIR) mbar_wait_wd(&tempty_bar[acc], acc_ph ^ 1); else mbar_wait(&tempty_bar[acc], acc_ph ^ 1);     // epilogue has drained this accumulator
         if (lane == 0) ITN_TRACE_AT(7, gt);
         tc_fence_after();
         const uint32_t tacc = tmem_base + acc * Cfg::kAccCols;
         for (int kb = 0; kb < num_kb; ++kb, ++gk) {
-          mbar_wait(X3 ? &split_bar[s] : &full_bar[s], ph);
+          if (PAIR) mbar_wait_wd(&split_bar[s], ph); else mbar_wait(X3 ? &split_bar[s] : &full_bar[s], ph);
           tc_fence_after();
           if (elect_one()) {
             ITN_TRACE_AT(3, gk);
@@ -470,18 +496,29 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                        : umma_smem_desc(sa + k * 32, 16, kKSbo, kKLayout);
               const uint64_t bd = B_MN ? umma_smem_desc(sb + k * 1024, kAtomBytes, 512, kLayoutSW128Base32)
                                        : umma_smem_desc(sb + k * 32, 16, kKSbo, kKLayout);
-              umma_tf32(tacc, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
-              if (X3 && !(p.dbg & 32)) {     // dbg 32 (timing experiments only): main product alone
-                // residual tiles live kRawBytes after their raw twins, same layout: the descriptor
-                // start address is in 16-byte units
-                constexpr uint64_t kLoOff = static_cast<uint64_t>(Cfg::kRawBytes >> 4);
-                umma_tf32(tacc, ad + kLoOff, bd, idesc, 1u);   // A_lo * B_hi
-                umma_tf32(tacc, ad, bd + kLoOff, idesc, 1u);   // A_hi * B_lo
+              constexpr uint64_t kLoOff = static_cast<uint64_t>(Cfg::kRawBytes >> 4);
+              if (PAIR) {                    // one 256 x BN x 8 product over both CTAs' tiles (same smem offsets)
+                umma_tf32_pair(tacc, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+                umma_tf32_pair(tacc, ad + kLoOff, bd, idesc, 1u);
+                umma_tf32_pair(tacc, ad, bd + kLoOff, idesc, 1u);
+              } else {
+                umma_tf32(tacc, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+                if (X3 && !(p.dbg & 32)) {     // dbg 32 (timing experiments only): main product alone
+                  // residual tiles live kRawBytes after their raw twins, same layout: the descriptor
+                  // start address is in 16-byte units
+                  umma_tf32(tacc, ad + kLoOff, bd, idesc, 1u);   // A_lo * B_hi
+                  umma_tf32(tacc, ad, bd + kLoOff, idesc, 1u);   // A_hi * B_lo
+                }
               }
             }
-            umma_commit(&empty_bar[s]);  // frees the smem slot once the MMAs have read it
-            ITN_TRACE_AT(4, gk);
-            if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);  // accumulator complete
+            if (PAIR) {
+              umma_commit_pair(&empty_bar[s]);                          // frees the slot in both CTAs
+              if (kb == num_kb - 1) umma_commit_pair(&tfull_bar[acc]);  // both epilogues
+            } else {
+              umma_commit(&empty_bar[s]);  // frees the smem slot once the MMAs have read it
+              ITN_TRACE_AT(4, gk);
+              if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);  // accumulator complete
+            }
           }
           __syncwarp();
           if (++s == STAGES) { s = 0; ph ^= 1; }
@@ -501,9 +538,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t ph = 0;
     const int tid = threadIdx.x - 64;               // 0..127
     int gk = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    for (int tile = cta_id; tile < p.num_tiles; tile += cta_n) {
       for (int kb = 0; kb < num_kb; ++kb, ++gk) {
-        mbar_wait(&full_bar[s], ph);
+        if (PAIR) mbar_wait_wd(&full_bar[s], ph); else mbar_wait(&full_bar[s], ph);
         if (tid == 0) ITN_TRACE_AT(1, gk);
         const float4* raw = reinterpret_cast<const float4*>(smem + s * Cfg::kStageBytes);
         float4* lo = reinterpret_cast<float4*>(smem + s * Cfg::kStageBytes + Cfg::kRawBytes);
@@ -531,7 +568,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         fence_proxy_async();
         __syncwarp();
         if (tid == 0) ITN_TRACE_AT(2, gk);
-        if (lane == 0) mbar_arrive(&split_bar[s]);
+        if (lane == 0) { if (PAIR) mbar_arrive_cluster(&split_bar[s], 0); else mbar_arrive(&split_bar[s]); }
         if (++s == STAGES) { s = 0; ph ^= 1; }
       }
     }
@@ -544,10 +581,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int acc = 0;
     uint32_t acc_ph = 0;
     int gt = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++gt) {
+    for (int tile = cta_id; tile < p.num_tiles; tile += cta_n, ++gt) {
       const int nb = tile % p.tiles_n;
       const int t2 = tile / p.tiles_n;
-      const int mb = t2 % p.tiles_m;
+      const int mb = PAIR ? 2 * (t2 % p.tiles_m) + (int)rank : t2 % p.tiles_m;
       const int z = t2 / p.tiles_m;
       const int n0 = nb * BN;
       const int row_base = mb * kBM + lg * 32;
@@ -574,7 +611,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       };
       // chunk 0 of the stream is fetched while the tensor core is still working on this tile
       if (vec && xsp && rmax > 0) prefetch(0);
-      mbar_wait(&tfull_bar[acc], acc_ph);
+      if (PAIR) mbar_wait_wd(&tfull_bar[acc], acc_ph); else mbar_wait(&tfull_bar[acc], acc_ph);
       if (warp == Cfg::kEpiWarp0 && lane == 0) ITN_TRACE_AT(5, gt);
       tc_fence_after();
       const uint32_t tacc = tmem_base + acc * Cfg::kAccCols + (static_cast<uint32_t>(lg * 32) << 16);
@@ -582,7 +619,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // nothing to store: hand the accumulator straight back to the issuer
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        if (lane == 0) { if (PAIR) mbar_arrive_cluster(&tempty_bar[acc], 0); else mbar_arrive(&tempty_bar[acc]); }
       }
 #pragma unroll 1
       for (int c = 0; c < nchunks && rmax > 0; ++c) {
@@ -627,7 +664,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           // last chunk of this tile is out of TMEM: hand the accumulator back to the issuer
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+          if (lane == 0) { if (PAIR) mbar_arrive_cluster(&tempty_bar[acc], 0); else mbar_arrive(&tempty_bar[acc]); }
         }
         __syncwarp();
 #ifdef ITN_TRACE
@@ -687,9 +724,11 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   if (threadIdx.x == 0) ITN_TRACE_AT(8, 10);   // all roles done
+  if (PAIR) cluster_sync_all();                // the peer may still be signalling our barriers / reading our tiles
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    if (PAIR) tmem_dealloc_pair<Cfg::kTmemCols>(tmem_base);
+    else tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
 }
 
@@ -914,12 +953,13 @@ static int sm_count() {
   return n;
 }
 
-template <int BN, bool A_MN, bool B_MN, bool X3>
+template <int BN, bool A_MN, bool B_MN, bool X3, bool PAIR = false>
 static int launch_tile(const itn_gemm_desc_t* d, cudaStream_t stream) {
-  using Cfg = TileCfg<BN, X3>;
+  using Cfg = TileCfg<BN, X3, PAIR>;
   GemmKParams p;
   fill_kparams(p, d);
   p.tiles_m = (d->M + kBM - 1) / kBM;
+  if (PAIR) p.tiles_m = (p.tiles_m + 1) / 2;          // pairs of m-tiles: one 256-row tile per CTA pair
   p.tiles_n = (d->N + BN - 1) / BN;
   const long long nt = (long long)p.tiles_m * p.tiles_n * d->nb0 * d->nb1;
   if (nt > 0x7fffffffLL) return set_error(ITN_ERR_ARG, "gemm: too many tiles");
@@ -928,17 +968,17 @@ static int launch_tile(const itn_gemm_desc_t* d, cudaStream_t stream) {
   int rc = d->conv_kh > 0 ? make_im2col_map(&tmA, d)
                           : make_operand_map(&tmA, d->A, d->M, d->K, d->nb0, d->nb1, kBM, &p.a_m0, &p.a_m1);
   if (rc) return rc;
-  rc = make_operand_map(&tmB, d->B, d->N, d->K, d->nb0, d->nb1, BN, &p.b_m0, &p.b_m1);
+  rc = make_operand_map(&tmB, d->B, d->N, d->K, d->nb0, d->nb1, Cfg::kBRows, &p.b_m0, &p.b_m1);
   if (rc) return rc;
   tmBlo = tmB;
   if (p.b_presplit) {
     itn_operand_t blo = d->B;
     blo.ptr = d->B_lo;
     int m0 = 0, m1 = 0;
-    rc = make_operand_map(&tmBlo, blo, d->N, d->K, d->nb0, d->nb1, BN, &m0, &m1);
+    rc = make_operand_map(&tmBlo, blo, d->N, d->K, d->nb0, d->nb1, Cfg::kBRows, &m0, &m1);
     if (rc) return rc;
   }
-  auto kern = gemm_tf32_kernel<BN, A_MN, B_MN, X3>;
+  auto kern = gemm_tf32_kernel<BN, A_MN, B_MN, X3, PAIR>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
     cudaError_t e =
@@ -947,6 +987,12 @@ static int launch_tile(const itn_gemm_desc_t* d, cudaStream_t stream) {
       return set_error(ITN_ERR_CUDA, "gemm: cudaFuncSetAttribute(%d B): %s", Cfg::kSmemBytes,
                        cudaGetErrorString(e));
     attr_set = true;
+  }
+  if (PAIR) {
+    const int pairs = sm_count() / 2;
+    const int grid = 2 * (p.num_tiles < pairs ? p.num_tiles : pairs);   // persistent: one CTA pair per TPC
+    launch_cluster(2, kern, grid, Cfg::kThreads, Cfg::kSmemBytes, stream, tmA, tmB, tmBlo, p);
+    return check_launch("gemm_tf32_kernel (CTA pairs)");
   }
   int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();   // persistent: <= 1 CTA per SM
   // A CTA walks tiles blockIdx.x, blockIdx.x + grid, ... with n fastest.  When the last n-tile is partial
@@ -962,8 +1008,23 @@ static int launch_tile(const itn_gemm_desc_t* d, cudaStream_t stream) {
   return check_launch("gemm_tf32_kernel");
 }
 
+// CTA pairs (cta_group::2) pay off where the 128 x 256 tf32x3 main loop is shared-memory bound: K-major operands,
+// enough 256-row tiles to fill the 74 TPCs.  ITN_GEMM_PAIR=0/1 overrides (experiments).
+static bool want_pair(const itn_gemm_desc_t* d) {
+  static const int env = getenv("ITN_GEMM_PAIR") ? atoi(getenv("ITN_GEMM_PAIR")) : ITN_GEMM_PAIR_DEFAULT;
+  if (!env || d->precision != ITN_PREC_TF32X3 || d->A.major != 0 || d->B.major != 0 || kBK != 32) return false;
+  const long long tiles_m = (d->M + kBM - 1) / kBM, tiles_n = (d->N + 255) / 256;
+  const long long pair_tiles = ((tiles_m + 1) / 2) * tiles_n * d->nb0 * d->nb1;
+  // measured (tools/gemm_pair_check.py): +12 % at K = 2048 (57760 x 256), +4 % at K = 1496, -1 ... -3 % at K <= 512
+  // where the epilogue, not the main loop, sets the pace
+  return tiles_m >= 2 && d->N >= 192 && d->K >= 1024 && pair_tiles >= sm_count() / 2;
+}
+
 template <int BN, bool X3>
 static int launch_major2(const itn_gemm_desc_t* d, cudaStream_t s) {
+  if constexpr (BN == 256 && X3 && kBK == 32) {
+    if (want_pair(d)) return launch_tile<256, false, false, true, true>(d, s);
+  }
   if (d->A.major == 0) {
     return d->B.major == 0 ? launch_tile<BN, false, false, X3>(d, s)
                            : launch_tile<BN, false, true, X3>(d, s);

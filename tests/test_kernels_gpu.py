@@ -497,3 +497,32 @@ def test_gemm_presplit_weights_bit_identical(ops3):
     after = ops.matmul(x, w.transpose(-1, -2))
     ops2 = CudaOps()
     assert torch.equal(after, ops2.matmul(x, w.transpose(-1, -2)))
+
+
+def test_gemm_cta_pair_variant_is_bit_identical(ops3):
+    """The cta_group::2 kernel (two CTAs share one 256-row MMA, each holding half of the B tile) issues the same
+    products in the same order as the single-CTA kernel: results must be bit-identical.  Child processes, because
+    the ITN_GEMM_PAIR switch is read once per process."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    child = (
+        "import sys, torch\n"
+        f"sys.path.insert(0, {root!r})\n"
+        "from interactron_b200.ops import CudaOps\n"
+        "ops = CudaOps(); torch.manual_seed(0)\n"
+        "for M, N, K in ((40000, 256, 2048), (19000, 1236, 1024), (25000, 512, 1496)):\n"
+        "    a = torch.randn(M, K, device='cuda'); w = torch.randn(N, K, device='cuda'); b = torch.randn(N, device='cuda')\n"
+        "    r = torch.randn(M, N, device='cuda')\n"
+        "    y = ops.matmul(a, w.t(), bias=b, residual=r)\n"
+        "    ref = a.double() @ w.double().t() + b.double() + r.double()\n"
+        "    print(repr(y.double().sum().item()), repr(y.abs().double().sum().item()), ((y.double() - ref).norm() / ref.norm()).item())\n")
+    outs = []
+    for pair in ("0", "1"):
+        r = subprocess.run([sys.executable, "-c", child], env=dict(os.environ, ITN_GEMM_PAIR=pair), capture_output=True,
+                           text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(r.stdout.strip().splitlines())
+    assert outs[0] == outs[1] and len(outs[0]) == 3
+    assert all(float(line.split()[2]) < 3e-6 for line in outs[0])
