@@ -294,10 +294,10 @@ def gemm_roofline(loop, frames, masks, bf16_peak):
                              "frac_of_tf32_peak": a_fl / (a_ms * 1e-3) / 1e12 / peak,
                              "algorithmic_gb_per_step": sum(r[3] for r in att) / 1e9}
     # DRAM traffic of the same kernel family over one step, from the committed ncu launch list of
-    # `tools/profile_step.py 32 interactron_random` (dram__bytes_read.sum + dram__bytes_write.sum)
+    # `tools/profile_step.py E interactron_random` (dram__bytes_read.sum + dram__bytes_write.sum), same E as this run
     import glob
-    cands = sorted(glob.glob(os.path.join(ROOT, "profiles", "r0[2-9]*_traffic_e32_interactron_random.json")))
-    if cands and frames.shape[0] == 32 and loop.kind == "B":
+    cands = sorted(glob.glob(os.path.join(ROOT, "profiles", f"r0[2-9]*_traffic_e{frames.shape[0]}_interactron_random.json")))
+    if cands and loop.kind == "B":
         tp = cands[-1]
         prof = json.load(open(tp))
         k = prof["kernels"].get("itn::gemm_tf32_kernel")
