@@ -568,7 +568,7 @@ struct DkvCfg {
   static constexpr int kSmem = kStages * kStage + 2 * kStages * BLK * 4 + 16 * 8 + 1024;
 };
 
-template <int HD, int BLK, int MINB>
+template <int HD, int BLK, int MINB, bool DROP>
 __global__ void __launch_bounds__(kThreads, MINB)
 attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQk, const __grid_constant__ CUtensorMap tmDOk,
                     const __grid_constant__ CUtensorMap tmQm, const __grid_constant__ CUtensorMap tmDOm,
@@ -689,8 +689,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQk, const __grid_const
     float dvacc[HD], dkacc[HD];
 #pragma unroll
     for (int d = 0; d < HD; ++d) dvacc[d] = dkacc[d] = 0.0f;
-    const bool drop = p.drop.seed != nullptr;
-    const unsigned long long dseed = drop ? *p.drop.seed : 0ull;
+    constexpr bool drop = DROP;
+    const unsigned long long dseed = DROP ? *p.drop.seed : 0ull;
     const unsigned long long qrow0 = (unsigned long long)bh * p.Lq;
     for (int j = 0; j < n_blk; ++j) {
       const float* ls = lse_s + (j & 1) * BLK;
@@ -793,7 +793,7 @@ struct PipeCfg {
   static_assert(kSmem <= 227 * 1024, "exceeds shared memory per CTA");
 };
 
-template <int MODE, int HD, int BLK, int MINB>
+template <int MODE, int HD, int BLK, int MINB, bool DROP>
 __global__ void __launch_bounds__(kPipeThreads, MINB)
 attn_pipe_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
                  const __grid_constant__ CUtensorMap tm2, const __grid_constant__ CUtensorMap tm3,
@@ -999,8 +999,9 @@ attn_pipe_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
     }
     float m_run = -INFINITY, l_run = 0.0f, alpha_pend = 1.0f;
     // train()-mode dropout of the probabilities: keep(seed, site, query row, key) regenerated per element
-    const bool drop = p.drop.seed != nullptr;
-    const unsigned long long dseed = drop ? *p.drop.seed : 0ull;
+    // (compile-time switch: the eval() kernels carry none of it)
+    constexpr bool drop = DROP;
+    const unsigned long long dseed = DROP ? *p.drop.seed : 0ull;
     const unsigned long long qrow0 = (unsigned long long)bh * p.Lq;     // + query index = mask row
 
     auto consume = [&](int blk) {            // read back the second-phase products of block `blk`
@@ -1303,8 +1304,8 @@ static int launch_dq(const itn_attention_desc_t* d, cudaStream_t s) {
   return check_launch("attn_bwd_dq_kernel");
 }
 
-template <int HD, int BLK, int MINB>
-static int launch_dkv(const itn_attention_desc_t* d, cudaStream_t s) {
+template <int HD, int BLK, int MINB, bool DROP>
+static int launch_dkv_t(const itn_attention_desc_t* d, cudaStream_t s) {
   using Cfg = DkvCfg<HD, BLK>;
   Params p = make_params(d, d->Lk);
   CUtensorMap tmQk, tmDOk, tmQm, tmDOm;
@@ -1316,7 +1317,7 @@ static int launch_dkv(const itn_attention_desc_t* d, cudaStream_t s) {
   if (rc) return rc;
   rc = make_map(&tmDOm, d->d_o, d->do_ld, d->do_sb, d->Lq, d->nh, HD, d->B, BLK, true);
   if (rc) return rc;
-  auto kern = attn_bwd_dkv_kernel<HD, BLK, MINB>;
+  auto kern = attn_bwd_dkv_kernel<HD, BLK, MINB, DROP>;
   static bool attr = false;
   rc = set_smem(kern, Cfg::kSmem, &attr);
   if (rc) return rc;
@@ -1324,8 +1325,8 @@ static int launch_dkv(const itn_attention_desc_t* d, cudaStream_t s) {
   return check_launch("attn_bwd_dkv_kernel");
 }
 
-template <int MODE, int HD, int BLK, int MINB = 1>
-static int launch_pipe(const itn_attention_desc_t* d, cudaStream_t s) {
+template <int MODE, int HD, int BLK, int MINB, bool DROP>
+static int launch_pipe_t(const itn_attention_desc_t* d, cudaStream_t s) {
   using Cfg = PipeCfg<MODE, HD, BLK>;
   Params p = make_params(d, MODE == M_DKV ? d->Lk : d->Lq);
   CUtensorMap tm[4];
@@ -1347,12 +1348,22 @@ static int launch_pipe(const itn_attention_desc_t* d, cudaStream_t s) {
     tm[3] = tm[0];
   }
   if (rc) return rc;
-  auto kern = attn_pipe_kernel<MODE, HD, BLK, MINB>;
+  auto kern = attn_pipe_kernel<MODE, HD, BLK, MINB, DROP>;
   static bool attr = false;
   rc = set_smem(kern, Cfg::kSmem, &attr);
   if (rc) return rc;
   launch(kern, d->B * d->nh * p.tiles, kPipeThreads, Cfg::kSmem, s, tm[0], tm[1], tm[2], tm[3], p);
   return check_launch("attn_pipe_kernel");
+}
+
+template <int HD, int BLK, int MINB>
+static int launch_dkv(const itn_attention_desc_t* d, cudaStream_t s) {
+  return d->drop_p > 0.f ? launch_dkv_t<HD, BLK, MINB, true>(d, s) : launch_dkv_t<HD, BLK, MINB, false>(d, s);
+}
+
+template <int MODE, int HD, int BLK, int MINB = 1>
+static int launch_pipe(const itn_attention_desc_t* d, cudaStream_t s) {
+  return d->drop_p > 0.f ? launch_pipe_t<MODE, HD, BLK, 1, true>(d, s) : launch_pipe_t<MODE, HD, BLK, MINB, false>(d, s);
 }
 
 static int env_int(const char* name, int dflt) {

@@ -89,12 +89,13 @@ __device__ __forceinline__ float rn_tf32(float x) {
   return __uint_as_float(r);
 }
 
-// The residual operand of the tf32x3 products: x - trunc_tf32(x) (exact in fp32, 13 significant bits).  tf32_lo
-// (the fused attention kernels) rounds it to nearest TF32 so that the tensor core's own truncation of it is exact
-// (attention outputs 2e-6 -> 1.1e-6 vs fp64); the GEMM splitter keeps tf32_lo_exact (see itn_gemm_tf32.cu).
-// ITN_LO_RN=0 (experiments) leaves the rounding to the tensor core everywhere.
+// The residual operand of the tf32x3 products: x - trunc_tf32(x) (exact in fp32, 13 significant bits; the tensor
+// core truncates it to 11).  ITN_LO_RN=1 rounds it to nearest TF32 first so that the truncation is exact.  Measured
+// on B200 (profiles/README.md): fused-attention outputs 2.0e-6 -> 1.1e-6 vs fp64 and small-K GEMMs 6.3e-7 -> 4.7e-7,
+// but the two extra integer ops per element cost the attention kernels 6 % and the GEMM splitter warps (the
+// critical path of the tf32x3 main loop) 16 %: off by default, every parity bound holds either way.
 #ifndef ITN_LO_RN
-#define ITN_LO_RN 1
+#define ITN_LO_RN 0
 #endif
 __device__ __forceinline__ float tf32_lo_rn(float lo) {
 #if ITN_LO_RN
