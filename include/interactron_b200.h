@@ -50,8 +50,11 @@ enum { ITN_ACT_NONE = 0, ITN_ACT_RELU = 1, ITN_ACT_GELU = 2 };
 /* ITN_PREC_TF32X3 (default, 0): error-compensated three-pass TF32 (A*B + A_lo*B + A*B_lo with the
  * residual tiles produced in shared memory), ~fp32 accuracy; needed for the 1e-3 parity bar
  * because the inner-loop gradient amplifies single-pass TF32 error to 1-10 %.
- * ITN_PREC_TF32 (1): one tensor-core pass (operands truncated to 10 mantissa bits). */
-enum { ITN_PREC_TF32X3 = 0, ITN_PREC_TF32 = 1 };
+ * ITN_PREC_TF32 (1): one tensor-core pass (operands truncated to 10 mantissa bits).
+ * ITN_PREC_TF32X3_SPLIT (2): tf32x3 with the two residual products accumulated in tensor-memory columns of
+ * their own and added in the epilogue: the main accumulator takes K/8 round-toward-zero accumulates instead
+ * of 3K/8 (~fp32 GEMM error; tiles at most 128 wide, slower).  The meta-training step uses it. */
+enum { ITN_PREC_TF32X3 = 0, ITN_PREC_TF32 = 1, ITN_PREC_TF32X3_SPLIT = 2 };
 enum { ITN_EPI_NONE = 0, ITN_EPI_RELU_MASK = 1, ITN_EPI_GELU_GRAD = 2 };
 /* act_pos: 0 = activation right after the bias (default), 1 = after residual/accumulate
  * (ResNet bottleneck: relu(conv(x) + identity)). */

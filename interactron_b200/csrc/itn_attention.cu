@@ -25,8 +25,12 @@
 //
 // tf32x3: kind::tf32 truncates fp32 operands to 10 mantissa bits.  Every product is issued as
 // A*B + A_lo*B + A*B_lo with x_lo = x - trunc_tf32(x) (3 MMAs per k-step), which restores ~fp32
-// accuracy; accumulation chains are short (<= 3*BLK/8 MMAs) and the per-block results are summed
-// in fp32 registers, so the round-toward-zero accumulate of TMEM needs no compensation here.
+// accuracy.  Accumulation chains are short (3*BLK/8 or 3*HD/8 MMAs; the per-block results are summed in
+// fp32 registers), but every tcgen05.mma accumulate rounds toward zero, and even a 24-MMA chain shrinks
+// its result by ~4e-7 on average: a systematic scale error on O = P V that the ill-conditioned
+// meta-gradients amplify (measured, tools/meta_parity.py: 1.46e-3 with the fused forward against 9.4e-4
+// with the compensated GEMM chain).  lo_comp() folds the same first-order compensation as the GEMM's
+// splitters (itn_gemm_tf32.cu) into the residual operand that is written to TMEM anyway.
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -75,6 +79,27 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
+#ifndef ITN_ATTN_RZ_EPS
+#define ITN_ATTN_RZ_EPS 1.2f    // mean loss of one round-toward-zero accumulate of these chains, in units of 2^-24 (fitted:
+                                // tools/attn_precision.py - nulls the scale bias of O for every shape class and regime)
+#endif
+#ifndef ITN_ATTN_RZ_COMP
+#define ITN_ATTN_RZ_COMP 1
+#endif
+// Residual (lo) operand of element x at k-index `col` of an NKS-step chain (3 MMAs per step), with the
+// round-toward-zero loss of the main product folded in: x * (1 - eps * later accumulates) is what
+// survives the chain, so x * eps * (3 * (NKS - ks) - 1) is added back through the residual (<= 1e-6 * x,
+// well inside the 2^-11 range of x_lo).  The GEMM's splitters do the same with their own fitted eps.
+template <int NKS>
+__device__ __forceinline__ float lo_comp(float x, int col) {
+#if ITN_ATTN_RZ_COMP
+  const float delta = ITN_ATTN_RZ_EPS * 5.9604645e-8f * (3.0f * static_cast<float>(NKS - (col >> 3)) - 1.0f);
+  return fmaf(x, delta, tf32_lo(x));
+#else
+  return tf32_lo(x);
+#endif
+}
+
 __device__ __forceinline__ float4 tf32_lo4(const float4 v) {
   return make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
 }
@@ -110,7 +135,7 @@ __device__ __forceinline__ void put_row(uint32_t t_hi, uint32_t t_lo, const floa
     load32(v, src + 32 * c, valid, mul);
     tmem_st_32x32(t_hi + 32 * c, v);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(tf32_lo(__uint_as_float(v[j])));
+    for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(lo_comp<HD / 8>(__uint_as_float(v[j]), 32 * c + j));
     tmem_st_32x32(t_lo + 32 * c, v);
   }
 }
@@ -342,7 +367,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__
         }
         tmem_st_32x32(tw + Cfg::cS + 32 * c, v);                // P over S
 #pragma unroll
-        for (int t = 0; t < 32; ++t) v[t] = __float_as_uint(tf32_lo(__uint_as_float(v[t])));
+        for (int t = 0; t < 32; ++t) v[t] = __float_as_uint(lo_comp<BLK / 8>(__uint_as_float(v[t]), 32 * c + t));
         tmem_st_32x32(tw + Cfg::cPL + 32 * c, v);
       }
       tmem_st_wait();
@@ -528,7 +553,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmKk, const __grid_consta
           const float pv = ex2(__uint_as_float(sv[t]) + kb[32 * c + t] - lse2);
           const float ds = pv * (__uint_as_float(dp[t]) - delta) * p.scale;
           dp[t] = __float_as_uint(ds);
-          sv[t] = __float_as_uint(tf32_lo(ds));
+          sv[t] = __float_as_uint(lo_comp<BLK / 8>(ds, 32 * c + t));
         }
         tmem_st_32x32(tw + Cfg::cDP + 32 * c, dp);
         tmem_st_32x32(tw + Cfg::cS + 32 * c, sv);
@@ -722,8 +747,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQk, const __grid_const
         tmem_st_32x32(tw + Cfg::cDPT + 32 * c, dp);             // dS^T over dP^T
 #pragma unroll
         for (int t = 0; t < 32; ++t) {
-          sv[t] = __float_as_uint(tf32_lo(__uint_as_float(sv[t])));
-          dp[t] = __float_as_uint(tf32_lo(__uint_as_float(dp[t])));
+          sv[t] = __float_as_uint(lo_comp<BLK / 8>(__uint_as_float(sv[t]), 32 * c + t));
+          dp[t] = __float_as_uint(lo_comp<BLK / 8>(__uint_as_float(dp[t]), 32 * c + t));
         }
         tmem_st_32x32(tw + Cfg::cPL + 32 * c, sv);
         tmem_st_32x32(tw + Cfg::cDSL + 32 * c, dp);
@@ -1063,7 +1088,7 @@ attn_pipe_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
           }
           tmem_st_32x32(ts + 32 * c, v);                          // P over S
 #pragma unroll
-          for (int t = 0; t < 32; ++t) v[t] = __float_as_uint(tf32_lo(__uint_as_float(v[t])));
+          for (int t = 0; t < 32; ++t) v[t] = __float_as_uint(lo_comp<BLK / 8>(__uint_as_float(v[t]), 32 * c + t));
           tmem_st_32x32(ts + BLK + 32 * c, v);
         }
         l_run = l_run * alpha + rs;
@@ -1087,7 +1112,7 @@ attn_pipe_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
             }
             const float ds = pv * (dpv - delta) * p.scale;
             dp[t] = __float_as_uint(ds);
-            sv[t] = __float_as_uint(tf32_lo(ds));
+            sv[t] = __float_as_uint(lo_comp<BLK / 8>(ds, 32 * c + t));
           }
           tmem_st_32x32(ts + BLK + 32 * c, dp);
           tmem_st_32x32(ts + 32 * c, sv);
@@ -1118,8 +1143,8 @@ attn_pipe_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant_
           tmem_st_32x32(ts + 2 * BLK + 32 * c, dp);               // dS^T over dP^T
 #pragma unroll
           for (int t = 0; t < 32; ++t) {
-            sv[t] = __float_as_uint(tf32_lo(__uint_as_float(sv[t])));
-            dp[t] = __float_as_uint(tf32_lo(__uint_as_float(dp[t])));
+            sv[t] = __float_as_uint(lo_comp<BLK / 8>(__uint_as_float(sv[t]), 32 * c + t));
+            dp[t] = __float_as_uint(lo_comp<BLK / 8>(__uint_as_float(dp[t]), 32 * c + t));
           }
           tmem_st_32x32(ts + BLK + 32 * c, sv);
           tmem_st_32x32(ts + 3 * BLK + 32 * c, dp);

@@ -81,6 +81,8 @@ struct GemmKParams {
   int act, epi, accumulate, round_out, act_pos;
   int variant;   // epilogue_variant(...)
   int vec;       // 1: 128-bit epilogue path is legal (alignment / N % 4 checked on the host)
+  int split_acc; // tf32x3, tiles <= 128 wide: residual products A_lo*B + A*B_lo accumulate in their own TMEM columns and
+                 // are added in the epilogue - the main accumulator sees K/8 round-toward-zero accumulates, not 3K/8
   float rz_eps;  // tf32x3: mean relative loss of one round-toward-zero TMEM accumulate (see splitters)
   // implicit-GEMM convolution (conv_kw > 0): A tiles come through an im2col tensor map
   int conv_kw, conv_c, conv_stride, conv_pad, conv_dil, conv_wo, conv_howo;
@@ -326,7 +328,10 @@ struct TileCfg {
   static constexpr int kStageCap = kBK == 32 ? 8 : 16;
   static constexpr int kStages = kMaxStages > kStageCap ? kStageCap : kMaxStages;
   static constexpr int kAccCols = BN < 32 ? 32 : BN;
-  static constexpr int kTmemCols = 2 * kAccCols;               // two accumulators (double buffer)
+  // two accumulators (double buffer); tiles up to 128 wide also hold a second pair for the residual products
+  // (GemmKParams::split_acc), 256-wide tiles fill tensor memory with the main pair alone
+  static constexpr bool kCanSplit = BN <= 128;
+  static constexpr int kTmemCols = kCanSplit ? 4 * kAccCols : 2 * kAccCols;
   static constexpr int kThreads = X3 ? 320 : 192;
   static constexpr int kEpiWarp0 = X3 ? 6 : 2;
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + (3 * kStages + 4) * 8 + 16 + 1024;
@@ -506,8 +511,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if (X3 && !(p.dbg & 32)) {     // dbg 32 (timing experiments only): main product alone
                   // residual tiles live kRawBytes after their raw twins, same layout: the descriptor
                   // start address is in 16-byte units
-                  umma_tf32(tacc, ad + kLoOff, bd, idesc, 1u);   // A_lo * B_hi
-                  umma_tf32(tacc, ad, bd + kLoOff, idesc, 1u);   // A_hi * B_lo
+                  const bool split = Cfg::kCanSplit && p.split_acc;
+                  const uint32_t tlo = split ? tacc + 2 * Cfg::kAccCols : tacc;
+                  umma_tf32(tlo, ad + kLoOff, bd, idesc, (!split || (kb | k) != 0) ? 1u : 0u);   // A_lo * B_hi
+                  umma_tf32(tlo, ad, bd + kLoOff, idesc, 1u);                                    // A_hi * B_lo
                 }
               }
             }
@@ -551,7 +558,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // by folding  x * delta_kb  into the residual tile of A (delta_kb <= 5e-5 sits well inside
         // the 2^-11 range of x_lo).  Measured (tools/gemm_precision.py): K=2048 random operands
         // 1.5e-5 -> see profiles/README.md.
-        constexpr float kAcc = 3.0f * (kBK / 8);      // accumulates per k-block
+        const float kAcc = (Cfg::kCanSplit && p.split_acc ? 1.0f : 3.0f) * (kBK / 8);   // accumulates per k-block
         const float delta = p.rz_eps * (kAcc * static_cast<float>(num_kb - kb) - 0.5f * (kAcc - 1.0f));
         constexpr int kAVec = Cfg::kABytes / 16;
         if (!(p.dbg & 16))                 // dbg 16 (timing experiments only): no residual pass, garbage lo tiles
@@ -639,7 +646,15 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #endif
           {
             tmem_ld_32x32(tacc + c * 32, v);
-            tmem_ld_wait();
+            if (Cfg::kCanSplit && p.split_acc) {       // + the residual products' accumulator (fp32 RN add)
+              uint32_t w[32];
+              tmem_ld_32x32(tacc + 2 * Cfg::kAccCols + c * 32, w);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
+            } else {
+              tmem_ld_wait();
+            }
           }
 #ifdef ITN_TRACE
           tp1 = clock64();
@@ -911,7 +926,8 @@ static void fill_kparams(GemmKParams& p, const itn_gemm_desc_t* d) {
   // mean loss per round-toward-zero accumulate, in units of 2^-24 (ITN_GEMM_RZ_COMP=0 disables)
   static const float rz = getenv("ITN_GEMM_RZ_COMP") ? (float)atof(getenv("ITN_GEMM_RZ_COMP")) : 0.59f;
   p.rz_eps = rz * 5.9604645e-8f;
-  p.b_presplit = (d->B_lo != nullptr && d->precision == ITN_PREC_TF32X3 && d->B.major == 0 &&
+  p.split_acc = 0;
+  p.b_presplit = (d->B_lo != nullptr && d->precision != ITN_PREC_TF32 && d->B.major == 0 &&
                   (reinterpret_cast<uintptr_t>(d->B_lo) & 15) == 0) ? 1 : 0;
 }
 
@@ -925,7 +941,7 @@ static int validate(const itn_gemm_desc_t* d) {
   ITN_REQUIRE(d->epi == ITN_EPI_NONE || d->aux != nullptr, "gemm: epi mode %d needs aux", d->epi);
   ITN_REQUIRE(d->A.major == 0 || d->A.major == 1, "gemm: bad A.major");
   ITN_REQUIRE(d->B.major == 0 || d->B.major == 1, "gemm: bad B.major");
-  ITN_REQUIRE(d->precision == ITN_PREC_TF32X3 || d->precision == ITN_PREC_TF32,
+  ITN_REQUIRE(d->precision == ITN_PREC_TF32X3 || d->precision == ITN_PREC_TF32 || d->precision == ITN_PREC_TF32X3_SPLIT,
               "gemm: bad precision %d", d->precision);
   if (d->conv_kh > 0) {
     ITN_REQUIRE(kBK == 32, "gemm: implicit convolution needs 32-float k-blocks");
@@ -940,6 +956,13 @@ static int validate(const itn_gemm_desc_t* d) {
     ITN_REQUIRE((reinterpret_cast<uintptr_t>(d->A.ptr) & 15) == 0, "gemm: activation must be 16-byte aligned");
   }
   return ITN_OK;
+}
+
+// tf32x3 with the residual products in their own accumulator (GemmKParams::split_acc): asked for per call
+// (ITN_PREC_TF32X3_SPLIT) or for every tf32x3 product of the process (ITN_GEMM_SPLITACC=1, experiments)
+static bool want_split(const itn_gemm_desc_t* d) {
+  static const int env = getenv("ITN_GEMM_SPLITACC") ? atoi(getenv("ITN_GEMM_SPLITACC")) : 0;
+  return d->precision == ITN_PREC_TF32X3_SPLIT || (env && d->precision == ITN_PREC_TF32X3);
 }
 
 static int sm_count() {
@@ -964,6 +987,7 @@ static int launch_tile(const itn_gemm_desc_t* d, cudaStream_t stream) {
   const long long nt = (long long)p.tiles_m * p.tiles_n * d->nb0 * d->nb1;
   if (nt > 0x7fffffffLL) return set_error(ITN_ERR_ARG, "gemm: too many tiles");
   p.num_tiles = (int)nt;
+  p.split_acc = (X3 && Cfg::kCanSplit && want_split(d)) ? 1 : 0;
   CUtensorMap tmA, tmB, tmBlo;
   int rc = d->conv_kh > 0 ? make_im2col_map(&tmA, d)
                           : make_operand_map(&tmA, d->A, d->M, d->K, d->nb0, d->nb1, kBM, &p.a_m0, &p.a_m1);
@@ -1012,12 +1036,13 @@ static int launch_tile(const itn_gemm_desc_t* d, cudaStream_t stream) {
 // enough 256-row tiles to fill the 74 TPCs.  ITN_GEMM_PAIR=0/1 overrides (experiments).
 static bool want_pair(const itn_gemm_desc_t* d) {
   static const int env = getenv("ITN_GEMM_PAIR") ? atoi(getenv("ITN_GEMM_PAIR")) : ITN_GEMM_PAIR_DEFAULT;
-  if (!env || d->precision != ITN_PREC_TF32X3 || d->A.major != 0 || d->B.major != 0 || kBK != 32) return false;
+  if (!env || d->precision != ITN_PREC_TF32X3 || want_split(d) || d->A.major != 0 || d->B.major != 0 || kBK != 32) return false;
   const long long tiles_m = (d->M + kBM - 1) / kBM, tiles_n = (d->N + 255) / 256;
   const long long pair_tiles = ((tiles_m + 1) / 2) * tiles_n * d->nb0 * d->nb1;
   // measured (tools/gemm_pair_check.py): +12 % at K = 2048 (57760 x 256), +4 % at K = 1496, -1 ... -3 % at K <= 512
   // where the epilogue, not the main loop, sets the pace
-  return tiles_m >= 2 && d->N >= 192 && d->K >= 1024 && pair_tiles >= sm_count() / 2;
+  static const int kmin = getenv("ITN_GEMM_PAIR_KMIN") ? atoi(getenv("ITN_GEMM_PAIR_KMIN")) : 1024;
+  return tiles_m >= 2 && d->N >= 192 && d->K >= kmin && pair_tiles >= sm_count() / 2;
 }
 
 template <int BN, bool X3>
@@ -1035,7 +1060,7 @@ static int launch_major2(const itn_gemm_desc_t* d, cudaStream_t s) {
 
 template <int BN>
 static int launch_major(const itn_gemm_desc_t* d, cudaStream_t s) {
-  return d->precision == ITN_PREC_TF32 ? launch_major2<BN, false>(d, s) : launch_major2<BN, true>(d, s);
+  return d->precision == ITN_PREC_TF32 ? launch_major2<BN, false>(d, s) : launch_major2<BN, true>(d, s);   // X3: either tf32x3 flavour
 }
 
 // Tile width: the widest tile that still yields at least one tile per SM (wide tiles re-read
@@ -1080,6 +1105,7 @@ extern "C" int itn_gemm_tf32(const itn_gemm_desc_t* d, void* stream) {
                           "multiples of 4 elements");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   int bn = itn::pick_bn(d);
+  if (bn > 128 && itn::want_split(d)) bn = 128;     // the split accumulators need half of tensor memory each
   if (const char* f = getenv("ITN_GEMM_BN")) {
     const int v = atoi(f);
     if (v == 32 || v == 64 || v == 128 || v == 256) bn = v;

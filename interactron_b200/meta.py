@@ -194,7 +194,7 @@ def _parts_runner(model, frames, masks, idx):
     bb_key = tuple((t.data_ptr(), t._version) for t in list(bb.parameters()) + list(bb.buffers()))
     # everything the capture bakes in as a kernel scalar or a branch is part of the key
     key = ("meta", tuple(frames.shape), tuple(masks.shape), loop.kind, bb_key, float(loop.lr), float(loop.clip),
-           loop.ops.precision, loop.backbone_impl, bool(loop.ops.fused_attention), train)
+           loop.ops.precision_key, loop.backbone_impl, bool(loop.ops.fused_attention), train)
     ent = model._graphs.get(key)
     if ent is None:
         for k in [k for k in model._graphs if k[0] == "meta"]:

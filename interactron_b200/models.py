@@ -185,7 +185,7 @@ class _Adaptive(_Base):
         from .graph import GraphedCall
         self._check_backbone_moved()
         # everything a capture bakes in as a kernel scalar or a branch is part of the key
-        key = (tag, tuple(frames.shape), tuple(masks.shape), self._loop.ops.precision, self._loop.backbone_tf32,
+        key = (tag, tuple(frames.shape), tuple(masks.shape), self._loop.ops.precision_key, self._loop.backbone_tf32,
                self._loop.backbone_impl, float(self._loop.lr), float(self._loop.clip),
                bool(self._loop.ops.fused_attention))
         g = self._graphs.get(key)
@@ -295,7 +295,7 @@ class interactron(_Adaptive):
         """CUDA-graph replay of fn(a, b) keyed by tag and input geometry (policy rollout pieces)."""
         from .graph import GraphedCall
         self._check_backbone_moved()
-        key = (tag, tuple(a.shape), tuple(b.shape), a.dtype, b.dtype, self._loop.ops.precision,
+        key = (tag, tuple(a.shape), tuple(b.shape), a.dtype, b.dtype, self._loop.ops.precision_key,
                bool(self._loop.ops.fused_attention))
         g = self._graphs.get(key)
         if g is None:

@@ -46,6 +46,10 @@ class CudaOps:
         # "tf32x3": error-compensated 3-pass TF32 (~fp32 accuracy, the parity mode, default);
         # "tf32": single pass with TF32-clean (round-to-nearest at the producer) operands.
         self.precision = os.environ.get("ITN_GEMM_PRECISION", "tf32x3")
+        # tf32x3 with the residual products in their own TMEM accumulator (ITN_PREC_TF32X3_SPLIT): ~fp32 GEMM
+        # error (measured 3.9e-7 / 5.8e-7 at K = 256 / 2048 against torch fp32's 2.9e-7 / 8.1e-7), tiles at most
+        # 128 wide so 8-20 % slower.  Off by default; flip per instance or with ITN_GEMM_SPLITACC=1.
+        self.split_acc = os.environ.get("ITN_GEMM_SPLITACC", "0") != "0"
         if self.precision not in PRECISION:
             raise ValueError(f"ITN_GEMM_PRECISION must be one of {sorted(PRECISION)}")
         self.n_tf32 = 0
@@ -77,6 +81,14 @@ class CudaOps:
 
     def launch_count(self):
         return int(self.lib.itn_launch_count())
+
+    @property
+    def precision_key(self):
+        """What a captured graph depends on (GEMM arithmetic mode)."""
+        return self.precision + ("+split" if self.split_acc else "")
+
+    def _prec(self):
+        return 2 if (self.split_acc and self.precision == "tf32x3") else PRECISION[self.precision]
 
     @property
     def _clean(self):
@@ -224,7 +236,7 @@ class CudaOps:
         d.epi = EPI[epi]
         d.accumulate = 1 if accumulate else 0
         d.round_out = 1 if (rnd and self._clean) else 0
-        d.precision = PRECISION[self.precision]
+        d.precision = self._prec()
         d.act_pos = 1 if act_after_residual else 0
         d.c_pad = 1 if out_pad else 0
         if not self.force_simt and self.lib.itn_gemm_tf32_supported(C.byref(d)):
@@ -333,7 +345,7 @@ class CudaOps:
         if residual is not None:
             assert residual.is_contiguous() and residual.numel() == M * Nn
             d.residual, d.ldr = residual.data_ptr(), Nn
-        d.alpha, d.act, d.precision = 1.0, ACT[act], PRECISION[self.precision]
+        d.alpha, d.act, d.precision = 1.0, ACT[act], self._prec()
         d.act_pos = 1 if act_after_residual else 0
         d.conv_kh, d.conv_kw, d.conv_stride, d.conv_pad, d.conv_dil = kh, kw, stride, pad, dil
         d.conv_n, d.conv_h, d.conv_w, d.conv_c, d.conv_ho, d.conv_wo = N, H, W_, Cc, Ho, Wo

@@ -526,3 +526,39 @@ def test_gemm_cta_pair_variant_is_bit_identical(ops3):
         outs.append(r.stdout.strip().splitlines())
     assert outs[0] == outs[1] and len(outs[0]) == 3
     assert all(float(line.split()[2]) < 3e-6 for line in outs[0])
+
+
+@pytest.mark.parametrize("a_mn", [False, True])
+@pytest.mark.parametrize("b_mn", [False, True])
+@pytest.mark.parametrize("shape", [(1805, 256, 256), (3000, 2048, 512), (1024, 512, 2048), (364, 32, 361), (250, 1236, 256),
+                                   (777, 92, 4608)])
+def test_gemm_tf32x3_split_accumulators_reach_fp32_error(a_mn, b_mn, shape):
+    """ITN_PREC_TF32X3_SPLIT (CudaOps.split_acc): the residual products accumulate in tensor-memory columns of
+    their own, so the main accumulator takes K/8 round-toward-zero accumulates instead of 3K/8.  Error against an
+    fp64 product: no worse than twice torch's strict-fp32 GEMM on the same operands, and below the default tf32x3
+    mode; bias / relu / residual epilogues and batches agree with the default mode to the same accuracy."""
+    from interactron_b200.ops import CudaOps
+    o3, os_ = CudaOps(), CudaOps()
+    os_.split_acc = True
+    M, N, K = shape
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = torch.randn(K, M, generator=g, device="cuda").t() if a_mn else torch.randn(M, K, generator=g, device="cuda")
+    b = torch.randn(N, K, generator=g, device="cuda").t() if not b_mn else torch.randn(K, N, generator=g, device="cuda")
+    want = a.double() @ b.double()
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        e_torch = rel(a @ b, want)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    e_split, e_x3 = rel(os_.matmul(a, b), want), rel(o3.matmul(a, b), want)
+    assert e_split < max(2.0 * e_torch, 4e-7), (e_split, e_torch)
+    assert e_split <= e_x3 * 1.05, (e_split, e_x3)
+    if N % 4 == 0:
+        bias = torch.randn(N, generator=g, device="cuda")
+        res = torch.randn(M, N, generator=g, device="cuda")
+        y = os_.matmul(a, b, bias=bias, act="relu", residual=res, act_after_residual=True)
+        assert rel(y, torch.relu(want + bias.double() + res.double())) < 1e-6
+    a3 = torch.randn(3, 2, 200, 96, generator=g, device="cuda")
+    b3 = torch.randn(3, 2, 96, 72, generator=g, device="cuda")
+    assert rel(os_.matmul(a3, b3), a3.double() @ b3.double()) < 1e-6

@@ -12,8 +12,10 @@ from interactron_b200.ops import CudaOps
 ops = CudaOps()
 torch.manual_seed(0)
 out = {}
-for (M, N, K, bias, res, presplit) in [(1000, 256, 96, False, False, False), (57760, 256, 2048, True, True, True), (16480, 2048, 512, False, False, False),
-                             (57760, 2048, 256, True, False, True), (20000, 1236, 256, True, False, False), (33333, 512, 1496, False, False, False)]:
+import json
+SHAPES = json.loads(os.environ.get("SHAPES", "null")) or [(1000, 256, 96, False, False, False), (57760, 256, 2048, True, True, True), (16480, 2048, 512, False, False, False),
+                             (57760, 2048, 256, True, False, True), (20000, 1236, 256, True, False, False), (33333, 512, 1496, False, False, False)]
+for (M, N, K, bias, res, presplit) in SHAPES:
     a = torch.randn(M, K, device="cuda")
     w = torch.randn(N, K, device="cuda")
     if presplit:
