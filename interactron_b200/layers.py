@@ -61,16 +61,6 @@ def attention_fwd(ops, q, k, v, B, Lq, Lk, nh, hd, scale, kmask, drop=None):
     fused = getattr(ops, "attention_supported", None)
     if fused is not None and fused(q, k, v, nh):
         o, lse = ops.attention_fwd(q, k, v, nh, scale, kmask, drop=drop)
-        import os
-        mix = os.environ.get("ITN_ATTN_MIX")           # EXPERIMENT
-        if mix and drop is None:
-            o2, P = _attention_fwd_unfused(ops, q, k, v, B, Lq, Lk, nh, hd, scale, kmask, None)
-            if mix == "fwd":
-                return o, P
-            if mix == "bwd":
-                return o2, FusedCtx(o, lse, kmask, None)
-            if mix == "bwd2":
-                return o2, FusedCtx(o2, lse, kmask, None)
         return o, FusedCtx(o, lse, kmask, drop)
     return _attention_fwd_unfused(ops, q, k, v, B, Lq, Lk, nh, hd, scale, kmask, drop)
 
