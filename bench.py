@@ -41,12 +41,19 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.stop_flag = index, [], threading.Event()
-        self.t_mark = None
+        self.t_mark = self.t_end = None
 
     def mark(self):
         """Start of the timed region.  The thread is started a little earlier (during the last warm-up
         steps, same load) because one nvidia-smi query takes 0.3-1 s on a multi-GPU box."""
         self.t_mark = time.perf_counter()
+
+    def finish(self):
+        """End of the timed region: stop, and let a query that is in flight (it overlaps the region) complete."""
+        self.t_end = time.perf_counter()
+        self.stop_flag.set()
+        if self.is_alive():
+            self.join(timeout=6.0)
 
     def run(self):
         while not self.stop_flag.is_set():
@@ -177,7 +184,7 @@ def eager_gpu_baseline(model, workload, n_episodes, local):
             one(i)
         e1.record()
         torch.cuda.synchronize()
-        sampler.stop_flag.set()
+        sampler.finish()
         ms = e0.elapsed_time(e1)
     finally:
         torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
@@ -385,7 +392,7 @@ def run_gpu_arm(args):
         torch.cuda.current_stream().synchronize()
         ev2.append((e0, e1))
     barrier()
-    sampler.stop_flag.set()
+    sampler.finish()
     e2e_ms = sum(a.elapsed_time(b) for a, b in ev2)
     # predict() ships the frames as they are and, of the int64 padding masks, only the 19x19 pixels per
     # frame that the nearest-neighbour down-sampling reads (episode.sample_masks_host), as uint8
@@ -412,7 +419,7 @@ def run_gpu_arm(args):
             extras["interactron_predict"] = measure_predict_extra("interactron", 16, 5, 3, rank, local, world)
         extras["rollout_config_3"] = measure_rollout(16, 2, 2, True, rank, local, world)
         e_meta = max(1, 16 // world) if world > 1 else 2
-        extras["meta_interactron_config_4"] = measure_meta("interactron", e_meta, 4, 3, 0, rank, local, world)
+        extras["meta_interactron_config_4"] = measure_meta("interactron", e_meta, 8, 3, 0, rank, local, world)
     if rank == 0:
         total_eps = E * world * args.steps
         cpu = None
@@ -536,7 +543,7 @@ def measure_rollout(E, steps, warmup, lock, rank, local, world):
             episode(d)
     e1.record()
     _barrier(world)
-    sampler.stop_flag.set()
+    sampler.finish()
     ms = _max_over_ranks([e0.elapsed_time(e1)], world)[0]
     v = E * world * steps / (ms * 1e-3)
     h2d = sum(5 * 3 * 300 * 300 * 4 * s // 5 for s in (1, 2, 3, 4, 5))
@@ -621,7 +628,7 @@ def measure_meta(name, E, steps, warmup, cpu_episodes, rank, local, world, train
         if red is not None:
             ar.append(red.ms())
     _barrier(world)
-    sampler.stop_flag.set()
+    sampler.finish()
     launches = launches_per_step * steps
     n_ar = max(1, len(ar))
     ms, ar_side, ar_exposed = _max_over_ranks([sum(a.elapsed_time(b) for a, b in ev), sum(a for a, _ in ar) / n_ar,
@@ -711,7 +718,7 @@ def measure_predict_extra(name, E, steps, warmup, rank, local, world):
         e1.record()
         ev.append((e0, e1))
     _barrier(world)
-    sampler.stop_flag.set()
+    sampler.finish()
     ms = _max_over_ranks([sum(a.elapsed_time(b_) for a, b_ in ev)], world)[0]
     out = {"metric": METRIC, "value": E * world * steps / (ms * 1e-3), "unit": "episodes/s", "n_gpus": world,
            "steps": steps, "warmup": warmup, "ms_per_step": ms / steps,

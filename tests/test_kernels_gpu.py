@@ -559,7 +559,7 @@ def test_gemm_tf32x3_split_accumulators_reach_fp32_error(a_mn, b_mn, shape):
         bias = torch.randn(N, generator=g, device="cuda")
         res = torch.randn(M, N, generator=g, device="cuda")
         y = os_.matmul(a, b, bias=bias, act="relu", residual=res, act_after_residual=True)
-        assert rel(y, torch.relu(want + bias.double() + res.double())) < 1e-6
+        assert rel(y, torch.relu(want + bias.double() + res.double())) < max(1e-6, 2.0 * e_split)
     a3 = torch.randn(3, 2, 200, 96, generator=g, device="cuda")
     b3 = torch.randn(3, 2, 96, 72, generator=g, device="cuda")
     assert rel(os_.matmul(a3, b3), a3.double() @ b3.double()) < 1e-6
