@@ -176,6 +176,16 @@ int itn_layernorm_fwd(const float* x, const float* gamma, const float* beta,
                       float* y, float* y_r, float* mean, float* rstd,
                       long long rows, int cols, int groups, long long gb_stride,
                       float eps, void* stream);
+/* LayerNorm forward that also writes y_plus = y + plus, the input of the next attention's q/k projection
+ * (`src + pos`, `tgt + query_pos`: detr_models/transformer.py:144-150,207-219), saving the separate add
+ * launch and a re-read of y.  plus follows itn_add's broadcast rule: a block of plus_elems values (whole
+ * rows) repeated inside each group of plus_group consecutive elements, one block per group
+ * (plus_group_stride elements apart; 0 = one block for everything). */
+int itn_layernorm_fwd_plus(const float* x, const float* gamma, const float* beta,
+                           float* y, float* mean, float* rstd,
+                           long long rows, int cols, int groups, long long gb_stride, float eps,
+                           const float* plus, float* y_plus, long long plus_elems,
+                           long long plus_group, long long plus_group_stride, void* stream);
 /* dx = d LayerNorm; dgamma/dbeta (may be NULL; group g at + g*dgb_stride, e.g. a slice
  * of the flat per-episode gradient buffer) are OVERWRITTEN with the per-group sums;
  * dx_r (may be NULL) is a TF32-rounded copy of dx.
@@ -185,6 +195,20 @@ int itn_layernorm_bwd(const float* dy, const float* x, const float* mean,
                       float* dx, float* dx_r, float* dgamma, float* dbeta,
                       long long rows, int cols, int groups, long long gb_stride,
                       long long dgb_stride, void* stream);
+
+/* The same backward in ONE launch: dx, dgamma, dbeta and (optionally) dxsum = per-group column sums of dx,
+ * i.e. the bias gradient of the linear layer feeding the residual this LayerNorm normalises (post-norm
+ * blocks, detr_models/transformer.py:148-160,205-228), which otherwise is a separate column-sum launch.
+ * Any of dgamma/dbeta/dxsum may be NULL.  Column sums are combined in a fixed order (deterministic).
+ * workspace: itn_layernorm_bwd_fused_workspace(rows, cols, groups) bytes, 16-byte aligned, zero-filled
+ * ONCE by the caller (the kernel leaves its counters zero); cols in {128, 256, 512}. */
+long long itn_layernorm_bwd_fused_workspace(long long rows, int cols, int groups);
+int itn_layernorm_bwd_fused(const float* dy, const float* x, const float* mean,
+                            const float* rstd, const float* gamma, float* dx,
+                            float* dgamma, float* dbeta, float* dxsum,
+                            long long rows, int cols, int groups, long long gb_stride,
+                            long long dgb_stride, long long dxsum_stride,
+                            void* workspace, long long workspace_bytes, void* stream);
 
 /* In-place row softmax of scale*s + mask over `cols` (row stride ld).
  * key_mask (may be NULL) is uint8 [mask_batches, cols], 1 = padded key (-inf);

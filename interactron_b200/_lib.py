@@ -73,7 +73,10 @@ SIGNATURES = {
     "itn_attention_fwd": (_I, [C.POINTER(AttentionDesc), _P]),
     "itn_attention_bwd": (_I, [C.POINTER(AttentionDesc), _P]),
     "itn_layernorm_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _LL, _I, _I, _LL, _F, _P]),
+    "itn_layernorm_fwd_plus": (_I, [_P, _P, _P, _P, _P, _P, _LL, _I, _I, _LL, _F, _P, _P, _LL, _LL, _LL, _P]),
     "itn_layernorm_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _LL, _I, _I, _LL, _LL, _P]),
+    "itn_layernorm_bwd_fused_workspace": (_LL, [_LL, _I, _I]),
+    "itn_layernorm_bwd_fused": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _LL, _I, _I, _LL, _LL, _LL, _P, _LL, _P]),
     "itn_softmax_fwd": (_I, [_P, _LL, _I, _LL, _F, _P, _LL, _I, _P]),
     "itn_softmax_bwd": (_I, [_P, _P, _LL, _I, _LL, _F, _I, _P]),
     "itn_colsum": (_I, [_P, _P, _I, _LL, _I, _LL, _LL, _P]),

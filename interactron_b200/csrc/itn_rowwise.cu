@@ -12,7 +12,9 @@ __global__ void __launch_bounds__(256)
 layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                      const float* __restrict__ beta, float* __restrict__ y,
                      float* __restrict__ y_r, float* __restrict__ mean_out, float* __restrict__ rstd_out, long long rows,
-                     long long rows_per_group, long long gb_stride, float eps) {
+                     long long rows_per_group, long long gb_stride, float eps,
+                     const float* __restrict__ plus, float* __restrict__ y_plus, long long plus_elems,
+                     long long plus_group, long long plus_gs) {
   pdl_wait();
   pdl_trigger();
   constexpr int cols = VPL * 128;
@@ -40,6 +42,15 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
   const float4* br = reinterpret_cast<const float4*>(beta + g * gb_stride);
   float4* yr = reinterpret_cast<float4*>(y + row * cols);
   float4* yrr = y_r ? reinterpret_cast<float4*>(y_r + row * cols) : nullptr;
+  // second output y + plus (the `x + pos` / `tgt + query_pos` that feeds the next attention's q/k projection):
+  // plus is a block of plus_elems values repeated inside each group of plus_group elements, one block per group
+  const float4* pr = nullptr;
+  float4* ypr = nullptr;
+  if (y_plus) {
+    const long long i0 = row * cols;
+    pr = reinterpret_cast<const float4*>(plus + (i0 / plus_group) * plus_gs + i0 % plus_elems);
+    ypr = reinterpret_cast<float4*>(y_plus + i0);
+  }
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
     const float4 ga = gr[lane + 32 * i], be = br[lane + 32 * i];
@@ -50,6 +61,10 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
     o.w = (v[i].w - mean) * rstd * ga.w + be.w;
     yr[lane + 32 * i] = o;
     if (yrr) yrr[lane + 32 * i] = make_float4(rn_tf32(o.x), rn_tf32(o.y), rn_tf32(o.z), rn_tf32(o.w));
+    if (ypr) {
+      const float4 pv = pr[lane + 32 * i];
+      ypr[lane + 32 * i] = make_float4(o.x + pv.x, o.y + pv.y, o.z + pv.z, o.w + pv.w);
+    }
   }
   if (lane == 0) {
     if (mean_out) mean_out[row] = mean;
@@ -139,6 +154,125 @@ layernorm_bwd_gb_kernel(const float* __restrict__ dy, const float* __restrict__ 
     if (dgamma) dgamma[(long long)g * dgb_stride + c] = tg;
     if (dbeta) dbeta[(long long)g * dgb_stride + c] = tb;
   }
+}
+
+
+// One launch for the whole LayerNorm backward: dx, the per-group column sums dgamma = sum dy*xhat and
+// dbeta = sum dy, and (optionally) dxsum = sum dx - the bias gradient of the linear layer that feeds the
+// residual this LayerNorm normalises (post-norm blocks: d(x + sublayer(x)) = dx goes to both), which
+// otherwise costs a colsum launch re-reading dx.  CTA (chunk, g) walks `chunk_rows` rows of group g, one
+// warp per row, column partials in registers; the CTA's partial goes to `partials`, and the CTA that
+// arrives last at the group's counter adds the partials up in chunk order: fixed summation order
+// (deterministic), no second launch.  The counter is reset by that CTA (workspace is reusable as is).
+template <int VPL>
+__global__ void __launch_bounds__(256)
+layernorm_bwd_fused_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                           const float* __restrict__ mean, const float* __restrict__ rstd,
+                           const float* __restrict__ gamma, float* __restrict__ dx,
+                           float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dxsum,
+                           float* __restrict__ partials, unsigned* __restrict__ counters,
+                           long long rows_per_group, int chunk_rows, long long gb_stride,
+                           long long dgb_stride, long long dxsum_stride) {
+  pdl_wait();
+  pdl_trigger();
+  constexpr int cols = VPL * 128;
+  __shared__ float red[3 * cols];
+  __shared__ bool last;
+  const int chunk = blockIdx.x, chunks = gridDim.x, g = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long r_begin = (long long)chunk * chunk_rows;
+  const long long r_end = r_begin + chunk_rows < rows_per_group ? r_begin + chunk_rows : rows_per_group;
+  const float4* gr = reinterpret_cast<const float4*>(gamma + g * gb_stride);
+  float4 ga[VPL], ag[VPL], ab[VPL], ax[VPL];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    ga[i] = gr[lane + 32 * i];
+    ag[i] = ab[i] = ax[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (long long r = r_begin + warp; r < r_end; r += 8) {
+    const long long row = (long long)g * rows_per_group + r;
+    const float mu = mean[row], rs = rstd[row];
+    const float4* xr = reinterpret_cast<const float4*>(x + row * cols);
+    const float4* dr = reinterpret_cast<const float4*>(dy + row * cols);
+    float4 xh[VPL], dg[VPL];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const float4 xv = xr[lane + 32 * i], dv = dr[lane + 32 * i];
+      xh[i].x = (xv.x - mu) * rs; xh[i].y = (xv.y - mu) * rs;
+      xh[i].z = (xv.z - mu) * rs; xh[i].w = (xv.w - mu) * rs;
+      dg[i].x = dv.x * ga[i].x; dg[i].y = dv.y * ga[i].y; dg[i].z = dv.z * ga[i].z; dg[i].w = dv.w * ga[i].w;
+      s1 += (dg[i].x + dg[i].y) + (dg[i].z + dg[i].w);
+      s2 += (dg[i].x * xh[i].x + dg[i].y * xh[i].y) + (dg[i].z * xh[i].z + dg[i].w * xh[i].w);
+      ag[i].x += dv.x * xh[i].x; ag[i].y += dv.y * xh[i].y; ag[i].z += dv.z * xh[i].z; ag[i].w += dv.w * xh[i].w;
+      ab[i].x += dv.x; ab[i].y += dv.y; ab[i].z += dv.z; ab[i].w += dv.w;
+    }
+    const float m1 = warp_sum(s1) * (1.0f / cols);
+    const float m2 = warp_sum(s2) * (1.0f / cols);
+    float4* or_ = reinterpret_cast<float4*>(dx + row * cols);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      float4 o;
+      o.x = rs * (dg[i].x - m1 - xh[i].x * m2);
+      o.y = rs * (dg[i].y - m1 - xh[i].y * m2);
+      o.z = rs * (dg[i].z - m1 - xh[i].z * m2);
+      o.w = rs * (dg[i].w - m1 - xh[i].w * m2);
+      or_[lane + 32 * i] = o;
+      ax[i].x += o.x; ax[i].y += o.y; ax[i].z += o.z; ax[i].w += o.w;
+    }
+  }
+  // warps add their column partials into shared memory one after the other (fixed order)
+  float4* red4 = reinterpret_cast<float4*>(red);
+  for (int w = 0; w < 8; ++w) {
+    if (warp == w) {
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        const int c4 = lane + 32 * i;
+        if (w == 0) {
+          red4[c4] = ag[i];
+          red4[cols / 4 + c4] = ab[i];
+          red4[2 * (cols / 4) + c4] = ax[i];
+        } else {
+          float4 t = red4[c4];
+          red4[c4] = make_float4(t.x + ag[i].x, t.y + ag[i].y, t.z + ag[i].z, t.w + ag[i].w);
+          t = red4[cols / 4 + c4];
+          red4[cols / 4 + c4] = make_float4(t.x + ab[i].x, t.y + ab[i].y, t.z + ab[i].z, t.w + ab[i].w);
+          t = red4[2 * (cols / 4) + c4];
+          red4[2 * (cols / 4) + c4] = make_float4(t.x + ax[i].x, t.y + ax[i].y, t.z + ax[i].z, t.w + ax[i].w);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  float* outs[3] = {dgamma ? dgamma + (long long)g * dgb_stride : nullptr, dbeta ? dbeta + (long long)g * dgb_stride : nullptr,
+                    dxsum ? dxsum + (long long)g * dxsum_stride : nullptr};
+  if (chunks == 1) {            // nothing to combine
+    for (int idx = threadIdx.x; idx < 3 * cols; idx += 256) {
+      float* o = outs[idx / cols];
+      if (o) o[idx % cols] = red[idx];
+    }
+    return;
+  }
+  float* mine = partials + ((long long)g * chunks + chunk) * (3 * cols);
+  for (int idx = threadIdx.x; idx < 3 * cols; idx += 256) mine[idx] = red[idx];
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned old = atomicAdd(&counters[g], 1u);
+    last = (old == (unsigned)chunks - 1u);
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  const float* gp = partials + (long long)g * chunks * (3 * cols);
+  for (int idx = threadIdx.x; idx < 3 * cols; idx += 256) {
+    float* o = outs[idx / cols];
+    if (!o) continue;
+    float t = 0.f;
+    for (int ch = 0; ch < chunks; ++ch) t += __ldcg(gp + (long long)ch * (3 * cols) + idx);
+    o[idx % cols] = t;
+  }
+  if (threadIdx.x == 0) counters[g] = 0u;
 }
 
 // ------------------------------------------------------------------ softmax
@@ -337,23 +471,48 @@ colsum_kernel(const float* __restrict__ x, float* __restrict__ out, long long ro
 
 using namespace itn;
 
-extern "C" int itn_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y,
-                                 float* y_r, float* mean, float* rstd, long long rows, int cols, int groups,
-                                 long long gb_stride, float eps, void* stream) {
+static int layernorm_fwd_launch(const float* x, const float* gamma, const float* beta, float* y,
+                                float* y_r, float* mean, float* rstd, long long rows, int cols, int groups,
+                                long long gb_stride, float eps, const float* plus, float* y_plus,
+                                long long plus_elems, long long plus_group, long long plus_gs, void* stream) {
   ITN_REQUIRE(x && gamma && beta && y, "layernorm_fwd: null pointer");
   ITN_REQUIRE(rows > 0 && groups > 0 && rows % groups == 0,
               "layernorm_fwd: rows (%lld) must be a positive multiple of groups (%d)", rows, groups);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const unsigned grid = (unsigned)((rows + 7) / 8);
   const long long rpg = rows / groups;
+#define ITN_LNF(V) launch(layernorm_fwd_kernel<V>, grid, 256, 0, s, x, gamma, beta, y, y_r, mean, rstd, rows, rpg, gb_stride, eps, \
+                          plus, y_plus, plus_elems, plus_group, plus_gs)
   switch (cols) {
-    case 128: launch(layernorm_fwd_kernel<1>, grid, 256, 0, s, x, gamma, beta, y, y_r, mean, rstd, rows, rpg, gb_stride, eps); break;
-    case 256: launch(layernorm_fwd_kernel<2>, grid, 256, 0, s, x, gamma, beta, y, y_r, mean, rstd, rows, rpg, gb_stride, eps); break;
-    case 512: launch(layernorm_fwd_kernel<4>, grid, 256, 0, s, x, gamma, beta, y, y_r, mean, rstd, rows, rpg, gb_stride, eps); break;
-    case 1024: launch(layernorm_fwd_kernel<8>, grid, 256, 0, s, x, gamma, beta, y, y_r, mean, rstd, rows, rpg, gb_stride, eps); break;
+    case 128: ITN_LNF(1); break;
+    case 256: ITN_LNF(2); break;
+    case 512: ITN_LNF(4); break;
+    case 1024: ITN_LNF(8); break;
     default: return set_error(ITN_ERR_UNSUPPORTED, "layernorm_fwd: cols must be 128/256/512/1024, got %d", cols);
   }
+#undef ITN_LNF
   return check_launch("layernorm_fwd_kernel");
+}
+
+extern "C" int itn_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y,
+                                 float* y_r, float* mean, float* rstd, long long rows, int cols, int groups,
+                                 long long gb_stride, float eps, void* stream) {
+  return layernorm_fwd_launch(x, gamma, beta, y, y_r, mean, rstd, rows, cols, groups, gb_stride, eps, nullptr, nullptr,
+                              1, 1, 0, stream);
+}
+
+extern "C" int itn_layernorm_fwd_plus(const float* x, const float* gamma, const float* beta, float* y,
+                                      float* mean, float* rstd, long long rows, int cols, int groups,
+                                      long long gb_stride, float eps, const float* plus, float* y_plus,
+                                      long long plus_elems, long long plus_group, long long plus_group_stride,
+                                      void* stream) {
+  ITN_REQUIRE(plus && y_plus, "layernorm_fwd_plus: null pointer");
+  ITN_REQUIRE(plus_elems > 0 && plus_elems % cols == 0 && plus_group > 0 && plus_group % plus_elems == 0 &&
+              (rows * (long long)cols) % plus_group == 0 && plus_group_stride % 4 == 0 &&
+              (reinterpret_cast<uintptr_t>(plus) & 15) == 0 && (reinterpret_cast<uintptr_t>(y_plus) & 15) == 0,
+              "layernorm_fwd_plus: the added block must be whole rows (plus_elems %% cols == 0) tiling each group, 16-byte aligned");
+  return layernorm_fwd_launch(x, gamma, beta, y, nullptr, mean, rstd, rows, cols, groups, gb_stride, eps, plus, y_plus,
+                              plus_elems, plus_group, plus_group_stride, stream);
 }
 
 extern "C" int itn_layernorm_bwd(const float* dy, const float* x, const float* mean,
@@ -381,6 +540,55 @@ extern "C" int itn_layernorm_bwd(const float* dy, const float* x, const float* m
     rc = check_launch("layernorm_bwd_gb_kernel");
   }
   return rc;
+}
+
+
+// chunks of rows per group so that the grid has ~2 CTAs per SM and every warp still gets >= 1 row
+static int ln_bwd_chunks(long long rpg, int groups) {
+  long long want = (296 + groups - 1) / groups;
+  const long long cap = (rpg + 7) / 8;
+  if (want > cap) want = cap;
+  if (want > 512) want = 512;
+  return want < 1 ? 1 : (int)want;
+}
+
+extern "C" long long itn_layernorm_bwd_fused_workspace(long long rows, int cols, int groups) {
+  if (rows <= 0 || groups <= 0 || rows % groups) return 0;
+  const int chunks = ln_bwd_chunks(rows / groups, groups);
+  return 4LL * groups * chunks * 3 * cols + 4LL * ((groups + 63) / 64 * 64);
+}
+
+extern "C" int itn_layernorm_bwd_fused(const float* dy, const float* x, const float* mean, const float* rstd,
+                                       const float* gamma, float* dx, float* dgamma, float* dbeta, float* dxsum,
+                                       long long rows, int cols, int groups, long long gb_stride,
+                                       long long dgb_stride, long long dxsum_stride, void* workspace,
+                                       long long workspace_bytes, void* stream) {
+  ITN_REQUIRE(dy && x && mean && rstd && gamma && dx, "layernorm_bwd_fused: null pointer");
+  ITN_REQUIRE(rows > 0 && groups > 0 && rows % groups == 0,
+              "layernorm_bwd_fused: rows (%lld) must be a positive multiple of groups (%d)", rows, groups);
+  ITN_REQUIRE(groups <= 65535, "layernorm_bwd_fused: too many groups (%d)", groups);
+  const long long need = itn_layernorm_bwd_fused_workspace(rows, cols, groups);
+  ITN_REQUIRE(workspace && workspace_bytes >= need && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0,
+              "layernorm_bwd_fused: workspace of %lld bytes (16-byte aligned, counters zeroed once) needed, got %lld",
+              need, workspace_bytes);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const long long rpg = rows / groups;
+  const int chunks = ln_bwd_chunks(rpg, groups);
+  const int chunk_rows = (int)((rpg + chunks - 1) / chunks);
+  // counters first (zeroed by the caller once; the kernel leaves them zero), partial sums behind them
+  unsigned* counters = static_cast<unsigned*>(workspace);
+  float* partials = reinterpret_cast<float*>(counters + (groups + 63) / 64 * 64);
+  dim3 grid(chunks, groups);
+#define ITN_LNB(V) launch(layernorm_bwd_fused_kernel<V>, grid, 256, 0, s, dy, x, mean, rstd, gamma, dx, dgamma, dbeta, dxsum, \
+                          partials, counters, rpg, chunk_rows, gb_stride, dgb_stride, dxsum_stride)
+  switch (cols) {
+    case 128: ITN_LNB(1); break;
+    case 256: ITN_LNB(2); break;
+    case 512: ITN_LNB(4); break;
+    default: return set_error(ITN_ERR_UNSUPPORTED, "layernorm_bwd_fused: cols must be 128/256/512, got %d", cols);
+  }
+#undef ITN_LNB
+  return check_launch("layernorm_bwd_fused_kernel");
 }
 
 extern "C" int itn_softmax_fwd(float* sc, long long rows, int cols, long long ld, float scale,

@@ -17,7 +17,7 @@ the `_r` twins of LayerNorm outputs); residual streams and gradients accumulate 
 import math
 
 from .layers import (DecDims, GradSink, MultiSink, NullSink, T, attention_bwd, attention_fwd,  # noqa: F401
-                     decoder_layer_bwd, decoder_layer_fwd, lin, mlp_bwd, mlp_fwd, _drop_res, _next)
+                     cross_kv_all, decoder_layer_bwd, decoder_layer_fwd, lin, ln_plus, mlp_bwd, mlp_fwd, _drop_res, _next)
 
 D, H, HD, FFN, NQ = 256, 8, 32, 2048, 50
 N_ENC, N_DEC = 6, 6
@@ -43,10 +43,11 @@ def detr_t_forward(ops, W, src_r, pos, kmask, E, Fe, L, preds=None, need_cache=T
     x = ops.empty(E, R, D)
     x_r = lin(ops, src_r, ip_w, W.p("input_proj.bias"), out_pre=x, rnd=True)        # x (fp32), x_r
     enc = []
+    x_pos = None                     # x + pos of the current layer input (fused into the previous layer's norm2)
     for i in range(N_ENC):
         pre = f"transformer.encoder.layers.{i}."
         ipw, ipb = W.w(pre + "self_attn.in_proj_weight"), W.p(pre + "self_attn.in_proj_bias")
-        qk_in = ops.add(x.view(E * R, D), pos, rnd=True).view(1, E * R, D)
+        qk_in = (x_pos if x_pos is not None else ops.add(x.view(E * R, D), pos, rnd=True)).view(1, E * R, D)
         qk = lin(ops, qk_in, ipw[:, :2 * D], ipb[:, :2 * D], rnd=True)               # [1,E*R,512]
         v = lin(ops, x_r.view(1, E * R, D), ipw[:, 2 * D:], ipb[:, 2 * D:], rnd=True)
         qk3, v3 = qk.view(B, L, 2 * D), v.view(B, L, D)
@@ -69,23 +70,29 @@ def detr_t_forward(ops, W, src_r, pos, kmask, E, Fe, L, preds=None, need_cache=T
         else:
             h = ops.dropout(h, kf, out=h)
             f = _drop_res(ops, lin(ops, h, W.w(pre + "linear2.weight"), W.p(pre + "linear2.bias")), kd2, x1.view(E, R, D))
-        x2, x2_r, m2, r2 = ops.layernorm_fwd(f.view(E * R, D), W.p(pre + "norm2.weight"),
-                                             W.p(pre + "norm2.bias"))
+        x2, x2_r, m2, r2, x_pos = ln_plus(ops, f.view(E * R, D), W.p(pre + "norm2.weight"), W.p(pre + "norm2.bias"),
+                                          pos, (E * R, D))
         if need_cache:
             enc.append(dict(x_r=x_r, qk_in=qk_in, qk3=qk3, v3=v3, P=P, o=o, a=a, m1=m1, r1=r1,
                             x1_r=x1_r, h=h, f=f, m2=m2, r2=r2, drop=None if drop is None else (kd1, kf, kd2)))
         x, x_r = x2.view(E, R, D), x2_r.view(E, R, D)
     memory, memory_r = x, x_r
-    mem_pos_r = ops.add(memory.view(E * R, D), pos, rnd=True).view(1, E * R, D)
+    mem_pos_r = x_pos.view(1, E * R, D)                          # memory + pos: the last norm2's second output
 
     qpos = W.p("query_embed.weight")                                                  # [Gw,50,256]
     dm = DecDims(E, B, NQ, L, D, H)
     tgt = ops.zeros(E, Q, D)
     tgt_r = tgt
     dec = []
+    tq = None                        # tgt + query_pos, fused into the previous layer's norm3
+    kvs = cross_kv_all(ops, W, [f"transformer.decoder.layers.{j}." for j in range(N_DEC)], dm, mem_pos_r,
+                       memory_r.view(1, E * R, D))
     for j in range(N_DEC):
-        tgt, tgt_r, dc = decoder_layer_fwd(ops, W, f"transformer.decoder.layers.{j}.", dm, tgt, tgt_r, qpos,
-                                           mem_pos_r, memory_r.view(1, E * R, D), kmask, need_cache, drop=drop)
+        res = decoder_layer_fwd(ops, W, f"transformer.decoder.layers.{j}.", dm, tgt, tgt_r, qpos,
+                                mem_pos_r, memory_r.view(1, E * R, D), kmask, need_cache, drop=drop,
+                                tgt_plus=tq, want_plus=j < N_DEC - 1, kv=None if kvs is None else kvs[j])
+        tgt, tgt_r, dc = res[:3]
+        tq = res[3] if j < N_DEC - 1 else None
         dec.append(dc)
 
     # only hs[-1] is used (reference detr.py:69), so decoder.norm runs once
@@ -161,10 +168,11 @@ def detr_t_backward(ops, W, cache, sink, dpreds=None, dmemory=None, dlogits=None
         pre = f"transformer.encoder.layers.{i}."
         s = cache["enc"][i]
         ip_name, ip_bias = pre + "self_attn.in_proj_weight", pre + "self_attn.in_proj_bias"
-        df, df_r = ops.layernorm_bwd(dx, s["f"].view(E * R, D), s["m2"], s["r2"], W.p(pre + "norm2.weight"),
-                                     **sink.norm(pre + "norm2"))
-        df3, df3_r = df.view(E, R, D), df_r.view(E, R, D)
         dk_ = s.get("drop")
+        # without dropout the residual branch's gradient IS the LayerNorm's dx: its linear's bias gradient is fused
+        df, df_r = ops.layernorm_bwd(dx, s["f"].view(E * R, D), s["m2"], s["r2"], W.p(pre + "norm2.weight"),
+                                     **sink.norm(pre + "norm2", bias_of=pre + "linear2" if dk_ is None else None))
+        df3, df3_r = df.view(E, R, D), df_r.view(E, R, D)
         kd1, kf, kd2 = dk_ if dk_ is not None else (None,) * 3
         if dk_ is not None:                   # gradient of the dropped branch; the residual path keeps df3
             dfm = ops.dropout(df3, kd2)
@@ -178,7 +186,8 @@ def detr_t_backward(ops, W, cache, sink, dpreds=None, dmemory=None, dlogits=None
         sink.linear(pre + "linear1", dh, s["x1_r"].view(E, R, D))
         dx1 = ops.matmul(dh, W.bwd(pre + "linear1.weight"), residual=df3)
         da, da_r = ops.layernorm_bwd(dx1.view(E * R, D), s["a"].view(E * R, D), s["m1"], s["r1"],
-                                     W.p(pre + "norm1.weight"), **sink.norm(pre + "norm1"))
+                                     W.p(pre + "norm1.weight"),
+                                     **sink.norm(pre + "norm1", bias_of=pre + "self_attn.out_proj" if dk_ is None else None))
         da3, da3_r = da.view(E, R, D), da_r.view(E, R, D)
         dam, dam_r = da3, da3_r
         if dk_ is not None:

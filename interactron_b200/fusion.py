@@ -14,7 +14,7 @@ needed on the inner loop (the fusion parameters phi are not adapted): `backward`
 d memory and d preds for detr_t.detr_t_backward.
 """
 from .layers import (DecDims, NullSink, T, attention_bwd, attention_fwd, decoder_layer_bwd,  # noqa: F401
-                     decoder_layer_fwd, lin, mlp_bwd, mlp_fwd, _drop_res, _next)
+                     cross_kv_all, decoder_layer_fwd, lin, mlp_bwd, mlp_fwd, _drop_res, _next)
 
 DF, NH, NP, NA = 512, 8, 50, 5          # width, heads, predictions per frame, action tokens
 N_LAYERS = 4
@@ -48,9 +48,14 @@ def fusion_b_forward(ops, W, memory_r, preds, E, S, L, need_cache=True, drop=Non
     dm = DecDims(E, E, Q, R, DF, NH)
     caches = []
     x, x_r = tgt, tgt_r
+    xq = None                        # x + query_pos, fused into the previous layer's norm3
+    kvs = cross_kv_all(ops, W, [f"transformer.layers.{j}." for j in range(N_LAYERS)], dm, mem_pos_r, mem_r)
     for j in range(N_LAYERS):
-        x, x_r, c = decoder_layer_fwd(ops, W, f"transformer.layers.{j}.", dm, x, x_r, qpos, mem_pos_r, mem_r,
-                                      None, need_cache, drop=drop)
+        res = decoder_layer_fwd(ops, W, f"transformer.layers.{j}.", dm, x, x_r, qpos, mem_pos_r, mem_r,
+                                None, need_cache, drop=drop, tgt_plus=xq, want_plus=j < N_LAYERS - 1,
+                                kv=None if kvs is None else kvs[j])
+        x, x_r, c = res[:3]
+        xq = res[3] if j < N_LAYERS - 1 else None
         caches.append(c)
     y, y_r, my, ry = ops.layernorm_fwd(x.view(E * Q, DF), W.p("transformer.norm.weight"),
                                        W.p("transformer.norm.bias"))

@@ -6,6 +6,7 @@ are token-major 2-D/3-D tensors; attention heads are strided views of [batch, to
 Tensors that feed a GEMM are stored TF32-rounded by their producer (rnd=True / `_r` twins);
 residual streams and gradient accumulators stay full fp32.
 """
+import torch
 
 
 def pad4(n):
@@ -179,7 +180,7 @@ class NullSink:
     def rows(self, name_w, name_b, lo, hi, dy, x):
         pass
 
-    def norm(self, name):
+    def norm(self, name, bias_of=None):
         return {}
 
     def colsum(self, name, x):
@@ -202,6 +203,7 @@ class GradSink(NullSink):
 
     def __init__(self, ops, pack, g, shared=False):
         self.ops, self.pack, self.g, self.shared = ops, pack, g, shared
+        self._bias_done = set()          # biases whose gradient came out of a fused LayerNorm backward
 
     def wants(self, name):
         return name in self.pack
@@ -222,6 +224,9 @@ class GradSink(NullSink):
                         accumulate=accumulate)
         if self.wants(name + ".bias"):
             assert not accumulate
+            if name in self._bias_done:
+                self._bias_done.discard(name)
+                return
             self.ops.colsum(self._flat(dy_full if dy_full is not None else dy_r), out=self.view(name + ".bias"))
 
     def rows(self, name_w, name_b, lo, hi, dy, x):
@@ -231,10 +236,19 @@ class GradSink(NullSink):
         self.ops.matmul(T(self._flat(dy)), self._flat(x), out=self.view(name_w)[:, lo:hi])
         self.ops.colsum(self._flat(dy), out=self.view(name_b)[:, lo:hi])
 
-    def norm(self, name):
+    def norm(self, name, bias_of=None):
+        """Keyword arguments for ops.layernorm_bwd.  bias_of: the linear layer whose output is the residual
+        branch this LayerNorm normalises (post-norm block, no dropout in between): its bias gradient is
+        colsum(dx), which the fused LayerNorm backward of the B200 backend produces in the same launch
+        (`dxsum`); `linear(bias_of, ...)` then skips its column sum."""
         if not self.wants(name + ".weight"):
             return {}
-        return dict(dgamma=self.view(name + ".weight"), dbeta=self.view(name + ".bias"))
+        kw = dict(dgamma=self.view(name + ".weight"), dbeta=self.view(name + ".bias"))
+        if bias_of is not None and getattr(self.ops, "fused_ln_bwd", False) and self.wants(bias_of + ".bias"):
+            b = self.view(bias_of + ".bias")
+            kw["dxsum"] = b.reshape(b.shape[0], -1)
+            self._bias_done.add(bias_of)
+        return kw
 
     def colsum(self, name, x):
         """x [G, rows, cols] summed over rows into parameter `name` (numel = cols per group)."""
@@ -268,10 +282,10 @@ class MultiSink(NullSink):
         for s in self.sinks:
             s.rows(name_w, name_b, lo, hi, dy, x)
 
-    def norm(self, name):
+    def norm(self, name, bias_of=None):
         for s in self.sinks:
             if s.wants(name + ".weight"):
-                return s.norm(name)
+                return s.norm(name, bias_of)
         return {}
 
     def colsum(self, name, x):
@@ -295,15 +309,67 @@ class DecDims:
         self.R = B * Lk // E           # memory rows per episode
 
 
-def decoder_layer_fwd(ops, W, pre, dm, tgt, tgt_r, qpos, mem_pos_r, memory_r, kmask, need_cache=True, drop=None):
+def ln_plus(ops, x, gamma, beta, plus, shape):
+    """LayerNorm forward + `y + plus` (the q/k input of the next attention): one launch where the backend has
+    layernorm_fwd_plus (B200), LayerNorm then add elsewhere.  -> y, y_r, mean, rstd, y_plus [rows, cols]."""
+    f = getattr(ops, "layernorm_fwd_plus", None)
+    if f is not None:
+        return f(x, gamma, beta, plus, shape)
+    y, y_r, mean, rstd = ops.layernorm_fwd(x, gamma, beta)
+    return y, y_r, mean, rstd, ops.add(y.view(shape), plus, rnd=True).view(x.shape)
+
+
+def _stacked(views):
+    """Equally spaced, identically shaped views of one buffer -> one view with a new dim 1 (layer) inserted
+    after the group dim; None if the views do not line up (or are not plain tensors, e.g. dual numbers)."""
+    v0 = views[0]
+    if not all(isinstance(v, torch.Tensor) for v in views) or len(views) < 2:
+        return None
+    base = v0.untyped_storage().data_ptr()
+    step = views[1].storage_offset() - v0.storage_offset()
+    for j, v in enumerate(views):
+        if (v.untyped_storage().data_ptr() != base or v.shape != v0.shape or v.stride() != v0.stride()
+                or v.dtype != v0.dtype or v.storage_offset() != v0.storage_offset() + j * step):
+            return None
+    if step <= 0:
+        return None
+    return torch.as_strided(v0, (v0.shape[0], len(views)) + tuple(v0.shape[1:]),
+                            (v0.stride(0), step) + tuple(v0.stride()[1:]), v0.storage_offset())
+
+
+def cross_kv_all(ops, W, pres, dm, mem_pos_r, memory_r):
+    """Cross-attention key / value projections of ALL decoder layers `pres` at once: they depend on the encoder
+    memory only (reference detr_models/transformer.py:222-226 recomputes them inside every layer), so the n
+    layers' K projections are ONE GEMM batched over the layer dim (and one for V) when the layers'
+    in_proj tensors are equally spaced views of one flat parameter buffer (they are: identical layers packed
+    back to back).  -> [(kc_j, vc_j)] per layer ([B, Lk, D] each), or None (caller projects per layer)."""
+    D, B, Lk = dm.D, dm.B, dm.Lk
+    ws = [W.w(p + "multihead_attn.in_proj_weight") for p in pres]
+    bs = [W.p(p + "multihead_attn.in_proj_bias") for p in pres]
+    if not isinstance(mem_pos_r, torch.Tensor) or ws[0].shape[0] != 1:
+        return None
+    wk, wv = _stacked([w[:, D:2 * D] for w in ws]), _stacked([w[:, 2 * D:] for w in ws])
+    bk, bv = _stacked([b[:, D:2 * D] for b in bs]), _stacked([b[:, 2 * D:] for b in bs])
+    if wk is None or wv is None or bk is None or bv is None:
+        return None
+    kc = ops.matmul(mem_pos_r.unsqueeze(1), wk.transpose(-1, -2), bias=bk, rnd=True)       # [1, n, E*R, D]
+    vc = ops.matmul(memory_r.unsqueeze(1), wv.transpose(-1, -2), bias=bv, rnd=True)
+    return [(kc[0, j].view(B, Lk, D), vc[0, j].view(B, Lk, D)) for j in range(len(pres))]
+
+
+def decoder_layer_fwd(ops, W, pre, dm, tgt, tgt_r, qpos, mem_pos_r, memory_r, kmask, need_cache=True, drop=None,
+                      tgt_plus=None, want_plus=False, kv=None):
     """DETR post-norm decoder layer (reference detr_models/transformer.py:211-232).
     tgt/tgt_r [E,Q,D]; qpos [Gw,Lq,D] added to the queries of every batch; mem_pos_r / memory_r
-    [1,E*R,D] TF32-clean keys-input (memory+pos) and values-input (memory).  -> t3, t3_r, cache."""
+    [1,E*R,D] TF32-clean keys-input (memory+pos) and values-input (memory).  -> t3, t3_r, cache.
+    tgt_plus: tgt + qpos if the caller already has it (the previous layer's want_plus output);
+    want_plus: also return t3 + qpos (fused into the last LayerNorm) as a fourth value.
+    kv: this layer's (kc, vc) from cross_kv_all (projected for all layers at once), else projected here."""
     E, B, Lq, Lk, D, nh, hd, Q, R = dm.E, dm.B, dm.Lq, dm.Lk, dm.D, dm.nh, dm.hd, dm.Q, dm.R
     sw, sb = W.w(pre + "self_attn.in_proj_weight"), W.p(pre + "self_attn.in_proj_bias")
     cw, cb = W.w(pre + "multihead_attn.in_proj_weight"), W.p(pre + "multihead_attn.in_proj_bias")
     # self attention among the Lq queries of each batch
-    qk_in = ops.add(tgt, qpos, rnd=True).view(1, E * Q, D)
+    qk_in = (tgt_plus if tgt_plus is not None else ops.add(tgt, qpos, rnd=True)).view(1, E * Q, D)
     qk = lin(ops, qk_in, sw[:, :2 * D], sb[:, :2 * D], rnd=True)
     v = lin(ops, tgt_r.view(1, E * Q, D), sw[:, 2 * D:], sb[:, 2 * D:], rnd=True)
     qk3, v3 = qk.view(B, Lq, 2 * D), v.view(B, Lq, D)
@@ -318,12 +384,16 @@ def decoder_layer_fwd(ops, W, pre, dm, tgt, tgt_r, qpos, mem_pos_r, memory_r, km
     else:
         a1 = _drop_res(ops, lin(ops, o.view(E, Q, D), W.w(pre + "self_attn.out_proj.weight"),
                                 W.p(pre + "self_attn.out_proj.bias")), kd1, tgt)
-    t1, t1_r, m1, r1 = ops.layernorm_fwd(a1.view(E * Q, D), W.p(pre + "norm1.weight"), W.p(pre + "norm1.bias"))
+    t1, t1_r, m1, r1, q_in = ln_plus(ops, a1.view(E * Q, D), W.p(pre + "norm1.weight"), W.p(pre + "norm1.bias"),
+                                     qpos, (E, Q, D))
     # cross attention into the Lk memory tokens of the batch
-    q_in = ops.add(t1.view(E, Q, D), qpos, rnd=True).view(1, E * Q, D)
+    q_in = q_in.view(1, E * Q, D)
     qc = lin(ops, q_in, cw[:, :D], cb[:, :D], rnd=True).view(B, Lq, D)
-    kc = lin(ops, mem_pos_r, cw[:, D:2 * D], cb[:, D:2 * D], rnd=True).view(B, Lk, D)
-    vc = lin(ops, memory_r, cw[:, 2 * D:], cb[:, 2 * D:], rnd=True).view(B, Lk, D)
+    if kv is not None:
+        kc, vc = kv
+    else:
+        kc = lin(ops, mem_pos_r, cw[:, D:2 * D], cb[:, D:2 * D], rnd=True).view(B, Lk, D)
+        vc = lin(ops, memory_r, cw[:, 2 * D:], cb[:, 2 * D:], rnd=True).view(B, Lk, D)
     ka2 = _next(drop, "attn")
     o2, P2 = attention_fwd(ops, qc, kc, vc, B, Lq, Lk, nh, hd, dm.scale, kmask, drop=ka2)
     kd2 = _next(drop)
@@ -341,13 +411,20 @@ def decoder_layer_fwd(ops, W, pre, dm, tgt, tgt_r, qpos, mem_pos_r, memory_r, km
     else:
         h = ops.dropout(h, kf, out=h)
         f = _drop_res(ops, lin(ops, h, W.w(pre + "linear2.weight"), W.p(pre + "linear2.bias")), kd3, t2.view(E, Q, D))
-    t3, t3_r, m3, r3 = ops.layernorm_fwd(f.view(E * Q, D), W.p(pre + "norm3.weight"), W.p(pre + "norm3.bias"))
+    t3_plus = None
+    if want_plus:
+        t3, t3_r, m3, r3, t3_plus = ln_plus(ops, f.view(E * Q, D), W.p(pre + "norm3.weight"), W.p(pre + "norm3.bias"),
+                                            qpos, (E, Q, D))
+    else:
+        t3, t3_r, m3, r3 = ops.layernorm_fwd(f.view(E * Q, D), W.p(pre + "norm3.weight"), W.p(pre + "norm3.bias"))
     cache = None
     if need_cache:
         cache = dict(qk3=qk3, v3=v3, P=P, o=o, a1=a1, m1=m1, r1=r1, qc=qc, kc=kc, vc=vc, P2=P2, o2=o2,
                      a2=a2, m2=m2, r2=r2, t2_r=t2_r, h=h, f=f, m3=m3, r3=r3,
                      qk_in=qk_in, tgt_r=tgt_r, q_in=q_in, mem_pos_r=mem_pos_r, memory_r=memory_r,
                      drop=None if drop is None else (kd1, kd2, kf, kd3))
+    if want_plus:
+        return t3.view(E, Q, D), t3_r.view(E, Q, D), cache, t3_plus.view(E, Q, D)
     return t3.view(E, Q, D), t3_r.view(E, Q, D), cache
 
 
@@ -360,11 +437,12 @@ def decoder_layer_bwd(ops, W, pre, dm, s, dt, sink, dqpos, dmp, dmem):
     sa_w, ca_w = pre + "self_attn.in_proj_weight", pre + "multihead_attn.in_proj_weight"
     sa_b, ca_b = pre + "self_attn.in_proj_bias", pre + "multihead_attn.in_proj_bias"
     sink = sink if sink is not None else NullSink()
-    nk = lambda n: sink.norm(pre + n)
-    df, df_r = ops.layernorm_bwd(dt, s["f"].view(E * Q, D), s["m3"], s["r3"], W.p(pre + "norm3.weight"),
-                                 **nk("norm3"))
-    df3, df3_r = df.view(E, Q, D), df_r.view(E, Q, D)
     dk_ = s.get("drop")
+    # without dropout the residual branch's gradient IS the LayerNorm's dx: its linear's bias gradient is fused
+    nk = lambda n, lin: sink.norm(pre + n, bias_of=pre + lin if dk_ is None else None)
+    df, df_r = ops.layernorm_bwd(dt, s["f"].view(E * Q, D), s["m3"], s["r3"], W.p(pre + "norm3.weight"),
+                                 **nk("norm3", "linear2"))
+    df3, df3_r = df.view(E, Q, D), df_r.view(E, Q, D)
     kd1, kd2, kf, kd3 = dk_ if dk_ is not None else (None,) * 4
     if dk_ is not None:                       # gradient of the dropped branch; the residual path keeps df3
         dfm = ops.dropout(df3, kd3)
@@ -378,7 +456,7 @@ def decoder_layer_bwd(ops, W, pre, dm, s, dt, sink, dqpos, dmp, dmem):
     sink.linear(pre + "linear1", dh, s["t2_r"].view(E, Q, D))
     dt2 = ops.matmul(dh, W.bwd(pre + "linear1.weight"), residual=df3)
     da2, da2_r = ops.layernorm_bwd(dt2.view(E * Q, D), s["a2"].view(E * Q, D), s["m2"], s["r2"],
-                                   W.p(pre + "norm2.weight"), **nk("norm2"))
+                                   W.p(pre + "norm2.weight"), **nk("norm2", "multihead_attn.out_proj"))
     da2_3r = da2_r.view(E, Q, D)
     da2m = da2.view(E, Q, D)
     if dk_ is not None:
@@ -400,7 +478,7 @@ def decoder_layer_bwd(ops, W, pre, dm, s, dt, sink, dqpos, dmp, dmem):
     ops.matmul(dkc.view(1, E * R, D), W.bwd(ca_w, D, 2 * D), out=dmp, accumulate=True)
     ops.matmul(dvc.view(1, E * R, D), W.bwd(ca_w, 2 * D, 3 * D), out=dmem, accumulate=True)
     da1, da1_r = ops.layernorm_bwd(dt1.view(E * Q, D), s["a1"].view(E * Q, D), s["m1"], s["r1"],
-                                   W.p(pre + "norm1.weight"), **nk("norm1"))
+                                   W.p(pre + "norm1.weight"), **nk("norm1", "self_attn.out_proj"))
     da1_3r = da1_r.view(E, Q, D)
     da1m = da1.view(E, Q, D)
     if dk_ is not None:

@@ -68,6 +68,12 @@ class CudaOps:
         # convolutions as implicit GEMMs (TMA im2col tensor maps); ITN_IMPLICIT_CONV=0: explicit itn_im2col_nhwc + GEMM
         self.implicit_conv = os.environ.get("ITN_IMPLICIT_CONV", "1") != "0"
         self.n_attn = 0
+        # LayerNorm backward in one launch (dx + dgamma/dbeta + the bias gradient colsum(dx)); ITN_FUSED_LN_BWD=0:
+        # the dx kernel, the dgamma/dbeta kernel and a separate column sum
+        self.fused_ln_bwd = os.environ.get("ITN_FUSED_LN_BWD", "1") != "0"
+        self._ln_ws = None
+        # LayerNorm forward that also emits y + pos / y + query_pos for the next attention (ITN_FUSED_LN_PLUS=0: add kernel)
+        self.fused_ln_plus = os.environ.get("ITN_FUSED_LN_PLUS", "1") != "0"
 
     # ------------------------------------------------------------ plumbing
     def _stream(self):
@@ -413,13 +419,44 @@ class CudaOps:
                                               eps, self._stream()))
         return y, (y_r if y_r is not None else y), mean, rstd
 
-    def layernorm_bwd(self, dy, x, mean, rstd, gamma, dgamma=None, dbeta=None):
-        """-> dx, dx_r (TF32-rounded copy) [rows,D].  dgamma/dbeta: optional [G, D] views
+    def layernorm_fwd_plus(self, x, gamma, beta, plus, shape, eps=1e-5):
+        """layernorm_fwd that also returns y + plus, with `add`'s broadcast rule applied to y viewed as `shape`
+        ([G, n, cols]) - one launch instead of LayerNorm + add.  -> y, y_r, mean, rstd, y_plus [rows, cols]."""
+        if self._clean or not self.fused_ln_plus:
+            y, y_r, mean, rstd = self.layernorm_fwd(x, gamma, beta, eps)
+            return y, y_r, mean, rstd, self.add(y.view(shape), plus, rnd=True).view(x.shape)
+        rows, cols = x.shape
+        g2, b2 = gamma.reshape(-1, cols), beta.reshape(-1, cols)
+        groups = g2.shape[0]
+        assert x.is_contiguous() and g2.stride(1) == 1 and b2.stride(1) == 1
+        assert groups == 1 or g2.stride(0) == b2.stride(0)
+        n = x.numel()
+        grouped = plus.dim() >= 2 and plus.shape[0] == shape[0] and plus.shape[0] > 1
+        if grouped and (n != plus.numel() or not plus.is_contiguous()):
+            G = shape[0]
+            assert plus[0].is_contiguous()
+            b_elems, a_group, b_gs = plus.numel() // G, n // G, plus.stride(0)
+        else:
+            assert plus.is_contiguous()
+            b_elems, a_group, b_gs = plus.numel(), n, 0
+        assert n % b_elems == 0
+        y, y_plus = self.empty(rows, cols), self.empty(rows, cols)
+        mean, rstd = self.empty(rows), self.empty(rows)
+        _lib.check(self.lib.itn_layernorm_fwd_plus(_ptr(x), _ptr(g2), _ptr(b2), _ptr(y), _ptr(mean), _ptr(rstd), rows,
+                                                   cols, groups, g2.stride(0) if groups > 1 else 0, eps, _ptr(plus),
+                                                   _ptr(y_plus), b_elems, a_group, b_gs, self._stream()))
+        return y, y, mean, rstd, y_plus
+
+    def layernorm_bwd(self, dy, x, mean, rstd, gamma, dgamma=None, dbeta=None, dxsum=None):
+        """-> (dx, dx_r).  dgamma/dbeta: optional [groups, cols] views
         (row stride arbitrary, e.g. slices of the flat gradient buffer) that receive the
-        per-group affine gradients."""
+        per-group affine gradients.  dxsum (fused_ln_bwd only): optional [groups, cols] view that receives
+        the per-group column sums of dx (the bias gradient of the linear layer feeding the residual)."""
         rows, cols = x.shape
         g2 = gamma.reshape(-1, cols)
         groups = g2.shape[0] if dgamma is None else dgamma.shape[0]
+        if dgamma is None and dxsum is not None:
+            groups = dxsum.shape[0]
         assert dy.is_contiguous() and x.is_contiguous() and g2.stride(1) == 1
         assert g2.shape[0] in (1, groups)
         dx = self.empty(rows, cols)
@@ -430,6 +467,21 @@ class CudaOps:
             stride = dgamma.stride(0) if groups > 1 else cols
             assert groups == 1 or dbeta.stride(0) == stride
         gb_stride = g2.stride(0) if g2.shape[0] > 1 else 0
+        if self.fused_ln_bwd and not self._clean and cols in (128, 256, 512) and (dgamma is not None or dxsum is not None):
+            xs_stride = 0
+            if dxsum is not None:
+                assert dxsum.shape == (groups, cols) and dxsum.stride(1) == 1
+                xs_stride = dxsum.stride(0) if groups > 1 else cols
+            need = int(self.lib.itn_layernorm_bwd_fused_workspace(rows, cols, groups))
+            if self._ln_ws is None or self._ln_ws.numel() < need:
+                # allocated (and zeroed) outside of graph capture by the eager warm-up pass; grows monotonically
+                self._ln_ws = torch.zeros(max(need, 8 << 20), dtype=torch.uint8, device=self.device)
+            _lib.check(self.lib.itn_layernorm_bwd_fused(_ptr(dy), _ptr(x), _ptr(mean), _ptr(rstd), _ptr(g2), _ptr(dx),
+                                                        _ptr(dgamma), _ptr(dbeta), _ptr(dxsum), rows, cols, groups,
+                                                        gb_stride, stride, xs_stride, _ptr(self._ln_ws),
+                                                        self._ln_ws.numel(), self._stream()))
+            return dx, dx
+        assert dxsum is None, "dxsum needs the fused LayerNorm backward"
         _lib.check(self.lib.itn_layernorm_bwd(_ptr(dy), _ptr(x), _ptr(mean), _ptr(rstd), _ptr(g2), _ptr(dx),
                                               _ptr(dx_r), _ptr(dgamma), _ptr(dbeta), rows, cols, groups,
                                               gb_stride, stride, self._stream()))

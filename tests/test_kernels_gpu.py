@@ -563,3 +563,80 @@ def test_gemm_tf32x3_split_accumulators_reach_fp32_error(a_mn, b_mn, shape):
     a3 = torch.randn(3, 2, 200, 96, generator=g, device="cuda")
     b3 = torch.randn(3, 2, 96, 72, generator=g, device="cuda")
     assert rel(os_.matmul(a3, b3), a3.double() @ b3.double()) < 1e-6
+
+
+@pytest.mark.parametrize("cols", [128, 256, 512])
+@pytest.mark.parametrize("groups,rpg", [(1, 3000), (3, 250), (62, 50), (4, 1805), (2, 5)])
+def test_layernorm_bwd_fused_one_launch(ops3, cols, groups, rpg):
+    """itn_layernorm_bwd_fused: dx, dgamma, dbeta and colsum(dx) from one launch; same values as the
+    dx / dgamma-dbeta / colsum kernels to fp32 rounding and as float64 autograd; strided outputs (slices of a
+    flat gradient buffer); bit-identical across repeats (fixed summation order); optional outputs may be absent."""
+    gen = torch.Generator(device="cuda").manual_seed(cols + groups + rpg)
+    rows = groups * rpg
+    x = torch.randn(rows, cols, generator=gen, device="cuda") * 2 + 0.5
+    gamma = torch.randn(groups, cols, generator=gen, device="cuda")
+    beta = torch.randn(groups, cols, generator=gen, device="cuda")
+    dy = torch.randn(rows, cols, generator=gen, device="cuda")
+    _, _, mean, rstd = ops3.layernorm_fwd(x, gamma, beta)
+    flat = torch.zeros(groups, 3 * cols + 12, device="cuda")
+    dg, db, ds = flat[:, :cols], flat[:, cols + 4:2 * cols + 4], flat[:, 2 * cols + 8:3 * cols + 8]
+    assert ops3.fused_ln_bwd
+    n0 = ops3.launch_count()
+    dx, _ = ops3.layernorm_bwd(dy, x, mean, rstd, gamma, dgamma=dg, dbeta=db, dxsum=ds)
+    assert ops3.launch_count() - n0 == 1
+    xr = x.double().view(groups, -1, cols).requires_grad_(True)
+    gr = gamma.double().requires_grad_(True)
+    br = beta.double().requires_grad_(True)
+    yr = torch.nn.functional.layer_norm(xr, (cols,)) * gr[:, None] + br[:, None]
+    yr.backward(dy.double().view(groups, -1, cols))
+    assert rel(dx, xr.grad.reshape(rows, cols)) < FP32_TOL
+    assert rel(dg, gr.grad) < FP32_TOL and rel(db, br.grad) < FP32_TOL
+    want_ds = xr.grad.sum(1)
+    assert (ds.double() - want_ds).abs().max().item() < 1e-5 * xr.grad.abs().sum(1).max().item()
+    pads = torch.cat([flat[:, cols:cols + 4], flat[:, 2 * cols + 4:2 * cols + 8], flat[:, 3 * cols + 8:]], 1)
+    assert float(pads.abs().sum()) == 0.0
+    first = flat.clone()
+    dx2, _ = ops3.layernorm_bwd(dy, x, mean, rstd, gamma, dgamma=dg, dbeta=db, dxsum=ds)
+    assert torch.equal(flat, first) and torch.equal(dx2, dx)
+    # the three-kernel path computes the same thing
+    ops3.fused_ln_bwd = False
+    try:
+        dg2, db2 = torch.empty(groups, cols, device="cuda"), torch.empty(groups, cols, device="cuda")
+        dx3, _ = ops3.layernorm_bwd(dy, x, mean, rstd, gamma, dgamma=dg2, dbeta=db2)
+    finally:
+        ops3.fused_ln_bwd = True
+    assert torch.equal(dx3, dx) and rel(dg2, dg) < 1e-6 and rel(db2, db) < 1e-6
+    # only the bias gradient requested
+    only = torch.zeros(groups, cols, device="cuda")
+    dx4, _ = ops3.layernorm_bwd(dy, x, mean, rstd, gamma, dxsum=only)
+    assert torch.equal(dx4, dx) and torch.equal(only, ds)
+
+
+@pytest.mark.parametrize("case", ["full", "block", "grouped", "grouped_strided"])
+def test_layernorm_fwd_plus_matches_layernorm_then_add(ops3, case):
+    """itn_layernorm_fwd_plus: y and y + plus from one launch, bit-identical to layernorm_fwd followed by add,
+    for every broadcast shape `add` is used with (full tensor, one block for all, one block per group)."""
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    G, n, cols = 6, 50, 256
+    x = torch.randn(G * n, cols, generator=gen, device="cuda") * 1.5 - 0.2
+    gamma = torch.randn(G, cols, generator=gen, device="cuda")
+    beta = torch.randn(G, cols, generator=gen, device="cuda")
+    if case == "full":
+        plus, shape = torch.randn(G * n, cols, generator=gen, device="cuda"), (G * n, cols)
+    elif case == "block":
+        plus, shape = torch.randn(1, n, cols, generator=gen, device="cuda"), (G, n, cols)
+    elif case == "grouped":
+        plus, shape = torch.randn(G, n, cols, generator=gen, device="cuda"), (G, n, cols)
+    else:
+        flat = torch.randn(G, n * cols + 1000, generator=gen, device="cuda")
+        plus, shape = flat[:, 200:200 + n * cols].view(G, n, cols), (G, n, cols)
+    assert ops3.fused_ln_plus
+    n0 = ops3.launch_count()
+    y, y_r, mean, rstd, yp = ops3.layernorm_fwd_plus(x, gamma, beta, plus, shape)
+    assert ops3.launch_count() - n0 == 1
+    y0, _, m0, r0 = ops3.layernorm_fwd(x, gamma, beta)
+    yp0 = ops3.add(y0.view(shape), plus)
+    assert torch.equal(y, y0) and torch.equal(mean, m0) and torch.equal(rstd, r0)
+    assert torch.equal(yp.view(shape), yp0)
+    want = y0.view(G, n, cols) + (plus.view(-1, n, cols) if case != "full" else plus.view(G, n, cols))
+    assert torch.equal(yp.view(G, n, cols), want)
