@@ -93,3 +93,22 @@ def test_policy_steps_match_reference_and_reuse_features():
         o = dict(both)
         o["frames"], o["masks"] = both["frames"][:, :s], both["masks"][:, :s]
         assert model.get_next_actions(o) == [a[s - 1] for a in acts]
+
+
+def test_policy_action_logits_match_golden_on_the_cpu_simulation():
+    """The committed action-logit goldens (tools/make_golden_policy.py, unmodified reference) against the host
+    logic run on the CPU simulation of the kernels: pins the fixture itself and `_policy_logits` without a GPU."""
+    import os
+    import interactron_b200 as ib
+    from interactron_b200.synthetic import synthetic_episode
+    gold = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "interactron_action_logits.pt"))
+    model = ib.build_model(ib.default_config("interactron", weights="synthetic").MODEL).eval()
+    model._ops = SimOps()
+    data = synthetic_episode(3)
+    for s in (1, 2):
+        d = dict(data)
+        d["frames"], d["masks"] = data["frames"][:, :s], data["masks"][:, :s]
+        lg = model._policy_logits(d, 1, s)[0, s - 1].float()
+        want = gold["logits"][(3, s)][s - 1]
+        assert ((lg - want).norm() / want.norm()).item() < 1e-4
+        assert int(lg.argmax()) == gold["actions"][(3, s)]

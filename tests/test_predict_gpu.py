@@ -174,6 +174,40 @@ def test_policy_actions_match_reference(full_model):
         assert full_model.get_next_action(d) == acts[s]
 
 
+def test_policy_action_logits_match_reference(full_model):
+    """A1 pinned on the continuous quantity: the action LOGITS of the policy step (reference
+    models/interactron.py:174-197, `fusion_out['actions']`) for 4 episodes x 1..4 frames seen, against the
+    unmodified reference (tests/golden/interactron_action_logits.pt, tools/make_golden_policy.py) to 1e-3
+    relative - with random-init weights the argmax is the same action everywhere, the logits are not
+    (they differ by ~1 % between episodes) - through both the single-episode and the lock-step batched call."""
+    from interactron_b200.synthetic import collate_episodes, synthetic_episode
+    gold = torch.load(os.path.join(GOLD, "interactron_action_logits.pt"))
+    eps = {ep: synthetic_episode(ep) for ep in gold["episodes"]}
+
+    def cut(d, s):
+        o = dict(d)
+        o["frames"], o["masks"] = d["frames"][:, :s], d["masks"][:, :s]
+        return o
+
+    worst = 0.0
+    for ep, data in eps.items():
+        for s in range(1, 5):
+            lg = full_model._policy_logits(cut(data, s), 1, s)[0, s - 1].float().cpu()
+            want = gold["logits"][(ep, s)][s - 1]
+            worst = max(worst, rel(lg, want))
+            assert rel(lg, want) < TOL, (ep, s, lg, want)
+            assert int(lg.argmax()) == gold["actions"][(ep, s)]
+            assert full_model.get_next_action(cut(data, s)) == gold["actions"][(ep, s)]
+    batch = collate_episodes([eps[ep] for ep in gold["episodes"]])
+    for s in (2, 4):
+        lg = full_model._policy_logits(cut(batch, s), len(eps), s)[:, s - 1].float().cpu()
+        for i, ep in enumerate(gold["episodes"]):
+            assert rel(lg[i], gold["logits"][(ep, s)][s - 1]) < TOL
+    # the goldens discriminate: neighbouring episodes are further apart than the tolerance
+    a, b = gold["logits"][(0, 1)][0], gold["logits"][(3, 1)][0]
+    assert rel(a, b) > 5 * TOL and worst < TOL
+
+
 def test_batched_policy_step_equals_single_episodes(full_model):
     """get_next_actions (extension: b environments in lock-step) == get_next_action per episode."""
     from interactron_b200.synthetic import collate_episodes, synthetic_episode
