@@ -134,7 +134,8 @@ class GemmTrunk:
         N, H, W, Cin = x.shape
         if L["kh"] == 1 and L["stride"] == 1:
             a, Ho, Wo = x.view(N * H * W, Cin), H, W
-        elif Cin % 32 == 0 and getattr(ops, "implicit_conv", False) and not ops._clean and not ops.force_simt:
+        elif ((Cin % 32 == 0 or (Cin == 4 and getattr(ops, "implicit_stem", False))) and getattr(ops, "implicit_conv", False)
+              and not ops._clean and not ops.force_simt):
             # 3x3 / strided convolutions: the TMA unit gathers the patches (im2col tensor map), nothing is materialised
             res = residual.reshape(-1, L["cout"]) if residual is not None else None
             y, Ho, Wo = ops.conv_gemm(x, L["w"], L["kh"], L["kw"], L["stride"], L["pad"], L["dil"], bias=L["b"],

@@ -85,7 +85,7 @@ struct GemmKParams {
                  // are added in the epilogue - the main accumulator sees K/8 round-toward-zero accumulates, not 3K/8
   float rz_eps;  // tf32x3: mean relative loss of one round-toward-zero TMEM accumulate (see splitters)
   // implicit-GEMM convolution (conv_kw > 0): A tiles come through an im2col tensor map
-  int conv_kw, conv_c, conv_stride, conv_pad, conv_dil, conv_wo, conv_howo;
+  int conv_kh, conv_kw, conv_c, conv_stride, conv_pad, conv_dil, conv_wo, conv_howo;
   int b_presplit;  // tf32x3, K-major B: the residual tile of B is loaded through tmBlo (itn_gemm_desc_t::B_lo)
   int dbg;       // ITN_TRACE builds only: 1 = skip global stores, 2 = skip TMEM read, 4 = skip smem transpose;
                  // any build (ITN_GEMM_DBG, timing experiments): 16 = skip the residual split, 32 = skip the correction MMAs
@@ -437,7 +437,24 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             uint8_t* sa = smem + s * Cfg::kStageBytes;
             uint8_t* sb = sa + Cfg::kABytes;
             const int k0 = kb * kBK;
-            if (!A_MN && p.conv_kw > 0) {
+            if (!A_MN && p.conv_kw > 0 && p.conv_c == 4) {
+              // 4-channel input (the RGB stem, padded): one k-block = 8 filter taps x 4 channels.  Each tap is its own
+              // im2col load of [128 pixels x 16 bytes] into a 2 KB slab: unswizzled K-major core matrices (8 rows x 16 B),
+              // slabs = consecutive 16-byte K chunks (descriptor: LBO = slab, SBO = 128 B).  Taps beyond kh*kw re-read
+              // the last tap; their weights are the zero-filled K tail of B.
+              const int n = m0 / p.conv_howo, rem = m0 - n * p.conv_howo;
+              const int py = rem / p.conv_wo, px = rem - py * p.conv_wo;
+              const int taps = p.conv_kh * p.conv_kw;
+#pragma unroll
+              for (int j = 0; j < kBK / 4; ++j) {
+                int tap = k0 / 4 + j;
+                tap = tap < taps ? tap : taps - 1;
+                const int ky = tap / p.conv_kw, kx = tap - ky * p.conv_kw;
+                tma_load_im2col_4d(sa + j * (kBM * 16), &tmA, &full_bar[s], 0, px * p.conv_stride - p.conv_pad,
+                                   py * p.conv_stride - p.conv_pad, n, (unsigned short)(kx * p.conv_dil),
+                                   (unsigned short)(ky * p.conv_dil));
+              }
+            } else if (!A_MN && p.conv_kw > 0) {
               // k-block -> filter tap (ky, kx) and first channel; tile row m0 -> output pixel (n, py, px)
               const int tap = k0 / p.conv_c, c0 = k0 - tap * p.conv_c;
               const int ky = tap / p.conv_kw, kx = tap - ky * p.conv_kw;
@@ -488,6 +505,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             ITN_TRACE_AT(3, gk);
             const uint32_t sa = smem_u32(smem + s * Cfg::kStageBytes);
             const uint32_t sb = sa + Cfg::kABytes;
+            const bool narrow = !A_MN && p.conv_kw > 0 && p.conv_c == 4;     // unswizzled tap slabs (see the producer)
 #pragma unroll
             for (int k = 0; k < kBK / 8; ++k) {
               // K-major (SWIZZLE_128B): rows of 32 floats, 8-row groups 1024 B apart (SBO); the
@@ -498,7 +516,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               constexpr uint32_t kKLayout = kBK == 32 ? kLayoutSW128 : kLayoutSW64;   // K-major: rows of kBK floats
               constexpr uint32_t kKSbo = 8 * kBK * 4;                                 // 8-row groups
               const uint64_t ad = A_MN ? umma_smem_desc(sa + k * 1024, kAtomBytes, 512, kLayoutSW128Base32)
-                                       : umma_smem_desc(sa + k * 32, 16, kKSbo, kKLayout);
+                                  : narrow ? umma_smem_desc(sa + k * (2 * kBM * 16), kBM * 16, 128, 0u)   // 2 tap slabs per MMA
+                                           : umma_smem_desc(sa + k * 32, 16, kKSbo, kKLayout);
               const uint64_t bd = B_MN ? umma_smem_desc(sb + k * 1024, kAtomBytes, 512, kLayoutSW128Base32)
                                        : umma_smem_desc(sb + k * 32, 16, kKSbo, kKLayout);
               constexpr uint64_t kLoOff = static_cast<uint64_t>(Cfg::kRawBytes >> 4);
@@ -882,8 +901,11 @@ static int make_im2col_map(CUtensorMap* tm, const itn_gemm_desc_t* d) {
   int lower[2] = {-d->conv_pad, -d->conv_pad};
   int upper[2] = {d->conv_pad - (d->conv_kw - 1) * d->conv_dil, d->conv_pad - (d->conv_kh - 1) * d->conv_dil};
   cuuint32_t estr[4] = {1, (cuuint32_t)d->conv_stride, (cuuint32_t)d->conv_stride, 1};
+  // 4-channel input: boxes of [128 pixels x 4 channels = 16 bytes], unswizzled (one load per filter tap)
+  const bool narrow = d->conv_c == 4;
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(d->A.ptr), gdim, gstr, lower, upper,
-                   (cuuint32_t)kBK, (cuuint32_t)kBM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   (cuuint32_t)(narrow ? 4 : kBK), (cuuint32_t)kBM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   narrow ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return set_error(ITN_ERR_CUDA, "cuTensorMapEncodeIm2col failed (%d): [%d,%d,%d,%d] k %dx%d stride %d pad %d dil %d",
@@ -895,6 +917,7 @@ static int make_im2col_map(CUtensorMap* tm, const itn_gemm_desc_t* d) {
 static void fill_kparams(GemmKParams& p, const itn_gemm_desc_t* d) {
   p.M = d->M; p.N = d->N; p.K = d->K;
   p.conv_kw = d->conv_kh > 0 ? d->conv_kw : 0;
+  p.conv_kh = d->conv_kh;
   p.conv_c = d->conv_c; p.conv_stride = d->conv_stride; p.conv_pad = d->conv_pad; p.conv_dil = d->conv_dil;
   p.conv_wo = d->conv_wo; p.conv_howo = d->conv_ho * d->conv_wo;
   p.nb1 = d->nb1 < 1 ? 1 : d->nb1;
@@ -946,7 +969,9 @@ static int validate(const itn_gemm_desc_t* d) {
   if (d->conv_kh > 0) {
     ITN_REQUIRE(kBK == 32, "gemm: implicit convolution needs 32-float k-blocks");
     ITN_REQUIRE(d->conv_kw > 0 && d->conv_stride > 0 && d->conv_dil > 0 && d->conv_pad >= 0, "gemm: bad convolution geometry");
-    ITN_REQUIRE(d->conv_c > 0 && d->conv_c % 32 == 0, "gemm: implicit convolution needs channels %% 32 == 0 (got %d)", d->conv_c);
+    ITN_REQUIRE(d->conv_c > 0 && (d->conv_c % 32 == 0 || d->conv_c == 4),
+                "gemm: implicit convolution needs channels %% 32 == 0, or 4 (got %d)", d->conv_c);
+    ITN_REQUIRE(d->conv_c != 4 || d->A.major == 0, "gemm: the 4-channel implicit convolution takes a K-major activation");
     ITN_REQUIRE(d->nb0 == 1 && d->nb1 == 1, "gemm: implicit convolution is not batched");
     ITN_REQUIRE((long long)d->conv_n * d->conv_ho * d->conv_wo == d->M && d->conv_kh * d->conv_kw * d->conv_c == d->K,
                 "gemm: implicit convolution M/K do not match the geometry");
@@ -1091,7 +1116,7 @@ extern "C" int itn_debug_set_trace(long long* buf) {
 
 extern "C" int itn_gemm_tf32_supported(const itn_gemm_desc_t* d) {
   if (!d || d->M <= 0 || d->N <= 0 || d->K <= 0) return 0;
-  const bool a_ok = d->conv_kh > 0 ? (d->conv_c % 32 == 0 && (reinterpret_cast<uintptr_t>(d->A.ptr) & 15) == 0)
+  const bool a_ok = d->conv_kh > 0 ? ((d->conv_c % 32 == 0 || d->conv_c == 4) && (reinterpret_cast<uintptr_t>(d->A.ptr) & 15) == 0)
                                    : itn::operand_tma_ok(d->A, d->nb0, d->nb1);
   return a_ok && itn::operand_tma_ok(d->B, d->nb0, d->nb1);
 }

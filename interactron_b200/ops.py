@@ -67,6 +67,9 @@ class CudaOps:
         self.fused_attention = os.environ.get("ITN_FUSED_ATTN", "1") != "0"
         # convolutions as implicit GEMMs (TMA im2col tensor maps); ITN_IMPLICIT_CONV=0: explicit itn_im2col_nhwc + GEMM
         self.implicit_conv = os.environ.get("ITN_IMPLICIT_CONV", "1") != "0"
+        # the 4-channel (zero-padded RGB) 7x7 stem as an implicit GEMM too (one TMA im2col load per filter tap);
+        # ITN_IMPLICIT_STEM=0: explicit im2col of the stem (5.5 GB written and re-read at 62 episodes)
+        self.implicit_stem = os.environ.get("ITN_IMPLICIT_STEM", "1") != "0"
         self.n_attn = 0
         # LayerNorm backward in one launch (dx + dgamma/dbeta + the bias gradient colsum(dx)); ITN_FUSED_LN_BWD=0:
         # the dx kernel, the dgamma/dbeta kernel and a separate column sum
@@ -327,13 +330,14 @@ class CudaOps:
     def conv_gemm(self, x, w, kh, kw, stride, pad, dil, bias=None, act=None, residual=None, act_after_residual=False):
         """Convolution of channels-last x [N,H,W,C] with w [Cout, kh*kw*C] (columns in (ky, kx, c) order) as ONE
         tcgen05 GEMM whose A tiles the TMA unit gathers in im2col mode (no patch matrix in HBM) -> [N*Ho*Wo, Cout].
-        C % 32 == 0; bias / activation / residual fused as in `matmul`."""
+        C % 32 == 0, or C == 4 (the zero-padded RGB stem: one im2col load per filter tap, 8 taps per k-block);
+        bias / activation / residual fused as in `matmul`."""
         assert x.is_contiguous() and x.dim() == 4 and w.dim() == 2 and w.stride(1) == 1
         N, H, W_, Cc = x.shape
         Ho = (H + 2 * pad - dil * (kh - 1) - 1) // stride + 1
         Wo = (W_ + 2 * pad - dil * (kw - 1) - 1) // stride + 1
         M, K, Nn = N * Ho * Wo, kh * kw * Cc, w.shape[0]
-        assert Cc % 32 == 0 and w.shape[1] >= K
+        assert (Cc % 32 == 0 or Cc == 4) and w.shape[1] >= K
         out = self.empty(M, Nn)
         d = _lib.GemmDesc()
         d.M, d.N, d.K, d.nb0, d.nb1 = M, Nn, K, 1, 1

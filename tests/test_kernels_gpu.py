@@ -640,3 +640,31 @@ def test_layernorm_fwd_plus_matches_layernorm_then_add(ops3, case):
     assert torch.equal(yp.view(shape), yp0)
     want = y0.view(G, n, cols) + (plus.view(-1, n, cols) if case != "full" else plus.view(G, n, cols))
     assert torch.equal(yp.view(G, n, cols), want)
+
+
+@pytest.mark.parametrize("geom", [(1, 8, 8, 32, 32, 3, 1, 1, 1), (2, 19, 19, 64, 64, 3, 1, 2, 2), (3, 38, 38, 64, 128, 3, 2, 1, 1),
+                                  (3, 38, 38, 64, 128, 1, 2, 0, 1), (2, 75, 75, 64, 64, 3, 1, 1, 1),
+                                  (1, 16, 16, 4, 64, 3, 1, 1, 1), (2, 30, 30, 4, 64, 7, 2, 3, 1), (3, 300, 300, 4, 64, 7, 2, 3, 1)])
+def test_implicit_gemm_convolution_matches_explicit_im2col(ops3, geom):
+    """Convolutions as ONE tcgen05 GEMM whose A tiles the TMA unit gathers in im2col mode (32-channel k-blocks, or -
+    for the zero-padded RGB stem - 8 filter taps x 4 channels per k-block): bit-identical to the explicit
+    im2col + GEMM path (same products, same order) and equal to float64 conv2d, on the trunk's geometries
+    (3x3, dilated, strided 3x3 and 1x1, the 7x7/2 stem), with bias + ReLU (+ residual) fused."""
+    import torch.nn.functional as F
+    N, H, W, Cin, Cout, k, stride, pad, dil = geom
+    g = torch.Generator(device="cuda").manual_seed(sum(geom))
+    x = torch.randn(N, H, W, Cin, device="cuda", generator=g)
+    w = torch.randn(Cout, k, k, Cin, device="cuda", generator=g) * (k * k * Cin) ** -0.5
+    b = torch.randn(Cout, device="cuda", generator=g)
+    wm = w.reshape(Cout, -1).contiguous()
+    y, Ho, Wo = ops3.conv_gemm(x, wm, k, k, stride, pad, dil, bias=b, act="relu")
+    a, Ho2, Wo2 = ops3.im2col_nhwc(x, k, k, stride, pad, dil)
+    assert (Ho, Wo) == (Ho2, Wo2)
+    y2 = ops3.matmul(a, wm.t(), bias=b, act="relu")
+    assert torch.equal(y, y2)
+    ref = F.conv2d(x.permute(0, 3, 1, 2).double(), w.permute(0, 3, 1, 2).double(), b.double(), stride, pad, dil)
+    ref = ref.permute(0, 2, 3, 1).reshape(-1, Cout)
+    assert rel(y, torch.relu(ref)) < 1e-5
+    z = torch.randn(N * Ho * Wo, Cout, device="cuda", generator=g)
+    y3, _, _ = ops3.conv_gemm(x, wm, k, k, stride, pad, dil, bias=b, act="relu", residual=z, act_after_residual=True)
+    assert rel(y3, torch.relu(ref + z.double())) < 1e-5

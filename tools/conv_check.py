@@ -61,9 +61,13 @@ def main():
     ok &= run(ops, 3, 38, 38, 64, 128, 3, 2, 1, 1)         # strided 3x3 (layer2/3 first block)
     ok &= run(ops, 3, 38, 38, 64, 128, 1, 2, 0, 1)         # strided 1x1 (downsample)
     ok &= run(ops, 2, 75, 75, 64, 64, 3, 1, 1, 1)
+    ok &= run(ops, 1, 16, 16, 4, 64, 3, 1, 1, 1)           # 4-channel mode: 9 taps = 2 k-blocks
+    ok &= run(ops, 2, 30, 30, 4, 64, 7, 2, 3, 1)           # the stem's geometry, small
+    ok &= run(ops, 3, 300, 300, 4, 64, 7, 2, 3, 1)         # the RGB stem (zero-padded to 4 channels)
     if len(sys.argv) > 1:
         return 0 if ok else 1
     E = 160
+    run(ops, 310, 300, 300, 4, 64, 7, 2, 3, 1, True)        # stem at 62 episodes
     run(ops, E, 75, 75, 64, 64, 3, 1, 1, 1, True)           # layer1 conv2
     run(ops, E, 75, 75, 128, 128, 3, 2, 1, 1, True)         # layer2.0 conv2
     run(ops, E, 38, 38, 128, 128, 3, 1, 1, 1, True)         # layer2 conv2
