@@ -43,6 +43,7 @@ class MetaTrainerStep:
         self.lr_decay, self.warmup_tokens, self.final_tokens = bool(lr_decay), float(warmup_tokens), float(final_tokens)
         self.tokens = 0
         self.t = 0
+        self._slot_steps = None             # per-parameter Adam step counts (host ints), see _flat_grads
         self.loop = model._get_loop()
         self._own_g = None
         self._alias_parameters()
@@ -96,6 +97,21 @@ class MetaTrainerStep:
         `forward()` since the last zero_grad every .grad is a view of `model.last_meta_grads["all"]`
         (zero copies); anything else (several accumulated forwards into foreign tensors, grads set by
         hand) is gathered into an own buffer.  Parameters without a gradient get the no-gradient marker."""
+        # torch.optim.Adam keeps one step count PER parameter and advances it only when .grad is not None; the
+        # fused step applies ONE count (self.t + 1) to every parameter it updates.  The two agree as long as every
+        # parameter updated now was also updated on all earlier steps - tracked per parameter and checked, not
+        # assumed (a parameter that stops receiving gradients is fine until it receives one again).
+        if self._slot_steps is None or len(self._slot_steps) != len(self._slots):
+            self._slot_steps = [self.t] * len(self._slots)
+        late = [i for i, s in enumerate(self._slots) if s[0].grad is not None and self._slot_steps[i] != self.t]
+        if late:
+            raise RuntimeError("MetaTrainerStep: %d parameters (e.g. %s) receive a gradient now but skipped earlier steps; "
+                               "torch.optim.Adam would bias-correct them with their own step count (%d), the fused step "
+                               "has one count (%d) per weight buffer" % (len(late), [self._slots[i][5] for i in late[:3]],
+                                                                          self._slot_steps[late[0]] + 1, self.t + 1))
+        for i, s in enumerate(self._slots):
+            if s[0].grad is not None:
+                self._slot_steps[i] = self.t + 1
         last = getattr(self.model, "last_meta_grads", None)
         G = last["all"] if last is not None else None
         ok = G is not None
@@ -152,6 +168,22 @@ class MetaTrainerStep:
                                 self.max_norm, lr, self.betas, self.eps, self.t, zero_grad=True,
                                 norm_out=self.norm if base == 0 else None)
             base += n
+
+    # ------------------------------------------------------------------ resume
+    def state_dict(self):
+        """Optimiser state for resuming: Adam moments on the flat [theta | psi | phi] layout, the step count, the
+        LR-schedule position and the per-parameter step counts (the weights themselves are the model's)."""
+        return {"m": self.m.detach().clone(), "v": self.v.detach().clone(), "t": self.t, "tokens": self.tokens,
+                "supervisor_lr": self.supervisor_lr, "sizes": list(self._sizes()),
+                "slot_steps": None if self._slot_steps is None else list(self._slot_steps)}
+
+    def load_state_dict(self, sd):
+        if list(sd["sizes"]) != list(self._sizes()):
+            raise ValueError(f"optimizer state was saved for flat buffers {sd['sizes']}, this model has {self._sizes()}")
+        self.m.copy_(sd["m"].to(self.m.device))
+        self.v.copy_(sd["v"].to(self.v.device))
+        self.t, self.tokens, self.supervisor_lr = int(sd["t"]), sd["tokens"], float(sd["supervisor_lr"])
+        self._slot_steps = None if sd.get("slot_steps") is None else list(sd["slot_steps"])
 
     def step(self, n_frames=0):
         """clip + both Adam steps + zero_grad.  n_frames = batch * frames of this iteration (drives the

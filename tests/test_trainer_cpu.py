@@ -143,3 +143,43 @@ def test_windowed_checkpoint_average(model_type):
         n_flat += int(out[k].data_ptr() != saved[k].data_ptr())
     moved = [k for k in saved if not torch.equal(saved[k], model.state_dict()[k].to(saved[k].dtype))]
     assert len(moved) > 250                                                       # it is an average, not the last snapshot
+
+
+def test_optimizer_state_roundtrip_and_step_count_guard():
+    """state_dict()/load_state_dict() resume the fused step bit-exactly; a parameter that skipped steps and then
+    receives a gradient (torch.optim.Adam would use its own step count) is refused instead of silently diverging."""
+    import interactron_b200 as ib
+    from interactron_b200.trainer import MetaTrainerStep
+    torch.manual_seed(1)
+
+    def make():
+        m = ib.build_model(ib.default_config("interactron_random", weights="synthetic").MODEL).eval().double()
+        m._ops = SimOps(torch.float64)
+        return m, MetaTrainerStep(m, 1e-3, 3e-3, 1.0)
+
+    def set_grads(m, seed, only=None):
+        g = torch.Generator().manual_seed(seed)
+        m.last_meta_grads = None
+        for n, p in m.named_parameters():
+            take = n.startswith("detector.transformer.decoder") if only is None else only(n)
+            p.grad = torch.randn(p.shape, generator=g, dtype=p.dtype) if take else None
+
+    a, ta = make()
+    for it in range(2):
+        set_grads(a, it)
+        ta.step()
+    sd, weights = ta.state_dict(), copy.deepcopy(a.state_dict())
+    set_grads(a, 7)
+    ta.step()
+    b, tb = make()
+    b.load_state_dict(weights)
+    tb.load_state_dict(sd)
+    assert tb.t == 2
+    set_grads(b, 7)
+    tb.step()
+    for (n, p), (_, q) in zip(a.named_parameters(), b.named_parameters()):
+        assert torch.equal(p, q), n
+    # a parameter group that never had a gradient gets one at step 4: refused
+    set_grads(a, 8, only=lambda n: n.startswith("detector.transformer.encoder"))
+    with pytest.raises(RuntimeError, match="skipped earlier steps"):
+        ta.step()
