@@ -128,6 +128,31 @@ def test_predict_batch_equals_single_and_is_deterministic(rand_model):
         assert rel(both["pred_boxes"][i], one["pred_boxes"][0]) < 1e-4
 
 
+def test_predict_at_the_bench_batch_size_matches_reference_and_singles(rand_model):
+    """The bench's full configuration (62 episodes per step, BASELINE configs[2]): episodes 0 and 1 of the batch
+    equal the reference goldens, sampled episodes equal their single-episode predict() (independence of the
+    episodes inside the batched kernels: per-episode fast weights, tile tails, CTA-pair and batched-layer GEMMs
+    all take their large-batch paths here), and a replay is bit-identical."""
+    from interactron_b200.synthetic import collate_episodes, synthetic_episode
+    gold = torch.load(os.path.join(GOLD, "interactron_random_predict.pt"))["episodes"]
+    m = rand_model
+    E = 62
+    batch = collate_episodes([synthetic_episode(i, with_targets=False) for i in range(E)])
+    out = m.predict(batch)
+    assert out["pred_logits"].shape == (E, 1, 50, 1236)
+    for ep in (0, 1):
+        assert rel(out["pred_logits"][ep], gold[ep]["pred_logits"][0]) < TOL
+        assert rel(out["pred_boxes"][ep], gold[ep]["pred_boxes"][0]) < TOL
+    for ep in (5, 37, 61):
+        one = m.predict(synthetic_episode(ep, with_targets=False))
+        assert rel(out["pred_logits"][ep], one["pred_logits"][0]) < 1e-4
+        assert rel(out["pred_boxes"][ep], one["pred_boxes"][0]) < 1e-4
+    again = m.predict(batch)
+    assert torch.equal(out["pred_logits"], again["pred_logits"]) and torch.equal(out["pred_boxes"], again["pred_boxes"])
+    m._graphs.clear()
+    torch.cuda.empty_cache()
+
+
 def test_predict_leaves_parameters_intact_and_tracks_updates(rand_model):
     from interactron_b200.synthetic import synthetic_episode
     m = rand_model
