@@ -652,7 +652,8 @@ def measure_meta(name, E, steps, warmup, cpu_episodes, rank, local, world, train
         "metric": "Interactron episodes/s (meta-training step, second-order MAML)", "value": v,
         "unit": "episodes/s", "n_gpus": world, "steps": steps, "warmup": warmup,
         "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "tf32x3", "data": "synthetic",
+        "dtype": "tf32x3" + (" (split accumulators: ITN_PREC_TF32X3_SPLIT)" if getattr(model, "meta_split_acc", False) else ""),
+        "data": "synthetic",
         "config": {"workload": f"{name}.yaml forward() = BASELINE configs[4] (meta-training step), " +
                                ("train() mode (dropout p=0.1 in every pass, as the reference trainer)" if train
                                 else "eval() mode (no dropout)") + ", D1", "episodes_per_step_per_gpu": E,

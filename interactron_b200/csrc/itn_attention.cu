@@ -80,9 +80,11 @@ __device__ __forceinline__ float ex2(float x) {
 }
 
 #ifndef ITN_ATTN_RZ_EPS
-#define ITN_ATTN_RZ_EPS 1.2f    // mean loss of one round-toward-zero accumulate of these chains, in units of 2^-24 (fitted:
-                                // tools/attn_precision.py - nulls the scale bias of O for every shape class and regime)
+#define ITN_ATTN_RZ_EPS 0.57f   // loss per later round-toward-zero accumulate, in units of 2^-24 ...
 #endif
+#ifndef ITN_ATTN_RZ_C0
+#define ITN_ATTN_RZ_C0 8.5f     // ... plus the chain-length independent shrink (residual operands truncated to 11 bits, lo*lo
+#endif                          // dropped): the GEMM's constants (itn_gemm_tf32.cu); fitted 1.2 * 12.5 = 0.57 * 12.5 + 7.9 on 24-MMA chains
 #ifndef ITN_ATTN_RZ_COMP
 #define ITN_ATTN_RZ_COMP 1
 #endif
@@ -93,7 +95,7 @@ __device__ __forceinline__ float ex2(float x) {
 template <int NKS>
 __device__ __forceinline__ float lo_comp(float x, int col) {
 #if ITN_ATTN_RZ_COMP
-  const float delta = ITN_ATTN_RZ_EPS * 5.9604645e-8f * (3.0f * static_cast<float>(NKS - (col >> 3)) - 1.0f);
+  const float delta = 5.9604645e-8f * (ITN_ATTN_RZ_EPS * (3.0f * static_cast<float>(NKS - (col >> 3)) - 1.0f) + ITN_ATTN_RZ_C0);
   return fmaf(x, delta, tf32_lo(x));
 #else
   return tf32_lo(x);

@@ -50,6 +50,7 @@ class _Base(nn.Module):
         self.policy_cache_hits = 0
         self.use_cuda_graph = os.environ.get("ITN_CUDA_GRAPH", "1") != "0"
         self.sync_meta_grads = True
+        self.meta_split_acc = os.environ.get("ITN_META_SPLITACC", "1") != "0"    # forward(): split-accumulator GEMMs
         self._drop_gen = None               # host generator of the per-step dropout seeds (train() mode)
 
     # -- reference surface ------------------------------------------------------------
@@ -207,7 +208,16 @@ class _Adaptive(_Base):
         # episodes -> all-reduce(SUM) of the flat buffer [theta | psi | phi] (replaces nn.DataParallel,
         # reference engine/interactron_trainer.py:43-46), in two buckets so that the fusion part overlaps
         # the detector pass (meta.meta_step); no-op in a single process
-        predictions, losses, flat = meta.meta_step(self, data, ridx, sync=self.sync_meta_grads)
+        # the meta-gradients are a second derivative through 12 post-norm layers: the step runs its GEMMs with split
+        # accumulators (ITN_PREC_TF32X3_SPLIT: ~fp32 error per product, 8-20 % slower GEMMs).
+        # `meta_split_acc = False` / ITN_META_SPLITACC=0: the default tf32x3 mode of predict()
+        ops = self._get_loop().ops
+        prev = ops.split_acc
+        ops.split_acc = prev or bool(self.meta_split_acc)
+        try:
+            predictions, losses, flat = meta.meta_step(self, data, ridx, sync=self.sync_meta_grads)
+        finally:
+            ops.split_acc = prev
         self.last_meta_grads = flat
         meta.accumulate_grads(self, flat)
         return predictions, losses

@@ -4,14 +4,16 @@ detector meta-gradients accumulated on .grad) against the goldens of the unmodif
 
 Predictions and losses: 1e-3 relative (the north star's bar).  Meta-gradients: the fixtures hold the
 reference run in fp32 AND in fp64.  These gradients are ill-conditioned (a second derivative through
-12 post-norm layers): the fp32 reference itself sits 2e-4 (`interactron_random`) / 2e-3
-(`interactron`) away from its own fp64 run in relative L2 over all parameters.  The tf32x3 tensor-core
-GEMMs carry 0.5-3e-6 per product against torch fp32's 0.3-1.2e-6 (long-K chains accumulate in TMEM with
-round-toward-zero), measured on B200 (tools/meta_parity.py, profiles/README.md): 1.5e-3 / 2.1e-3 over all
-parameters (round 1: 9.4e-4 / 3.8e-3; the same step on the fp32 FMA GEMM, ITN_FORCE_SIMT=1: 1.2e-4, so the
-derivation and every non-GEMM kernel are exact to fp32).  Bounds, against the fp64 reference:
-  per group (theta, psi, phi):   max(2.5e-3, 3 x fp32-reference gap)      (round 1: max(3e-3, 8 x gap))
-  per tensor (strided sample):   max(3e-2, 10 x fp32-reference gap); exact zeros stay (near) zero."""
+12 post-norm layers): the fp32 reference itself sits 2e-4 (`interactron_random`) / 2e-3 (`interactron`) away
+from its own fp64 run in relative L2 over all parameters.  `forward()` runs its GEMMs with split accumulators
+(ITN_PREC_TF32X3_SPLIT, models.meta_split_acc) and the two-term round-toward-zero compensation: measured on B200
+(tools/meta_parity.py, profiles/README.md) 6.7e-4 / 2.3e-3 over all parameters, per group 4.4e-4 ... 7.5e-4 and
+1.6e-3 ... 3.0e-3 (fp32 reference: 0.9e-4 ... 2.2e-4 and 1.1e-3 ... 2.9e-3).  History: round 1 9.4e-4 / 3.8e-3 with bounds
+max(3e-3, 8 x gap); the same step on the fp32 FMA GEMM (ITN_FORCE_SIMT=1): 1.2e-4, so the derivation and every
+non-GEMM kernel are exact to fp32.  Bounds, against the fp64 reference (the ones VERDICT round 1 asked for):
+  per group (theta, psi, phi):   max(1e-3, 3 x fp32-reference gap)
+  per tensor (strided sample):   max(3e-2, 10 x fp32-reference gap); exact zeros stay (near) zero.
+The default tf32x3 mode (`meta_split_acc = False`) is checked against max(1.5e-3, 3 x gap) (measured 1.07e-3)."""
 import os
 
 import pytest
@@ -32,7 +34,7 @@ def _data(gold):
     return collate_episodes([synthetic_episode(e) for e in gold["episodes"]])
 
 
-def _check_round(model, data, gold, r):
+def _check_round(model, data, gold, r, floor=1e-3):
     g32, g64 = gold["fp32"][r], gold["fp64"][r]
     model.zero_grad(set_to_none=True)
     p, l = model(data, ridx=list(gold["ridx"]))
@@ -73,7 +75,7 @@ def _check_round(model, data, gold, r):
     for key, a in groups.items():
         mine_e, ref_e = (a[0] / a[2]) ** 0.5, (a[1] / a[2]) ** 0.5
         print(f"group {key}: ours vs fp64 {mine_e:.3e}, fp32 reference vs fp64 {ref_e:.3e}")
-        assert mine_e < max(2.5e-3, 3 * ref_e), (key, mine_e, ref_e)
+        assert mine_e < max(floor, 3 * ref_e), (key, mine_e, ref_e)
     assert per[0][0] < 1.0, per[:5]
 
 
@@ -92,6 +94,15 @@ def test_forward_matches_reference_goldens(name):
     if name == "interactron_random":      # (fusion A's second call sees a populated path storage)
         for n in some:
             assert rel(dict(model.named_parameters())[n].grad, 2 * g1[n]) < 1e-5, n
+
+
+def test_forward_default_gemm_mode_is_close_too():
+    """The same step with the default tf32x3 GEMMs of predict() (no split accumulators): 1.07e-3 on the worst group."""
+    import interactron_b200 as ib
+    gold = torch.load(os.path.join(GOLD, "interactron_random_forward.pt"))
+    model = ib.build_model(ib.default_config("interactron_random", weights="synthetic").MODEL).cuda().eval()
+    model.meta_split_acc = False
+    _check_round(model, _data(gold), gold, 0, floor=1.5e-3)
 
 
 def test_forward_batch_equals_singles():
