@@ -417,7 +417,7 @@ def run_gpu_arm(args):
         extras["baselines_configs_0_1"] = measure_baseline_models(rank, local, world)
         if args.workload != "interactron":
             extras["interactron_predict"] = measure_predict_extra("interactron", 16, 5, 3, rank, local, world)
-        extras["rollout_config_3"] = measure_rollout(16, 2, 2, True, rank, local, world)
+        extras["rollout_config_3"] = measure_rollout(16, 4, 2, True, rank, local, world)
         e_meta = max(1, 16 // world) if world > 1 else 2
         extras["meta_interactron_config_4"] = measure_meta("interactron", e_meta, 8, 3, 0, rank, local, world)
     if rank == 0:

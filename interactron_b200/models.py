@@ -212,12 +212,14 @@ class _Adaptive(_Base):
         # accumulators (ITN_PREC_TF32X3_SPLIT: ~fp32 error per product, 8-20 % slower GEMMs).
         # `meta_split_acc = False` / ITN_META_SPLITACC=0: the default tf32x3 mode of predict()
         ops = self._get_loop().ops
-        prev = ops.split_acc
-        ops.split_acc = prev or bool(self.meta_split_acc)
+        prev = getattr(ops, "split_acc", None)          # None: a backend without the mode (the CPU simulation in tests)
+        if prev is not None:
+            ops.split_acc = prev or bool(self.meta_split_acc)
         try:
             predictions, losses, flat = meta.meta_step(self, data, ridx, sync=self.sync_meta_grads)
         finally:
-            ops.split_acc = prev
+            if prev is not None:
+                ops.split_acc = prev
         self.last_meta_grads = flat
         meta.accumulate_grads(self, flat)
         return predictions, losses
