@@ -137,15 +137,21 @@ class InnerLoop:
         return Weights((self.phi_pack, self.phi, self.phi_r, self.phi_t))
 
     # ------------------------------------------------------------------ pieces
-    def features(self, frames, masks):
-        """frames [N,3,H,W], masks [N,H,W] (nonzero = padded) -> (src_r [N,L,2048] TF32-clean
-        token-major, pos [N*L,256], kmask uint8 [N,L], hw).  self.src keeps the unrounded features."""
-        ops = self.ops
+    def trunk(self, frames):
+        """The frozen backbone on frames [N,3,H,W] -> channels-last features [N,h,w,2048]."""
         body = self.detector.backbone[0].body
         if self.backbone_impl == "gemm":
-            src = run_backbone_gemm(body, frames, ops)                                    # [N,h,w,2048]
-        else:
-            src = run_backbone(body, frames, self.backbone_tf32)
+            return run_backbone_gemm(body, frames, self.ops)
+        return run_backbone(body, frames, self.backbone_tf32)
+
+    def features(self, frames, masks, src=None):
+        """frames [N,3,H,W], masks [N,H,W] (nonzero = padded) -> (src_r [N,L,2048] TF32-clean
+        token-major, pos [N*L,256], kmask uint8 [N,L], hw).  self.src keeps the unrounded features.
+        src: trunk features [N,h,w,2048] computed by the caller (graph.PipelinedPredict runs the trunk chunk by
+        chunk while the rest of the frames is still crossing PCIe); `frames` is then not read."""
+        ops = self.ops
+        if src is None:
+            src = self.trunk(frames)                                                      # [N,h,w,2048]
         N, h, w, C = src.shape
         self.src = src.reshape(N, h * w, C)
         src_r = ops.round_tf32(self.src)
@@ -187,14 +193,14 @@ class InnerLoop:
         return DropCtx(self.drop_p, self.drop_seed, self.PASS_SITES[which])
 
     # ------------------------------------------------------------------ the hot path
-    def adapt_detect(self, frames, masks, post_frames=(0,), want_trace=False, train=False):
+    def adapt_detect(self, frames, masks, post_frames=(0,), want_trace=False, train=False, src=None):
         """frames [E,S,3,H,W], masks [E,S,H,W] on the device -> dict with post-adapt
         pred_logits [E,P,50,C], pred_boxes [E,P,50,4] (P = len(post_frames)) and features.
         train: the reference's train() mode - dropout in the pre-adapt pass, the fusion network and the
         post-adapt pass (models/interactron.py:31-59 run under model.train())."""
         ops = self.ops
         E, S = frames.shape[:2]
-        src_r, pos, kmask, (h, w) = self.features(frames.flatten(0, 1), masks.flatten(0, 1))
+        src_r, pos, kmask, (h, w) = self.features(frames.flatten(0, 1), masks.flatten(0, 1), src=src)
         L = h * w
         C = self.detector.class_embed.out_features
         # -- pre-adapt pass (shared theta) and learned loss

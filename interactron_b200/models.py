@@ -50,6 +50,10 @@ class _Base(nn.Module):
         self.policy_cache_hits = 0
         self.use_cuda_graph = os.environ.get("ITN_CUDA_GRAPH", "1") != "0"
         self.sync_meta_grads = True
+        # predict() on host frames: hide the H2D copy behind the trunk (graph.PipelinedPredict).  Off by default: measured
+        # bit-identical and NOT faster on the power-capped B200 (tools/e2e_probe.py: the idle copy time is repaid by
+        # higher clocks afterwards); ITN_PIPELINED_INPUT=1 enables it
+        self.pipelined_input = os.environ.get("ITN_PIPELINED_INPUT", "0") != "0"
         self.meta_split_acc = os.environ.get("ITN_META_SPLITACC", "1") != "0"    # forward(): split-accumulator GEMMs
         self._drop_gen = None               # host generator of the per-step dropout seeds (train() mode)
 
@@ -161,8 +165,13 @@ class _Adaptive(_Base):
         train = self.mode == "train"         # the reference applies dropout here too when left in train() mode
         if train:
             self._new_dropout_seed(loop)
-        frames, masks = self._frames_masks(data, loop.ops.device)
         keys = ("pred_logits", "pred_boxes", "image_features", "embedded_memory_features", "box_features")
+        hf = data["frames"]
+        if (self.use_cuda_graph and self.pipelined_input and not hf.is_cuda and hf.dim() == 5
+                and hf.shape[0] * hf.shape[1] >= 40 and torch.device(loop.ops.device).type == "cuda"):
+            # host frames, many of them: the copy runs behind the trunk (graph.PipelinedPredict)
+            return self._predict_pipelined(loop, data, keys, train)
+        frames, masks = self._frames_masks(data, loop.ops.device)
 
         def run(f, m):
             out = loop.adapt_detect(f, m, post_frames=(0,), train=train)
@@ -171,6 +180,21 @@ class _Adaptive(_Base):
         if not (self.use_cuda_graph and frames.is_cuda):
             return run(frames, masks)
         return self._graphed("predict_train" if train else "predict", run, frames, masks)
+
+    def _predict_pipelined(self, loop, data, keys, train):
+        from .episode import sample_masks_host
+        from .graph import PipelinedPredict
+        frames, masks = data["frames"], data["masks"]
+        if not masks.is_cuda:
+            masks = sample_masks_host(masks)
+        self._check_backbone_moved()
+        key = ("predict_pipe_train" if train else "predict_pipe", tuple(frames.shape), tuple(masks.shape), masks.dtype,
+               loop.ops.precision_key, loop.backbone_tf32, loop.backbone_impl, float(loop.lr), float(loop.clip),
+               bool(loop.ops.fused_attention))
+        g = self._graphs.get(key)
+        if g is None:
+            g = self._graphs[key] = PipelinedPredict(loop, frames, masks, keys, train=train)
+        return g(frames, masks)
 
     def _check_backbone_moved(self):
         bb = self._detector().backbone

@@ -153,6 +153,36 @@ def test_predict_at_the_bench_batch_size_matches_reference_and_singles(rand_mode
     torch.cuda.empty_cache()
 
 
+def test_pipelined_host_input_is_bit_identical(rand_model):
+    """predict() on host frames hides the H2D copy behind the trunk (graph.PipelinedPredict: trunk on the first
+    quarter of the frames, trunk on the rest, then the step, as three graphs fed by a copy stream).  Same bits as
+    the copy-first single-graph path, for pageable and pinned inputs, over repeated calls with different data."""
+    from interactron_b200.synthetic import collate_episodes, synthetic_episode
+    m = rand_model
+    m.pipelined_input = True          # opt-in (off by default: no gain on the power-capped board, DESIGN.md section 4)
+    batches = [collate_episodes([synthetic_episode(i, with_targets=False) for i in range(k, k + 16)]) for k in (0, 20)]
+    piped = []
+    for b in batches + batches[:1]:
+        pinned = dict(b)
+        pinned["frames"] = b["frames"].pin_memory()
+        o = m.predict(pinned)
+        piped.append({k: v.clone() for k, v in o.items()})
+    assert any(k[0] == "predict_pipe" for k in m._graphs)
+    assert all(torch.equal(piped[0][k], piped[2][k]) for k in piped[0])
+    o_pageable = m.predict(batches[1])
+    assert all(torch.equal(o_pageable[k], piped[1][k]) for k in o_pageable)
+    m.pipelined_input = False
+    try:
+        for b, want in zip(batches, piped):
+            o = m.predict(b)
+            for k in want:
+                assert torch.equal(o[k], want[k]), k
+    finally:
+        m.pipelined_input = False
+    m._graphs.clear()
+    torch.cuda.empty_cache()
+
+
 def test_predict_leaves_parameters_intact_and_tracks_updates(rand_model):
     from interactron_b200.synthetic import synthetic_episode
     m = rand_model
