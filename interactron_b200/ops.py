@@ -75,6 +75,7 @@ class CudaOps:
         # the dx kernel, the dgamma/dbeta kernel and a separate column sum
         self.fused_ln_bwd = os.environ.get("ITN_FUSED_LN_BWD", "1") != "0"
         self._ln_ws = None
+        self._ln_ws_keep = []
         # LayerNorm forward that also emits y + pos / y + query_pos for the next attention (ITN_FUSED_LN_PLUS=0: add kernel)
         self.fused_ln_plus = os.environ.get("ITN_FUSED_LN_PLUS", "1") != "0"
 
@@ -478,8 +479,12 @@ class CudaOps:
                 xs_stride = dxsum.stride(0) if groups > 1 else cols
             need = int(self.lib.itn_layernorm_bwd_fused_workspace(rows, cols, groups))
             if self._ln_ws is None or self._ln_ws.numel() < need:
-                # allocated (and zeroed) outside of graph capture by the eager warm-up pass; grows monotonically
+                # allocated (and zeroed) outside of graph capture by the eager warm-up pass; grows monotonically.
+                # Captured graphs keep the address of the workspace they were recorded with: outgrown ones stay alive.
+                if torch.cuda.is_current_stream_capturing():
+                    raise RuntimeError("layernorm_bwd: workspace must be sized by an eager pass before graph capture")
                 self._ln_ws = torch.zeros(max(need, 8 << 20), dtype=torch.uint8, device=self.device)
+                self._ln_ws_keep.append(self._ln_ws)
             _lib.check(self.lib.itn_layernorm_bwd_fused(_ptr(dy), _ptr(x), _ptr(mean), _ptr(rstd), _ptr(g2), _ptr(dx),
                                                         _ptr(dgamma), _ptr(dbeta), _ptr(dxsum), rows, cols, groups,
                                                         gb_stride, stride, xs_stride, _ptr(self._ln_ws),

@@ -668,3 +668,41 @@ def test_implicit_gemm_convolution_matches_explicit_im2col(ops3, geom):
     z = torch.randn(N * Ho * Wo, Cout, device="cuda", generator=g)
     y3, _, _ = ops3.conv_gemm(x, wm, k, k, stride, pad, dil, bias=b, act="relu", residual=z, act_after_residual=True)
     assert rel(y3, torch.relu(ref + z.double())) < 1e-5
+
+
+def test_layernorm_bwd_workspace_growth_keeps_captured_graphs_valid():
+    """A captured graph holds the address of the LayerNorm-backward workspace it was recorded with; when a later,
+    larger problem makes the ops object allocate a bigger one, the old one must stay alive and usable."""
+    from interactron_b200.ops import CudaOps
+    o = CudaOps()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    rows, cols, groups = 6 * 250, 256, 6
+    x = torch.randn(rows, cols, generator=g, device="cuda")
+    dy = torch.randn(rows, cols, generator=g, device="cuda")
+    gamma = torch.randn(groups, cols, generator=g, device="cuda")
+    beta = torch.zeros(groups, cols, device="cuda")
+    _, _, mean, rstd = o.layernorm_fwd(x, gamma, beta)
+    dg, db, ds = (torch.zeros(groups, cols, device="cuda") for _ in range(3))
+    want_dx, _ = o.layernorm_bwd(dy, x, mean, rstd, gamma, dgamma=dg, dbeta=db, dxsum=ds)       # eager: sizes the workspace
+    want = [t.clone() for t in (want_dx, dg, db, ds)]
+    small_ws = o._ln_ws
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        got_dx, _ = o.layernorm_bwd(dy, x, mean, rstd, gamma, dgamma=dg, dbeta=db, dxsum=ds)
+    # a problem whose workspace does not fit the first allocation (2048 groups x 3 x 512 floats)
+    G2 = 2048
+    x2 = torch.randn(G2 * 2, 512, generator=g, device="cuda")
+    ga2 = torch.ones(G2, 512, device="cuda")
+    _, _, m2, r2 = o.layernorm_fwd(x2, ga2, torch.zeros(G2, 512, device="cuda"))
+    o.layernorm_bwd(torch.randn(G2 * 2, 512, generator=g, device="cuda"), x2, m2, r2, ga2,
+                    dgamma=torch.zeros(G2, 512, device="cuda"), dbeta=torch.zeros(G2, 512, device="cuda"))
+    assert o._ln_ws is not small_ws and any(w is small_ws for w in o._ln_ws_keep)
+    junk = [torch.full((1 << 20,), float("nan"), device="cuda") for _ in range(16)]      # would land in a freed workspace
+    for t in (dg, db, ds):
+        t.zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    for a, b in zip((got_dx, dg, db, ds), want):
+        assert torch.equal(a, b)
+    del junk
